@@ -1,0 +1,157 @@
+/*
+ * skp_b200.h -- C ABI of libskp_b200.so: hand-written sm_100a CUDA for the StableKeypoints hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a cudaStream_t (as void*),
+ * allocates nothing, never throws and never synchronises; it returns 0 on success or a negative
+ * skp_status.  `skp_last_error()` gives a human-readable message for the calling thread.
+ * All tensors are dense row-major fp32 unless a leading dimension (ld*) is given; indices are int64
+ * (torch.long) so they can be shared with the host code without conversion.
+ *
+ * Each function names the reference code it replaces (paths relative to
+ * /root/reference/unsupervised_keypoints).  The reference itself has no FFI: these are the calls
+ * its Python would bind via ctypes.
+ */
+#ifndef SKP_B200_H
+#define SKP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SKP_OK = 0,
+  SKP_ERR_INVALID = -1,   /* bad argument (null pointer, non-positive size, unsupported shape) */
+  SKP_ERR_LAUNCH = -2,    /* cudaGetLastError() after a launch */
+  SKP_ERR_UNSUPPORTED = -3,
+  SKP_ERR_DRIVER = -4     /* TMA descriptor encode / driver entry point failure */
+} skp_status;
+
+#define SKP_MAX_LAYERS 8
+
+int skp_version(void);
+const char* skp_last_error(void);
+/* Number of kernels launched by this library in this process (bench.py "gpu_launches"). */
+int64_t skp_launch_count(void);
+
+/* ------------------------------------------------------------------ dense projections
+ * C[M,N] = alpha * A[M,K] . B[N,K]^T (+ bias[N]) (+ residual[M,N]); fp32 in/out.
+ * Replaces the to_q / to_k / to_v / to_out Linear calls of ptp_utils.py:483-491,541 and their
+ * input-gradients (frozen weights: only dgrad exists, optimize_token.py:71-76).
+ * _simt : fp32 FMA tiles (exact fp32).  _tc : tcgen05 tensor cores, split-bf16 (hi+lo, 3 MMAs, fp32
+ * accumulate in TMEM), operands pre-split by skp_split_bf16 into K-major bf16 pairs and fed by TMA. */
+int skp_gemm_nt_simt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                     int M, int N, int K, float alpha, const float* bias, const float* residual,
+                     int64_t ldr, void* stream);
+/* x[rows, cols] (ld) fp32 -> hi[rows, cols_pad], lo[rows, cols_pad] bf16 with x ~= hi + lo;
+ * cols_pad >= cols is a multiple of 64 and the pad is zero-filled. */
+int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, int cols_pad, void* hi, void* lo,
+                   void* stream);
+int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad,
+                   float* C, int64_t ldc, int M, int N, float alpha, const float* bias,
+                   const float* residual, int64_t ldr, void* stream);
+
+/* ------------------------------------------------------------------ cross-attention core
+ * ptp_utils.py:493-506: sim = q k^T * scale; attn = softmax(sim, -1); out = attn v, per head.
+ * q,o: [S, heads*d] (ld = heads*d); k,v: [N, heads*d] with leading dims ldk/ldv (slices of the batched
+ * K|V projection).  logits[heads, S, N] receives the scaled scores (kept for backward and for the
+ * capture kernels). */
+int skp_cross_attn_fwd(const float* q, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                       float* o, float* logits, int S, int N, int heads, int d, float scale, void* stream);
+/* Backward of the above.  d_logits_extra (nullable) is added to d(sim) -- it carries the gradient that
+ * arrives through the captured maps.  dk/dv must be zero-initialised [N, heads*d] (atomically
+ * accumulated); ds_ws is a workspace of heads*S*(N+2) floats (d(sim) + per-row softmax statistics). */
+int skp_cross_attn_bwd(const float* d_o, const float* q, const float* k, int64_t ldk, const float* v,
+                       int64_t ldv, const float* logits, const float* d_logits_extra, float* ds_ws,
+                       float* dq, float* dk, float* dv, int S, int N, int heads, int d, float scale,
+                       void* stream);
+
+/* ------------------------------------------------------------------ attention-store ("capture")
+ * ptp_utils.py:508-538: bicubic (align_corners=False, A=-0.75, clamped taps) upsample of the layer
+ * input to R x R, to_q, q' k^T * scale, softmax over the TOKEN axis, stored as [heads, R*R, N].
+ * Because to_q is bias-free and bicubic resampling is linear, q'k^T == bicubic(q k^T): the kernels take
+ * the layer's own low-res scaled logits [heads, s, s, N] (SURVEY.md 8a note).
+ * _store : materialises probs[heads, R*R, N] (what AttentionStore.step_store["attn"] holds).
+ * _store_bwd : d_logits[heads,s,s,N] += bicubic^T( softmax-backward(probs, d_probs) ).  */
+int skp_capture_store_fwd(const float* logits, float* probs, int heads, int s, int N, int R, void* stream);
+int skp_capture_store_bwd(const float* logits, const float* d_probs, float* d_logits, int heads, int s,
+                          int N, int R, void* stream);
+/* Fused capture + collect_maps (optimize.py:50-75 with upsample_res=-1, indices=None): over the given
+ * layers (each with its own s), maps[N, R, R] = mean over (layer, head) of the captured probabilities,
+ * never materialising them.  _bwd recomputes and accumulates into d_logits[l] (zero-initialised). */
+int skp_capture_mean_fwd(const float* const* logits, const int* s, int n_layers, float* maps, int heads,
+                         int N, int R, void* stream);
+int skp_capture_mean_bwd(const float* const* logits, const int* s, int n_layers, const float* d_maps,
+                         float* const* d_logits, int heads, int N, int R, void* stream);
+
+/* ------------------------------------------------------------------ collect_maps (optimize.py:27-79)
+ * stored[l] : [BH, R*R, N].  out[T, R2, R2] = bilinear_{R->R2}( mean_{l,bh} stored[l][bh, :, idx[t]] ),
+ * T = n_idx if idx != NULL else N; R2 == R means no resize.  (Mean-then-resize equals the reference's
+ * resize-then-mean: both are linear.)  tmp is a [T, R, R] workspace (may alias out when R2 == R). */
+int skp_collect_maps_fwd(const float* const* stored, int n_layers, int BH, int R, int N,
+                         const int64_t* idx, int n_idx, int R2, float* tmp, float* out, void* stream);
+/* d_stored[l][bh, pix, idx[t]] = bilinear^T(d_out)[t, pix] / (n_layers*BH); other tokens get 0.
+ * d_stored buffers are fully written (no pre-zeroing needed). */
+int skp_collect_maps_bwd(const float* d_out, int n_layers, int BH, int R, int N, const int64_t* idx,
+                         int n_idx, int R2, float* tmp, float* const* d_stored, void* stream);
+
+/* ------------------------------------------------------------------ arg-max / selection
+ * eval.py:39-60 find_max_pixel: first-occurrence arg-max of each [H*W] map; flat index out. */
+int skp_argmax_rows(const float* maps, int T, int P, int64_t* flat_idx, void* stream);
+/* eval.py:62-111 find_k_max_pixels with num>1: arg-max, then multiply by 0 inside radius 0.05*H
+ * (integer pixel coords vs the +0.5 centre), repeated; flat_idx[num, T].  work is a [T,H,W] scratch. */
+int skp_k_argmax(const float* maps, int T, int H, int W, int num, float* work, int64_t* flat_idx,
+                 void* stream);
+/* ptp_utils.py:97-108: KL( normalised(Gaussian@argmax + eps) || softmax_pixels(map + eps) ) per token.
+ * peaks[num, T] are flat arg-max indices (num_subjects of them; the target is their mean). */
+int skp_gaussian_kl_scores(const float* maps, int T, int H, int W, const int64_t* peaks, int num,
+                           float sigma, float eps, float* kl, void* stream);
+/* ptp_utils.py:110-112: ascending arg-sort of T scores (stable), first top_k indices. */
+int skp_argsort_topk(const float* scores, int T, int top_k, int64_t* out_idx, void* stream);
+/* ptp_utils.py:115-159 furthest_point_sampling on arg-max locations (flat indices of the maps it is
+ * given, normalised by H): furthest pair then greedy max-min distance, strict '>' tie-breaking.
+ * n_out receives the number of indices written (== top_k unless candidates run out). */
+int skp_furthest_point_sampling(const int64_t* peaks_flat, int H, int W, const int64_t* candidates,
+                                int n_cand, int top_k, int64_t* out_idx, int32_t* n_out, void* stream);
+
+/* ------------------------------------------------------------------ losses
+ * optimize.py:166-206 sharpening_loss on maps[sel[k]] : mean over (K,H,W) of (map - G)^2 with
+ * G = mean over num peaks of exp(-|p - peak|^2 / (2 sigma^2)) on the +0.5 grid (optimize_token.py:203-241).
+ * peaks[num, K] are flat arg-max indices of the SELECTED maps.  loss is a device scalar (overwritten). */
+int skp_sharpen_loss_fwd(const float* maps, int H, int W, const int64_t* sel, int K, const int64_t* peaks,
+                         int num, float sigma, float* loss, void* stream);
+/* d_maps[sel[k], :] += g * 2 (map - G) / (K H W), g read from the device scalar d_loss times weight. */
+int skp_sharpen_loss_bwd(const float* maps, int H, int W, const int64_t* sel, int K, const int64_t* peaks,
+                         int num, float sigma, const float* d_loss, float weight, float* d_maps,
+                         void* stream);
+/* optimize.py:157-163 + invertable_transform.py:72-92: mean (maps[sel] - unwarp(maps_t[sel]))^2 where
+ * unwarp = bilinear grid_sample(zeros padding, align_corners=False) on affine_grid(theta_inv[2x3]).
+ * theta_inv is a 6-float DEVICE array. */
+int skp_equivariance_loss_fwd(const float* maps, const float* maps_t, int H, int W, const int64_t* sel,
+                              int K, const float* theta_inv, float* loss, void* stream);
+int skp_equivariance_loss_bwd(const float* maps, const float* maps_t, int H, int W, const int64_t* sel,
+                              int K, const float* theta_inv, const float* d_loss, float weight,
+                              float* d_maps, float* d_maps_t, void* stream);
+/* invertable_transform.py:65-68 / :87-90: out[b,c] = grid_sample(img[b,c], affine_grid(theta[b])) for
+ * [B,C,H,W]; theta is a [B,2,3] DEVICE array. */
+int skp_affine_warp(const float* img, int B, int C, int H, int W, const float* theta, float* out,
+                    void* stream);
+/* Transposed sampler: d_img (zero-initialised) += scatter of d_out through the same bilinear taps. */
+int skp_affine_warp_bwd(const float* d_out, int B, int C, int H, int W, const float* theta, float* d_img,
+                        void* stream);
+/* eval.py:113-155 pixel_from_weighted_avg: zero (in place) beyond `distance` px of the arg-max,
+ * normalise by sum+1e-6, expectation of (row, col) + 0.5 -> out[T,2].  peaks: flat arg-max per map. */
+int skp_soft_argmax(float* heatmaps, int T, int H, int W, const int64_t* peaks, float distance,
+                    float* out, void* stream);
+
+/* ------------------------------------------------------------------ optimiser (optimize.py:320,424)
+ * torch.optim.Adam defaults (no weight decay / amsgrad); grad is scaled by grad_scale first (the
+ * 1/world_size of the data-parallel mean, optimize.py:405-406). */
+int skp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int step,
+                  float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKP_B200_H */

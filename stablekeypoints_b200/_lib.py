@@ -1,0 +1,157 @@
+"""ctypes binding of libskp_b200.so (C ABI declared in include/skp_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Dict, List, Optional
+
+import torch
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libskp_b200.so")
+HEADER = os.path.join(PKG, "..", "include", "skp_b200.h")
+
+
+class SkpError(RuntimeError):
+    pass
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPE)
+_SIGNATURES: Dict[str, list] = {
+    "skp_version": [],
+    "skp_last_error": [],
+    "skp_launch_count": [],
+    "skp_gemm_nt_simt": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P, _P, _L, _P],
+    "skp_split_bf16": [_P, _L, _I, _I, _I, _P, _P, _P],
+    "skp_gemm_nt_tc": [_P, _P, _P, _P, _I, _P, _L, _I, _I, _F, _P, _P, _L, _P],
+    "skp_cross_attn_fwd": [_P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P],
+    "skp_cross_attn_bwd": [_P, _P, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "skp_capture_store_fwd": [_P, _P, _I, _I, _I, _I, _P],
+    "skp_capture_store_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "skp_capture_mean_fwd": [_P, _P, _I, _P, _I, _I, _I, _P],
+    "skp_capture_mean_bwd": [_P, _P, _I, _P, _P, _I, _I, _I, _P],
+    "skp_collect_maps_fwd": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P],
+    "skp_collect_maps_bwd": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P],
+    "skp_argmax_rows": [_P, _I, _I, _P, _P],
+    "skp_k_argmax": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "skp_gaussian_kl_scores": [_P, _I, _I, _I, _P, _I, _F, _F, _P, _P],
+    "skp_argsort_topk": [_P, _I, _I, _P, _P],
+    "skp_furthest_point_sampling": [_P, _I, _I, _P, _I, _I, _P, _P, _P],
+    "skp_sharpen_loss_fwd": [_P, _I, _I, _P, _I, _P, _I, _F, _P, _P],
+    "skp_sharpen_loss_bwd": [_P, _I, _I, _P, _I, _P, _I, _F, _P, _F, _P, _P],
+    "skp_equivariance_loss_fwd": [_P, _P, _I, _I, _P, _I, _P, _P, _P],
+    "skp_equivariance_loss_bwd": [_P, _P, _I, _I, _P, _I, _P, _P, _F, _P, _P, _P],
+    "skp_affine_warp": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "skp_affine_warp_bwd": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "skp_soft_argmax": [_P, _I, _I, _I, _P, _F, _P, _P],
+    "skp_adam_step": [_P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _P],
+}
+_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64}
+
+
+def declared_symbols() -> List[str]:
+    """Every function name declared in include/skp_b200.h."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(skp_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib: Optional[C.CDLL] = None
+_profile: Optional[list] = None  # when a list: (name, start_event, end_event) per C-ABI call (bench.py kernel shares)
+
+
+class _Profiled:
+    """Proxy that brackets every kernel-launching C-ABI call with CUDA events on the current stream."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if _profile is None or name in ("skp_last_error", "skp_version", "skp_launch_count"):
+            return fn
+
+        def wrapped(*args):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            _profile.append((name, s, e))
+            return rc
+
+        return wrapped
+
+
+def start_profile() -> None:
+    global _profile
+    _profile = []
+
+
+def stop_profile() -> Dict[str, list]:
+    """Returns {kernel entry point: [ms per call]} and disables profiling."""
+    global _profile
+    rec, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    out: Dict[str, list] = {}
+    for name, s, e in rec:
+        out.setdefault(name, []).append(s.elapsed_time(e))
+    return out
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SkpError(f"{LIB_PATH} not built: run `python -m stablekeypoints_b200.build` (no CPU fallback exists)")
+        handle = C.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, C.c_int)
+        _lib = handle
+    return _Profiled(_lib) if _profile is not None else _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise SkpError(f"{what} failed with status {rc}: {lib().skp_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SkpError("stablekeypoints_b200 kernels need CUDA tensors (the product has no CPU path)")
+
+
+def launch_count() -> int:
+    return int(lib().skp_launch_count())
+
+
+def ptr_array(tensors) -> "C.Array":
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def int_array(values) -> "C.Array":
+    arr = (C.c_int * len(values))()
+    for i, v in enumerate(values):
+        arr[i] = int(v)
+    return arr

@@ -1,0 +1,320 @@
+// tcgen05 tensor-core GEMM for the frozen projections of the cross-attention blocks (to_q / to_k / to_v / to_out
+// of ptp_utils.py:483-491,541 and their dgrads):   C[M,N] = alpha * A[M,K] . B[N,K]^T (+bias) (+residual), fp32 I/O.
+//
+// Precision: the captured attention maps must match the fp32 reference to 1e-3 AFTER a softmax, which plain bf16
+// operands miss by 1.4e-3..2e-2.  Operands are therefore split x = hi + lo (two bf16) and
+// each K-step issues three MMAs (hi.hi + hi.lo + lo.hi) into one fp32 TMEM accumulator: ~4e-6..4e-5 on the maps.
+//
+// Structure (one 128 x BN output tile per CTA, sm_100a only):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2D loads of the four K-major bf16 tiles (128B swizzle)
+//                              into a STAGES-deep shared-memory ring, mbarrier expect_tx / complete_tx
+//   warp 1      MMA issuer   : allocates TMEM, one lane issues tcgen05.mma.cta_group::1.kind::f16
+//                              (M=128, N=BN, K=16) x 4 K-steps x 3 split terms per stage, tcgen05.commit
+//                              releases the stage and finally signals the epilogue
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 (one accumulator row per thread), alpha/bias/residual,
+//                              vectorised global stores
+#include "skp_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace skp {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups 1024 B apart (SBO), LBO unused (=1).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN, int STAGES>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                  float* __restrict__ C, int64_t ldc, int M, int N, int num_kb, float alpha,
+                  const float* __restrict__ bias, const float* __restrict__ residual, int64_t ldr) {
+  using Cfg = TcCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (STAGES + s), 1);
+    }
+    mbar_init(bars + 8 * (2 * STAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+        const uint32_t full = bars + 8 * s;
+        const uint32_t st = base + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+        tma_load_2d(st, &tm_a_hi, full, kb * TC_BK, m0);
+        tma_load_2d(st + Cfg::A_BYTES, &tm_a_lo, full, kb * TC_BK, m0);
+        tma_load_2d(st + 2 * Cfg::A_BYTES, &tm_b_hi, full, kb * TC_BK, n0);
+        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bars + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t st = base + s * Cfg::STAGE_BYTES;
+        const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + Cfg::A_BYTES);
+        const uint64_t b_hi = make_smem_desc(st + 2 * Cfg::A_BYTES), b_lo = make_smem_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 bf16 = 32 B along K inside the swizzle row
+          umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+          umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(bars + 8 * (STAGES + s));  // stage free once these MMAs retire
+      }
+      umma_commit(bars + 8 * (2 * STAGES));    // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(bars + 8 * (2 * STAGES), 0);
+    tc_fence_after();
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + quarter * 32 + lane;
+    const bool vec = ((ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0) && ((N & 3) == 0) &&
+                     (!residual || (((ldr & 3) == 0) && ((((uintptr_t)residual) & 15) == 0))) &&
+                     (!bias || ((((uintptr_t)bias) & 15) == 0));
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+      const int nb = n0 + c * 32;
+      if (row < M && nb < N) {
+        float* crow = C + (size_t)row * ldc + nb;
+        const float* rrow = residual ? residual + (size_t)row * ldr + nb : nullptr;
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (nb + j < N) {
+              float4 o = make_float4(v[j] * alpha, v[j + 1] * alpha, v[j + 2] * alpha, v[j + 3] * alpha);
+              if (bias) {
+                float4 b = *reinterpret_cast<const float4*>(bias + nb + j);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (rrow) {
+                float4 r = *reinterpret_cast<const float4*>(rrow + j);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              *reinterpret_cast<float4*>(crow + j) = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j < N) {
+              float o = v[j] * alpha;
+              if (bias) o += bias[nb + j];
+              if (rrow) o += rrow[j];
+              crow[j] = o;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN));
+  }
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, int cols_pad,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  size_t total = (size_t)rows * cols_pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols_pad), c = (int)(i - (size_t)r * cols_pad);
+    float v = (c < cols) ? x[(size_t)r * ld + c] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, int rows, int kpad, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("gemm_nt_tc: cuTensorMapEncodeTiled entry point unavailable"); return SKP_ERR_DRIVER; }
+  cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_nt_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return SKP_ERR_DRIVER; }
+  return SKP_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C, int64_t ldc,
+                     int M, int N, float alpha, const float* bias, const float* residual, int64_t ldr, cudaStream_t st) {
+  using Cfg = TcCfg<BN, STAGES>;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_map(&ta_hi, A_hi, M, Kpad, TC_BM))) return rc;
+  if ((rc = make_map(&ta_lo, A_lo, M, Kpad, TC_BM))) return rc;
+  if ((rc = make_map(&tb_hi, B_hi, N, Kpad, BN))) return rc;
+  if ((rc = make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
+  cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) { set_error("gemm_nt_tc: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
+  dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM);
+  gemm_nt_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, Kpad / TC_BK, alpha,
+                                                                    bias, residual, ldr);
+  SKP_CHECK_LAUNCH("gemm_nt_tc");
+  return SKP_OK;
+}
+
+}  // namespace skp
+
+using namespace skp;
+
+extern "C" int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, int cols_pad, void* hi, void* lo, void* stream) {
+  SKP_REQUIRE(x && hi && lo && rows > 0 && cols > 0, "split_bf16: bad arguments");
+  SKP_REQUIRE(cols_pad >= cols && cols_pad % TC_BK == 0, "split_bf16: cols_pad=%d must be a multiple of 64 >= cols", cols_pad);
+  size_t total = (size_t)rows * cols_pad;
+  size_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  split_bf16_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  SKP_CHECK_LAUNCH("split_bf16");
+  return SKP_OK;
+}
+
+extern "C" int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C,
+                              int64_t ldc, int M, int N, float alpha, const float* bias, const float* residual, int64_t ldr,
+                              void* stream) {
+  SKP_REQUIRE(A_hi && A_lo && B_hi && B_lo && C, "gemm_nt_tc: null pointer");
+  SKP_REQUIRE(M > 0 && N > 0 && Kpad > 0 && Kpad % TC_BK == 0, "gemm_nt_tc: bad sizes M=%d N=%d Kpad=%d", M, N, Kpad);
+  SKP_REQUIRE(((((uintptr_t)A_hi) | ((uintptr_t)A_lo) | ((uintptr_t)B_hi) | ((uintptr_t)B_lo)) & 15) == 0,
+              "gemm_nt_tc: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long tiles128 = (long)((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
+  if (tiles128 >= 148 && N >= 128)
+    return launch_tc<128, 3>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, st);
+  return launch_tc<64, 4>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, st);
+}

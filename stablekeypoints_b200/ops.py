@@ -1,0 +1,419 @@
+"""torch-facing wrappers (autograd.Function) over the C ABI of libskp_b200.so.
+
+Every op launches hand-written sm_100a kernels on the current CUDA stream into torch-allocated buffers.
+There is no CPU or PyTorch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, int_array, lib, ptr, ptr_array, require_cuda, stream
+
+# "tc": tcgen05 split-bf16 tensor-core GEMM (default); "simt": exact-fp32 FMA GEMM.
+GEMM_IMPL = os.environ.get("SKP_GEMM_IMPL", "tc")
+
+
+def set_gemm_impl(name: str) -> None:
+    global GEMM_IMPL
+    if name not in ("tc", "simt"):
+        raise ValueError(name)
+    GEMM_IMPL = name
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------- dense projections
+def _pad64(k: int) -> int:
+    return (k + 63) // 64 * 64
+
+
+def split_bf16(x: torch.Tensor):
+    """x[rows, cols] fp32 -> (hi, lo) bf16 [rows, pad64(cols)], x ~= hi + lo."""
+    require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    kp = _pad64(cols)
+    hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
+    check(lib().skp_split_bf16(ptr(x), x.stride(0), rows, cols, kp, ptr(hi), ptr(lo), stream()), "skp_split_bf16")
+    return hi, lo
+
+
+class FrozenWeight:
+    """A frozen [out, in] projection weight prepared once for both directions:
+    forward  y = x W^T   (B operand = W,   [out, in]  K-major)
+    dgrad    dx = dy W   (B operand = W^T, [in, out]  K-major)
+    each as fp32 (SIMT path) and as split-bf16 pairs (tcgen05 path)."""
+
+    def __init__(self, w: torch.Tensor, need_dgrad: bool = True):
+        require_cuda(w)
+        self.w = _f32c(w.detach())
+        self.out_features, self.in_features = self.w.shape
+        self.w_split = split_bf16(self.w)
+        self.wt = self.wt_split = None
+        if need_dgrad:
+            self.wt = self.w.t().contiguous()
+            self.wt_split = split_bf16(self.wt)
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, b_split, bias: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+    """out[M, N] = alpha * a[M, K] @ b[N, K]^T (+ bias[N]) (+ residual[M, N])."""
+    require_cuda(a, b)
+    assert a.dim() == 2 and a.stride(1) == 1 and a.dtype == torch.float32
+    m, k = a.shape
+    n = b.shape[0]
+    assert b.shape[1] == k
+    out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    if residual is not None:
+        assert residual.shape == (m, n) and residual.stride(1) == 1 and residual.dtype == torch.float32
+    ldr = residual.stride(0) if residual is not None else 0
+    if GEMM_IMPL == "tc":
+        a_hi, a_lo = split_bf16(a)
+        b_hi, b_lo = b_split
+        check(lib().skp_gemm_nt_tc(ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), a_hi.shape[1], ptr(out), out.stride(0),
+                                   m, n, alpha, ptr(bias), ptr(residual), ldr, stream()), "skp_gemm_nt_tc")
+    else:
+        check(lib().skp_gemm_nt_simt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), m, n, k, alpha,
+                                     ptr(bias), ptr(residual), ldr, stream()), "skp_gemm_nt_simt")
+    return out
+
+
+class _FrozenLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, fw: FrozenWeight, bias):
+        ctx.fw = fw
+        ctx.has_res = residual is not None
+        return gemm_nt(_f32c(x), fw.w, fw.w_split, bias, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        fw = ctx.fw
+        dy = _f32c(dy)
+        dx = gemm_nt(dy, fw.wt, fw.wt_split) if ctx.needs_input_grad[0] else None
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        return dx, dres, None, None
+
+
+def frozen_linear(x: torch.Tensor, fw: FrozenWeight, bias: Optional[torch.Tensor] = None,
+                  residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x W^T + bias + residual with a frozen weight (only input gradients exist)."""
+    return _FrozenLinear.apply(x, residual, fw, bias)
+
+
+# ----------------------------------------------------------------------------- cross-attention core
+class _CrossAttnCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float, want_logits: bool):
+        require_cuda(q, k, v)
+        q = _f32c(q)
+        assert k.stride(1) == 1 and v.stride(1) == 1 and k.dtype == torch.float32 and v.dtype == torch.float32
+        s, c = q.shape
+        n = k.shape[0]
+        d = c // heads
+        o = torch.empty_like(q)
+        logits = torch.empty(heads, s, n, dtype=torch.float32, device=q.device)
+        check(lib().skp_cross_attn_fwd(ptr(q), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), ptr(logits), s, n, heads, d,
+                                       scale, stream()), "skp_cross_attn_fwd")
+        ctx.save_for_backward(q, k, v, logits)
+        ctx.heads, ctx.scale = heads, scale
+        if not want_logits:
+            ctx.mark_non_differentiable(logits)
+        return o, logits
+
+    @staticmethod
+    def backward(ctx, d_o, d_logits):
+        q, k, v, logits = ctx.saved_tensors
+        heads, scale = ctx.heads, ctx.scale
+        s, c = q.shape
+        n = k.shape[0]
+        d = c // heads
+        if d_o is None:
+            d_o = torch.zeros_like(q)
+        d_o = _f32c(d_o)
+        extra = _f32c(d_logits) if d_logits is not None else None
+        ws = torch.empty(heads * s * (n + 2), dtype=torch.float32, device=q.device)
+        dq = torch.empty_like(q)
+        dk = torch.zeros(n, c, dtype=torch.float32, device=q.device)
+        dv = torch.zeros(n, c, dtype=torch.float32, device=q.device)
+        check(lib().skp_cross_attn_bwd(ptr(d_o), ptr(q), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(logits), ptr(extra),
+                                       ptr(ws), ptr(dq), ptr(dk), ptr(dv), s, n, heads, d, scale, stream()),
+              "skp_cross_attn_bwd")
+        return dq, dk, dv, None, None, None
+
+
+def cross_attn_core(q, k, v, heads: int, scale: float, want_logits: bool = False):
+    """(out[S,C], scaled logits[h,S,N]) = softmax(q k^T scale) v per head."""
+    return _CrossAttnCore.apply(q, k, v, heads, scale, want_logits)
+
+
+# ----------------------------------------------------------------------------- capture (attention store)
+def _side(logits: torch.Tensor) -> int:
+    s = int(round(logits.shape[1] ** 0.5))
+    assert s * s == logits.shape[1], "captured layers must have a square token grid"
+    return s
+
+
+class _CaptureStore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, res: int):
+        require_cuda(logits)
+        logits = _f32c(logits)
+        h, _, n = logits.shape
+        s = _side(logits)
+        probs = torch.empty(h, res * res, n, dtype=torch.float32, device=logits.device)
+        check(lib().skp_capture_store_fwd(ptr(logits), ptr(probs), h, s, n, res, stream()), "skp_capture_store_fwd")
+        ctx.save_for_backward(logits)
+        ctx.res = res
+        return probs
+
+    @staticmethod
+    def backward(ctx, d_probs):
+        (logits,) = ctx.saved_tensors
+        h, _, n = logits.shape
+        d_logits = torch.zeros_like(logits)
+        check(lib().skp_capture_store_bwd(ptr(logits), ptr(_f32c(d_probs)), ptr(d_logits), h, _side(logits), n, ctx.res,
+                                          stream()), "skp_capture_store_bwd")
+        return d_logits, None
+
+
+def capture_store(logits: torch.Tensor, res: int) -> torch.Tensor:
+    """probs[h, res*res, N]: what AttentionStore.step_store["attn"] holds (ptp_utils.py:508-538)."""
+    return _CaptureStore.apply(logits, res)
+
+
+class _CaptureMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, res: int, *logits):
+        require_cuda(*logits)
+        logits = [_f32c(l) for l in logits]
+        h, _, n = logits[0].shape
+        sides = [_side(l) for l in logits]
+        maps = torch.empty(n, res, res, dtype=torch.float32, device=logits[0].device)
+        check(lib().skp_capture_mean_fwd(ptr_array(logits), int_array(sides), len(logits), ptr(maps), h, n, res, stream()),
+              "skp_capture_mean_fwd")
+        ctx.save_for_backward(*logits)
+        ctx.res, ctx.sides = res, sides
+        return maps
+
+    @staticmethod
+    def backward(ctx, d_maps):
+        logits = list(ctx.saved_tensors)
+        h, _, n = logits[0].shape
+        d_logits = [torch.zeros_like(l) for l in logits]
+        check(lib().skp_capture_mean_bwd(ptr_array(logits), int_array(ctx.sides), len(logits), ptr(_f32c(d_maps)),
+                                         ptr_array(d_logits), h, n, ctx.res, stream()), "skp_capture_mean_bwd")
+        return (None, *d_logits)
+
+
+def capture_mean(logits: Sequence[torch.Tensor], res: int) -> torch.Tensor:
+    """maps[N, res, res] = mean over (layer, head) of the captured probabilities (capture + collect_maps fused)."""
+    return _CaptureMean.apply(res, *logits)
+
+
+# ----------------------------------------------------------------------------- collect_maps
+class _CollectMaps(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, res2: int, *stored):
+        require_cuda(*stored)
+        stored = [_f32c(s) for s in stored]
+        bh, rr, n = stored[0].shape
+        r = int(round(rr ** 0.5))
+        assert r * r == rr
+        for s in stored:
+            assert s.shape == stored[0].shape, "stored maps must share a shape"
+        t = n if idx is None else idx.numel()
+        if idx is not None:
+            idx = idx.to(device=stored[0].device, dtype=torch.int64).contiguous()
+        r2 = r if res2 in (-1, r) else res2
+        out = torch.empty(t, r2, r2, dtype=torch.float32, device=stored[0].device)
+        tmp = torch.empty(t, r, r, dtype=torch.float32, device=out.device) if r2 != r else None
+        check(lib().skp_collect_maps_fwd(ptr_array(stored), len(stored), bh, r, n, ptr(idx), t if idx is not None else 0, r2,
+                                         ptr(tmp), ptr(out), stream()), "skp_collect_maps_fwd")
+        ctx.meta = (len(stored), bh, r, n, r2, t)
+        ctx.idx = idx
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        nl, bh, r, n, r2, t = ctx.meta
+        d_out = _f32c(d_out)
+        d_stored = [torch.empty(bh, r * r, n, dtype=torch.float32, device=d_out.device) for _ in range(nl)]
+        tmp = torch.empty(t, r, r, dtype=torch.float32, device=d_out.device) if r2 != r else None
+        idx = ctx.idx
+        check(lib().skp_collect_maps_bwd(ptr(d_out), nl, bh, r, n, ptr(idx), t if idx is not None else 0, r2, ptr(tmp),
+                                         ptr_array(d_stored), stream()), "skp_collect_maps_bwd")
+        return (None, None, *d_stored)
+
+
+def collect_maps_op(stored: Sequence[torch.Tensor], upsample_res: int = -1, indices=None) -> torch.Tensor:
+    return _CollectMaps.apply(indices, upsample_res, *stored)
+
+
+# ----------------------------------------------------------------------------- arg-max / selection
+def argmax_flat(maps: torch.Tensor) -> torch.Tensor:
+    """First-occurrence flat arg-max of each [H, W] map -> int64 [T]."""
+    require_cuda(maps)
+    maps = _f32c(maps.detach())
+    t = maps.shape[0]
+    out = torch.empty(t, dtype=torch.int64, device=maps.device)
+    check(lib().skp_argmax_rows(ptr(maps), t, maps[0].numel(), ptr(out), stream()), "skp_argmax_rows")
+    return out
+
+
+def k_argmax_flat(maps: torch.Tensor, num: int) -> torch.Tensor:
+    """eval.find_k_max_pixels as flat indices [num, T]."""
+    require_cuda(maps)
+    maps = _f32c(maps.detach())
+    t, h, w = maps.shape
+    out = torch.empty(num, t, dtype=torch.int64, device=maps.device)
+    check(lib().skp_k_argmax(ptr(maps), t, h, w, num, None, ptr(out), stream()), "skp_k_argmax")
+    return out
+
+
+def gaussian_kl_scores(maps: torch.Tensor, peaks: torch.Tensor, sigma: float, eps: float = 1e-5) -> torch.Tensor:
+    require_cuda(maps, peaks)
+    maps = _f32c(maps.detach())
+    t, h, w = maps.shape
+    kl = torch.empty(t, dtype=torch.float32, device=maps.device)
+    check(lib().skp_gaussian_kl_scores(ptr(maps), t, h, w, ptr(peaks), peaks.shape[0], float(sigma), float(eps), ptr(kl),
+                                       stream()), "skp_gaussian_kl_scores")
+    return kl
+
+
+def argsort_topk(scores: torch.Tensor, top_k: int) -> torch.Tensor:
+    require_cuda(scores)
+    scores = _f32c(scores)
+    out = torch.empty(top_k, dtype=torch.int64, device=scores.device)
+    check(lib().skp_argsort_topk(ptr(scores), scores.numel(), top_k, ptr(out), stream()), "skp_argsort_topk")
+    return out
+
+
+def furthest_point_sampling_flat(peaks_flat: torch.Tensor, h: int, w: int, candidates: torch.Tensor, top_k: int):
+    """Returns (indices int64 [top_k], count int32 [1]) on device; no host sync."""
+    require_cuda(peaks_flat, candidates)
+    candidates = candidates.to(device=peaks_flat.device, dtype=torch.int64).contiguous()
+    out = torch.zeros(top_k, dtype=torch.int64, device=peaks_flat.device)
+    n_out = torch.zeros(1, dtype=torch.int32, device=peaks_flat.device)
+    check(lib().skp_furthest_point_sampling(ptr(peaks_flat), h, w, ptr(candidates), candidates.numel(), top_k, ptr(out),
+                                            ptr(n_out), stream()), "skp_furthest_point_sampling")
+    return out, n_out
+
+
+# ----------------------------------------------------------------------------- losses
+class _SharpenLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, maps, sel, peaks, sigma: float):
+        require_cuda(maps, sel, peaks)
+        maps = _f32c(maps)
+        _, h, w = maps.shape
+        loss = torch.empty((), dtype=torch.float32, device=maps.device)
+        check(lib().skp_sharpen_loss_fwd(ptr(maps), h, w, ptr(sel), sel.numel(), ptr(peaks), peaks.shape[0], float(sigma),
+                                         ptr(loss), stream()), "skp_sharpen_loss_fwd")
+        ctx.save_for_backward(maps, sel, peaks)
+        ctx.sigma = sigma
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        maps, sel, peaks = ctx.saved_tensors
+        _, h, w = maps.shape
+        d_maps = torch.zeros_like(maps)
+        check(lib().skp_sharpen_loss_bwd(ptr(maps), h, w, ptr(sel), sel.numel(), ptr(peaks), peaks.shape[0], float(ctx.sigma),
+                                         ptr(_f32c(d_loss)), 1.0, ptr(d_maps), stream()), "skp_sharpen_loss_bwd")
+        return d_maps, None, None, None
+
+
+def sharpen_loss_op(maps: torch.Tensor, sel: torch.Tensor, sigma: float, num_subjects: int = 1) -> torch.Tensor:
+    """optimize.sharpening_loss(maps[sel]) without materialising the gather or the target."""
+    sel = sel.to(device=maps.device, dtype=torch.int64).contiguous()
+    picked = maps.detach()[sel]
+    peaks = k_argmax_flat(picked, num_subjects)
+    return _SharpenLoss.apply(maps, sel, peaks, sigma)
+
+
+class _EquivLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, maps, maps_t, sel, theta_inv):
+        require_cuda(maps, maps_t, sel, theta_inv)
+        maps, maps_t = _f32c(maps), _f32c(maps_t)
+        _, h, w = maps.shape
+        loss = torch.empty((), dtype=torch.float32, device=maps.device)
+        check(lib().skp_equivariance_loss_fwd(ptr(maps), ptr(maps_t), h, w, ptr(sel), sel.numel(), ptr(theta_inv), ptr(loss),
+                                              stream()), "skp_equivariance_loss_fwd")
+        ctx.save_for_backward(maps, maps_t, sel, theta_inv)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        maps, maps_t, sel, theta_inv = ctx.saved_tensors
+        _, h, w = maps.shape
+        d_maps = torch.zeros_like(maps) if ctx.needs_input_grad[0] else None
+        d_maps_t = torch.zeros_like(maps_t) if ctx.needs_input_grad[1] else None
+        check(lib().skp_equivariance_loss_bwd(ptr(maps), ptr(maps_t), h, w, ptr(sel), sel.numel(), ptr(theta_inv),
+                                              ptr(_f32c(d_loss)), 1.0, ptr(d_maps), ptr(d_maps_t), stream()),
+              "skp_equivariance_loss_bwd")
+        return d_maps, d_maps_t, None, None
+
+
+def equivariance_loss_op(maps: torch.Tensor, maps_t: torch.Tensor, sel: torch.Tensor, theta_inv: torch.Tensor):
+    """MSE(maps[sel], unwarp(maps_t[sel])) with theta_inv a [2,3] (or flat 6) fp32 device tensor."""
+    sel = sel.to(device=maps.device, dtype=torch.int64).contiguous()
+    theta_inv = theta_inv.to(device=maps.device, dtype=torch.float32).reshape(6).contiguous()
+    return _EquivLoss.apply(maps, maps_t, sel, theta_inv)
+
+
+class _AffineWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, theta):
+        require_cuda(img, theta)
+        img = _f32c(img)
+        b, c, h, w = img.shape
+        out = torch.empty_like(img)
+        check(lib().skp_affine_warp(ptr(img), b, c, h, w, ptr(theta), ptr(out), stream()), "skp_affine_warp")
+        ctx.save_for_backward(theta)
+        ctx.shape = (b, c, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (theta,) = ctx.saved_tensors
+        b, c, h, w = ctx.shape
+        d_out = _f32c(d_out)
+        d_img = torch.zeros_like(d_out)
+        check(lib().skp_affine_warp_bwd(ptr(d_out), b, c, h, w, ptr(theta), ptr(d_img), stream()), "skp_affine_warp_bwd")
+        return d_img, None
+
+
+def affine_warp(img: torch.Tensor, theta: torch.Tensor) -> torch.Tensor:
+    """grid_sample(img, affine_grid(theta)), bilinear, zeros, align_corners=False; img [B,C,H,W], theta [B,2,3]."""
+    b = img.shape[0]
+    theta = theta.detach().to(device=img.device, dtype=torch.float32).reshape(b, 6).contiguous()
+    return _AffineWarp.apply(img, theta)
+
+
+def soft_argmax_(heatmaps: torch.Tensor, distance: float = 5.0) -> torch.Tensor:
+    """eval.pixel_from_weighted_avg; zeroes `heatmaps` in place like the reference. Returns [T, 2]."""
+    require_cuda(heatmaps)
+    assert heatmaps.dtype == torch.float32 and heatmaps.is_contiguous()
+    t, h, w = heatmaps.shape
+    peaks = argmax_flat(heatmaps)
+    out = torch.empty(t, 2, dtype=torch.float32, device=heatmaps.device)
+    check(lib().skp_soft_argmax(ptr(heatmaps), t, h, w, ptr(peaks), float(distance), ptr(out), stream()), "skp_soft_argmax")
+    return out
+
+
+def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr=5e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    require_cuda(param, grad, exp_avg, exp_avg_sq)
+    assert param.is_contiguous() and grad.is_contiguous() and param.dtype == torch.float32
+    check(lib().skp_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), int(step), lr, beta1,
+                              beta2, eps, grad_scale, stream()), "skp_adam_step")
+    return param

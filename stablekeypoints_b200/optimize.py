@@ -1,0 +1,258 @@
+"""Mirror of the live part of the reference's ``unsupervised_keypoints/optimize.py`` (collect_maps :27-79, losses
+:157-206, optimize_embedding :269-452) on the B200 kernels, one process per GPU."""
+from __future__ import annotations
+
+import time
+from typing import Optional
+
+import torch
+
+from . import ops, ptp_utils
+from .invertable_transform import RandomAffineWithInverse, invert_theta
+
+
+def collect_maps(controller, from_where=["up_cross"], upsample_res=512, layers=[0, 1, 2, 3], indices=None):
+    """optimize.py:27-79: mean over the selected stored layers and the B*h axis, optional token gather and bilinear
+    resize, returns [N or K, R', R'] and RESETS the controller (side effect at :77).  `from_where` is accepted and
+    ignored exactly like the reference."""
+    stored = [m for i, m in enumerate(controller.step_store["attn"]) if i in layers]
+    if not stored:
+        raise RuntimeError("collect_maps: the controller holds no stored attention maps for layers %s" % (layers,))
+    if indices is not None:
+        indices = torch.as_tensor(indices)
+    r = int(stored[0].shape[1] ** 0.5)
+    n_tok = stored[0].shape[2] if indices is None else indices.numel()
+    # the reference's guard compares sqrt(#tokens) with upsample_res (optimize.py:63)
+    resize = upsample_res != -1 and n_tok ** 0.5 != upsample_res
+    out = ops.collect_maps_op(stored, upsample_res if resize else -1, indices)
+    controller.reset()
+    return out
+
+
+def equivariance_loss(embeddings_initial, embeddings_transformed, transform, index):
+    """optimize.py:157-163: MSE(initial, transform.inverse(transformed)[index]); transformed is [G,K,R,R]."""
+    theta_inv = invert_theta(transform.last_params["theta"])[int(index)]
+    k = embeddings_initial.shape[0]
+    sel = torch.arange(k, device=embeddings_initial.device)
+    return ops.equivariance_loss_op(embeddings_initial, embeddings_transformed[int(index)], sel, theta_inv)
+
+
+def sharpening_loss(attn_map, sigma=1.0, temperature=1e1, device="cuda", num_subjects=1):
+    """optimize.py:166-179: MSE(map, Gaussian centred on the map's own arg-max)."""
+    sel = torch.arange(attn_map.shape[0], device=attn_map.device)
+    return ops.sharpen_loss_op(attn_map, sel, sigma, num_subjects)
+
+
+def find_gaussian_loss_at_point(attn_map, pos, sigma=1.0, temperature=1e-1, device="cuda", indices=None, num_subjects=1):
+    """optimize.py:182-206 with explicit positions: pos [num, T, 2] in [0,1] -> nearest pixel-centre peaks."""
+    _, h, w = attn_map.shape
+    cell = (pos.to(attn_map.device) * torch.tensor([h, w], device=attn_map.device)).floor().long()
+    peaks = (cell[..., 0].clamp(0, h - 1) * w + cell[..., 1].clamp(0, w - 1)).contiguous()
+    sel = torch.arange(attn_map.shape[0], device=attn_map.device) if indices is None else torch.as_tensor(indices)
+    if indices is not None:
+        peaks = peaks[:, sel.to(peaks.device)].contiguous()
+    return ops._SharpenLoss.apply(attn_map, sel.to(attn_map.device, torch.int64).contiguous(), peaks, sigma)
+
+
+# ----------------------------------------------------------------------------- one Stage-1 iteration
+def stage1_losses(attn_map, attn_map_t, theta, *, top_k=10, num_candidates=25, sigma=2.0, num_subjects=1,
+                  top_k_strategy="gaussian", forced_indices=None):
+    """optimize.py:380-401 for this rank's image: candidates by Gaussian-KL on the ORIGINAL maps, furthest-point
+    sampling on the TRANSFORMED maps' arg-maxes, then both losses on the selected tokens -- all on device, the
+    token indices never visit the host."""
+    if forced_indices is not None:
+        idx = torch.as_tensor(forced_indices, device=attn_map.device)
+    else:
+        if top_k_strategy == "entropy":
+            cand = ptp_utils.entropy_sort(attn_map, num_candidates)
+        elif top_k_strategy == "gaussian":
+            cand = ptp_utils.find_top_k_gaussian(attn_map, num_candidates, sigma=sigma, num_subjects=num_subjects)
+        elif top_k_strategy == "consistent":
+            cand = torch.arange(num_candidates, device=attn_map.device)
+        else:
+            raise NotImplementedError
+        idx = ptp_utils.furthest_point_sampling(attn_map_t, top_k, cand)
+    sharp = ops.sharpen_loss_op(attn_map, idx, sigma, num_subjects)
+    equiv = ops.equivariance_loss_op(attn_map, attn_map_t, idx, invert_theta(theta)[0])
+    return idx, sharp, equiv
+
+
+def stage1_iteration(ldm, controllers, image, context, transform: RandomAffineWithInverse, args, *, accum: int = 1,
+                     theta=None, noise_a=None, noise_b=None, forced_indices=None, from_where=None):
+    """optimize.py:341-422 for one rank: two captured forwards, selection, loss = w_e*equiv + w_s*sharp, / accum,
+    backward into ``context`` (its .grad accumulates)."""
+    kw = dict(layers=args.layers, noise_level=args.noise_level, from_where=from_where, upsample_res=-1,
+              device=args.device, controllers=controllers)
+    dev = ldm.unet.device
+    image = image.to(dev, non_blocking=True) if isinstance(image, torch.Tensor) else image
+    attn_maps = ptp_utils.run_and_find_attn(ldm, image, context, noise=noise_a, **kw)
+    transformed_img = transform(image, theta=theta)
+    attn_maps_t = ptp_utils.run_and_find_attn(ldm, transformed_img, context, noise=noise_b, **kw)
+    idx, sharp, equiv = stage1_losses(attn_maps[0], attn_maps_t[0], transform.last_params["theta"], top_k=args.top_k,
+                                      num_candidates=args.furthest_point_num_samples, sigma=args.sigma,
+                                      num_subjects=args.num_subjects, top_k_strategy=args.top_k_strategy,
+                                      forced_indices=forced_indices)
+    loss = equiv * args.equivariance_attn_loss_weight + sharp * args.sharpening_loss_weight
+    (loss / accum).backward()
+    return {"loss": loss.detach(), "sharp": sharp.detach(), "equiv": equiv.detach(), "indices": idx,
+            "maps": attn_maps[0].detach(), "maps_t": attn_maps_t[0].detach()}
+
+
+def allreduce_sum_(grad: torch.Tensor, group=None) -> int:
+    """The only collective of the path: sum of d(context) over ranks (NCCL on GPUs, gloo in the CPU tests).
+    Returns the world size so the caller can fold the 1/world mean into the optimizer kernel."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    ws = dist.get_world_size(group)
+    if ws > 1:
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+    return ws
+
+
+def rank_shard(n_items: int, rank: int, world: int, epoch: int = 0, seed: int = 0):
+    """Indices of the dataset this rank visits in `epoch` (same partition DistributedSampler(shuffle, drop_last) makes)."""
+    g = torch.Generator().manual_seed(seed + epoch)
+    perm = torch.randperm(n_items, generator=g).tolist()
+    per = n_items // world
+    return perm[: per * world][rank::world]
+
+
+class EmbeddingOptimizer:
+    """Adam on the [1,N,D] embedding (optimize.py:320,424-425) with the data-parallel gradient mean fused in:
+    one NCCL all-reduce(sum) of the N*D fp32 gradient per optimizer step, then skp_adam_step with grad_scale =
+    1/world_size on every rank (replicated state, identical updates)."""
+
+    def __init__(self, context: torch.Tensor, lr: float = 5e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+        self.context, self.lr, self.betas, self.eps, self.group = context, lr, betas, eps, group
+        self.exp_avg = torch.zeros_like(context)
+        self.exp_avg_sq = torch.zeros_like(context)
+        self.steps = 0
+
+    def step(self):
+        g = self.context.grad
+        ws = allreduce_sum_(g, self.group)
+        self.steps += 1
+        with torch.no_grad():
+            ops.adam_step_(self.context, g, self.exp_avg, self.exp_avg_sq, self.steps, self.lr, self.betas[0],
+                           self.betas[1], self.eps, 1.0 / ws)
+        # the kernel wrote through the raw pointer: tell autograd / the engine's K|V cache the tensor changed
+        torch.autograd.graph.increment_version(self.context)
+
+    def zero_grad(self):
+        self.context.grad = None
+
+
+class SyntheticKeypointDataset(torch.utils.data.Dataset):
+    """{"img": [3,S,S] float in [0,1]} of seeded Gaussian blobs + low-frequency noise: the output contract of the
+    reference datasets (datasets/celeba.py:94-114) for the synthetic 512^2 configs of BASELINE.json."""
+
+    def __init__(self, length: int = 64, size: int = 512, seed: int = 1, blobs: int = 12):
+        self.length, self.size, self.seed, self.blobs = length, size, seed, blobs
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed * 100003 + i)
+        s = self.size
+        ys = ((torch.arange(s).float() + 0.5) / s).reshape(1, s, 1)
+        xs = ((torch.arange(s).float() + 0.5) / s).reshape(1, 1, s)
+        img = torch.zeros(3, s, s)
+        for _ in range(self.blobs):
+            cy, cx = torch.rand(2, generator=g).tolist()
+            sd = 0.03 + 0.08 * torch.rand(1, generator=g).item()
+            img += torch.rand(3, 1, 1, generator=g) * torch.exp(-((ys - cy) ** 2 + (xs - cx) ** 2) / (2 * sd * sd))
+        low = torch.nn.functional.interpolate(torch.rand(1, 3, 8, 8, generator=g), size=(s, s), mode="bilinear",
+                                              align_corners=False)[0]
+        return {"img": (0.7 * img + 0.3 * low).clamp(0, 1), "kpts": torch.zeros(1, 2), "visibility": torch.ones(1)}
+
+
+def _make_dataset(args):
+    """optimize.py:277-303.  The reference's dataset classes are host-side file readers that are out of scope here;
+    they are imported from the user's ``datasets`` package when present, `args.dataset` (an object) wins, and
+    "synthetic" builds the seeded synthetic set."""
+    if getattr(args, "dataset", None) is not None:
+        return args.dataset
+    name = args.dataset_name
+    if name == "synthetic":
+        return SyntheticKeypointDataset(length=getattr(args, "max_len", 64) if getattr(args, "max_len", -1) > 0 else 64)
+    import importlib
+    table = {"celeba_aligned": ("datasets.celeba", "CelebA", dict(split="train", dataset_loc=args.dataset_loc, max_len=args.max_len)),
+             "celeba_wild": ("datasets.celeba", "CelebA", dict(split="train", dataset_loc=args.dataset_loc, align=False, max_len=args.max_len)),
+             "cub_aligned": ("datasets.cub", "TrainSet", dict(data_root=args.dataset_loc, image_size=512)),
+             "cub_001": ("datasets.cub_parts", "CUBDataset", dict(dataset_root=args.dataset_loc, split="train", single_class=1)),
+             "cub_002": ("datasets.cub_parts", "CUBDataset", dict(dataset_root=args.dataset_loc, split="train", single_class=2)),
+             "cub_003": ("datasets.cub_parts", "CUBDataset", dict(dataset_root=args.dataset_loc, split="train", single_class=3)),
+             "cub_all": ("datasets.cub_parts", "CUBDataset", dict(dataset_root=args.dataset_loc, split="train")),
+             "taichi": ("datasets.taichi", "TrainSet", dict(data_root=args.dataset_loc, image_size=512)),
+             "human3.6m": ("datasets.human36m", "TrainSet", dict(data_root=args.dataset_loc, validation=getattr(args, "validation", False))),
+             "unaligned_human3.6m": ("datasets.unaligned_human36m", "TrainSet", dict(data_root=args.dataset_loc, image_size=512)),
+             "deepfashion": ("datasets.deepfashion", "TrainSet", dict(data_root=args.dataset_loc, image_size=512)),
+             "custom": ("datasets.custom_images", "CustomDataset", dict(data_root=args.dataset_loc, image_size=512))}
+    if name not in table:
+        raise NotImplementedError
+    mod, cls, kw = table[name]
+    return getattr(importlib.import_module(mod), cls)(**kw)
+
+
+def optimize_embedding(ldm, args, controllers, num_gpus, context=None,
+                       from_where=["down_cross", "mid_cross", "up_cross"]):
+    """optimize.py:269-452.  Same loop, same flags (`args` is the reference's argparse Namespace), same printed
+    scalars.  Data parallelism: this process owns one GPU (num_gpus == 1 here); under torch.distributed every rank
+    draws its own shard of the shuffled dataset and the embedding gradient is all-reduced once per optimizer step,
+    which reproduces the reference's mean over devices (optimize.py:405-406) and its B//G accumulation (:420-425)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    dataset = _make_dataset(args)
+    transform = RandomAffineWithInverse(degrees=args.augment_degrees, scale=args.augment_scale,
+                                        translate=args.augment_translate)
+    dev = ldm.unet.device
+    if context is None:
+        context = ptp_utils.init_random_noise(dev, num_words=args.num_tokens)
+        if world > 1:
+            dist.broadcast(context, src=0)
+    context = context.to(dev).detach().clone().contiguous()
+    context.requires_grad = True
+    optimizer = EmbeddingOptimizer(context, lr=args.lr)
+    accum = max(1, args.batch_size // (num_gpus * world))
+    start = it_start = time.time()
+    running = {"equiv": 0.0, "sharp": 0.0, "total": 0.0}
+    sampler = None
+    if world > 1:
+        sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True,
+                                                                  drop_last=True)
+    loader = torch.utils.data.DataLoader(dataset, batch_size=num_gpus, shuffle=sampler is None, sampler=sampler,
+                                         drop_last=True, pin_memory=True)
+    it = iter(loader)
+    for iteration in range(int(int(args.num_steps) * accum)):
+        try:
+            batch = next(it)
+        except StopIteration:
+            it = iter(loader)
+            batch = next(it)
+        out = stage1_iteration(ldm, controllers, batch["img"], context, transform, args, accum=accum,
+                               from_where=from_where)
+        running["equiv"] += out["equiv"] / accum * args.equivariance_attn_loss_weight
+        running["sharp"] += out["sharp"] / accum * args.sharpening_loss_weight
+        running["total"] += out["loss"] / accum
+        if (iteration + 1) % accum == 0:
+            optimizer.step()
+            optimizer.zero_grad()
+            ldm.unet.invalidate_context_cache()
+            if rank == 0:
+                msg = {"loss": float(running["total"]), "running_equivariance_attn_loss": float(running["equiv"]),
+                       "running_sharpening_loss": float(running["sharp"]), "iteration time": time.time() - it_start}
+                if getattr(args, "wandb", False):
+                    import wandb
+                    wandb.log(msg)
+                else:
+                    print(f"loss: {float(out['loss'] / accum)}, _loss_equivariance_attn: {msg['running_equivariance_attn_loss']} "
+                          f"sharpening_loss: {msg['running_sharpening_loss']}, running_total_loss: {msg['loss']}, "
+                          f"iteration time: {msg['iteration time']}")
+            running = {"equiv": 0.0, "sharp": 0.0, "total": 0.0}
+            it_start = time.time()
+    if rank == 0:
+        print(f"optimization took {time.time() - start} seconds")
+    return context.detach()

@@ -1,0 +1,317 @@
+"""-m gpu: every C-ABI kernel of libskp_b200 against the CPU oracle / torch-CPU autograd on the same seeded inputs,
+and against the committed golden fixtures minted by the reference's own code."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hotpath as hp
+from tests._util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from stablekeypoints_b200 import ops as _ops
+    return _ops
+
+
+def cu(t):
+    return torch.as_tensor(t).cuda()
+
+
+# ----------------------------------------------------------------------------- GEMMs
+GEMM_SHAPES = [(77, 24960, 768), (256, 1280, 1280), (4096, 320, 320), (64, 1280, 1280), (1024, 640, 640),
+               (77, 768, 24960), (16, 32, 48), (300, 200, 100)]
+
+
+@pytest.mark.parametrize("impl,tol", [("simt", 2e-6), ("tc", 3e-5)])
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_nt(ops, impl, tol, m, n, k):
+    g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn(m, k, generator=g)
+    b = torch.randn(n, k, generator=g) / k ** 0.5
+    bias = torch.randn(n, generator=g)
+    res = torch.randn(m, n, generator=g)
+    want = (a.double() @ b.double().t() + bias.double() + res.double())
+    ops.set_gemm_impl(impl)
+    try:
+        bw = ops.FrozenWeight(cu(b))
+        got = ops.frozen_linear(cu(a), bw, cu(bias), residual=cu(res))
+        plain = ops.frozen_linear(cu(a), bw)
+    finally:
+        ops.set_gemm_impl("tc")
+    assert rel_err(got.cpu(), want) < tol
+    assert rel_err(plain.cpu(), a.double() @ b.double().t()) < tol
+
+
+def test_gemm_tc_dgrad_matches_autograd(ops):
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(200, 320, generator=g)
+    w = torch.randn(640, 320, generator=g) / 18
+    dy = torch.randn(200, 640, generator=g)
+    x = cu(a).requires_grad_(True)
+    y = ops.frozen_linear(x, ops.FrozenWeight(cu(w)))
+    y.backward(cu(dy))
+    assert rel_err(x.grad.cpu(), dy.double() @ w.double()) < 3e-5
+
+
+# ----------------------------------------------------------------------------- cross-attention core
+def _attn_ref(q, k, v, heads, scale, extra_w=None):
+    s, c = q.shape
+    n = k.shape[0]
+    d = c // heads
+    qh = q.reshape(s, heads, d).transpose(0, 1)
+    kh = k.reshape(n, heads, d).transpose(0, 1)
+    vh = v.reshape(n, heads, d).transpose(0, 1)
+    logits = torch.bmm(qh, kh.transpose(1, 2)) * scale
+    o = torch.bmm(torch.softmax(logits, -1), vh).transpose(0, 1).reshape(s, c)
+    return o, logits
+
+
+@pytest.mark.parametrize("s,n,heads,d", [(256, 77, 8, 160), (1024, 77, 8, 80), (64, 500, 8, 40), (16, 12, 4, 8),
+                                         (4096, 100, 8, 40), (100, 33, 2, 24)])
+def test_cross_attn_fwd_bwd(ops, s, n, heads, d):
+    g = torch.Generator().manual_seed(s + n)
+    c = heads * d
+    q = torch.randn(s, c, generator=g, dtype=torch.float64)
+    kv = torch.randn(n, 2 * c + 8, generator=g, dtype=torch.float64)   # strided K/V views like the batched projection
+    do = torch.randn(s, c, generator=g, dtype=torch.float64)
+    dl = torch.randn(heads, s, n, generator=g, dtype=torch.float64) * 0.1
+    scale = d ** -0.5
+    qr, kvr = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    o_ref, l_ref = _attn_ref(qr, kvr[:, :c], kvr[:, c:2 * c], heads, scale)
+    ((o_ref * do).sum() + (l_ref * dl).sum()).backward()
+    qc, kvc = cu(q.float()).requires_grad_(True), cu(kv.float()).requires_grad_(True)
+    o, logits = ops.cross_attn_core(qc, kvc[:, :c], kvc[:, c:2 * c], heads, scale, want_logits=True)
+    ((o * cu(do.float())).sum() + (logits * cu(dl.float())).sum()).backward()
+    assert rel_err(o.detach().cpu(), o_ref.detach()) < 1e-5
+    assert rel_err(logits.detach().cpu(), l_ref.detach()) < 1e-5
+    assert rel_err(qc.grad.cpu(), qr.grad) < 2e-5
+    assert rel_err(kvc.grad.cpu(), kvr.grad) < 2e-5
+
+
+# ----------------------------------------------------------------------------- capture
+def _capture_ref(logits, res):
+    """softmax_tokens(bicubic_pixels(low-res logits)) -> [h, res*res, N]  (linearity form of ptp_utils.py:513-536)."""
+    h, s2, n = logits.shape
+    s = int(s2 ** 0.5)
+    up = F.interpolate(logits.reshape(h, s, s, n).permute(0, 3, 1, 2), size=(res, res), mode="bicubic", align_corners=False)
+    return torch.softmax(up.permute(0, 2, 3, 1).reshape(h, res * res, n), dim=-1)
+
+
+@pytest.mark.parametrize("heads,s,n,res", [(8, 16, 77, 128), (8, 32, 77, 128), (4, 4, 12, 16), (8, 16, 500, 128),
+                                            (8, 8, 100, 64), (2, 16, 20, 24), (8, 32, 16, 16)])
+def test_capture_store_fwd_bwd(ops, heads, s, n, res):
+    g = torch.Generator().manual_seed(heads + s + n)
+    logits = torch.randn(heads, s * s, n, generator=g) * 3
+    dp = torch.randn(heads, res * res, n, generator=g)
+    lr = logits.clone().requires_grad_(True)
+    pref = _capture_ref(lr, res)
+    (pref * dp).sum().backward()
+    lc = cu(logits).requires_grad_(True)
+    p = ops.capture_store(lc, res)
+    (p * cu(dp)).sum().backward()
+    assert p.shape == (heads, res * res, n)
+    assert rel_err(p.detach().cpu(), pref.detach()) < 2e-5
+    assert torch.allclose(p.detach().sum(-1).cpu(), torch.ones(heads, res * res), atol=1e-5)
+    assert rel_err(lc.grad.cpu(), lr.grad) < 5e-5
+
+
+def test_capture_matches_literal_reference_formulation(ops):
+    """The kernel's linearity form vs the reference's literal form (bicubic of x, second to_q) on one layer."""
+    torch.manual_seed(3)
+    heads, d, s, n, res, cdim = 8, 20, 16, 40, 64, 96
+    from oracle import sd15
+    mod = sd15.CrossAttention(heads * d, cdim, heads, d)
+    x = torch.randn(1, s * s, heads * d)
+    ctx = torch.randn(1, n, cdim)
+    store = hp.AttentionStore()
+    hp.attention_with_capture(mod, x, ctx, store, res)
+    want = store.step_store["attn"][0]
+    q = mod.to_q(x)[0]
+    k = mod.to_k(ctx)[0]
+    logits = torch.einsum("shd,nhd->hsn", q.reshape(s * s, heads, d), k.reshape(n, heads, d)) * mod.scale
+    got = ops.capture_store(cu(logits.detach().contiguous()), res)
+    assert rel_err(got.cpu(), want.detach()) < 2e-5
+
+
+@pytest.mark.parametrize("heads,sides,n,res", [(8, (16, 16, 16, 32), 77, 128), (4, (4, 4, 4, 8), 12, 16),
+                                                (8, (16, 32), 500, 128), (8, (16, 16, 16, 32), 100, 128)])
+def test_capture_mean_fwd_bwd(ops, heads, sides, n, res):
+    g = torch.Generator().manual_seed(n)
+    logits = [torch.randn(heads, s * s, n, generator=g) * 3 for s in sides]
+    dm = torch.randn(n, res, res, generator=g)
+    lr = [l.clone().requires_grad_(True) for l in logits]
+    stack = torch.stack([_capture_ref(l, res) for l in lr])            # [L, h, R*R, N]
+    mref = stack.mean(dim=(0, 1)).t().reshape(n, res, res)
+    (mref * dm).sum().backward()
+    lc = [cu(l).requires_grad_(True) for l in logits]
+    m = ops.capture_mean(lc, res)
+    (m * cu(dm)).sum().backward()
+    assert rel_err(m.detach().cpu(), mref.detach()) < 2e-5
+    for a, b in zip(lc, lr):
+        assert rel_err(a.grad.cpu(), b.grad) < 5e-5
+
+
+# ----------------------------------------------------------------------------- collect_maps
+def _store(tensors):
+    c = hp.AttentionStore()
+    c.step_store = {"attn": list(tensors)}
+    return c
+
+
+def test_collect_maps_golden(ops):
+    from stablekeypoints_b200 import optimize, ptp_utils
+    post = load_golden("post_unet.npz")
+    st = [cu(post[f"store_{i}"]) for i in range(4)]
+
+    def run(**kw):
+        c = ptp_utils.AttentionStore()
+        c.step_store = {"attn": list(st)}
+        out = optimize.collect_maps(c, **kw)
+        assert c.step_store["attn"] == []
+        return out.cpu()
+
+    assert rel_err(run(upsample_res=-1, layers=[0, 1, 2, 3]), post["collect_train"]) < 2e-6
+    assert rel_err(run(upsample_res=-1, layers=[0, 2]), post["collect_layers_02"]) < 2e-6
+    assert rel_err(run(upsample_res=48, layers=[0, 1, 2, 3], indices=torch.from_numpy(post["collect_idx"])), post["collect_eval_48"]) < 2e-6
+    assert rel_err(run(upsample_res=16, layers=[0, 1, 2, 3]), post["collect_same_res"]) < 2e-6
+
+
+@pytest.mark.parametrize("layers,bh,r,n,idx,r2", [(4, 8, 128, 77, None, -1), (4, 8, 128, 77, [5, 0, 76, 33, 9, 1, 2, 3, 4, 10], 512),
+                                                    (2, 8, 64, 500, None, -1), (4, 4, 16, 12, [3, 3, 1], 40),
+                                                    (3, 8, 32, 13, None, 20)])
+def test_collect_maps_fwd_bwd_vs_oracle(ops, layers, bh, r, n, idx, r2):
+    g = torch.Generator().manual_seed(r + n)
+    st = [torch.rand(bh, r * r, n, generator=g) for _ in range(layers)]
+    ref_in = [s.clone().requires_grad_(True) for s in st]
+    it = torch.tensor(idx) if idx is not None else None
+    want = hp.collect_maps(_store(ref_in), r2, tuple(range(layers)), it)
+    dout = torch.randn(want.shape, generator=g)
+    (want * dout).sum().backward()
+    cin = [cu(s).requires_grad_(True) for s in st]
+    resize = r2 != -1 and (n if idx is None else len(idx)) ** 0.5 != r2
+    got = ops.collect_maps_op(cin, r2 if resize else -1, cu(it) if it is not None else None)
+    (got * cu(dout)).sum().backward()
+    assert got.shape == want.shape
+    assert rel_err(got.detach().cpu(), want.detach()) < 3e-6
+    for a, b in zip(cin, ref_in):
+        assert rel_err(a.grad.cpu(), b.grad) < 3e-6
+
+
+# ----------------------------------------------------------------------------- selection (bit-exact)
+def test_selection_golden(ops):
+    from stablekeypoints_b200 import eval as skp_eval, ptp_utils
+    post = load_golden("post_unet.npz")
+    maps, maps_t = cu(post["maps"]), cu(post["maps_t"])
+    assert np.array_equal(skp_eval.find_max_pixel(maps).cpu().numpy(), post["find_max_pixel"])
+    assert np.array_equal(skp_eval.find_k_max_pixels(maps, 3).cpu().numpy(), post["find_k_max_pixels_3"])
+    peaks = ops.k_argmax_flat(maps, 1)
+    assert rel_err(ops.gaussian_kl_scores(maps, peaks, 2.0).cpu(), post["kl_s2.0"]) < 2e-5
+    for s in (1.0, 2.0):
+        cand = ptp_utils.find_top_k_gaussian(maps, 9, sigma=s)
+        assert np.array_equal(cand.cpu().numpy(), post[f"topk_gaussian_s{s}"])
+        fps = ptp_utils.furthest_point_sampling(maps_t, 5, cand)
+        assert np.array_equal(fps.cpu().numpy(), post[f"fps_s{s}"])
+    allc = ptp_utils.furthest_point_sampling(maps, 6, torch.arange(maps.shape[0]).cuda())
+    assert np.array_equal(allc.cpu().numpy(), post["fps_all_candidates"])
+
+
+@pytest.mark.parametrize("t,h,seed", [(77, 128, 0), (500, 128, 1), (10, 512, 2), (25, 33, 3)])
+def test_selection_vs_oracle_full_size(ops, t, h, seed):
+    from stablekeypoints_b200 import ptp_utils
+    g = torch.Generator().manual_seed(seed)
+    maps = torch.rand(t, h, h, generator=g) ** 8
+    maps_t = torch.rand(t, h, h, generator=g) ** 8
+    assert np.array_equal(ops.argmax_flat(cu(maps)).cpu().numpy(), maps.reshape(t, -1).argmax(-1).numpy())
+    if h <= 128:
+        ncand, k = min(25, t), min(10, t)
+        cand_ref = hp.find_top_k_gaussian(maps, ncand, sigma=2.0)
+        cand = ptp_utils.find_top_k_gaussian(cu(maps), ncand, sigma=2.0)
+        assert np.array_equal(cand.cpu().numpy(), cand_ref.numpy())
+        assert np.array_equal(ptp_utils.furthest_point_sampling(cu(maps_t), k, cand).cpu().numpy(),
+                              hp.furthest_point_sampling(maps_t, k, cand_ref).numpy())
+
+
+# ----------------------------------------------------------------------------- losses
+def test_losses_golden(ops):
+    post = load_golden("post_unet.npz")
+    maps = cu(post["maps"]).requires_grad_(True)
+    maps_t = cu(post["maps_t"]).requires_grad_(True)
+    sel = cu(post["sel"])
+    from stablekeypoints_b200.invertable_transform import invert_theta
+    sharp = ops.sharpen_loss_op(maps, sel, 2.0)
+    equiv = ops.equivariance_loss_op(maps, maps_t, sel, invert_theta(torch.from_numpy(post["theta"]))[0])
+    (100.0 * sharp + 1000.0 * equiv).backward()
+    assert rel_err(sharp.detach().cpu(), post["sharp"]) < 5e-6
+    assert rel_err(equiv.detach().cpu(), post["equiv"]) < 5e-6
+    assert rel_err(maps.grad.cpu(), post["dmaps"]) < 1e-5
+    assert rel_err(maps_t.grad.cpu(), post["dmaps_t"]) < 1e-5
+
+
+def test_reference_style_loss_api(ops):
+    """optimize.sharpening_loss / equivariance_loss called the way optimize.py:397-401 calls them."""
+    from stablekeypoints_b200 import optimize
+    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+    post = load_golden("post_unet.npz")
+    maps, maps_t, sel = cu(post["maps"]), cu(post["maps_t"]), cu(post["sel"])
+    tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
+    tr.last_params = {"theta": torch.from_numpy(post["theta"])}
+    sharp = optimize.sharpening_loss(maps[sel], device="cuda", sigma=2.0, num_subjects=1)
+    equiv = optimize.equivariance_loss(maps[sel], maps_t[sel][None].repeat(1, 1, 1, 1), tr, 0)
+    assert rel_err(sharp.cpu(), post["sharp"]) < 5e-6
+    assert rel_err(equiv.cpu(), post["equiv"]) < 5e-6
+    assert rel_err(tr.inverse(maps_t[sel][None]).cpu(), post["unwarp"]) < 5e-6
+
+
+def test_affine_warp_and_rng_order(ops):
+    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+    post = load_golden("post_unet.npz")
+    tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
+    out = tr(cu(post["img"]), theta=torch.from_numpy(post["theta2"]))
+    assert rel_err(out.cpu(), post["warp"]) < 5e-6
+    torch.manual_seed(123)
+    tr(torch.zeros(3, 1, 4, 4).cuda())
+    assert np.allclose(tr.last_params["theta"].cpu().numpy(), post["theta_seed123"], atol=1e-7)
+    # 512^2 image, gradient of the sampler vs torch autograd
+    g = torch.Generator().manual_seed(0)
+    img = torch.rand(1, 3, 512, 512, generator=g)
+    th = hp.affine_theta(7.0, 0.93, 0.2, -0.1)
+    ir = img.clone().requires_grad_(True)
+    wr = hp.affine_warp(ir, th)
+    dy = torch.randn(wr.shape, generator=g)
+    (wr * dy).sum().backward()
+    ic = cu(img).requires_grad_(True)
+    wc = ops.affine_warp(ic, th)
+    (wc * cu(dy)).sum().backward()
+    assert rel_err(wc.detach().cpu(), wr.detach()) < 5e-6
+    assert rel_err(ic.grad.cpu(), ir.grad) < 2e-5
+
+
+def test_soft_argmax_golden_and_full_size(ops):
+    from stablekeypoints_b200 import eval as skp_eval
+    post = load_golden("post_unet.npz")
+    hm = cu(post["soft_in"]).clone()
+    out = skp_eval.pixel_from_weighted_avg(hm)
+    assert rel_err(out.cpu(), post["soft_out"]) < 2e-6
+    assert np.array_equal(hm.cpu().numpy(), post["soft_in_after"])
+    g = torch.Generator().manual_seed(5)
+    big = torch.rand(10, 512, 512, generator=g) ** 6
+    want = hp.pixel_from_weighted_avg(big.clone())
+    assert rel_err(skp_eval.pixel_from_weighted_avg(cu(big).clone()).cpu(), want) < 2e-6
+
+
+def test_adam_step(ops):
+    g = torch.Generator().manual_seed(9)
+    p = torch.randn(1, 77, 768, generator=g)
+    pc, m, v = cu(p).clone(), torch.zeros(1, 77, 768).cuda(), torch.zeros(1, 77, 768).cuda()
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=5e-3)
+    for step in range(1, 4):
+        grad = torch.randn(1, 77, 768, generator=g) * 0.1
+        pr.grad = grad.clone()
+        opt.step()
+        ops.adam_step_(pc, cu(grad * 2), m, v, step, grad_scale=0.5)
+    assert rel_err(pc.cpu(), pr.detach()) < 1e-6

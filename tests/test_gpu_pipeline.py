@@ -1,0 +1,176 @@
+"""-m gpu: the drop-in surface end to end (load_ldm / find_pred_noise / run_and_find_attn / Stage-1 iteration) against
+the golden fixture minted by the reference's own code on the tiny UNet, and against the CPU oracle on the
+full SD1.5-shaped model."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hotpath as hp
+from tests._util import TINY, check_tiny_weights, load_golden, rel_err, tiny_pipeline
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(**kw):
+    base = dict(layers=[0, 1, 2, 3], noise_level=-1, device="cuda", top_k=10, furthest_point_num_samples=25, sigma=2.0,
+                num_subjects=1, top_k_strategy="gaussian", equivariance_attn_loss_weight=1000.0,
+                sharpening_loss_weight=100.0)
+    base.update(kw)
+    return argparse.Namespace(**base)
+
+
+def _product_ldm(pipe, res, precision="fp32"):
+    from stablekeypoints_b200 import optimize_token
+    from stablekeypoints_b200.sd15_engine import UNetConfig, VAEConfig
+    oc, vc = pipe.unet.cfg, pipe.vae.cfg
+    ucfg = UNetConfig(block_out_channels=oc.block_out_channels, cross_attention_dim=oc.cross_attention_dim,
+                      heads=oc.attention_head_dim, norm_num_groups=oc.norm_num_groups)
+    vcfg = VAEConfig(block_out_channels=vc.block_out_channels, norm_num_groups=vc.norm_num_groups)
+    return optimize_token.load_ldm("cuda", feature_upsample_res=res, unet_state_dict=pipe.unet.state_dict(),
+                                   vae_state_dict=pipe.vae.state_dict(), unet_config=ucfg, vae_config=vcfg,
+                                   precision=precision)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    g = load_golden("tiny_stage1.npz")
+    pipe = tiny_pipeline()
+    check_tiny_weights(pipe, g)
+    return g, pipe
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_tiny_store_dump_matches_reference_golden(tiny, impl):
+    """BASELINE cfg1 shape of the test: find_pred_noise + AttentionStore dump, then collect_maps variants."""
+    from stablekeypoints_b200 import eval as skp_eval, ops, optimize, ptp_utils
+    g, pipe = tiny
+    ops.set_gemm_impl(impl)
+    try:
+        ldm, controllers, ngpu = _product_ldm(pipe, TINY["res"])
+        assert ngpu == 1 and len(controllers) == 1
+        ctl = next(iter(controllers.values()))
+        ctx = torch.from_numpy(g["context"]).cuda()
+        assert rel_err(ptp_utils.image2latent(ldm, torch.from_numpy(g["image"]), "cuda").cpu(), g["latent"]) < 1e-4
+        with torch.no_grad():
+            _, pred = ptp_utils.find_pred_noise(ldm, torch.from_numpy(g["image"]), ctx, noise=torch.from_numpy(g["noise_a"]))
+        store = ctl.step_store["attn"]
+        assert len(store) == 4 and ctl.num_att_layers == 18
+        for i, s in enumerate(store):
+            assert tuple(s.shape) == g[f"stored_{i}"].shape
+            assert rel_err(s.cpu(), g[f"stored_{i}"]) < 1e-3          # north_star tolerance: 1e-3 relative
+        assert rel_err(pred.cpu(), g["pred_noise"]) < 1e-3
+        keep = [s.clone() for s in store]
+        ev = optimize.collect_maps(ctl, upsample_res=64, layers=[0, 1, 2, 3], indices=torch.from_numpy(g["eval_indices"]))
+        assert ctl.step_store["attn"] == []
+        assert rel_err(ev.cpu(), g["eval_maps"]) < 1e-3
+        assert np.array_equal(skp_eval.find_max_pixel(ev).cpu().numpy(), g["eval_argmax"])
+        assert rel_err(skp_eval.pixel_from_weighted_avg(ev.clone()).cpu(), g["eval_softargmax"]) < 1e-3
+        ctl.step_store = {"attn": keep}
+        assert rel_err(optimize.collect_maps(ctl, upsample_res=-1, layers=[1, 3]).cpu(), g["maps_layers_1_3"]) < 1e-3
+    finally:
+        ops.set_gemm_impl("tc")
+
+
+@pytest.mark.parametrize("impl,mode", [("tc", "fused"), ("tc", "store"), ("simt", "fused")])
+def test_tiny_stage1_iteration_matches_reference_golden(tiny, impl, mode, monkeypatch):
+    from stablekeypoints_b200 import ops, optimize
+    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+    g, pipe = tiny
+    monkeypatch.setenv("SKP_CAPTURE_MODE", mode)
+    ops.set_gemm_impl(impl)
+    try:
+        ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
+        ctx = torch.from_numpy(g["context"]).cuda().requires_grad_(True)
+        tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
+        args = _args(top_k=TINY["top_k"], furthest_point_num_samples=TINY["num_candidates"], sigma=TINY["sigma"])
+        out = optimize.stage1_iteration(ldm, controllers, torch.from_numpy(g["image"]), ctx, tr, args,
+                                        theta=torch.from_numpy(g["theta"]), noise_a=torch.from_numpy(g["noise_a"]),
+                                        noise_b=torch.from_numpy(g["noise_b"]))
+        assert rel_err(out["maps"].cpu(), g["maps"]) < 1e-3
+        assert rel_err(out["maps_t"].cpu(), g["maps_t"]) < 1e-3
+        assert np.array_equal(out["indices"].cpu().numpy(), g["indices"])
+        assert rel_err(out["sharp"].cpu(), g["sharp"]) < 1e-3
+        assert rel_err(out["equiv"].cpu(), g["equiv"]) < 1e-3
+        assert rel_err(out["loss"].cpu(), g["loss"]) < 1e-3
+        assert rel_err(ctx.grad.cpu(), g["dcontext"]) < 1e-3
+        opt = optimize.EmbeddingOptimizer(ctx, lr=5e-3)
+        opt.step()
+        assert rel_err(ctx.detach().cpu(), g["context_after_adam"]) < 1e-5
+    finally:
+        ops.set_gemm_impl("tc")
+
+
+def test_tiny_early_exit_same_maps(tiny):
+    from stablekeypoints_b200 import ptp_utils
+    g, pipe = tiny
+    ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
+    ctx = torch.from_numpy(g["context"]).cuda()
+    kw = dict(layers=[0, 1, 2, 3], upsample_res=-1, controllers=controllers, noise=torch.from_numpy(g["noise_a"]))
+    with torch.no_grad():
+        full = ptp_utils.run_and_find_attn(ldm, torch.from_numpy(g["image"]), ctx, **kw)[0]
+        ldm.unet.early_exit = True
+        early = ptp_utils.run_and_find_attn(ldm, torch.from_numpy(g["image"]), ctx, **kw)[0]
+    assert torch.equal(full, early)
+
+
+def test_engine_rejects_cpu_and_bad_batch(tiny):
+    from stablekeypoints_b200 import _lib, ops, optimize_token
+    with pytest.raises(RuntimeError):
+        optimize_token.load_ldm("cpu", "synthetic")
+    with pytest.raises(_lib.SkpError):
+        ops.argmax_flat(torch.zeros(2, 4, 4))
+    g, pipe = tiny
+    ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
+    with pytest.raises(ValueError):
+        ldm.unet(torch.zeros(2, 4, 16, 16).cuda(), 0, torch.zeros(1, 12, 48).cuda())
+
+
+# ----------------------------------------------------------------------------- full SD1.5 shapes vs the CPU oracle
+@pytest.fixture(scope="module")
+def full():
+    from oracle import sd15
+    torch.manual_seed(0)
+    pipe = sd15.make_pipeline(seed=0, attn_gain=4.0)
+    g = torch.Generator().manual_seed(2)
+    n = 77
+    context = torch.randn(1, n, 768, generator=g)
+    latent_noise = torch.randn(1, 4, 64, 64, generator=g)
+    noise_b = torch.randn(1, 4, 64, 64, generator=g)
+    image = hp.synthetic_image(seed=1, size=512)
+    return pipe, image, context, latent_noise, noise_b
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("reference", 1e-3)])
+def test_full_sd15_stage1_iteration_vs_oracle(full, precision, tol):
+    """cfg2 at full size: two captured forwards + losses + d(context), token indices forced equal."""
+    from stablekeypoints_b200 import optimize
+    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+    pipe, image, context, noise_a, noise_b = full
+    theta = hp.affine_theta(8.0, 0.9, 0.1, -0.05)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    # oracle (CPU fp32)
+    if not hasattr(test_full_sd15_stage1_iteration_vs_oracle, "_ref"):
+        ldm_o, ctl_o, _ = hp.load_oracle_ldm(pipe, 128)
+        ctx_o = context.clone().requires_grad_(True)
+        ref = hp.stage1_iteration(ldm_o, ctl_o, image, ctx_o, theta, noise_a, noise_b, top_k=10, num_candidates=25, sigma=2.0)
+        ref["dcontext"] = ctx_o.grad.clone()
+        test_full_sd15_stage1_iteration_vs_oracle._ref = ref
+    ref = test_full_sd15_stage1_iteration_vs_oracle._ref
+    ldm, controllers, _ = _product_ldm(pipe, 128, precision=precision)
+    ctx = context.clone().cuda().requires_grad_(True)
+    tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
+    out = optimize.stage1_iteration(ldm, controllers, image, ctx, tr, _args(), theta=theta, noise_a=noise_a, noise_b=noise_b,
+                                    forced_indices=ref["indices"])
+    errs = {"maps": rel_err(out["maps"].cpu(), ref["maps"]), "maps_t": rel_err(out["maps_t"].cpu(), ref["maps_t"]),
+            "sharp": rel_err(out["sharp"].cpu(), ref["sharp"]), "equiv": rel_err(out["equiv"].cpu(), ref["equiv"]),
+            "dcontext": rel_err(ctx.grad.cpu(), ref["dcontext"])}
+    print(f"[full-size parity, precision={precision}] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    # discrete choices on their own, unforced
+    cand = hp.find_top_k_gaussian(ref["maps"], 25, sigma=2.0)
+    from stablekeypoints_b200 import ptp_utils
+    cand_gpu = ptp_utils.find_top_k_gaussian(out["maps"], 25, sigma=2.0)
+    print("candidate agreement:", int((cand == cand_gpu.cpu()).sum()), "/ 25")
+    for k, v in errs.items():
+        assert v < tol, (k, v)

@@ -1,0 +1,178 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every declared symbol, the engine's
+parameter table matches the diffusers-0.8.0 key/shape table of the oracle model, the reference-surface mirrors
+have the reference's signatures, there is no CPU fallback, and the N>1 host logic works over gloo (world_size 2)."""
+import inspect
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests._util import rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from stablekeypoints_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    import ctypes
+    from stablekeypoints_b200 import _lib
+    handle = ctypes.CDLL(built)
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 27
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/skp_b200.h but not exported"
+    assert set(declared) == set(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.lib().skp_version() == 100
+    assert _lib.launch_count() == 0
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(built):
+    """The shipped cubin targets sm_100a and contains tcgen05 MMA / TMEM load / TMA SASS (B200_PROFILING.md table)."""
+    out = subprocess.run(["cuobjdump", "-sass", built], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in out.stdout, mnemonic
+
+
+def test_no_cpu_fallback():
+    from stablekeypoints_b200 import _lib, ops
+    with pytest.raises(_lib.SkpError):
+        ops.argmax_flat(torch.zeros(3, 4, 4))
+    with pytest.raises(_lib.SkpError):
+        ops.capture_mean([torch.zeros(2, 16, 5)], 8)
+    from stablekeypoints_b200 import optimize_token
+    with pytest.raises(RuntimeError):
+        optimize_token.load_ldm("cpu", "synthetic")
+
+
+def test_product_never_imports_oracle():
+    import re
+    pkg = os.path.join(ROOT, "stablekeypoints_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+@pytest.mark.parametrize("which", ["sd15", "tiny"])
+def test_engine_param_table_matches_oracle_model(which):
+    from oracle import sd15
+    from stablekeypoints_b200 import sd15_engine as eng
+    if which == "sd15":
+        ocfg, ovae = sd15.UNetConfig.sd15(), sd15.VAEConfig()
+    else:
+        ocfg, ovae = sd15.UNetConfig.tiny(), sd15.VAEConfig.tiny()
+    with torch.device("meta"):
+        unet = sd15.UNet2DConditionModel(ocfg)
+        vae = sd15.AutoencoderKL(ovae)
+    ucfg = eng.UNetConfig(block_out_channels=ocfg.block_out_channels, cross_attention_dim=ocfg.cross_attention_dim,
+                          heads=ocfg.attention_head_dim, norm_num_groups=ocfg.norm_num_groups)
+    vcfg = eng.VAEConfig(block_out_channels=ovae.block_out_channels, norm_num_groups=ovae.norm_num_groups)
+    want = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    assert eng.unet_param_shapes(ucfg) == want
+    want_v = {k: tuple(v.shape) for k, v in vae.state_dict().items()}
+    assert eng.vae_encoder_param_shapes(vcfg) == want_v
+    if which == "sd15":
+        assert sum(torch.Size(s).numel() for s in want.values()) == 859520964  # SD1.x UNet
+
+
+def test_reference_surface_signatures():
+    """Same parameter names (and order) as the reference functions they replace."""
+    from stablekeypoints_b200 import eval as e, invertable_transform as it, optimize as o, optimize_token as ot, ptp_utils as p
+
+    def names(fn):
+        return list(inspect.signature(fn).parameters)
+
+    assert names(p.run_and_find_attn)[:10] == ["ldm", "image", "context", "noise_level", "device", "from_where", "layers",
+                                               "upsample_res", "indices", "controllers"]          # ptp_utils.py:234-245
+    assert names(p.find_pred_noise)[:5] == ["ldm", "image", "context", "noise_level", "device"]      # :205-211
+    assert names(p.register_attention_control) == ["model", "controller", "feature_upsample_res"]    # :472
+    assert names(p.find_top_k_gaussian) == ["attention_maps", "top_k", "sigma", "epsilon", "num_subjects"]  # :86
+    assert names(p.furthest_point_sampling) == ["attention_maps", "top_k", "top_initial_candidates"]  # :115
+    assert names(p.init_random_noise) == ["device", "num_words"]                                      # :649
+    assert names(o.collect_maps) == ["controller", "from_where", "upsample_res", "layers", "indices"]  # optimize.py:27-33
+    assert names(o.equivariance_loss) == ["embeddings_initial", "embeddings_transformed", "transform", "index"]  # :157
+    assert names(o.sharpening_loss) == ["attn_map", "sigma", "temperature", "device", "num_subjects"]  # :166
+    assert names(o.optimize_embedding) == ["ldm", "args", "controllers", "num_gpus", "context", "from_where"]  # :269-276
+    assert names(ot.load_ldm)[:4] == ["device", "type", "feature_upsample_res", "my_token"]           # optimize_token.py:24
+    assert names(e.find_max_pixel) == ["map"] and names(e.find_k_max_pixels) == ["map", "num"]        # eval.py:39,62
+    assert names(e.pixel_from_weighted_avg) == ["heatmaps", "distance"]                               # eval.py:113
+    assert names(it.RandomAffineWithInverse.__init__) == ["self", "degrees", "scale", "translate"]
+    s = p.AttentionStore()
+    assert s.step_store == {"attn": []} and s.num_att_layers == -1
+    s({"attn": torch.zeros(1)}, True, "up")
+    assert len(s.step_store["attn"]) == 1
+    s.reset()
+    assert s.step_store == {"attn": []}
+
+
+def test_compat_aliases():
+    code = ("import sys; sys.path.insert(0, %r); import stablekeypoints_b200.compat as c; c.install();"
+            "from unsupervised_keypoints import ptp_utils, optimize; import stablekeypoints_b200.ptp_utils as p;"
+            "assert ptp_utils is p; print('ok')" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_invert_theta_matches_torch_inverse():
+    from oracle import hotpath as hp
+    from stablekeypoints_b200.invertable_transform import invert_theta
+    th = torch.cat([hp.affine_theta(-12.0, 0.85, -0.2, 0.15), hp.affine_theta(15.0, 1.0, 0.25, -0.25)], 0)
+    full = torch.cat([th, torch.tensor([[[0.0, 0.0, 1.0]]]).expand(2, -1, -1)], dim=1)
+    assert rel_err(invert_theta(th), torch.inverse(full)[:, :2]) < 1e-6
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SKP_ROOT"])
+from stablekeypoints_b200.optimize import allreduce_sum_, rank_shard
+from oracle import hotpath as hp
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# every rank: same context, its own shard of 8 "images" -> per-image gradient is a deterministic function of the index
+ctx = torch.arange(12, dtype=torch.float32).reshape(1, 3, 4)
+m, v = torch.zeros_like(ctx), torch.zeros_like(ctx)
+shard = rank_shard(8, rank, world, epoch=0, seed=5)
+grads = [torch.full_like(ctx, float(i + 1)) * 0.01 for i in range(8)]
+for step, idx in enumerate(shard, 1):
+    g = grads[idx].clone()
+    ws = allreduce_sum_(g)
+    hp.adam_step(ctx, g / ws, m, v, step)
+allshards = [None] * world
+dist.all_gather_object(allshards, shard)
+flat = sorted(i for s in allshards for i in s)
+gathered = [torch.zeros_like(ctx) for _ in range(world)]
+dist.all_gather(gathered, ctx)
+if rank == 0:
+    assert flat == list(range(8)), flat                      # disjoint cover of the dataset
+    assert all(torch.equal(gathered[0], t) for t in gathered)  # replicated update stays bit-identical across ranks
+    # equals a single process doing the mean of the same per-step pairs
+    ref = torch.arange(12, dtype=torch.float32).reshape(1, 3, 4); rm, rv = torch.zeros_like(ref), torch.zeros_like(ref)
+    for step in range(len(shard)):
+        g = sum(grads[s[step]] for s in allshards) / world
+        hp.adam_step(ref, g, rm, rv, step + 1)
+    assert torch.allclose(ref, ctx, atol=1e-7), (ref - ctx).abs().max()
+    print("GLOO_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_data_parallel_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, SKP_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GLOO_OK" in outs[0]
