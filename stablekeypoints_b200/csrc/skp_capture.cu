@@ -22,7 +22,7 @@ namespace skp {
 
 constexpr int CAP_TX = 16;
 constexpr int CAP_THREADS = 256;
-constexpr int CAP_MAX_W = 12;  // max footprint extent per axis we stage
+constexpr int CAP_MAX_W = 48;  // max footprint extent per axis we stage (covers 2x down-sampling of a 16-px tile)
 
 struct CapParams {
   const float* logits[SKP_MAX_LAYERS];
@@ -33,6 +33,7 @@ struct CapParams {
   int Nf;       // footprint row stride (floats), multiple of 4, Nf/4 odd
   int Nb;       // [pix][Nb] tile stride, odd
   int max_slots;
+  int mwy, mwx;  // max footprint extent per axis over all tiles/layers (table strides)
   const float* g;   // MEAN bwd: d_maps [N,R,R]; STORE bwd: d_probs [h,R*R,N]
   float* out;       // MEAN fwd: maps [N,R,R]; STORE fwd: probs [h,R*R,N]
   float w;          // 1/(layers*heads) for MEAN
@@ -216,11 +217,12 @@ __global__ void __launch_bounds__(CAP_THREADS) capture_bwd_kernel(CapParams p) {
   float* fp = smem;                                // [max_slots][Nf]
   float* gt = fp + (size_t)p.max_slots * Nf;       // [TP][Nb] upstream gradient g
   float* ds = gt + (size_t)TP * Nb;                // [TP][Nb] probs, then dS'
-  float* tmpx = ds + (size_t)TP * Nb;              // [TY][CAP_MAX_W][Nb]
-  float* st_m = tmpx + (size_t)TY * CAP_MAX_W * Nb;  // [NQ][TP]
+  const int MWY = p.mwy, MWX = p.mwx;
+  float* tmpx = ds + (size_t)TP * Nb;              // [TY][MWX][Nb]
+  float* st_m = tmpx + (size_t)TY * MWX * Nb;      // [NQ][TP]
   float* st_s = st_m + NQ * TP;                    // [NQ][TP]
-  float* Wy = st_s + NQ * TP;                      // [TY][CAP_MAX_W]
-  float* Wx = Wy + TY * CAP_MAX_W;                 // [CAP_TX][CAP_MAX_W]
+  float* Wy = st_s + NQ * TP;                      // [TY][MWY]
+  float* Wx = Wy + TY * MWY;                       // [CAP_TX][MWX]
 
   const int pix = threadIdx.x % TP, q = threadIdx.x / TP;
   const int py = pix / CAP_TX, px = pix % CAP_TX;
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(CAP_THREADS) capture_bwd_kernel(CapParams p) {
     make_taps(tp, Yc, Xc, R, s, wy0, wx0, wsx, Nf4);
     __syncthreads();
     // dense separable transposed-stencil tables for this tile/layer (clamped duplicate taps add up)
-    for (int i = threadIdx.x; i < TY * CAP_MAX_W + CAP_TX * CAP_MAX_W; i += CAP_THREADS) Wy[i] = 0.f;
+    for (int i = threadIdx.x; i < TY * MWY + CAP_TX * MWX; i += CAP_THREADS) Wy[i] = 0.f;
     __syncthreads();
     if (threadIdx.x < TY + CAP_TX) {
       bool isy = threadIdx.x < TY;
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(CAP_THREADS) capture_bwd_kernel(CapParams p) {
         float cw[4];
         cubic_coeffs(rc - f, cw);
         int w0 = isy ? wy0 : wx0;
-        float* row = isy ? (Wy + r * CAP_MAX_W) : (Wx + r * CAP_MAX_W);
+        float* row = isy ? (Wy + r * MWY) : (Wx + r * MWX);
         for (int t = 0; t < 4; ++t) row[clampi((int)f - 1 + t, 0, s - 1) - w0] += cw[t];
       }
     }
@@ -332,8 +334,8 @@ __global__ void __launch_bounds__(CAP_THREADS) capture_bwd_kernel(CapParams p) {
         int sx = r % wsx, yy = r / wsx;
         float a = 0.f;
 #pragma unroll
-        for (int xx = 0; xx < CAP_TX; ++xx) a = fmaf(Wx[xx * CAP_MAX_W + sx], ds[(size_t)(yy * CAP_TX + xx) * Nb + n], a);
-        tmpx[(size_t)(yy * CAP_MAX_W + sx) * Nb + n] = a;
+        for (int xx = 0; xx < CAP_TX; ++xx) a = fmaf(Wx[xx * MWX + sx], ds[(size_t)(yy * CAP_TX + xx) * Nb + n], a);
+        tmpx[(size_t)(yy * MWX + sx) * Nb + n] = a;
       }
       __syncthreads();
       float* dl = p.dlogits[l];
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(CAP_THREADS) capture_bwd_kernel(CapParams p) {
         int sx = r % wsx, sy = r / wsx;
         float a = 0.f;
 #pragma unroll
-        for (int yy = 0; yy < TY; ++yy) a = fmaf(Wy[yy * CAP_MAX_W + sy], tmpx[(size_t)(yy * CAP_MAX_W + sx) * Nb + n], a);
+        for (int yy = 0; yy < TY; ++yy) a = fmaf(Wy[yy * MWY + sy], tmpx[(size_t)(yy * MWX + sx) * Nb + n], a);
         if (a != 0.f) atomicAdd(dl + ((size_t)(h * s + wy0 + sy) * s + wx0 + sx) * N + n, a);
       }
     }
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(CAP_THREADS) capture_bwd_kernel(CapParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int footprint_slots(int R, int s, int TY, int* ok) {
+static int footprint_slots(int R, int s, int TY, int* ok, int* mwy, int* mwx) {
   int best = 0;
   *ok = 1;
   for (int Y0 = 0; Y0 < R; Y0 += TY) {
@@ -358,11 +360,13 @@ static int footprint_slots(int R, int s, int TY, int* ok) {
     window(Y0, TY, R, s, &a, &b);
     int wy = b - a + 1;
     if (wy > CAP_MAX_W) *ok = 0;
+    if (wy > *mwy) *mwy = wy;
     for (int X0 = 0; X0 < R; X0 += CAP_TX) {
       int c, d;
       window(X0, CAP_TX, R, s, &c, &d);
       int wx = d - c + 1;
       if (wx > CAP_MAX_W) *ok = 0;
+      if (wx > *mwx) *mwx = wx;
       if (wy * wx > best) best = wy * wx;
     }
   }
@@ -373,16 +377,17 @@ template <int TY>
 static size_t smem_bytes(const CapParams& p, bool bwd) {
   constexpr int TP = TY * CAP_TX, NQ = CAP_THREADS / TP;
   size_t f = (size_t)p.max_slots * p.Nf + (size_t)TP * p.Nb + 2 * NQ * TP;
-  if (bwd) f += (size_t)TP * p.Nb + (size_t)TY * CAP_MAX_W * p.Nb + (TY + CAP_TX) * CAP_MAX_W;
+  if (bwd) f += (size_t)TP * p.Nb + (size_t)TY * p.mwx * p.Nb + (size_t)TY * p.mwy + (size_t)CAP_TX * p.mwx;
   return f * sizeof(float);
 }
 
 template <int TY, bool STORE, bool BWD>
 static int launch_ty(CapParams& p, cudaStream_t st, bool* fits) {
   int slots = 0;
+  p.mwy = p.mwx = 1;
   for (int l = 0; l < p.n_layers; ++l) {
     int ok;
-    int v = footprint_slots(p.R, p.s[l], TY, &ok);
+    int v = footprint_slots(p.R, p.s[l], TY, &ok, &p.mwy, &p.mwx);
     if (!ok) { *fits = false; return SKP_OK; }
     if (v > slots) slots = v;
   }

@@ -74,7 +74,9 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, b_split, bias: Optional[torch.Tens
     assert b.shape[1] == k
     out = torch.empty(m, n, dtype=torch.float32, device=a.device)
     if residual is not None:
-        assert residual.shape == (m, n) and residual.stride(1) == 1 and residual.dtype == torch.float32
+        assert tuple(residual.shape) == (m, n), f"residual shape {tuple(residual.shape)} != {(m, n)}"
+        if residual.stride(1) != 1 or residual.dtype != torch.float32:
+            residual = _f32c(residual)
     ldr = residual.stride(0) if residual is not None else 0
     if GEMM_IMPL == "tc":
         a_hi, a_lo = split_bf16(a)

@@ -345,7 +345,7 @@ class UNetEngine:
         res = x
         h = F.group_norm(x, cfg.norm_num_groups, w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], 1e-6)
         h = F.conv2d(h, w[f"{p}.proj_in.weight"], w[f"{p}.proj_in.bias"])
-        h = h.permute(0, 2, 3, 1).reshape(hh * ww, c)
+        h = h.permute(0, 2, 3, 1).reshape(hh * ww, c).contiguous()  # reshape alone returns a column-major view
         t = f"{p}.transformer_blocks.0"
         h = h + self._self_attention(f"{t}.attn1", F.layer_norm(h, (c,), w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"]))
         y = F.layer_norm(h, (c,), w[f"{t}.norm2.weight"], w[f"{t}.norm2.bias"])
