@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SKP_PRECISION", "reference"), choices=["fp32", "reference", "tf32"])
     ap.add_argument("--early-exit", action="store_true", help="stop the forward after the 4th captured layer (outputs identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trunk", default=os.environ.get("SKP_TRUNK", "tc"), choices=["tc", "torch"],
+                    help="tc: trunk convs/linears on the tcgen05 split-bf16 GEMM (fp32-grade accuracy); torch: cuDNN/cuBLAS")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="drive the step from Python instead of one CUDA graph")
     ap.add_argument("--no-vae", action="store_true", help="feed latents directly (VAE encoder is a 'next' row)")
     return ap.parse_args()
 
@@ -145,7 +148,8 @@ def run_reference_arm(a):
 def workload_config(a, cpu=False):
     return {"workload": "cfg2: CelebA-wild-like synthetic 512x512 embedding optimisation, K=10 of N tokens, batch=1 per GPU",
             "tokens": a.tokens, "feature_upsample_res": a.res, "top_k": 10, "candidates": 25,
-            "precision": "fp32" if cpu else a.precision, "early_exit": bool(a.early_exit) and not cpu,
+            "precision": "fp32" if cpu else a.precision, "trunk": "cpu" if cpu else a.trunk, "early_exit": bool(a.early_exit) and not cpu,
+            "cuda_graph": (not cpu) and bool(getattr(a, "graph", False)),
             "vae_encode": "included" if (cpu or not a.no_vae) else "skipped (latents fed directly)",
             "l2": "no flush needed: 3.4 GB of fp32 UNet weights are streamed every forward (>> 126 MB L2)",
             "weights": "random-init SD1.5-shaped (no checkpoints offline)"}
@@ -171,12 +175,12 @@ def run_b200_arm(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ldm, controllers, _ = optimize_token.load_ldm(f"cuda:{local}", "synthetic:0", feature_upsample_res=a.res, attn_gain=4.0,
-                                                  precision=a.precision)
+                                                  precision=a.precision, trunk=a.trunk)
     ldm.unet.early_exit = a.early_exit
     args = stage1_args(a.tokens)
     g = torch.Generator().manual_seed(2)
     context = torch.randn(1, a.tokens, 768, generator=g).to(dev).requires_grad_(True)
-    opt = optimize.EmbeddingOptimizer(context, lr=args.lr)
+    opt = optimize.EmbeddingOptimizer(context, lr=args.lr, capturable=True)
     tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
     ds = SyntheticKeypointDataset(length=8, seed=1 + rank)
     host_imgs = [ds[i]["img"][None].contiguous().pin_memory() for i in range(4)]
@@ -186,17 +190,34 @@ def run_b200_arm(a):
         dev_imgs = [ptp_utils.image2latent(ldm, x, "cuda") for x in dev_imgs]
     torch.manual_seed(1000 + rank)
 
-    def step(img):
+    def eager_step(img):
         out = optimize.stage1_iteration(ldm, controllers, img, context, tr, args, accum=1)
         opt.step()
         opt.zero_grad()
         return out
+
+    step = eager_step
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    graph = None
+    launches_per_step = None
+    if a.graph:
+        # the whole optimizer step (2 captured forwards + selection + losses + backward + all-reduce + Adam) as ONE
+        # CUDA graph; per-step inputs (image, theta) go through static buffers
+        graph = optimize.Stage1Graph(ldm, controllers, context, opt, args, image_shape=tuple(dev_imgs[0].shape))
+        graph.set_inputs(dev_imgs[0], tr.sample_theta(1))
+        l0 = _lib.launch_count()
+        graph.capture()
+        launches_per_step = (_lib.launch_count() - l0) // (graph._warmup + 1)
+
+        def step(img):  # noqa: F811
+            graph.set_inputs(img, tr.sample_theta(1))   # pinned host -> static device buffer (async H2D) or D2D
+            return graph.replay()
 
     def timed(n, feed_host):
         barrier()
@@ -205,7 +226,7 @@ def run_b200_arm(a):
         s.record()
         for i in range(n):
             if feed_host:
-                out = step(host_imgs[i % len(host_imgs)])      # H2D of the pinned image inside stage1_iteration
+                out = step(host_imgs[i % len(host_imgs)])      # H2D of the pinned image inside the step
                 float(out["loss"])                             # D2H read of the step's result
             else:
                 step(dev_imgs[i % len(dev_imgs)])
@@ -214,7 +235,8 @@ def run_b200_arm(a):
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), _lib.launch_count() - l0
+        nl = launches_per_step * n if launches_per_step is not None else _lib.launch_count() - l0
+        return float(ms.item()), nl
 
     for i in range(a.warmup):
         step(dev_imgs[i % len(dev_imgs)])
@@ -233,20 +255,30 @@ def run_b200_arm(a):
         _lib.start_profile()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        step(dev_imgs[0])
+        eager_step(dev_imgs[0])
         e.record()
         prof = _lib.stop_profile()
         step_ms = s.elapsed_time(e)
         shares = {k: {"calls": len(v), "ms": round(sum(v), 4)} for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1]))}
         extra["skp_kernel_ms_in_one_profiled_step"] = shares
-        extra["profiled_step_ms"] = round(step_ms, 3)
-        extra["skp_share_of_step"] = round(sum(sum(v) for v in prof.values()) / step_ms, 4)
+        extra["profiled_eager_step_ms"] = round(step_ms, 3)
+        extra["skp_kernel_ms_total"] = round(sum(sum(v) for k, v in prof.items() if k != "skp_gemm_nt_tc_plan"), 3)
+        extra["skp_share_of_timed_step"] = round(extra["skp_kernel_ms_total"] / (ms / a.steps), 4)
         extra["roofline"] = attn_store_roofline(a, dev)
-        if a.early_exit is False:
+        if a.early_exit is False and world == 1:
             ldm.unet.early_exit = True
+            ee_step = eager_step
+            if a.graph:
+                g2 = optimize.Stage1Graph(ldm, controllers, context, opt, args, image_shape=tuple(dev_imgs[0].shape))
+                g2.set_inputs(dev_imgs[0], tr.sample_theta(1))
+                g2.capture()
+
+                def ee_step(img):
+                    g2.set_inputs(img, tr.sample_theta(1))
+                    return g2.replay()
             for i in range(2):
-                step(dev_imgs[i % len(dev_imgs)])
-            ms_ee, _ = timed_single(step, dev_imgs, a.steps)
+                ee_step(dev_imgs[i % len(dev_imgs)])
+            ms_ee, _ = timed_single(ee_step, dev_imgs, a.steps)
             extra["early_exit_images_per_s_1gpu"] = round(a.steps / (ms_ee / 1e3), 3)
             ldm.unet.early_exit = False
     if world > 1:

@@ -48,9 +48,18 @@ int skp_gemm_nt_simt(const float* A, int64_t lda, const float* B, int64_t ldb, f
  * cols_pad >= cols is a multiple of 64 and the pad is zero-filled. */
 int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, int cols_pad, void* hi, void* lo,
                    void* stream);
+/* splits > 1 runs split-K over blockIdx.z (partial sums in splitk_ws[splits*M*N], then one reduce+epilogue
+ * kernel); skp_gemm_nt_tc_plan returns the split count that fills the 148 SMs for a given problem. */
+int skp_gemm_nt_tc_plan(int M, int N, int Kpad);
 int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad,
                    float* C, int64_t ldc, int M, int N, float alpha, const float* bias,
-                   const float* residual, int64_t ldr, void* stream);
+                   const float* residual, int64_t ldr, int splits, float* splitk_ws, void* stream);
+/* 3x3 im2col of a channels-last activation x[H*W, C] (row stride ldx) written directly as the split-bf16 K-major
+ * A operand [Ho*Wo, Kpad] (column = tap*C + c; zero outside the image and in the K padding).  Together with
+ * skp_gemm_nt_tc this is the frozen 3x3 convolution (and, with flipped weights, its input gradient) of the
+ * UNet / VAE resnets the path runs through (diffusers ResnetBlock2D). */
+int skp_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int Ho, int Wo, int stride, int pad,
+                        int Kpad, void* hi, void* lo, void* stream);
 
 /* ------------------------------------------------------------------ cross-attention core
  * ptp_utils.py:493-506: sim = q k^T * scale; attn = softmax(sim, -1); out = attn v, per head.
@@ -150,6 +159,12 @@ int skp_soft_argmax(float* heatmaps, int T, int H, int W, const int64_t* peaks, 
  * 1/world_size of the data-parallel mean, optimize.py:405-406). */
 int skp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int step,
                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* Same update with the step count kept on the device (incremented by the call), so that an optimizer step
+ * captured in a CUDA graph stays correct on replay. */
+int skp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      int* step_dev, float lr, float beta1, float beta2, float eps, float grad_scale,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -103,9 +103,13 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                  float* __restrict__ C, int64_t ldc, int M, int N, int num_kb, float alpha,
-                  const float* __restrict__ bias, const float* __restrict__ residual, int64_t ldr) {
+                  float* C, int64_t ldc, int M, int N, int num_kb_total, int kb_per_split, float alpha,
+                  const float* bias, const float* residual, int64_t ldr, float* __restrict__ splitk_ws) {
   using Cfg = TcCfg<BN, STAGES>;
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb); partial sums go to splitk_ws[z][M][N] (reduced afterwards)
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int num_kb = min(kb_per_split, num_kb_total - kb0);
+  const bool partial = gridDim.z > 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -142,10 +146,11 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const uint32_t full = bars + 8 * s;
         const uint32_t st = base + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        tma_load_2d(st, &tm_a_hi, full, kb * TC_BK, m0);
-        tma_load_2d(st + Cfg::A_BYTES, &tm_a_lo, full, kb * TC_BK, m0);
-        tma_load_2d(st + 2 * Cfg::A_BYTES, &tm_b_hi, full, kb * TC_BK, n0);
-        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kb * TC_BK, n0);
+        const int kc = (kb0 + kb) * TC_BK;
+        tma_load_2d(st, &tm_a_hi, full, kc, m0);
+        tma_load_2d(st + Cfg::A_BYTES, &tm_a_lo, full, kc, m0);
+        tma_load_2d(st + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc, n0);
+        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc, n0);
       }
     }
   } else if (warp == 1) {
@@ -177,6 +182,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     tc_fence_after();
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = m0 + quarter * 32 + lane;
+    if (partial) {  // raw partial sums, dense [M][N]
+      C = splitk_ws + (size_t)blockIdx.z * M * N;
+      ldc = N; alpha = 1.f; bias = nullptr; residual = nullptr;
+    }
     const bool vec = ((ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0) && ((N & 3) == 0) &&
                      (!residual || (((ldr & 3) == 0) && ((((uintptr_t)residual) & 15) == 0))) &&
                      (!bias || ((((uintptr_t)bias) & 15) == 0));
@@ -238,6 +247,67 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t ld, int r
   }
 }
 
+// out[m,n] = alpha * sum_z ws[z][m][n] + bias[n] + residual[m][n]
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float* __restrict__ C, int64_t ldc,
+                                     float alpha, const float* __restrict__ bias, const float* __restrict__ residual,
+                                     int64_t ldr) {
+  size_t total = (size_t)M * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    float a = 0.f;
+    for (int z = 0; z < splits; ++z) a += ws[(size_t)z * total + i];
+    a *= alpha;
+    if (bias) a += bias[n];
+    if (residual) a += residual[(size_t)m * ldr + n];
+    C[(size_t)m * ldc + n] = a;
+  }
+}
+
+// 3x3 im2col of a channels-last activation x[H*W, C] (row stride ldx) straight into the split-bf16 K-major operand:
+// row = output pixel, column = tap*C + c, zero outside the image and in the K padding.  One warp per (pixel, tap).
+__global__ void im2col3x3_split_kernel(const float* __restrict__ x, int64_t ldx, int H, int W, int C, int Ho, int Wo,
+                                       int stride, int pad, int Kpad, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const long items = (long)Ho * Wo * 9;
+  const bool vec = (C & 3) == 0 && (ldx & 3) == 0 && ((((uintptr_t)x) & 15) == 0);
+  for (long it = warp; it < items; it += nwarps) {
+    const int tap = (int)(it % 9);
+    const long row = it / 9;
+    const int oy = (int)(row / Wo), ox = (int)(row - (long)oy * Wo);
+    const int iy = oy * stride + tap / 3 - pad, ix = ox * stride + tap % 3 - pad;
+    const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    const float* src = x + ((size_t)(inside ? iy : 0) * W + (inside ? ix : 0)) * ldx;
+    const size_t dst = (size_t)row * Kpad + (size_t)tap * C;
+    if (vec) {
+      for (int c = lane * 4; c < C; c += 128) {
+        float4 v = inside ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+        __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
+        __nv_bfloat162 la = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
+        __nv_bfloat162 lb = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+        uint2 hv = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+        uint2 lv = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+        *reinterpret_cast<uint2*>(hi + dst + c) = hv;
+        *reinterpret_cast<uint2*>(lo + dst + c) = lv;
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        float v = inside ? src[c] : 0.f;
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[dst + c] = h;
+        lo[dst + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+    if (tap == 8)
+      for (int c = 9 * C + lane; c < Kpad; c += 32) {
+        hi[(size_t)row * Kpad + c] = __float2bfloat16_rn(0.f);
+        lo[(size_t)row * Kpad + c] = __float2bfloat16_rn(0.f);
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -273,7 +343,8 @@ static int make_map(CUtensorMap* m, const void* ptr, int rows, int kpad, int box
 
 template <int BN, int STAGES>
 static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C, int64_t ldc,
-                     int M, int N, float alpha, const float* bias, const float* residual, int64_t ldr, cudaStream_t st) {
+                     int M, int N, float alpha, const float* bias, const float* residual, int64_t ldr, int splits, float* ws,
+                     cudaStream_t st) {
   using Cfg = TcCfg<BN, STAGES>;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
@@ -283,10 +354,20 @@ static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const
   if ((rc = make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
   cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) { set_error("gemm_nt_tc: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
-  dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM);
-  gemm_nt_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, Kpad / TC_BK, alpha,
-                                                                    bias, residual, ldr);
+  const int num_kb = Kpad / TC_BK;
+  const int per = (num_kb + splits - 1) / splits;
+  const int zs = (num_kb + per - 1) / per;  // every z gets >= 1 k-block
+  dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM, zs);
+  gemm_nt_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, num_kb, per, alpha,
+                                                                    bias, residual, ldr, ws);
   SKP_CHECK_LAUNCH("gemm_nt_tc");
+  if (zs > 1) {
+    size_t total = (size_t)M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+    SKP_CHECK_LAUNCH("splitk_reduce");
+  }
   return SKP_OK;
 }
 
@@ -305,16 +386,47 @@ extern "C" int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, in
   return SKP_OK;
 }
 
+static bool use_bn128(int M, int N) {
+  const long tiles128 = (long)((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
+  return tiles128 >= 120 && N >= 128;
+}
+
+extern "C" int skp_gemm_nt_tc_plan(int M, int N, int Kpad) {
+  if (M <= 0 || N <= 0 || Kpad <= 0) return 1;
+  const int bn = use_bn128(M, N) ? 128 : 64;
+  const long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  const int num_kb = Kpad / TC_BK;
+  long splits = 148 / tiles;            // fill the 148 SMs once
+  if (splits > num_kb / 4) splits = num_kb / 4;  // keep >= 4 k-blocks (256 of K) per split
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  return (int)splits;
+}
+
+extern "C" int skp_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int Ho, int Wo, int stride, int pad,
+                                   int Kpad, void* hi, void* lo, void* stream) {
+  SKP_REQUIRE(x && hi && lo && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && stride > 0, "im2col3x3_split: bad arguments");
+  SKP_REQUIRE(Kpad >= 9 * C && Kpad % TC_BK == 0, "im2col3x3_split: Kpad=%d must be a multiple of 64 >= 9*C", Kpad);
+  long items = (long)Ho * Wo * 9;
+  long blocks = (items * 32 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col3x3_split_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, H, W, C, Ho, Wo, stride, pad, Kpad,
+                                                                       (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  SKP_CHECK_LAUNCH("im2col3x3_split");
+  return SKP_OK;
+}
+
 extern "C" int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C,
                               int64_t ldc, int M, int N, float alpha, const float* bias, const float* residual, int64_t ldr,
-                              void* stream) {
+                              int splits, float* splitk_ws, void* stream) {
   SKP_REQUIRE(A_hi && A_lo && B_hi && B_lo && C, "gemm_nt_tc: null pointer");
   SKP_REQUIRE(M > 0 && N > 0 && Kpad > 0 && Kpad % TC_BK == 0, "gemm_nt_tc: bad sizes M=%d N=%d Kpad=%d", M, N, Kpad);
   SKP_REQUIRE(((((uintptr_t)A_hi) | ((uintptr_t)A_lo) | ((uintptr_t)B_hi) | ((uintptr_t)B_lo)) & 15) == 0,
               "gemm_nt_tc: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const long tiles128 = (long)((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
-  if (tiles128 >= 148 && N >= 128)
-    return launch_tc<128, 3>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, st);
-  return launch_tc<64, 4>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, st);
+  if (splits < 1) splits = 1;
+  SKP_REQUIRE(splits == 1 || splitk_ws != nullptr, "gemm_nt_tc: split-K needs a workspace of splits*M*N floats");
+  if (use_bn128(M, N))
+    return launch_tc<128, 3>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, splits, splitk_ws, st);
+  return launch_tc<64, 4>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, splits, splitk_ws, st);
 }

@@ -219,6 +219,24 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// CUDA-graph friendly variant: the step count lives on the device so a captured optimizer step stays correct on replay.
+__global__ void adam_bump_step_kernel(int* step) { *step += 1; }
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                int64_t n, const int* __restrict__ step, float lr, float b1, float b2, float eps, float gscale) {
+  const double t = (double)*step;
+  const float lr_over_bc1 = (float)((double)lr / (1.0 - pow((double)b1, t)));
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = m[i] * b1 + (1.f - b1) * gi;
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - lr_over_bc1 * (mi / denom);
+  }
+}
+
 static inline int grid_for(size_t n, int threads) {
   size_t b = (n + threads - 1) / threads;
   if (b > 148 * 8) b = 148 * 8;
@@ -298,5 +316,16 @@ extern "C" int skp_adam_step(float* param, const float* grad, float* exp_avg, fl
                                                                          (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)),
                                                                          beta1, beta2, eps, grad_scale);
   SKP_CHECK_LAUNCH("adam");
+  return SKP_OK;
+}
+
+extern "C" int skp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int* step_dev,
+                                 float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  SKP_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0, "adam_step_dev: bad arguments");
+  adam_bump_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  SKP_CHECK_LAUNCH("adam_bump_step");
+  adam_dev_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, step_dev, lr,
+                                                                             beta1, beta2, eps, grad_scale);
+  SKP_CHECK_LAUNCH("adam_dev");
   return SKP_OK;
 }

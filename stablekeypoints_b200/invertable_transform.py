@@ -34,18 +34,21 @@ class RandomAffineWithInverse:
         theta[:, :2] = theta[:, :2] * scale
         return theta.unsqueeze(0)
 
+    def sample_theta(self, batch: int) -> torch.Tensor:
+        """invertable_transform.py:42-57: four host-side torch.rand(1) draws per image, in the reference's order."""
+        theta = []
+        for _ in range(batch):
+            angle = torch.rand(1).item() * (2 * self.degrees) - self.degrees
+            scale_factor = torch.rand(1).item() * (self.scale[1] - self.scale[0]) + self.scale[0]
+            tr = (torch.rand(1).item() * (2 * self.translate[0]) - self.translate[0],
+                  torch.rand(1).item() * (2 * self.translate[1]) - self.translate[1])
+            theta.append(self.create_affine_matrix(angle, scale_factor, tr))
+        return torch.cat(theta, dim=0)
+
     def __call__(self, img_tensor, theta=None):
-        """invertable_transform.py:38-70: same four host-side torch.rand(1) draws per image, in the same order;
-        the warp itself runs on the GPU (the reference warps on the CPU)."""
+        """invertable_transform.py:38-70; the warp itself runs on the GPU (the reference warps on the CPU)."""
         if theta is None:
-            theta = []
-            for _ in range(img_tensor.shape[0]):
-                angle = torch.rand(1).item() * (2 * self.degrees) - self.degrees
-                scale_factor = torch.rand(1).item() * (self.scale[1] - self.scale[0]) + self.scale[0]
-                tr = (torch.rand(1).item() * (2 * self.translate[0]) - self.translate[0],
-                      torch.rand(1).item() * (2 * self.translate[1]) - self.translate[1])
-                theta.append(self.create_affine_matrix(angle, scale_factor, tr))
-            theta = torch.cat(theta, dim=0)
+            theta = self.sample_theta(img_tensor.shape[0])
         self.last_params = {"theta": theta}
         dev = img_tensor.device if img_tensor.is_cuda else torch.device("cuda", torch.cuda.current_device())
         return ops.affine_warp(img_tensor.to(dev, non_blocking=True), theta)

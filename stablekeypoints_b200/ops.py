@@ -80,13 +80,97 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, b_split, bias: Optional[torch.Tens
     ldr = residual.stride(0) if residual is not None else 0
     if GEMM_IMPL == "tc":
         a_hi, a_lo = split_bf16(a)
-        b_hi, b_lo = b_split
-        check(lib().skp_gemm_nt_tc(ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), a_hi.shape[1], ptr(out), out.stride(0),
-                                   m, n, alpha, ptr(bias), ptr(residual), ldr, stream()), "skp_gemm_nt_tc")
-    else:
-        check(lib().skp_gemm_nt_simt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), m, n, k, alpha,
-                                     ptr(bias), ptr(residual), ldr, stream()), "skp_gemm_nt_simt")
+        return gemm_nt_presplit(a_hi, a_lo, m, b_split, n, bias, residual, alpha, out)
+    check(lib().skp_gemm_nt_simt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), m, n, k, alpha,
+                                 ptr(bias), ptr(residual), ldr, stream()), "skp_gemm_nt_simt")
     return out
+
+
+def gemm_nt_presplit(a_hi, a_lo, m: int, b_split, n: int, bias=None, residual=None, alpha: float = 1.0, out=None):
+    """tcgen05 GEMM on operands that are already split-bf16 K-major pairs; split-K when the tile count is small."""
+    kp = a_hi.shape[1]
+    b_hi, b_lo = b_split
+    assert b_hi.shape[1] == kp, f"K padding mismatch: A {kp} vs B {b_hi.shape[1]}"
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a_hi.device)
+    if residual is not None and (residual.stride(1) != 1 or residual.dtype != torch.float32):
+        residual = _f32c(residual)
+    ldr = residual.stride(0) if residual is not None else 0
+    splits = lib().skp_gemm_nt_tc_plan(m, n, kp)
+    ws = torch.empty(splits * m * n, dtype=torch.float32, device=out.device) if splits > 1 else None
+    check(lib().skp_gemm_nt_tc(ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), kp, ptr(out), out.stride(0), m, n, alpha,
+                               ptr(bias), ptr(residual), ldr, splits, ptr(ws), stream()), "skp_gemm_nt_tc")
+    return out
+
+
+# ----------------------------------------------------------------------------- frozen 3x3 convolution (channels-last)
+def im2col3x3_split(x2d: torch.Tensor, h: int, w: int, ho: int, wo: int, stride: int, pad: int):
+    """x2d [h*w, C] fp32 channels-last -> split-bf16 im2col operand ([ho*wo, pad64(9C)] hi, lo)."""
+    require_cuda(x2d)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.shape[0] == h * w and x2d.dtype == torch.float32
+    c = x2d.shape[1]
+    kp = _pad64(9 * c)
+    hi = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
+    lo = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
+    check(lib().skp_im2col3x3_split(ptr(x2d), x2d.stride(0), h, w, c, ho, wo, stride, pad, kp, ptr(hi), ptr(lo), stream()),
+          "skp_im2col3x3_split")
+    return hi, lo
+
+
+class FrozenConv3x3:
+    """Frozen [Cout, Cin, 3, 3] filter prepared as GEMM operands: forward  W[cout, tap*Cin + cin]; input-gradient
+    (stride 1) W'[cin, tap*Cout + cout] with the taps flipped.  Both as split-bf16 K-major pairs."""
+
+    def __init__(self, w: torch.Tensor, need_dgrad: bool = True):
+        require_cuda(w)
+        w = w.detach().float()
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        self.fwd_split = split_bf16(w.permute(0, 2, 3, 1).reshape(self.cout, 9 * self.cin).contiguous())
+        self.dgrad_split = None
+        self.w_nchw = None
+        if need_dgrad:
+            self.dgrad_split = split_bf16(w.flip(2, 3).permute(1, 2, 3, 0).reshape(self.cin, 9 * self.cout).contiguous())
+            self.w_nchw = w.contiguous()  # only used by the stride-2 input gradient (3 down-samplers)
+
+
+class _FrozenConv3x3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, residual, fcw: FrozenConv3x3, bias, h, w, stride, pad, ho, wo):
+        x2d = _f32c(x2d)
+        hi, lo = im2col3x3_split(x2d, h, w, ho, wo, stride, pad)
+        ctx.fcw, ctx.geom, ctx.has_res = fcw, (h, w, stride, pad, ho, wo), residual is not None
+        return gemm_nt_presplit(hi, lo, ho * wo, fcw.fwd_split, fcw.cout, bias, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        fcw = ctx.fcw
+        h, w, stride, pad, ho, wo = ctx.geom
+        dy = _f32c(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if stride == 1 and pad == 1:
+                hi, lo = im2col3x3_split(dy, ho, wo, h, w, 1, 1)
+                dx = gemm_nt_presplit(hi, lo, h * w, fcw.dgrad_split, fcw.cin)
+            else:  # the three strided down-samplers: cuDNN dgrad on an NCHW view
+                g = dy.reshape(1, ho, wo, fcw.cout).permute(0, 3, 1, 2)
+                # the geometry is "rows/cols beyond the image read zero": the padded extent that makes (ho, wo) exact
+                hp_, wp_ = (ho - 1) * stride + 3 - pad, (wo - 1) * stride + 3 - pad
+                dxn = torch.nn.grad.conv2d_input((1, fcw.cin, max(h, hp_) + pad, max(w, wp_) + pad), fcw.w_nchw, g,
+                                                 stride=stride, padding=0)
+                dx = dxn[:, :, pad:pad + h, pad:pad + w].permute(0, 2, 3, 1).reshape(h * w, fcw.cin).contiguous()
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        return dx, dres, None, None, None, None, None, None, None, None
+
+
+def frozen_conv3x3(x2d, h: int, w: int, fcw: FrozenConv3x3, bias=None, residual=None, stride: int = 1, pad: int = 1,
+                   out_hw=None):
+    """3x3 convolution of a channels-last activation [h*w, Cin] with a frozen filter -> [ho*wo, Cout] (+bias +residual):
+    im2col straight to split-bf16, then the tcgen05 GEMM.  Returns (y2d, ho, wo)."""
+    if out_hw is None:
+        ho, wo = (h + 2 * pad - 3) // stride + 1, (w + 2 * pad - 3) // stride + 1
+    else:
+        ho, wo = out_hw
+    return _FrozenConv3x3.apply(x2d, residual, fcw, bias, h, w, stride, pad, ho, wo), ho, wo
 
 
 class _FrozenLinear(torch.autograd.Function):
@@ -413,9 +497,16 @@ def soft_argmax_(heatmaps: torch.Tensor, distance: float = 5.0) -> torch.Tensor:
     return out
 
 
-def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr=5e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+def adam_step_(param, grad, exp_avg, exp_avg_sq, step, lr=5e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """`step` is a Python int (1-based) or an int32 device tensor holding the number of steps taken so far (the kernel
+    increments it): the second form is CUDA-graph capturable."""
     require_cuda(param, grad, exp_avg, exp_avg_sq)
     assert param.is_contiguous() and grad.is_contiguous() and param.dtype == torch.float32
+    if isinstance(step, torch.Tensor):
+        assert step.dtype == torch.int32 and step.is_cuda
+        check(lib().skp_adam_step_dev(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(step), lr,
+                                      beta1, beta2, eps, grad_scale, stream()), "skp_adam_step_dev")
+        return param
     check(lib().skp_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), int(step), lr, beta1,
                               beta2, eps, grad_scale, stream()), "skp_adam_step")
     return param

@@ -56,7 +56,7 @@ def find_gaussian_loss_at_point(attn_map, pos, sigma=1.0, temperature=1e-1, devi
 
 # ----------------------------------------------------------------------------- one Stage-1 iteration
 def stage1_losses(attn_map, attn_map_t, theta, *, top_k=10, num_candidates=25, sigma=2.0, num_subjects=1,
-                  top_k_strategy="gaussian", forced_indices=None):
+                  top_k_strategy="gaussian", forced_indices=None, theta_inv=None):
     """optimize.py:380-401 for this rank's image: candidates by Gaussian-KL on the ORIGINAL maps, furthest-point
     sampling on the TRANSFORMED maps' arg-maxes, then both losses on the selected tokens -- all on device, the
     token indices never visit the host."""
@@ -73,12 +73,14 @@ def stage1_losses(attn_map, attn_map_t, theta, *, top_k=10, num_candidates=25, s
             raise NotImplementedError
         idx = ptp_utils.furthest_point_sampling(attn_map_t, top_k, cand)
     sharp = ops.sharpen_loss_op(attn_map, idx, sigma, num_subjects)
-    equiv = ops.equivariance_loss_op(attn_map, attn_map_t, idx, invert_theta(theta)[0])
+    if theta_inv is None:                       # host path; a device theta_inv keeps the step CUDA-graph capturable
+        theta_inv = invert_theta(theta)
+    equiv = ops.equivariance_loss_op(attn_map, attn_map_t, idx, theta_inv[0])
     return idx, sharp, equiv
 
 
 def stage1_iteration(ldm, controllers, image, context, transform: RandomAffineWithInverse, args, *, accum: int = 1,
-                     theta=None, noise_a=None, noise_b=None, forced_indices=None, from_where=None):
+                     theta=None, theta_inv=None, noise_a=None, noise_b=None, forced_indices=None, from_where=None):
     """optimize.py:341-422 for one rank: two captured forwards, selection, loss = w_e*equiv + w_s*sharp, / accum,
     backward into ``context`` (its .grad accumulates)."""
     kw = dict(layers=args.layers, noise_level=args.noise_level, from_where=from_where, upsample_res=-1,
@@ -91,7 +93,7 @@ def stage1_iteration(ldm, controllers, image, context, transform: RandomAffineWi
     idx, sharp, equiv = stage1_losses(attn_maps[0], attn_maps_t[0], transform.last_params["theta"], top_k=args.top_k,
                                       num_candidates=args.furthest_point_num_samples, sigma=args.sigma,
                                       num_subjects=args.num_subjects, top_k_strategy=args.top_k_strategy,
-                                      forced_indices=forced_indices)
+                                      forced_indices=forced_indices, theta_inv=theta_inv)
     loss = equiv * args.equivariance_attn_loss_weight + sharp * args.sharpening_loss_weight
     (loss / accum).backward()
     return {"loss": loss.detach(), "sharp": sharp.detach(), "equiv": equiv.detach(), "indices": idx,
@@ -123,24 +125,92 @@ class EmbeddingOptimizer:
     one NCCL all-reduce(sum) of the N*D fp32 gradient per optimizer step, then skp_adam_step with grad_scale =
     1/world_size on every rank (replicated state, identical updates)."""
 
-    def __init__(self, context: torch.Tensor, lr: float = 5e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+    def __init__(self, context: torch.Tensor, lr: float = 5e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None,
+                 capturable: bool = False):
         self.context, self.lr, self.betas, self.eps, self.group = context, lr, betas, eps, group
         self.exp_avg = torch.zeros_like(context)
         self.exp_avg_sq = torch.zeros_like(context)
         self.steps = 0
+        # capturable: the step count lives on the device so the update can be replayed from a CUDA graph
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=context.device) if capturable else None
 
     def step(self):
         g = self.context.grad
         ws = allreduce_sum_(g, self.group)
         self.steps += 1
         with torch.no_grad():
-            ops.adam_step_(self.context, g, self.exp_avg, self.exp_avg_sq, self.steps, self.lr, self.betas[0],
+            ops.adam_step_(self.context, g, self.exp_avg, self.exp_avg_sq,
+                           self.step_dev if self.step_dev is not None else self.steps, self.lr, self.betas[0],
                            self.betas[1], self.eps, 1.0 / ws)
         # the kernel wrote through the raw pointer: tell autograd / the engine's K|V cache the tensor changed
         torch.autograd.graph.increment_version(self.context)
 
     def zero_grad(self):
         self.context.grad = None
+
+
+class Stage1Graph:
+    """One whole Stage-1 optimizer step (optimize.py:341-425 for this rank: two captured forwards, selection, losses,
+    backward, gradient all-reduce, Adam) captured ONCE into a CUDA graph and replayed per image.
+
+    The step is ~10^4 small launches at batch 1, i.e. CPU-launch-bound when driven from Python; the graph removes that.
+    Everything data-dependent stays on the device (token selection included), the per-step inputs are written into
+    static buffers (`image`, `theta`, `theta_inv`) before each replay, noise comes from torch's graph-safe Philox state."""
+
+    def __init__(self, ldm, controllers, context, optimizer: "EmbeddingOptimizer", args, image_shape=(1, 3, 512, 512),
+                 accum: int = 1, warmup: int = 3, from_where=None):
+        assert optimizer.step_dev is not None, "Stage1Graph needs EmbeddingOptimizer(capturable=True)"
+        assert accum == 1, "gradient accumulation (B//G > 1) replays the eager step; the graph holds one full optimizer step"
+        dev = ldm.unet.device
+        self.ldm, self.controllers, self.context, self.optimizer, self.args = ldm, controllers, context, optimizer, args
+        self.image = torch.zeros(image_shape, device=dev)
+        self.theta = torch.zeros(image_shape[0], 2, 3, device=dev)
+        self.theta_inv = torch.zeros(image_shape[0], 2, 3, device=dev)
+        self.transform = RandomAffineWithInverse()
+        self.from_where = from_where
+        self.out = None
+        self.graph = None
+        self._warmup = warmup
+
+    def _step(self):
+        out = stage1_iteration(self.ldm, self.controllers, self.image, self.context, self.transform, self.args,
+                               theta=self.theta, theta_inv=self.theta_inv, from_where=self.from_where)
+        self.optimizer.step()
+        self.optimizer.zero_grad()
+        return out
+
+    def set_inputs(self, image: torch.Tensor, theta: torch.Tensor):
+        """image: [1,3,H,W] (host pinned or device); theta: [1,2,3] host tensor (inverse computed here in fp64)."""
+        self.image.copy_(image, non_blocking=True)
+        self.theta.copy_(theta.to(torch.float32), non_blocking=True)
+        self.theta_inv.copy_(invert_theta(theta), non_blocking=True)
+
+    def capture(self):
+        self.optimizer.zero_grad()
+        opt = self.optimizer
+        saved = [t.clone() for t in (self.context.detach(), opt.exp_avg, opt.exp_avg_sq, opt.step_dev)]
+        saved_steps = opt.steps
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self._warmup):      # cuDNN/cuBLAS autotuning, allocator warm-up, time-constant caches
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():                  # the warm-up steps must not count as training steps
+            for dst, src in zip((self.context, opt.exp_avg, opt.exp_avg_sq, opt.step_dev), saved):
+                dst.copy_(src)
+        opt.steps = saved_steps
+        torch.autograd.graph.increment_version(self.context)
+        self.ldm.unet.invalidate_context_cache()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._step()
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
 
 
 class SyntheticKeypointDataset(torch.utils.data.Dataset):

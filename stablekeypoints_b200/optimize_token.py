@@ -17,6 +17,9 @@ def set_precision(mode: str) -> None:
         raise ValueError(mode)
     torch.backends.cudnn.allow_tf32 = mode in ("tf32", "reference")
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+    # fixed shapes, one image per rank: let cuDNN time its algorithms once (its fp32 heuristics pick FFT convolutions
+    # that launch thousands of complex GEMVs per forward)
+    torch.backends.cudnn.benchmark = os.environ.get("SKP_CUDNN_BENCHMARK", "1") == "1"
 
 
 def _load_safetensors_dir(path: str, sub: str):
@@ -33,7 +36,7 @@ def _load_safetensors_dir(path: str, sub: str):
 
 def load_ldm(device, type="CompVis/stable-diffusion-v1-4", feature_upsample_res=256, my_token=None, *,
              unet_state_dict=None, vae_state_dict=None, unet_config: UNetConfig = None, vae_config: VAEConfig = None,
-             seed: int = 0, attn_gain: float = 1.0, precision: str = None):
+             seed: int = 0, attn_gain: float = 1.0, precision: str = None, trunk: str = None):
     """optimize_token.py:24-78 -> (ldm, controllers, effective_num_gpus).
 
     One process drives ONE GPU (the multi-GPU layout is one process per GPU + NCCL, not nn.DataParallel), so
@@ -58,8 +61,9 @@ def load_ldm(device, type="CompVis/stable-diffusion-v1-4", feature_upsample_res=
         else:
             raise FileNotFoundError(f"model '{type}' is not a local directory and there is no network: pass a "
                                     "diffusers-format directory or 'synthetic[:seed]'")
-    unet = UNetEngine(unet_state_dict, ucfg, dev)
-    vae = VAEEncoderEngine(vae_state_dict, vcfg, dev)
+    trunk = trunk or os.environ.get("SKP_TRUNK", "tc")
+    unet = UNetEngine(unet_state_dict, ucfg, dev, trunk=trunk)
+    vae = VAEEncoderEngine(vae_state_dict, vcfg, dev, trunk=trunk)
     ldm = Pipeline(unet, vae, DDIMSchedule(dev))
     controllers = {dev: ptp_utils.AttentionStore()}
     ptp_utils.register_attention_control(unet, controllers[dev], feature_upsample_res=feature_upsample_res)

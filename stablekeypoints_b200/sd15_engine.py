@@ -193,6 +193,10 @@ class DDIMSchedule:
 
     def add_noise(self, original, noise, timesteps):
         t = torch.as_tensor(timesteps).reshape(-1).to(torch.int64).cpu()
+        if t.numel() == 1 or bool((t == t[0]).all()):
+            # one timestep for the whole batch (the path's case): host scalars, no H2D copy (CUDA-graph safe)
+            a = self.alphas_cumprod[int(t[0])]
+            return float(a.sqrt()) * original + float((1.0 - a).sqrt()) * noise
         a = self.alphas_cumprod[t].to(original.device, original.dtype)
         shape = (-1,) + (1,) * (original.dim() - 1)
         return a.sqrt().reshape(shape) * original + (1.0 - a).sqrt().reshape(shape) * noise
@@ -212,7 +216,14 @@ class _EarlyExit(Exception):
 
 
 class UNetEngine:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: UNetConfig = UNetConfig(), device="cuda"):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: UNetConfig = UNetConfig(), device="cuda",
+                 trunk: str = "tc"):
+        # trunk = "tc": every convolution / linear of the frozen trunk runs on the tcgen05 split-bf16 GEMM of
+        #               libskp_b200 (fp32-grade accuracy at tensor-core speed), activations channels-last [H*W, C];
+        # trunk = "torch": cuDNN / cuBLAS for the un-named part of the trunk (the first slice; kept for A/B checks).
+        if trunk not in ("tc", "torch"):
+            raise ValueError(trunk)
+        self.trunk = trunk
         self.cfg = cfg
         self.device = torch.device(device)
         shapes = unet_param_shapes(cfg)
@@ -227,6 +238,9 @@ class UNetEngine:
         self._fw: Dict[str, ops.FrozenWeight] = {}
         self._qkv1: Dict[str, torch.Tensor] = {}
         self._prepare_attention()
+        self._conv: Dict[str, ops.FrozenConv3x3] = {}
+        if trunk == "tc":
+            self._prepare_trunk()
         self._temb_cache: Dict[int, Dict[str, torch.Tensor]] = {}
         # capture state (set through ptp_utils.register_attention_control)
         self.controller = None
@@ -270,6 +284,24 @@ class UNetEngine:
         self.kv_width = off
         self._fw["kv_all"] = ops.FrozenWeight(torch.cat(kv_rows, 0))   # [2*sum(C), 768]
         self._layer_by_prefix = {l.prefix: l for l in self.cross_layers}
+
+    def _prepare_trunk(self):
+        """One-time: every frozen filter / matrix of the trunk as split-bf16 K-major GEMM operands (both directions)."""
+        w = self.w
+        for k, t in list(w.items()):
+            if not k.endswith(".weight") or t.dim() < 2:
+                continue
+            p = k[: -len(".weight")]
+            if t.dim() == 4 and t.shape[-1] == 3:
+                self._conv[p] = ops.FrozenConv3x3(t, need_dgrad=(p != "conv_in"))
+            elif t.dim() == 4:                                   # 1x1 convs: proj_in / proj_out / conv_shortcut
+                self._fw[p] = ops.FrozenWeight(t.reshape(t.shape[0], t.shape[1]))
+            elif ".attn1.to_" in k or ".ff.net." in k:
+                if k.endswith("attn1.to_q.weight"):
+                    a1 = k[: -len(".to_q.weight")]
+                    self._fw[f"{a1}.qkv"] = ops.FrozenWeight(self._qkv1[a1])
+                elif k.endswith("attn1.to_out.0.weight") or ".ff.net." in k:
+                    self._fw[p] = ops.FrozenWeight(t)
 
     def _time_constants(self, t: int) -> Dict[str, torch.Tensor]:
         """Fold the constant-timestep embedding into per-resnet conv1 biases (b1 + time_emb_proj(silu(emb)))."""
@@ -356,6 +388,82 @@ class UNetEngine:
         h = h.reshape(1, hh, ww, c).permute(0, 3, 1, 2)
         return F.conv2d(h, w[f"{p}.proj_out.weight"], w[f"{p}.proj_out.bias"]) + res
 
+    # ---- channels-last tensor-core trunk: activations are [H*W, C] matrices
+    def _gn_cl(self, x2d, wname, eps, silu):
+        """GroupNorm (+SiLU) of a channels-last activation (torch group_norm on the [1,C,HW] view)."""
+        w, c = self.w, x2d.shape[1]
+        y = F.group_norm(x2d.t().reshape(1, c, -1), self.cfg.norm_num_groups, w[f"{wname}.weight"], w[f"{wname}.bias"], eps)
+        if silu:
+            y = F.silu(y)
+        return y.reshape(c, -1).t().contiguous()
+
+    def _resnet_cl(self, p, x, h, wd, tb):
+        w = self.w
+        y = self._gn_cl(x, f"{p}.norm1", self.cfg.norm_eps, True)
+        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv1"], tb[p])
+        y = self._gn_cl(y, f"{p}.norm2", self.cfg.norm_eps, True)
+        if f"{p}.conv_shortcut" in self._fw:
+            x = ops.frozen_linear(x, self._fw[f"{p}.conv_shortcut"], w[f"{p}.conv_shortcut.bias"])
+        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv2"], w[f"{p}.conv2.bias"], residual=x)
+        return y
+
+    def _transformer_cl(self, p, x, kv_all, state):
+        w, heads = self.w, self.cfg.heads
+        s, c = x.shape
+        t = f"{p}.transformer_blocks.0"
+        hdn = self._gn_cl(x, f"{p}.norm", 1e-6, False)
+        hdn = ops.frozen_linear(hdn, self._fw[f"{p}.proj_in"], w[f"{p}.proj_in.bias"])
+        # attn1 (self-attention): projections on the tcgen05 GEMM, softmax(QK^T)V on torch SDPA
+        y = F.layer_norm(hdn, (c,), w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"])
+        qkv = ops.frozen_linear(y, self._fw[f"{t}.attn1.qkv"]).reshape(s, 3, heads, c // heads).permute(1, 2, 0, 3)
+        o = F.scaled_dot_product_attention(qkv[0][None], qkv[1][None], qkv[2][None])[0].permute(1, 0, 2).reshape(s, c)
+        hdn = ops.frozen_linear(o, self._fw[f"{t}.attn1.to_out.0"], w[f"{t}.attn1.to_out.0.bias"], residual=hdn)
+        # attn2 (cross-attention + capture)
+        y = F.layer_norm(hdn, (c,), w[f"{t}.norm2.weight"], w[f"{t}.norm2.bias"])
+        hdn = self._cross_attention(f"{t}.attn2", y, hdn, kv_all, state)
+        # GEGLU feed-forward
+        y = F.layer_norm(hdn, (c,), w[f"{t}.norm3.weight"], w[f"{t}.norm3.bias"])
+        a, gate = ops.frozen_linear(y, self._fw[f"{t}.ff.net.0.proj"], w[f"{t}.ff.net.0.proj.bias"]).chunk(2, dim=-1)
+        hdn = ops.frozen_linear(a * F.gelu(gate), self._fw[f"{t}.ff.net.2"], w[f"{t}.ff.net.2.bias"], residual=hdn)
+        return ops.frozen_linear(hdn, self._fw[f"{p}.proj_out"], w[f"{p}.proj_out.bias"], residual=x)
+
+    def _forward_cl(self, sample, tb, kv_all, state):
+        cfg, w = self.cfg, self.w
+        _, cin, h, wd = sample.shape
+        x = sample[0].permute(1, 2, 0).reshape(h * wd, cin).contiguous()
+        x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv["conv_in"], w["conv_in.bias"])
+        skips = [x]
+        nb = len(cfg.block_out_channels)
+        for i in range(nb):
+            for j in range(cfg.layers_per_block):
+                x = self._resnet_cl(f"down_blocks.{i}.resnets.{j}", x, h, wd, tb)
+                if cfg.down_has_attn[i]:
+                    x = self._transformer_cl(f"down_blocks.{i}.attentions.{j}", x, kv_all, state)
+                skips.append(x)
+            if i != nb - 1:
+                p = f"down_blocks.{i}.downsamplers.0.conv"
+                x, h, wd = ops.frozen_conv3x3(x, h, wd, self._conv[p], w[f"{p}.bias"], stride=2, pad=1)
+                skips.append(x)
+        x = self._resnet_cl("mid_block.resnets.0", x, h, wd, tb)
+        x = self._transformer_cl("mid_block.attentions.0", x, kv_all, state)
+        x = self._resnet_cl("mid_block.resnets.1", x, h, wd, tb)
+        up_attn = tuple(reversed(cfg.down_has_attn))
+        for i in range(nb):
+            for j in range(cfg.layers_per_block + 1):
+                x = torch.cat([x, skips.pop()], dim=1)
+                x = self._resnet_cl(f"up_blocks.{i}.resnets.{j}", x, h, wd, tb)
+                if up_attn[i]:
+                    x = self._transformer_cl(f"up_blocks.{i}.attentions.{j}", x, kv_all, state)
+            if i != nb - 1:
+                c = x.shape[1]                                   # nearest x2 in channels-last
+                x = x.reshape(h, 1, wd, 1, c).expand(h, 2, wd, 2, c).reshape(4 * h * wd, c)
+                h, wd = 2 * h, 2 * wd
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv[p], w[f"{p}.bias"])
+        x = self._gn_cl(x, "conv_norm_out", cfg.norm_eps, True)
+        x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv["conv_out"], w["conv_out.bias"])
+        return x.reshape(1, h, wd, -1).permute(0, 3, 1, 2)
+
     # ---- K|V projection, once per context version
     def project_context(self, context: torch.Tensor) -> torch.Tensor:
         """[N, 768] -> [N, 2*sum(C)]: K|V of all cross-attention layers in one tcgen05 GEMM (autograd-connected)."""
@@ -391,6 +499,11 @@ class UNetEngine:
                  "logits": []}
         self.last_logits = state["logits"]
         x = sample.to(self.device, torch.float32)
+        if self.trunk == "tc":
+            try:
+                return {"sample": self._forward_cl(x, tb, kv_all, state)}
+            except _EarlyExit:
+                return {"sample": None}
         try:
             x = F.conv2d(x, w["conv_in.weight"], w["conv_in.bias"], padding=1)
             skips = [x]
@@ -444,14 +557,17 @@ class _LatentDist:
 class VAEEncoderEngine:
     """AutoencoderKL.encode(...)["latent_dist"].mean (ptp_utils.py:299-302): torch/cuDNN, no grad ("next" row f1)."""
 
-    def __init__(self, state_dict, cfg: VAEConfig = VAEConfig(), device="cuda"):
+    def __init__(self, state_dict, cfg: VAEConfig = VAEConfig(), device="cuda", trunk: str = "tc"):
         self.cfg = cfg
+        self.trunk = trunk
         self.device = torch.device(device)
         shapes = vae_encoder_param_shapes(cfg)
         missing = [k for k in shapes if k not in state_dict]
         if missing:
             raise KeyError(f"VAE state dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
         self.w = {k: state_dict[k].detach().to(self.device, torch.float32).contiguous() for k in shapes}
+        if trunk == "tc":
+            self._prepare_trunk()
 
     def _resnet(self, p, x):
         w, g = self.w, self.cfg.norm_num_groups
@@ -463,10 +579,72 @@ class VAEEncoderEngine:
             x = F.conv2d(x, w[f"{p}.conv_shortcut.weight"], w[f"{p}.conv_shortcut.bias"])
         return x + h
 
+    # ---- channels-last tensor-core path (same GEMM machinery as the UNet trunk; no gradients needed)
+    def _prepare_trunk(self):
+        self._conv, self._fw = {}, {}
+        for k, t in self.w.items():
+            if not k.endswith(".weight") or t.dim() < 2:
+                continue
+            p = k[: -len(".weight")]
+            if t.dim() == 4 and t.shape[-1] == 3:
+                self._conv[p] = ops.FrozenConv3x3(t, need_dgrad=False)
+            elif t.dim() == 4:
+                self._fw[p] = ops.FrozenWeight(t.reshape(t.shape[0], t.shape[1]), need_dgrad=False)
+            else:
+                self._fw[p] = ops.FrozenWeight(t, need_dgrad=False)
+
+    def _gn_cl(self, x2d, wname, silu):
+        c = x2d.shape[1]
+        y = F.group_norm(x2d.t().reshape(1, c, -1), self.cfg.norm_num_groups, self.w[f"{wname}.weight"],
+                         self.w[f"{wname}.bias"], 1e-6)
+        if silu:
+            y = F.silu(y)
+        return y.reshape(c, -1).t().contiguous()
+
+    def _resnet_cl(self, p, x, h, wd):
+        w = self.w
+        y = self._gn_cl(x, f"{p}.norm1", True)
+        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv1"], w[f"{p}.conv1.bias"])
+        y = self._gn_cl(y, f"{p}.norm2", True)
+        if f"{p}.conv_shortcut" in self._fw:
+            x = ops.frozen_linear(x, self._fw[f"{p}.conv_shortcut"], w[f"{p}.conv_shortcut.bias"])
+        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv2"], w[f"{p}.conv2.bias"], residual=x)
+        return y
+
+    def _encode_cl(self, img):
+        w, cfg = self.w, self.cfg
+        _, cin, h, wd = img.shape
+        x = img[0].permute(1, 2, 0).reshape(h * wd, cin).contiguous()
+        x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv["encoder.conv_in"], w["encoder.conv_in.bias"])
+        nb = len(cfg.block_out_channels)
+        for i in range(nb):
+            for j in range(cfg.layers_per_block):
+                x = self._resnet_cl(f"encoder.down_blocks.{i}.resnets.{j}", x, h, wd)
+            if i != nb - 1:  # F.pad(x, (0,1,0,1)) + stride-2 conv without padding: rows/cols past the image read zero
+                p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                x, h, wd = ops.frozen_conv3x3(x, h, wd, self._conv[p], w[f"{p}.bias"], stride=2, pad=0, out_hw=(h // 2, wd // 2))
+        x = self._resnet_cl("encoder.mid_block.resnets.0", x, h, wd)
+        a = "encoder.mid_block.attentions.0"
+        y = self._gn_cl(x, f"{a}.group_norm", False)
+        q = ops.frozen_linear(y, self._fw[f"{a}.query"], w[f"{a}.query.bias"])
+        k = ops.frozen_linear(y, self._fw[f"{a}.key"], w[f"{a}.key.bias"])
+        v = ops.frozen_linear(y, self._fw[f"{a}.value"], w[f"{a}.value.bias"])
+        o = F.scaled_dot_product_attention(q[None, None], k[None, None], v[None, None])[0, 0]
+        x = ops.frozen_linear(o, self._fw[f"{a}.proj_attn"], w[f"{a}.proj_attn.bias"], residual=x)
+        x = self._resnet_cl("encoder.mid_block.resnets.1", x, h, wd)
+        x = self._gn_cl(x, "encoder.conv_norm_out", True)
+        x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv["encoder.conv_out"], w["encoder.conv_out.bias"])
+        x = ops.frozen_linear(x, self._fw["quant_conv"], w["quant_conv.bias"])
+        return x.reshape(1, h, wd, -1).permute(0, 3, 1, 2)
+
     @torch.no_grad()
     def encode(self, x: torch.Tensor):
         w, cfg = self.w, self.cfg
         x = x.to(self.device, torch.float32)
+        if self.trunk == "tc":
+            if x.shape[0] != 1:
+                raise ValueError("VAEEncoderEngine encodes one image per call on the tensor-core path")
+            return {"latent_dist": _LatentDist(self._encode_cl(x))}
         x = F.conv2d(x, w["encoder.conv_in.weight"], w["encoder.conv_in.bias"], padding=1)
         nb = len(cfg.block_out_channels)
         for i in range(nb):

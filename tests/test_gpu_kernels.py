@@ -58,6 +58,30 @@ def test_gemm_tc_dgrad_matches_autograd(ops):
     assert rel_err(x.grad.cpu(), dy.double() @ w.double()) < 3e-5
 
 
+@pytest.mark.parametrize("h,w,cin,cout,stride,pad", [(16, 16, 1280, 1280, 1, 1), (64, 64, 320, 320, 1, 1), (8, 8, 2560, 1280, 1, 1),
+                                                      (64, 64, 4, 320, 1, 1), (32, 32, 640, 640, 2, 1), (16, 16, 320, 4, 1, 1),
+                                                      (17, 23, 12, 20, 1, 1), (32, 32, 128, 128, 2, 0)])
+def test_frozen_conv3x3_fwd_bwd_vs_torch(ops, h, w, cin, cout, stride, pad):
+    """im2col-to-split-bf16 + tcgen05 GEMM == F.conv2d (fp64 reference), forward and input gradient."""
+    g = torch.Generator().manual_seed(h + cin + cout)
+    x = torch.randn(1, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xr = x.double().requires_grad_(True)
+    xin = F.pad(xr, (0, 1, 0, 1)) if pad == 0 else xr            # the VAE down-sampler pads bottom/right only
+    yr = F.conv2d(xin, wt.double(), b.double(), stride=stride, padding=pad)
+    dy = torch.randn(yr.shape, generator=g, dtype=torch.float64)
+    yr.backward(dy)
+    ho, wo = yr.shape[2], yr.shape[3]
+    xc = cu(x[0].permute(1, 2, 0).reshape(h * w, cin).contiguous()).requires_grad_(True)
+    y, ho2, wo2 = ops.frozen_conv3x3(xc, h, w, ops.FrozenConv3x3(cu(wt)), cu(b), stride=stride, pad=pad, out_hw=(ho, wo))
+    assert (ho2, wo2) == (ho, wo)
+    y.backward(cu(dy[0].permute(1, 2, 0).reshape(ho * wo, cout).float().contiguous()))
+    tol = 3e-5 * max(1.0, (9 * cin / 1024) ** 0.5)
+    assert rel_err(y.detach().cpu(), yr.detach()[0].permute(1, 2, 0).reshape(ho * wo, cout)) < tol
+    assert rel_err(xc.grad.cpu(), xr.grad[0].permute(1, 2, 0).reshape(h * w, cin)) < 10 * tol
+
+
 # ----------------------------------------------------------------------------- cross-attention core
 def _attn_ref(q, k, v, heads, scale, extra_w=None):
     s, c = q.shape

@@ -102,6 +102,43 @@ def test_tiny_stage1_iteration_matches_reference_golden(tiny, impl, mode, monkey
         ops.set_gemm_impl("tc")
 
 
+def test_tiny_cuda_graph_step_equals_eager_step(tiny, monkeypatch):
+    """The whole optimizer step replayed from ONE CUDA graph == the same step driven from Python (same noise, image, theta)."""
+    import itertools
+    from stablekeypoints_b200 import optimize
+    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+    g, pipe = tiny
+    ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
+    noises = itertools.cycle([torch.from_numpy(g["noise_a"]).cuda(), torch.from_numpy(g["noise_b"]).cuda()])
+    monkeypatch.setattr(torch, "randn_like", lambda t, *a, **k: next(noises).clone())
+    args = _args(top_k=TINY["top_k"], furthest_point_num_samples=TINY["num_candidates"], sigma=TINY["sigma"])
+    image, theta = torch.from_numpy(g["image"]).cuda(), torch.from_numpy(g["theta"])
+    results = []
+    for use_graph in (False, True):
+        ctx = torch.from_numpy(g["context"]).cuda().requires_grad_(True)
+        opt = optimize.EmbeddingOptimizer(ctx, lr=5e-3, capturable=True)
+        losses = []
+        if use_graph:
+            runner = optimize.Stage1Graph(ldm, controllers, ctx, opt, args, image_shape=tuple(image.shape))
+            runner.set_inputs(image, theta)
+            runner.capture()
+            for _ in range(3):
+                runner.set_inputs(image, theta)
+                losses.append(float(runner.replay()["loss"]))
+        else:
+            tr = RandomAffineWithInverse()
+            for _ in range(3):
+                out = optimize.stage1_iteration(ldm, controllers, image, ctx, tr, args, theta=theta)
+                opt.step(); opt.zero_grad()
+                losses.append(float(out["loss"]))
+        results.append((losses, ctx.detach().clone(), int(opt.step_dev.item())))
+    (le, ce, se), (lg, cg, sg) = results
+    assert se == sg == 3
+    assert rel_err(torch.tensor(lg), torch.tensor(le)) < 1e-4, (le, lg)
+    assert rel_err(cg.cpu(), ce.cpu()) < 1e-4
+    assert rel_err(torch.tensor(le[0]), g["loss"]) < 1e-3      # first step still matches the reference golden
+
+
 def test_tiny_early_exit_same_maps(tiny):
     from stablekeypoints_b200 import ptp_utils
     g, pipe = tiny
