@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tokens", type=int, default=77, help="N learned tokens (north_star 77; notebook 100; CLI default 500)")
     ap.add_argument("--res", type=int, default=128, help="feature_upsample_res R")
-    ap.add_argument("--precision", default=os.environ.get("SKP_PRECISION", "reference"), choices=["fp32", "reference", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("SKP_PRECISION", "fp32"), choices=["fp32", "reference", "tf32"],
+                    help="numerics of the few torch ops left in the trunk (fp32 = no TF32 anywhere: the parity-tested setting)")
     ap.add_argument("--early-exit", action="store_true", help="stop the forward after the 4th captured layer (outputs identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trunk", default=os.environ.get("SKP_TRUNK", "tc"), choices=["tc", "torch"],
@@ -251,14 +252,15 @@ def run_b200_arm(a):
 
     # ---- per-kernel shares of one step (our C-ABI launches bracketed by CUDA events) + attn-store kernel roofline
     extra = {}
+    # the profiled step contains the gradient all-reduce: EVERY rank must run it (only rank 0 reports)
+    _lib.start_profile()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    eager_step(dev_imgs[0])
+    e.record()
+    prof = _lib.stop_profile()
+    step_ms = s.elapsed_time(e)
     if rank == 0:
-        _lib.start_profile()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        eager_step(dev_imgs[0])
-        e.record()
-        prof = _lib.stop_profile()
-        step_ms = s.elapsed_time(e)
         shares = {k: {"calls": len(v), "ms": round(sum(v), 4)} for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1]))}
         extra["skp_kernel_ms_in_one_profiled_step"] = shares
         extra["profiled_eager_step_ms"] = round(step_ms, 3)

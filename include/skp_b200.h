@@ -61,6 +61,24 @@ int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const v
 int skp_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int Ho, int Wo, int stride, int pad,
                         int Kpad, void* hi, void* lo, void* stream);
 
+/* ------------------------------------------------------------------ GroupNorm (+SiLU) of the frozen trunk
+ * Channels-last activations x[rows = H*W, C] (row stride ldx), `groups` groups of C/groups channels (diffusers
+ * ResnetBlock2D / Transformer2DModel norms).  sums[2*groups] (fp64: sum, sum of squares) is
+ * written by skp_gn_stats and consumed by the others.  The normalised tensor is never stored on its own:
+ * skp_gn_apply emits fp32 y[rows, C] and/or the split-bf16 K-major operand [rows, Kpad] of a following 1x1
+ * projection; skp_gn_im2col3x3_split emits the split-bf16 3x3 im2col operand of a following convolution.
+ * skp_gn_bwd: dx = d(loss)/dx from g = d(loss)/dy (gamma, beta frozen); bsums[2*groups] is fp64 workspace. */
+int skp_gn_stats(const float* x, int64_t ldx, int rows, int C, int groups, double* sums, void* stream);
+int skp_gn_apply(const float* x, int64_t ldx, int rows, int C, int groups, const double* sums, float eps,
+                 const float* gamma, const float* beta, int silu, float* y, int64_t ldy, void* hi, void* lo,
+                 int Kpad, void* stream);
+int skp_gn_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int groups, const double* sums,
+                           float eps, const float* gamma, const float* beta, int silu, int Ho, int Wo,
+                           int stride, int pad, int Kpad, void* hi, void* lo, void* stream);
+int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t ldg, int rows, int C, int groups,
+               const double* sums, float eps, const float* gamma, const float* beta, int silu, double* bsums,
+               float* dx, int64_t ldd, void* stream);
+
 /* ------------------------------------------------------------------ cross-attention core
  * ptp_utils.py:493-506: sim = q k^T * scale; attn = softmax(sim, -1); out = attn v, per head.
  * q,o: [S, heads*d] (ld = heads*d); k,v: [N, heads*d] with leading dims ldk/ldv (slices of the batched

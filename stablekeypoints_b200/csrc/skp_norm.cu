@@ -1,0 +1,274 @@
+// GroupNorm(+SiLU) of the frozen trunk on channels-last activations x[rows = H*W, C], fused with what follows it:
+//   * forward never materialises the normalised tensor: it is produced on the fly either as the split-bf16 K-major
+//     A operand of a 1x1 projection (gn_apply) or as the split-bf16 3x3 im2col operand of a convolution
+//     (gn_im2col3x3_split), ready for the tcgen05 GEMM;
+//   * statistics are (sum, sum of squares) per group in fp64 (per-thread fp32 partials, fp64 across threads/CTAs);
+//   * backward (d wrt the input only; gamma/beta are frozen): dz = g * silu'(z), then the standard GroupNorm
+//     input-gradient with two group reductions.
+// Replaces diffusers ResnetBlock2D / Transformer2DModel GroupNorm + SiLU inside the UNet / VAE the
+// path runs through (ptp_utils.py:227-229, 299-302).
+#include "skp_common.cuh"
+#include <cuda_bf16.h>
+
+namespace skp {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_GROUPS = 64;
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad(float z) {
+  float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+
+// sums[g] += (sum x, sum x^2) over this CTA's rows
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C, int cg,
+                                                              int rows_per_cta, double* __restrict__ sums) {
+  __shared__ double sg[GN_MAX_GROUPS * 2];
+  const int G = C / cg;
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sg[i] = 0.0;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    float s = 0.f, ss = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      float v = __ldg(x + (size_t)r * ldx + c);
+      s += v; ss = fmaf(v, v, ss);
+    }
+    atomicAdd(&sg[2 * (c / cg)], (double)s);
+    atomicAdd(&sg[2 * (c / cg) + 1], (double)ss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(sums + i, sg[i]);
+}
+
+// per-group (mean, rstd) from the fp64 sums into shared memory
+__device__ __forceinline__ void load_group_stats(const double* __restrict__ sums, int G, double count, float eps, float* mean, float* rstd) {
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double m = sums[2 * g] / count;
+    double var = sums[2 * g + 1] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[g] = (float)m;
+    rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// y = act(gamma (x - mean) rstd + beta): fp32 output (nullable) and/or split-bf16 [rows, Kpad] output (nullable)
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C, int cg,
+                                                              const double* __restrict__ sums, float eps,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int silu, float* __restrict__ y, int64_t ldy,
+                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Kpad) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS];
+  load_group_stats(sums, C / cg, (double)rows * cg, eps, mean, rstd);
+  const int width = hi ? Kpad : C;
+  const size_t total = (size_t)rows * width;
+  for (size_t i = blockIdx.x * (size_t)GN_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * GN_THREADS) {
+    const int r = (int)(i / width), c = (int)(i - (size_t)r * width);
+    float v = 0.f;
+    if (c < C) {
+      const int g = c / cg;
+      v = (__ldg(x + (size_t)r * ldx + c) - mean[g]) * rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
+      if (silu) v = silu_f(v);
+      if (y) y[(size_t)r * ldy + c] = v;
+    }
+    if (hi) store_split(hi, lo, i, v);
+  }
+}
+
+// fused GroupNorm(+SiLU) + 3x3 im2col to split-bf16 (column = tap*C + c); one warp per (output pixel, tap)
+__global__ void __launch_bounds__(GN_THREADS) gn_im2col3x3_split_kernel(const float* __restrict__ x, int64_t ldx, int H, int W, int C,
+                                                                        int cg, const double* __restrict__ sums, float eps,
+                                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                        int silu, int Ho, int Wo, int stride, int pad, int Kpad,
+                                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS];
+  load_group_stats(sums, C / cg, (double)H * W * cg, eps, mean, rstd);
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)GN_THREADS + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * GN_THREADS) >> 5;
+  const long items = (long)Ho * Wo * 9;
+  const bool vec = (C & 3) == 0 && (ldx & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)gamma) | ((uintptr_t)beta)) & 15) == 0;
+  for (long it = warp; it < items; it += nwarps) {
+    const int tap = (int)(it % 9);
+    const long row = it / 9;
+    const int oy = (int)(row / Wo), ox = (int)(row - (long)oy * Wo);
+    const int iy = oy * stride + tap / 3 - pad, ix = ox * stride + tap % 3 - pad;
+    const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    const float* src = x + ((size_t)(inside ? iy : 0) * W + (inside ? ix : 0)) * ldx;
+    const size_t dst = (size_t)row * Kpad + (size_t)tap * C;
+    // zero padding applies AFTER the normalisation/activation (the convolution pads its input)
+    if (vec) {
+      for (int c = lane * 4; c < C; c += 128) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (inside) {
+          const float4 xv = *reinterpret_cast<const float4*>(src + c);
+          const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gm.x, gm.y, gm.z, gm.w}, bs[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int g = (c + k) / cg;
+            float z = (xs[k] - mean[g]) * rstd[g] * gs[k] + bs[k];
+            v[k] = silu ? silu_f(z) : z;
+          }
+        }
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(v[k]); l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k])); }
+        __nv_bfloat162 ha = __halves2bfloat162(h[0], h[1]), hb = __halves2bfloat162(h[2], h[3]);
+        __nv_bfloat162 la = __halves2bfloat162(l[0], l[1]), lb = __halves2bfloat162(l[2], l[3]);
+        *reinterpret_cast<uint2*>(hi + dst + c) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+        *reinterpret_cast<uint2*>(lo + dst + c) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        float v = 0.f;
+        if (inside) {
+          const int g = c / cg;
+          v = (__ldg(src + c) - mean[g]) * rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
+          if (silu) v = silu_f(v);
+        }
+        store_split(hi, lo, dst + c, v);
+      }
+    }
+    if (tap == 8)
+      for (int c = 9 * C + lane; c < Kpad; c += 32) store_split(hi, lo, (size_t)row * Kpad + c, 0.f);
+  }
+}
+
+// backward reductions: bs[g] += (sum gamma dz, sum gamma dz xhat)
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
+                                                                   int64_t ldg, int rows, int C, int cg, const double* __restrict__ sums,
+                                                                   float eps, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, int silu, int rows_per_cta,
+                                                                   double* __restrict__ bs) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS];
+  __shared__ double sg[GN_MAX_GROUPS * 2];
+  const int G = C / cg;
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sg[i] = 0.0;
+  load_group_stats(sums, G, (double)rows * cg, eps, mean, rstd);
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cg;
+    const float gm = __ldg(gamma + c), bt = __ldg(beta + c), mu = mean[g], rs = rstd[g];
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      float xh = (__ldg(x + (size_t)r * ldx + c) - mu) * rs;
+      float dz = __ldg(gr + (size_t)r * ldg + c);
+      if (silu) dz *= silu_grad(gm * xh + bt);
+      float d = dz * gm;
+      s1 += d; s2 = fmaf(d, xh, s2);
+    }
+    atomicAdd(&sg[2 * g], (double)s1);
+    atomicAdd(&sg[2 * g + 1], (double)s2);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(bs + i, sg[i]);
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
+                                                                  int64_t ldg, int rows, int C, int cg, const double* __restrict__ sums,
+                                                                  float eps, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, int silu,
+                                                                  const double* __restrict__ bs, float* __restrict__ dx, int64_t ldd) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS], m1[GN_MAX_GROUPS], m2[GN_MAX_GROUPS];
+  const int G = C / cg;
+  const double count = (double)rows * cg;
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    m1[g] = (float)(bs[2 * g] / count);
+    m2[g] = (float)(bs[2 * g + 1] / count);
+  }
+  load_group_stats(sums, G, count, eps, mean, rstd);
+  const size_t total = (size_t)rows * C;
+  for (size_t i = blockIdx.x * (size_t)GN_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * GN_THREADS) {
+    const int r = (int)(i / C), c = (int)(i - (size_t)r * C);
+    const int g = c / cg;
+    const float gm = __ldg(gamma + c), rs = rstd[g];
+    float xh = (__ldg(x + (size_t)r * ldx + c) - mean[g]) * rs;
+    float dz = __ldg(gr + (size_t)r * ldg + c);
+    if (silu) dz *= silu_grad(gm * xh + __ldg(beta + c));
+    dx[(size_t)r * ldd + c] = rs * (dz * gm - m1[g] - xh * m2[g]);
+  }
+}
+
+static inline int gn_rows_per_cta(int rows) {
+  int per = (rows + 148 * 4 - 1) / (148 * 4);
+  return per < 8 ? 8 : per;
+}
+static inline int gn_grid(size_t n) {
+  size_t b = (n + GN_THREADS - 1) / GN_THREADS;
+  if (b > 148 * 16) b = 148 * 16;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace skp
+
+using namespace skp;
+
+#define SKP_GN_CHECK(name)                                                                                   \
+  SKP_REQUIRE(x && rows > 0 && C > 0 && groups > 0 && C % groups == 0, name ": bad arguments");              \
+  SKP_REQUIRE(groups <= GN_MAX_GROUPS, name ": at most %d groups supported", GN_MAX_GROUPS);
+
+extern "C" int skp_gn_stats(const float* x, int64_t ldx, int rows, int C, int groups, double* sums, void* stream) {
+  SKP_GN_CHECK("gn_stats");
+  SKP_REQUIRE(sums, "gn_stats: null sums");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups, st);
+  int per = gn_rows_per_cta(rows);
+  gn_stats_kernel<<<(rows + per - 1) / per, GN_THREADS, 0, st>>>(x, ldx, rows, C, C / groups, per, sums);
+  SKP_CHECK_LAUNCH("gn_stats");
+  return SKP_OK;
+}
+
+extern "C" int skp_gn_apply(const float* x, int64_t ldx, int rows, int C, int groups, const double* sums, float eps,
+                            const float* gamma, const float* beta, int silu, float* y, int64_t ldy, void* hi, void* lo, int Kpad,
+                            void* stream) {
+  SKP_GN_CHECK("gn_apply");
+  SKP_REQUIRE(sums && gamma && beta && (y || (hi && lo)), "gn_apply: null pointer");
+  SKP_REQUIRE(!hi || (Kpad >= C && Kpad % 64 == 0), "gn_apply: Kpad=%d must be a multiple of 64 >= C", Kpad);
+  size_t total = (size_t)rows * (hi ? Kpad : C);
+  gn_apply_kernel<<<gn_grid(total), GN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, C / groups, sums, eps, gamma, beta, silu,
+                                                                          y, ldy, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad);
+  SKP_CHECK_LAUNCH("gn_apply");
+  return SKP_OK;
+}
+
+extern "C" int skp_gn_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int groups, const double* sums, float eps,
+                                      const float* gamma, const float* beta, int silu, int Ho, int Wo, int stride, int pad,
+                                      int Kpad, void* hi, void* lo, void* stream) {
+  const int rows = H * W;
+  SKP_GN_CHECK("gn_im2col3x3_split");
+  SKP_REQUIRE(sums && gamma && beta && hi && lo && Ho > 0 && Wo > 0 && stride > 0, "gn_im2col3x3_split: bad arguments");
+  SKP_REQUIRE(Kpad >= 9 * C && Kpad % 64 == 0, "gn_im2col3x3_split: Kpad=%d must be a multiple of 64 >= 9*C", Kpad);
+  long items = (long)Ho * Wo * 9;
+  long blocks = (items * 32 + GN_THREADS - 1) / GN_THREADS;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gn_im2col3x3_split_kernel<<<(int)blocks, GN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, H, W, C, C / groups, sums, eps, gamma, beta,
+                                                                                 silu, Ho, Wo, stride, pad, Kpad, (__nv_bfloat16*)hi,
+                                                                                 (__nv_bfloat16*)lo);
+  SKP_CHECK_LAUNCH("gn_im2col3x3_split");
+  return SKP_OK;
+}
+
+extern "C" int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t ldg, int rows, int C, int groups, const double* sums,
+                          float eps, const float* gamma, const float* beta, int silu, double* bsums, float* dx, int64_t ldd,
+                          void* stream) {
+  SKP_GN_CHECK("gn_bwd");
+  SKP_REQUIRE(g && sums && gamma && beta && bsums && dx, "gn_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * groups, st);
+  int per = gn_rows_per_cta(rows);
+  gn_bwd_reduce_kernel<<<(rows + per - 1) / per, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu,
+                                                                     per, bsums);
+  SKP_CHECK_LAUNCH("gn_bwd_reduce");
+  gn_bwd_apply_kernel<<<gn_grid((size_t)rows * C), GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta,
+                                                                       silu, bsums, dx, ldd);
+  SKP_CHECK_LAUNCH("gn_bwd_apply");
+  return SKP_OK;
+}

@@ -195,6 +195,116 @@ def frozen_linear(x: torch.Tensor, fw: FrozenWeight, bias: Optional[torch.Tensor
     return _FrozenLinear.apply(x, residual, fw, bias)
 
 
+# ----------------------------------------------------------------------------- GroupNorm(+SiLU) fused into what follows
+def _gn_stats(x2d: torch.Tensor, groups: int) -> torch.Tensor:
+    sums = torch.empty(2 * groups, dtype=torch.float64, device=x2d.device)
+    check(lib().skp_gn_stats(ptr(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], groups, ptr(sums), stream()), "skp_gn_stats")
+    return sums
+
+
+def _gn_backward(x2d, g, sums, gamma, beta, groups, eps, silu):
+    g = _f32c(g)
+    dx = torch.empty_like(x2d)
+    bs = torch.empty(2 * groups, dtype=torch.float64, device=x2d.device)
+    check(lib().skp_gn_bwd(ptr(x2d), x2d.stride(0), ptr(g), g.stride(0), x2d.shape[0], x2d.shape[1], groups, ptr(sums), eps,
+                           ptr(gamma), ptr(beta), int(silu), ptr(bs), ptr(dx), dx.stride(0), stream()), "skp_gn_bwd")
+    return dx
+
+
+class _GNConv3x3(torch.autograd.Function):
+    """y = conv3x3(act(GroupNorm(x))) + bias (+ residual) on channels-last [h*w, C]; the normalised activation only ever
+    exists as the split-bf16 im2col operand."""
+
+    @staticmethod
+    def forward(ctx, x2d, residual, gamma, beta, fcw: FrozenConv3x3, bias, groups, eps, silu, h, w, stride, pad, ho, wo):
+        x2d = _f32c(x2d)
+        c = x2d.shape[1]
+        sums = _gn_stats(x2d, groups)
+        kp = _pad64(9 * c)
+        hi = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
+        lo = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
+        check(lib().skp_gn_im2col3x3_split(ptr(x2d), x2d.stride(0), h, w, c, groups, ptr(sums), eps, ptr(gamma), ptr(beta),
+                                           int(silu), ho, wo, stride, pad, kp, ptr(hi), ptr(lo), stream()),
+              "skp_gn_im2col3x3_split")
+        ctx.save_for_backward(x2d, sums, gamma, beta)
+        ctx.meta = (fcw, groups, eps, silu, h, w, stride, pad, ho, wo, residual is not None)
+        return gemm_nt_presplit(hi, lo, ho * wo, fcw.fwd_split, fcw.cout, bias, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, sums, gamma, beta = ctx.saved_tensors
+        fcw, groups, eps, silu, h, w, stride, pad, ho, wo, has_res = ctx.meta
+        dy = _f32c(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if stride == 1 and pad == 1:
+                hi, lo = im2col3x3_split(dy, ho, wo, h, w, 1, 1)
+                d_act = gemm_nt_presplit(hi, lo, h * w, fcw.dgrad_split, fcw.cin)
+            else:
+                g = dy.reshape(1, ho, wo, fcw.cout).permute(0, 3, 1, 2)
+                hp_, wp_ = (ho - 1) * stride + 3 - pad, (wo - 1) * stride + 3 - pad
+                dxn = torch.nn.grad.conv2d_input((1, fcw.cin, max(h, hp_) + pad, max(w, wp_) + pad), fcw.w_nchw, g,
+                                                 stride=stride, padding=0)
+                d_act = dxn[:, :, pad:pad + h, pad:pad + w].permute(0, 2, 3, 1).reshape(h * w, fcw.cin).contiguous()
+            dx = _gn_backward(x2d, d_act, sums, gamma, beta, groups, eps, silu)
+        dres = dy if (has_res and ctx.needs_input_grad[1]) else None
+        return (dx, dres) + (None,) * 13
+
+
+def gn_conv3x3(x2d, h, w, gamma, beta, groups, eps, silu, fcw: FrozenConv3x3, bias=None, residual=None, stride=1, pad=1,
+               out_hw=None):
+    if out_hw is None:
+        ho, wo = (h + 2 * pad - 3) // stride + 1, (w + 2 * pad - 3) // stride + 1
+    else:
+        ho, wo = out_hw
+    return _GNConv3x3.apply(x2d, residual, gamma, beta, fcw, bias, groups, eps, silu, h, w, stride, pad, ho, wo), ho, wo
+
+
+class _GNLinear(torch.autograd.Function):
+    """y = act(GroupNorm(x)) W^T + bias (+ residual): the normalised activation is written straight as the split-bf16
+    A operand of the projection."""
+
+    @staticmethod
+    def forward(ctx, x2d, residual, gamma, beta, fw: FrozenWeight, bias, groups, eps, silu):
+        x2d = _f32c(x2d)
+        rows, c = x2d.shape
+        sums = _gn_stats(x2d, groups)
+        kp = _pad64(c)
+        hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=x2d.device)
+        lo = torch.empty(rows, kp, dtype=torch.bfloat16, device=x2d.device)
+        check(lib().skp_gn_apply(ptr(x2d), x2d.stride(0), rows, c, groups, ptr(sums), eps, ptr(gamma), ptr(beta), int(silu),
+                                 None, 0, ptr(hi), ptr(lo), kp, stream()), "skp_gn_apply")
+        ctx.save_for_backward(x2d, sums, gamma, beta)
+        ctx.meta = (fw, groups, eps, silu, residual is not None)
+        return gemm_nt_presplit(hi, lo, rows, fw.w_split, fw.out_features, bias, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, sums, gamma, beta = ctx.saved_tensors
+        fw, groups, eps, silu, has_res = ctx.meta
+        dy = _f32c(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            d_act = gemm_nt(dy, fw.wt, fw.wt_split)
+            dx = _gn_backward(x2d, d_act, sums, gamma, beta, groups, eps, silu)
+        dres = dy if (has_res and ctx.needs_input_grad[1]) else None
+        return (dx, dres) + (None,) * 7
+
+
+def gn_linear(x2d, gamma, beta, groups, eps, silu, fw: FrozenWeight, bias=None, residual=None):
+    return _GNLinear.apply(x2d, residual, gamma, beta, fw, bias, groups, eps, silu)
+
+
+def group_norm_cl(x2d, gamma, beta, groups, eps, silu=False):
+    """Plain act(GroupNorm(x)) -> fp32 [rows, C] (forward only; used by tests and no-grad paths)."""
+    x2d = _f32c(x2d)
+    sums = _gn_stats(x2d, groups)
+    y = torch.empty_like(x2d)
+    check(lib().skp_gn_apply(ptr(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], groups, ptr(sums), eps, ptr(gamma), ptr(beta),
+                             int(silu), ptr(y), y.stride(0), None, None, 0, stream()), "skp_gn_apply")
+    return y
+
+
 # ----------------------------------------------------------------------------- cross-attention core
 class _CrossAttnCore(torch.autograd.Function):
     @staticmethod

@@ -398,21 +398,23 @@ class UNetEngine:
         return y.reshape(c, -1).t().contiguous()
 
     def _resnet_cl(self, p, x, h, wd, tb):
-        w = self.w
-        y = self._gn_cl(x, f"{p}.norm1", self.cfg.norm_eps, True)
-        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv1"], tb[p])
-        y = self._gn_cl(y, f"{p}.norm2", self.cfg.norm_eps, True)
+        """GN+SiLU -> conv1 (+folded time bias) -> GN+SiLU -> conv2 + skip; each GN+SiLU is fused into the im2col that
+        feeds the tcgen05 GEMM, the skip add into the GEMM epilogue."""
+        w, g, eps = self.w, self.cfg.norm_num_groups, self.cfg.norm_eps
+        y, _, _ = ops.gn_conv3x3(x, h, wd, w[f"{p}.norm1.weight"], w[f"{p}.norm1.bias"], g, eps, True,
+                                 self._conv[f"{p}.conv1"], tb[p])
         if f"{p}.conv_shortcut" in self._fw:
             x = ops.frozen_linear(x, self._fw[f"{p}.conv_shortcut"], w[f"{p}.conv_shortcut.bias"])
-        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv2"], w[f"{p}.conv2.bias"], residual=x)
+        y, _, _ = ops.gn_conv3x3(y, h, wd, w[f"{p}.norm2.weight"], w[f"{p}.norm2.bias"], g, eps, True,
+                                 self._conv[f"{p}.conv2"], w[f"{p}.conv2.bias"], residual=x)
         return y
 
     def _transformer_cl(self, p, x, kv_all, state):
         w, heads = self.w, self.cfg.heads
         s, c = x.shape
         t = f"{p}.transformer_blocks.0"
-        hdn = self._gn_cl(x, f"{p}.norm", 1e-6, False)
-        hdn = ops.frozen_linear(hdn, self._fw[f"{p}.proj_in"], w[f"{p}.proj_in.bias"])
+        hdn = ops.gn_linear(x, w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], self.cfg.norm_num_groups, 1e-6, False,
+                            self._fw[f"{p}.proj_in"], w[f"{p}.proj_in.bias"])
         # attn1 (self-attention): projections on the tcgen05 GEMM, softmax(QK^T)V on torch SDPA
         y = F.layer_norm(hdn, (c,), w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"])
         qkv = ops.frozen_linear(y, self._fw[f"{t}.attn1.qkv"]).reshape(s, 3, heads, c // heads).permute(1, 2, 0, 3)
@@ -460,8 +462,8 @@ class UNetEngine:
                 h, wd = 2 * h, 2 * wd
                 p = f"up_blocks.{i}.upsamplers.0.conv"
                 x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv[p], w[f"{p}.bias"])
-        x = self._gn_cl(x, "conv_norm_out", cfg.norm_eps, True)
-        x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv["conv_out"], w["conv_out.bias"])
+        x, _, _ = ops.gn_conv3x3(x, h, wd, w["conv_norm_out.weight"], w["conv_norm_out.bias"], cfg.norm_num_groups, cfg.norm_eps,
+                                 True, self._conv["conv_out"], w["conv_out.bias"])
         return x.reshape(1, h, wd, -1).permute(0, 3, 1, 2)
 
     # ---- K|V projection, once per context version
@@ -592,6 +594,10 @@ class VAEEncoderEngine:
                 self._fw[p] = ops.FrozenWeight(t.reshape(t.shape[0], t.shape[1]), need_dgrad=False)
             else:
                 self._fw[p] = ops.FrozenWeight(t, need_dgrad=False)
+        a = "encoder.mid_block.attentions.0"
+        self._fw[f"{a}.qkv"] = ops.FrozenWeight(torch.cat([self.w[f"{a}.{n}.weight"] for n in ("query", "key", "value")], 0),
+                                                need_dgrad=False)
+        self._qkv_bias = torch.cat([self.w[f"{a}.{n}.bias"] for n in ("query", "key", "value")], 0).contiguous()
 
     def _gn_cl(self, x2d, wname, silu):
         c = x2d.shape[1]
@@ -602,13 +608,13 @@ class VAEEncoderEngine:
         return y.reshape(c, -1).t().contiguous()
 
     def _resnet_cl(self, p, x, h, wd):
-        w = self.w
-        y = self._gn_cl(x, f"{p}.norm1", True)
-        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv1"], w[f"{p}.conv1.bias"])
-        y = self._gn_cl(y, f"{p}.norm2", True)
+        w, g = self.w, self.cfg.norm_num_groups
+        y, _, _ = ops.gn_conv3x3(x, h, wd, w[f"{p}.norm1.weight"], w[f"{p}.norm1.bias"], g, 1e-6, True,
+                                 self._conv[f"{p}.conv1"], w[f"{p}.conv1.bias"])
         if f"{p}.conv_shortcut" in self._fw:
             x = ops.frozen_linear(x, self._fw[f"{p}.conv_shortcut"], w[f"{p}.conv_shortcut.bias"])
-        y, _, _ = ops.frozen_conv3x3(y, h, wd, self._conv[f"{p}.conv2"], w[f"{p}.conv2.bias"], residual=x)
+        y, _, _ = ops.gn_conv3x3(y, h, wd, w[f"{p}.norm2.weight"], w[f"{p}.norm2.bias"], g, 1e-6, True,
+                                 self._conv[f"{p}.conv2"], w[f"{p}.conv2.bias"], residual=x)
         return y
 
     def _encode_cl(self, img):
@@ -625,15 +631,15 @@ class VAEEncoderEngine:
                 x, h, wd = ops.frozen_conv3x3(x, h, wd, self._conv[p], w[f"{p}.bias"], stride=2, pad=0, out_hw=(h // 2, wd // 2))
         x = self._resnet_cl("encoder.mid_block.resnets.0", x, h, wd)
         a = "encoder.mid_block.attentions.0"
-        y = self._gn_cl(x, f"{a}.group_norm", False)
-        q = ops.frozen_linear(y, self._fw[f"{a}.query"], w[f"{a}.query.bias"])
-        k = ops.frozen_linear(y, self._fw[f"{a}.key"], w[f"{a}.key.bias"])
-        v = ops.frozen_linear(y, self._fw[f"{a}.value"], w[f"{a}.value.bias"])
+        c = x.shape[1]
+        qkv = ops.gn_linear(x, w[f"{a}.group_norm.weight"], w[f"{a}.group_norm.bias"], cfg.norm_num_groups, 1e-6, False,
+                            self._fw[f"{a}.qkv"], self._qkv_bias)
+        q, k, v = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
         o = F.scaled_dot_product_attention(q[None, None], k[None, None], v[None, None])[0, 0]
         x = ops.frozen_linear(o, self._fw[f"{a}.proj_attn"], w[f"{a}.proj_attn.bias"], residual=x)
         x = self._resnet_cl("encoder.mid_block.resnets.1", x, h, wd)
-        x = self._gn_cl(x, "encoder.conv_norm_out", True)
-        x, _, _ = ops.frozen_conv3x3(x, h, wd, self._conv["encoder.conv_out"], w["encoder.conv_out.bias"])
+        x, _, _ = ops.gn_conv3x3(x, h, wd, w["encoder.conv_norm_out.weight"], w["encoder.conv_norm_out.bias"],
+                                 cfg.norm_num_groups, 1e-6, True, self._conv["encoder.conv_out"], w["encoder.conv_out.bias"])
         x = ops.frozen_linear(x, self._fw["quant_conv"], w["quant_conv.bias"])
         return x.reshape(1, h, wd, -1).permute(0, 3, 1, 2)
 

@@ -82,6 +82,48 @@ def test_frozen_conv3x3_fwd_bwd_vs_torch(ops, h, w, cin, cout, stride, pad):
     assert rel_err(xc.grad.cpu(), xr.grad[0].permute(1, 2, 0).reshape(h * w, cin)) < 10 * tol
 
 
+@pytest.mark.parametrize("h,w,c,cout,groups,silu", [(16, 16, 1280, 640, 32, True), (64, 64, 320, 320, 32, True), (8, 8, 2560, 1280, 32, True),
+                                                     (32, 32, 128, 64, 32, False), (9, 13, 24, 20, 4, True)])
+def test_groupnorm_fused_ops_vs_torch(ops, h, w, c, cout, groups, silu):
+    """skp_gn_* : plain GN(+SiLU), GN->3x3 conv and GN->1x1 projection, forward and input gradient, vs torch fp64."""
+    g = torch.Generator().manual_seed(h * w + c)
+    x = torch.randn(1, c, h, w, generator=g) * 2 + 0.5
+    gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g)
+    wt3 = torch.randn(cout, c, 3, 3, generator=g) / (9 * c) ** 0.5
+    wt1 = torch.randn(cout, c, generator=g) / c ** 0.5
+    bias = torch.randn(cout, generator=g)
+    eps = 1e-5
+
+    def ref_act(xx):
+        y = F.group_norm(xx, groups, gamma.double(), beta.double(), eps)
+        return F.silu(y) if silu else y
+
+    def cl(t4):  # [1,C,H,W] -> [HW, C]
+        return t4[0].permute(1, 2, 0).reshape(h * w, -1)
+
+    xr = x.double().requires_grad_(True)
+    act = ref_act(xr)
+    y3 = F.conv2d(act, wt3.double(), bias.double(), padding=1)
+    y1 = F.linear(cl(act), wt1.double(), bias.double())
+    d3, d1 = torch.randn(y3.shape, generator=g, dtype=torch.float64), torch.randn(y1.shape, generator=g, dtype=torch.float64)
+    g3, = torch.autograd.grad(y3, xr, d3, retain_graph=True)
+    g1, = torch.autograd.grad(y1, xr, d1)
+    xc = cu(cl(x).contiguous())
+    gm, bt = cu(gamma), cu(beta)
+    assert rel_err(ops.group_norm_cl(xc, gm, bt, groups, eps, silu).cpu(), cl(act.detach())) < 1e-5
+    x3 = xc.clone().requires_grad_(True)
+    o3, _, _ = ops.gn_conv3x3(x3, h, w, gm, bt, groups, eps, silu, ops.FrozenConv3x3(cu(wt3)), cu(bias))
+    o3.backward(cu(cl(d3).float().contiguous()))
+    x1 = xc.clone().requires_grad_(True)
+    o1 = ops.gn_linear(x1, gm, bt, groups, eps, silu, ops.FrozenWeight(cu(wt1)), cu(bias))
+    o1.backward(cu(d1.float()))
+    tol = 5e-5 * max(1.0, (9 * c / 1024) ** 0.5)
+    assert rel_err(o3.detach().cpu(), cl(y3.detach())) < tol
+    assert rel_err(o1.detach().cpu(), y1.detach()) < tol
+    assert rel_err(x3.grad.cpu(), cl(g3)) < 10 * tol
+    assert rel_err(x1.grad.cpu(), cl(g1)) < 10 * tol
+
+
 # ----------------------------------------------------------------------------- cross-attention core
 def _attn_ref(q, k, v, heads, scale, extra_w=None):
     s, c = q.shape
@@ -178,6 +220,19 @@ def test_capture_mean_fwd_bwd(ops, heads, sides, n, res):
     assert rel_err(m.detach().cpu(), mref.detach()) < 2e-5
     for a, b in zip(lc, lr):
         assert rel_err(a.grad.cpu(), b.grad) < 5e-5
+
+
+@pytest.mark.parametrize("quad", ["0", "1"])
+def test_capture_kernel_variants_agree(ops, monkeypatch, quad):
+    """Both forward implementations (v1 pixel/token-slice, v2 quad/separable) for both modes, forced by env."""
+    monkeypatch.setenv("SKP_CAPTURE_QUAD", quad)
+    g = torch.Generator().manual_seed(int(quad) + 5)
+    logits = [torch.randn(8, s * s, 77, generator=g) * 3 for s in (16, 32)]
+    stack = torch.stack([_capture_ref(l, 128) for l in logits])
+    m = ops.capture_mean([cu(l) for l in logits], 128)
+    assert rel_err(m.cpu(), stack.mean(dim=(0, 1)).t().reshape(77, 128, 128)) < 2e-5
+    p = ops.capture_store(cu(logits[1]), 128)
+    assert rel_err(p.cpu(), stack[1]) < 2e-5
 
 
 # ----------------------------------------------------------------------------- collect_maps
