@@ -298,9 +298,14 @@ def run_b200_arm(a):
         line.update(extra)
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the step's CUDA graph holds a captured NCCL all-reduce; tearing the communicator down underneath it can hang,
+        # so: make sure everyone is done, then leave without running destructors (exit code 0 for torchrun)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def timed_single(step, imgs, n):

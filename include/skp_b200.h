@@ -60,6 +60,13 @@ int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const v
  * UNet / VAE resnets the path runs through (diffusers ResnetBlock2D). */
 int skp_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int Ho, int Wo, int stride, int pad,
                         int Kpad, void* hi, void* lo, void* stream);
+/* Implicit-GEMM 3x3 convolution, stride 1, zero padding 1, on the same tcgen05 kernel: X_hi/X_lo are the split-bf16
+ * channels-last activation [H, W, Cin] (Cin % 64 == 0, W % 8 == 0), B the filter as [Cout, 9*Cin] (column = tap*Cin + c).
+ * Each k-block's A tile is a 3-D TMA box of the activation shifted by the tap; the image border is the TMA's
+ * out-of-bounds zero fill, so no im2col buffer exists.  Output C[H*W, Cout] (+bias +residual), split-K as above. */
+int skp_conv3x3_tc(const void* X_hi, const void* X_lo, int H, int W, int Cin, const void* B_hi, const void* B_lo,
+                   float* C, int64_t ldc, int Cout, float alpha, const float* bias, const float* residual,
+                   int64_t ldr, int splits, float* splitk_ws, void* stream);
 
 /* ------------------------------------------------------------------ GroupNorm (+SiLU) of the frozen trunk
  * Channels-last activations x[rows = H*W, C] (row stride ldx), `groups` groups of C/groups channels (diffusers

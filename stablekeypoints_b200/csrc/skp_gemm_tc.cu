@@ -49,6 +49,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
@@ -99,12 +105,20 @@ struct TcCfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int STAGES>
+// Implicit-GEMM 3x3 convolution (stride 1, zero padding 1) of a channels-last activation [H, W, Cin] (Cin % 64 == 0):
+// an M tile is a BH x BW patch of output pixels (BH*BW = 128) and the A operand of k-block (tap, channel block) is the
+// same patch shifted by the tap, fetched by ONE 3-D TMA box whose out-of-image part the hardware zero-fills -- the
+// 9x im2col expansion never exists in memory.
+struct ConvGeom {
+  int H, W, BW, BH, tiles_x, cb_per_tap;  // cb_per_tap = Cin / 64
+};
+
+template <int BN, int STAGES, bool CONV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                   float* C, int64_t ldc, int M, int N, int num_kb_total, int kb_per_split, float alpha,
-                  const float* bias, const float* residual, int64_t ldr, float* __restrict__ splitk_ws) {
+                  const float* bias, const float* residual, int64_t ldr, float* __restrict__ splitk_ws, ConvGeom cg) {
   using Cfg = TcCfg<BN, STAGES>;
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb); partial sums go to splitk_ws[z][M][N] (reduced afterwards)
   const int kb0 = blockIdx.z * kb_per_split;
@@ -119,6 +133,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int cy0 = CONV ? (int)(blockIdx.y / cg.tiles_x) * cg.BH : 0;   // top-left output pixel of this patch
+  const int cx0 = CONV ? (int)(blockIdx.y % cg.tiles_x) * cg.BW : 0;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -147,8 +163,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         const uint32_t st = base + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(full, Cfg::STAGE_BYTES);
         const int kc = (kb0 + kb) * TC_BK;
-        tma_load_2d(st, &tm_a_hi, full, kc, m0);
-        tma_load_2d(st + Cfg::A_BYTES, &tm_a_lo, full, kc, m0);
+        if (CONV) {
+          const int tap = (kb0 + kb) / cg.cb_per_tap, cb = (kb0 + kb) - tap * cg.cb_per_tap;
+          const int ax = cx0 + tap % 3 - 1, ay = cy0 + tap / 3 - 1;
+          tma_load_3d(st, &tm_a_hi, full, cb * TC_BK, ax, ay);
+          tma_load_3d(st + Cfg::A_BYTES, &tm_a_lo, full, cb * TC_BK, ax, ay);
+        } else {
+          tma_load_2d(st, &tm_a_hi, full, kc, m0);
+          tma_load_2d(st + Cfg::A_BYTES, &tm_a_lo, full, kc, m0);
+        }
         tma_load_2d(st + 2 * Cfg::A_BYTES, &tm_b_hi, full, kc, n0);
         tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc, n0);
       }
@@ -181,7 +204,11 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     mbar_wait(bars + 8 * (2 * STAGES), 0);
     tc_fence_after();
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + quarter * 32 + lane;
+    int row = m0 + quarter * 32 + lane;
+    if (CONV) {  // accumulator lane r is output pixel (cy0 + r / BW, cx0 + r % BW)
+      const int r = quarter * 32 + lane, py = cy0 + r / cg.BW, px = cx0 + r % cg.BW;
+      row = (py < cg.H && px < cg.W) ? py * cg.W + px : M;
+    }
     if (partial) {  // raw partial sums, dense [M][N]
       C = splitk_ws + (size_t)blockIdx.z * M * N;
       ldc = N; alpha = 1.f; bias = nullptr; residual = nullptr;
@@ -341,6 +368,58 @@ static int make_map(CUtensorMap* m, const void* ptr, int rows, int kpad, int box
   return SKP_OK;
 }
 
+static int make_map_3d(CUtensorMap* m, const void* ptr, int H, int W, int C, int BW, int BH) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv3x3_tc: cuTensorMapEncodeTiled entry point unavailable"); return SKP_ERR_DRIVER; }
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BW, (cuuint32_t)BH};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv3x3_tc: cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return SKP_ERR_DRIVER; }
+  return SKP_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin, const void* B_hi, const void* B_lo, float* C,
+                       int64_t ldc, int N, float alpha, const float* bias, const float* residual, int64_t ldr, int splits, float* ws,
+                       cudaStream_t st) {
+  using Cfg = TcCfg<BN, STAGES>;
+  ConvGeom cg;
+  cg.H = H; cg.W = W;
+  cg.BW = W >= 16 ? 16 : 8;
+  cg.BH = TC_BM / cg.BW;
+  cg.tiles_x = (W + cg.BW - 1) / cg.BW;
+  cg.cb_per_tap = Cin / TC_BK;
+  const int tiles_y = (H + cg.BH - 1) / cg.BH;
+  const int M = H * W, Kpad = 9 * Cin;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_map_3d(&ta_hi, X_hi, H, W, Cin, cg.BW, cg.BH))) return rc;
+  if ((rc = make_map_3d(&ta_lo, X_lo, H, W, Cin, cg.BW, cg.BH))) return rc;
+  if ((rc = make_map(&tb_hi, B_hi, N, Kpad, BN))) return rc;
+  if ((rc = make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
+  cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
+  const int num_kb = Kpad / TC_BK;
+  const int per = (num_kb + splits - 1) / splits;
+  const int zs = (num_kb + per - 1) / per;
+  dim3 grid((N + BN - 1) / BN, tiles_y * cg.tiles_x, zs);
+  gemm_nt_tc_kernel<BN, STAGES, true><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, num_kb, per, alpha,
+                                                                          bias, residual, ldr, ws, cg);
+  SKP_CHECK_LAUNCH("conv3x3_tc");
+  if (zs > 1) {
+    size_t total = (size_t)M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+    SKP_CHECK_LAUNCH("splitk_reduce");
+  }
+  return SKP_OK;
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C, int64_t ldc,
                      int M, int N, float alpha, const float* bias, const float* residual, int64_t ldr, int splits, float* ws,
@@ -352,14 +431,14 @@ static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const
   if ((rc = make_map(&ta_lo, A_lo, M, Kpad, TC_BM))) return rc;
   if ((rc = make_map(&tb_hi, B_hi, N, Kpad, BN))) return rc;
   if ((rc = make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
-  cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) { set_error("gemm_nt_tc: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
   const int num_kb = Kpad / TC_BK;
   const int per = (num_kb + splits - 1) / splits;
   const int zs = (num_kb + per - 1) / per;  // every z gets >= 1 k-block
   dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM, zs);
-  gemm_nt_tc_kernel<BN, STAGES><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, num_kb, per, alpha,
-                                                                    bias, residual, ldr, ws);
+  gemm_nt_tc_kernel<BN, STAGES, false><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, num_kb, per,
+                                                                           alpha, bias, residual, ldr, ws, ConvGeom{});
   SKP_CHECK_LAUNCH("gemm_nt_tc");
   if (zs > 1) {
     size_t total = (size_t)M * N;
@@ -414,6 +493,22 @@ extern "C" int skp_im2col3x3_split(const float* x, int64_t ldx, int H, int W, in
                                                                        (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   SKP_CHECK_LAUNCH("im2col3x3_split");
   return SKP_OK;
+}
+
+extern "C" int skp_conv3x3_tc(const void* X_hi, const void* X_lo, int H, int W, int Cin, const void* B_hi, const void* B_lo, float* C,
+                              int64_t ldc, int Cout, float alpha, const float* bias, const float* residual, int64_t ldr,
+                              int splits, float* splitk_ws, void* stream) {
+  SKP_REQUIRE(X_hi && X_lo && B_hi && B_lo && C, "conv3x3_tc: null pointer");
+  SKP_REQUIRE(H > 0 && W > 0 && Cout > 0 && Cin > 0 && Cin % TC_BK == 0, "conv3x3_tc: Cin=%d must be a positive multiple of 64", Cin);
+  SKP_REQUIRE(W % 8 == 0, "conv3x3_tc: W=%d must be a multiple of 8", W);
+  SKP_REQUIRE(((((uintptr_t)X_hi) | ((uintptr_t)X_lo) | ((uintptr_t)B_hi) | ((uintptr_t)B_lo)) & 15) == 0,
+              "conv3x3_tc: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (splits < 1) splits = 1;
+  SKP_REQUIRE(splits == 1 || splitk_ws != nullptr, "conv3x3_tc: split-K needs a workspace of splits*H*W*Cout floats");
+  if (use_bn128(H * W, Cout))
+    return launch_conv<128, 3>(X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st);
+  return launch_conv<64, 4>(X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st);
 }
 
 extern "C" int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C,

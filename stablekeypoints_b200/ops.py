@@ -117,6 +117,27 @@ def im2col3x3_split(x2d: torch.Tensor, h: int, w: int, ho: int, wo: int, stride:
     return hi, lo
 
 
+def _implicit_ok(w: int, cin: int) -> bool:
+    return cin % 64 == 0 and w % 8 == 0 and os.environ.get("SKP_CONV_IMPLICIT", "1") != "0"
+
+
+def conv3x3_implicit(x_hi, x_lo, h: int, w: int, b_split, cout: int, bias=None, residual=None):
+    """Stride-1 / pad-1 3x3 convolution as an implicit GEMM: the split-bf16 channels-last activation [h*w, Cin] is read
+    through 3-D TMA boxes shifted per tap (no im2col buffer)."""
+    cin = x_hi.shape[1]
+    b_hi, b_lo = b_split
+    assert b_hi.shape[1] == 9 * cin
+    out = torch.empty(h * w, cout, dtype=torch.float32, device=x_hi.device)
+    if residual is not None and (residual.stride(1) != 1 or residual.dtype != torch.float32):
+        residual = _f32c(residual)
+    ldr = residual.stride(0) if residual is not None else 0
+    splits = lib().skp_gemm_nt_tc_plan(h * w, cout, 9 * cin)
+    ws = torch.empty(splits * h * w * cout, dtype=torch.float32, device=out.device) if splits > 1 else None
+    check(lib().skp_conv3x3_tc(ptr(x_hi), ptr(x_lo), h, w, cin, ptr(b_hi), ptr(b_lo), ptr(out), out.stride(0), cout, 1.0,
+                               ptr(bias), ptr(residual), ldr, splits, ptr(ws), stream()), "skp_conv3x3_tc")
+    return out
+
+
 class FrozenConv3x3:
     """Frozen [Cout, Cin, 3, 3] filter prepared as GEMM operands: forward  W[cout, tap*Cin + cin]; input-gradient
     (stride 1) W'[cin, tap*Cout + cout] with the taps flipped.  Both as split-bf16 K-major pairs."""
@@ -137,8 +158,11 @@ class _FrozenConv3x3(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2d, residual, fcw: FrozenConv3x3, bias, h, w, stride, pad, ho, wo):
         x2d = _f32c(x2d)
-        hi, lo = im2col3x3_split(x2d, h, w, ho, wo, stride, pad)
         ctx.fcw, ctx.geom, ctx.has_res = fcw, (h, w, stride, pad, ho, wo), residual is not None
+        if stride == 1 and pad == 1 and _implicit_ok(w, fcw.cin):
+            hi, lo = split_bf16(x2d)
+            return conv3x3_implicit(hi, lo, h, w, fcw.fwd_split, fcw.cout, bias, residual)
+        hi, lo = im2col3x3_split(x2d, h, w, ho, wo, stride, pad)
         return gemm_nt_presplit(hi, lo, ho * wo, fcw.fwd_split, fcw.cout, bias, residual)
 
     @staticmethod
@@ -148,7 +172,10 @@ class _FrozenConv3x3(torch.autograd.Function):
         dy = _f32c(dy)
         dx = None
         if ctx.needs_input_grad[0]:
-            if stride == 1 and pad == 1:
+            if stride == 1 and pad == 1 and _implicit_ok(w, fcw.cout):
+                hi, lo = split_bf16(dy)
+                dx = conv3x3_implicit(hi, lo, h, w, fcw.dgrad_split, fcw.cin)
+            elif stride == 1 and pad == 1:
                 hi, lo = im2col3x3_split(dy, ho, wo, h, w, 1, 1)
                 dx = gemm_nt_presplit(hi, lo, h * w, fcw.dgrad_split, fcw.cin)
             else:  # the three strided down-samplers: cuDNN dgrad on an NCHW view
@@ -220,14 +247,21 @@ class _GNConv3x3(torch.autograd.Function):
         x2d = _f32c(x2d)
         c = x2d.shape[1]
         sums = _gn_stats(x2d, groups)
+        ctx.save_for_backward(x2d, sums, gamma, beta)
+        ctx.meta = (fcw, groups, eps, silu, h, w, stride, pad, ho, wo, residual is not None)
+        if stride == 1 and pad == 1 and _implicit_ok(w, c):
+            # normalised activation written ONCE as split-bf16 channels-last; the conv reads it through shifted TMA boxes
+            hi = torch.empty(h * w, c, dtype=torch.bfloat16, device=x2d.device)
+            lo = torch.empty(h * w, c, dtype=torch.bfloat16, device=x2d.device)
+            check(lib().skp_gn_apply(ptr(x2d), x2d.stride(0), h * w, c, groups, ptr(sums), eps, ptr(gamma), ptr(beta), int(silu),
+                                     None, 0, ptr(hi), ptr(lo), c, stream()), "skp_gn_apply")
+            return conv3x3_implicit(hi, lo, h, w, fcw.fwd_split, fcw.cout, bias, residual)
         kp = _pad64(9 * c)
         hi = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
         lo = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
         check(lib().skp_gn_im2col3x3_split(ptr(x2d), x2d.stride(0), h, w, c, groups, ptr(sums), eps, ptr(gamma), ptr(beta),
                                            int(silu), ho, wo, stride, pad, kp, ptr(hi), ptr(lo), stream()),
               "skp_gn_im2col3x3_split")
-        ctx.save_for_backward(x2d, sums, gamma, beta)
-        ctx.meta = (fcw, groups, eps, silu, h, w, stride, pad, ho, wo, residual is not None)
         return gemm_nt_presplit(hi, lo, ho * wo, fcw.fwd_split, fcw.cout, bias, residual)
 
     @staticmethod
@@ -237,7 +271,10 @@ class _GNConv3x3(torch.autograd.Function):
         dy = _f32c(dy)
         dx = None
         if ctx.needs_input_grad[0]:
-            if stride == 1 and pad == 1:
+            if stride == 1 and pad == 1 and _implicit_ok(w, fcw.cout):
+                hi, lo = split_bf16(dy)
+                d_act = conv3x3_implicit(hi, lo, h, w, fcw.dgrad_split, fcw.cin)
+            elif stride == 1 and pad == 1:
                 hi, lo = im2col3x3_split(dy, ho, wo, h, w, 1, 1)
                 d_act = gemm_nt_presplit(hi, lo, h * w, fcw.dgrad_split, fcw.cin)
             else:
