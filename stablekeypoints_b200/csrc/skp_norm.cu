@@ -1,10 +1,13 @@
 // GroupNorm(+SiLU) of the frozen trunk on channels-last activations x[rows = H*W, C], fused with what follows it:
-//   * forward never materialises the normalised tensor: it is produced on the fly either as the split-bf16 K-major
-//     A operand of a 1x1 projection (gn_apply) or as the split-bf16 3x3 im2col operand of a convolution
-//     (gn_im2col3x3_split), ready for the tcgen05 GEMM;
-//   * statistics are (sum, sum of squares) per group in fp64 (per-thread fp32 partials, fp64 across threads/CTAs);
-//   * backward (d wrt the input only; gamma/beta are frozen): dz = g * silu'(z), then the standard GroupNorm
-//     input-gradient with two group reductions.
+//   * forward never materialises the normalised tensor on its own: gn_apply emits it as fp32 and/or directly as the
+//     split-bf16 K-major operand that the tcgen05 GEMM / implicit-GEMM convolution reads through TMA;
+//     gn_im2col3x3_split emits the split-bf16 3x3 im2col operand (strided / odd-shaped convolutions);
+//   * statistics are (sum, sum of squares) per group: fp32 partials per thread, fp64 across CTAs;
+//   * backward (d wrt the input only; gamma/beta are frozen): dz = g * silu'(z), then the GroupNorm input-gradient
+//     with two group reductions.
+// Thread mapping (HBM-bound, no integer division in the row loops): a thread owns a FIXED set of 4-channel chunks
+// (c4 = cx + k*TPR) and walks rows, so its per-channel scale/shift live in registers and every access is a coalesced
+// 128-bit load/store.
 // Replaces diffusers ResnetBlock2D / Transformer2DModel GroupNorm + SiLU inside the UNet / VAE the
 // path runs through (ptp_utils.py:227-229, 299-302).
 #include "skp_common.cuh"
@@ -14,6 +17,7 @@ namespace skp {
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_NCH = 3;   // 4-channel chunks per thread -> C <= 4 * 256 * 3 = 3072
 
 __device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
 __device__ __forceinline__ float silu_grad(float z) {
@@ -21,25 +25,16 @@ __device__ __forceinline__ float silu_grad(float z) {
   return s * (1.f + z * (1.f - s));
 }
 
-// sums[g] += (sum x, sum x^2) over this CTA's rows
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C, int cg,
-                                                              int rows_per_cta, double* __restrict__ sums) {
-  __shared__ double sg[GN_MAX_GROUPS * 2];
-  const int G = C / cg;
-  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sg[i] = 0.0;
-  __syncthreads();
-  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    float s = 0.f, ss = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      float v = __ldg(x + (size_t)r * ldx + c);
-      s += v; ss = fmaf(v, v, ss);
-    }
-    atomicAdd(&sg[2 * (c / cg)], (double)s);
-    atomicAdd(&sg[2 * (c / cg) + 1], (double)ss);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(sums + i, sg[i]);
+struct GnMap {   // how the 256 threads of a CTA tile [rows, C/4]
+  int tpr;       // threads along the channel axis (each owns chunks cx, cx+tpr, ...)
+  int rl;        // row lanes
+};
+__host__ __device__ inline GnMap gn_map(int C) {
+  GnMap m;
+  int c4 = C / 4;
+  m.tpr = c4 < GN_THREADS ? c4 : GN_THREADS;
+  m.rl = GN_THREADS / m.tpr;
+  return m;
 }
 
 // per-group (mean, rstd) from the fp64 sums into shared memory
@@ -54,18 +49,186 @@ __device__ __forceinline__ void load_group_stats(const double* __restrict__ sums
   __syncthreads();
 }
 
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, const float v[4]) {
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(v[k]); l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k])); }
+  __nv_bfloat162 ha = __halves2bfloat162(h[0], h[1]), hb = __halves2bfloat162(h[2], h[3]);
+  __nv_bfloat162 la = __halves2bfloat162(l[0], l[1]), lb = __halves2bfloat162(l[2], l[3]);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+}
 __device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v) {
   __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[idx] = h;
   lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// y = act(gamma (x - mean) rstd + beta): fp32 output (nullable) and/or split-bf16 [rows, Kpad] output (nullable)
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C, int cg,
-                                                              const double* __restrict__ sums, float eps,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              int silu, float* __restrict__ y, int64_t ldy,
-                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Kpad) {
+// ------------------------------------------------------------------------------------------------ statistics
+// sums[g] += (sum x, sum x^2) over this CTA's rows.  MODE 0: plain statistics of x.  MODE 1: backward reductions
+// (sum gamma dz, sum gamma dz xhat) with dz = g * silu'(z).
+template <int MODE>
+__global__ void __launch_bounds__(GN_THREADS) gn_reduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
+                                                               int64_t ldg, int rows, int C, int cg, const double* __restrict__ sums,
+                                                               float eps, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int silu, int rows_per_cta,
+                                                               double* __restrict__ out) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS];
+  __shared__ float sg[GN_MAX_GROUPS * 2];
+  const int G = C / cg;
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sg[i] = 0.f;
+  if (MODE == 1) load_group_stats(sums, G, (double)rows * cg, eps, mean, rstd);
+  else __syncthreads();
+  const GnMap mp = gn_map(C);
+  const int cx = threadIdx.x % mp.tpr, ry = threadIdx.x / mp.tpr;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  if (ry < mp.rl) {
+#pragma unroll
+    for (int k = 0; k < GN_NCH; ++k) {
+      const int c = (cx + k * mp.tpr) * 4;
+      if (c >= C) break;
+      float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+      float sc[4], sh[4], gm[4];
+      if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = (c + j) / cg;
+          gm[j] = __ldg(gamma + c + j);
+          sc[j] = rstd[g];
+          sh[j] = -mean[g] * rstd[g];
+        }
+      }
+      for (int r = r0 + ry; r < r1; r += mp.rl) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx + c));
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { a1[j] += xs[j]; a2[j] = fmaf(xs[j], xs[j], a2[j]); }
+        } else {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(gr + (size_t)r * ldg + c));
+          const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xh = fmaf(xs[j], sc[j], sh[j]);
+            float dz = gs[j];
+            if (silu) dz *= silu_grad(fmaf(gm[j], xh, __ldg(beta + c + j)));
+            const float d = dz * gm[j];
+            a1[j] += d; a2[j] = fmaf(d, xh, a2[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c + j) / cg;
+        atomicAdd(&sg[2 * g], a1[j]);
+        atomicAdd(&sg[2 * g + 1], a2[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(out + i, (double)sg[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ apply
+// MODE 0: y = act(gamma (x - mean) rstd + beta) -> fp32 y (nullable) and/or split-bf16 hi/lo (nullable, row pitch Kpad).
+// MODE 1: dx = rstd (gamma dz - m1 - xhat m2)   (backward; `gr` = d loss / d y, `bs` = the two backward reductions)
+template <int MODE>
+__global__ void __launch_bounds__(GN_THREADS) gn_rowwise_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
+                                                                int64_t ldg, int rows, int C, int cg, const double* __restrict__ sums,
+                                                                float eps, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int silu, const double* __restrict__ bs,
+                                                                int rows_per_cta, float* __restrict__ y, int64_t ldy,
+                                                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Kpad) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS], m1[GN_MAX_GROUPS], m2[GN_MAX_GROUPS];
+  const int G = C / cg;
+  const double count = (double)rows * cg;
+  if (MODE == 1)
+    for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+      m1[g] = (float)(bs[2 * g] / count);
+      m2[g] = (float)(bs[2 * g + 1] / count);
+    }
+  load_group_stats(sums, G, count, eps, mean, rstd);
+  const GnMap mp = gn_map(C);
+  const int cx = threadIdx.x % mp.tpr, ry = threadIdx.x / mp.tpr;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  if (ry >= mp.rl) return;
+#pragma unroll
+  for (int k = 0; k < GN_NCH; ++k) {
+    const int c = (cx + k * mp.tpr) * 4;
+    if (c >= C) break;
+    float sc[4], sh[4], gm[4], bt[4], a1[4], a2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cg;
+      gm[j] = __ldg(gamma + c + j);
+      bt[j] = __ldg(beta + c + j);
+      if (MODE == 0) {             // y = x * sc + sh  with gamma/beta folded in
+        sc[j] = rstd[g] * gm[j];
+        sh[j] = fmaf(-mean[g], sc[j], bt[j]);
+      } else {                     // xhat = x * sc + sh
+        sc[j] = rstd[g];
+        sh[j] = -mean[g] * rstd[g];
+        a1[j] = m1[g]; a2[j] = m2[g];
+      }
+    }
+    for (int r = r0 + ry; r < r1; r += mp.rl) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx + c));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      float o[4];
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float z = fmaf(xs[j], sc[j], sh[j]);
+          o[j] = silu ? silu_f(z) : z;
+        }
+        if (y) *reinterpret_cast<float4*>(y + (size_t)r * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (hi) store_split4(hi, lo, (size_t)r * Kpad + c, o);
+      } else {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(gr + (size_t)r * ldg + c));
+        const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = fmaf(xs[j], sc[j], sh[j]);
+          float dz = gs[j];
+          if (silu) dz *= silu_grad(fmaf(gm[j], xh, bt[j]));
+          o[j] = sc[j] * (dz * gm[j] - a1[j] - xh * a2[j]);
+        }
+        *reinterpret_cast<float4*>(y + (size_t)r * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (MODE == 0 && hi && Kpad > C) {   // zero the K padding of the operand
+    for (int r = r0 + threadIdx.x / 32; r < r1; r += GN_THREADS / 32)
+      for (int c = C + (threadIdx.x & 31); c < Kpad; c += 32) store_split(hi, lo, (size_t)r * Kpad + c, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ scalar fallbacks (C % 4 != 0)
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_scalar_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C, int cg,
+                                                                     int rows_per_cta, double* __restrict__ sums) {
+  __shared__ float sg[GN_MAX_GROUPS * 2];
+  const int G = C / cg;
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sg[i] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    float s = 0.f, ss = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      float v = __ldg(x + (size_t)r * ldx + c);
+      s += v; ss = fmaf(v, v, ss);
+    }
+    atomicAdd(&sg[2 * (c / cg)], s);
+    atomicAdd(&sg[2 * (c / cg) + 1], ss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(sums + i, (double)sg[i]);
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_scalar_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C, int cg,
+                                                                     const double* __restrict__ sums, float eps,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     int silu, float* __restrict__ y, int64_t ldy,
+                                                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Kpad) {
   __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS];
   load_group_stats(sums, C / cg, (double)rows * cg, eps, mean, rstd);
   const int width = hi ? Kpad : C;
@@ -80,6 +243,61 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
       if (y) y[(size_t)r * ldy + c] = v;
     }
     if (hi) store_split(hi, lo, i, v);
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_scalar_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
+                                                                          int64_t ldg, int rows, int C, int cg,
+                                                                          const double* __restrict__ sums, float eps,
+                                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                          int silu, int rows_per_cta, double* __restrict__ bs) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS];
+  __shared__ float sg[GN_MAX_GROUPS * 2];
+  const int G = C / cg;
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sg[i] = 0.f;
+  load_group_stats(sums, G, (double)rows * cg, eps, mean, rstd);
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cg;
+    const float gm = __ldg(gamma + c), bt = __ldg(beta + c), mu = mean[g], rs = rstd[g];
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      float xh = (__ldg(x + (size_t)r * ldx + c) - mu) * rs;
+      float dz = __ldg(gr + (size_t)r * ldg + c);
+      if (silu) dz *= silu_grad(gm * xh + bt);
+      float d = dz * gm;
+      s1 += d; s2 = fmaf(d, xh, s2);
+    }
+    atomicAdd(&sg[2 * g], s1);
+    atomicAdd(&sg[2 * g + 1], s2);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(bs + i, (double)sg[i]);
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_scalar_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
+                                                                         int64_t ldg, int rows, int C, int cg,
+                                                                         const double* __restrict__ sums, float eps,
+                                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                         int silu, const double* __restrict__ bs, float* __restrict__ dx,
+                                                                         int64_t ldd) {
+  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS], m1[GN_MAX_GROUPS], m2[GN_MAX_GROUPS];
+  const int G = C / cg;
+  const double count = (double)rows * cg;
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    m1[g] = (float)(bs[2 * g] / count);
+    m2[g] = (float)(bs[2 * g + 1] / count);
+  }
+  load_group_stats(sums, G, count, eps, mean, rstd);
+  const size_t total = (size_t)rows * C;
+  for (size_t i = blockIdx.x * (size_t)GN_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * GN_THREADS) {
+    const int r = (int)(i / C), c = (int)(i - (size_t)r * C);
+    const int g = c / cg;
+    const float gm = __ldg(gamma + c), rs = rstd[g];
+    float xh = (__ldg(x + (size_t)r * ldx + c) - mean[g]) * rs;
+    float dz = __ldg(gr + (size_t)r * ldg + c);
+    if (silu) dz *= silu_grad(gm * xh + __ldg(beta + c));
+    dx[(size_t)r * ldd + c] = rs * (dz * gm - m1[g] - xh * m2[g]);
   }
 }
 
@@ -118,13 +336,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_im2col3x3_split_kernel(const fl
             v[k] = silu ? silu_f(z) : z;
           }
         }
-        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(v[k]); l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k])); }
-        __nv_bfloat162 ha = __halves2bfloat162(h[0], h[1]), hb = __halves2bfloat162(h[2], h[3]);
-        __nv_bfloat162 la = __halves2bfloat162(l[0], l[1]), lb = __halves2bfloat162(l[2], l[3]);
-        *reinterpret_cast<uint2*>(hi + dst + c) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
-        *reinterpret_cast<uint2*>(lo + dst + c) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+        store_split4(hi, lo, dst + c, v);
       }
     } else {
       for (int c = lane; c < C; c += 32) {
@@ -142,69 +354,21 @@ __global__ void __launch_bounds__(GN_THREADS) gn_im2col3x3_split_kernel(const fl
   }
 }
 
-// backward reductions: bs[g] += (sum gamma dz, sum gamma dz xhat)
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
-                                                                   int64_t ldg, int rows, int C, int cg, const double* __restrict__ sums,
-                                                                   float eps, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta, int silu, int rows_per_cta,
-                                                                   double* __restrict__ bs) {
-  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS];
-  __shared__ double sg[GN_MAX_GROUPS * 2];
-  const int G = C / cg;
-  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sg[i] = 0.0;
-  load_group_stats(sums, G, (double)rows * cg, eps, mean, rstd);
-  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    const int g = c / cg;
-    const float gm = __ldg(gamma + c), bt = __ldg(beta + c), mu = mean[g], rs = rstd[g];
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      float xh = (__ldg(x + (size_t)r * ldx + c) - mu) * rs;
-      float dz = __ldg(gr + (size_t)r * ldg + c);
-      if (silu) dz *= silu_grad(gm * xh + bt);
-      float d = dz * gm;
-      s1 += d; s2 = fmaf(d, xh, s2);
-    }
-    atomicAdd(&sg[2 * g], (double)s1);
-    atomicAdd(&sg[2 * g + 1], (double)s2);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(bs + i, sg[i]);
-}
-
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
-                                                                  int64_t ldg, int rows, int C, int cg, const double* __restrict__ sums,
-                                                                  float eps, const float* __restrict__ gamma,
-                                                                  const float* __restrict__ beta, int silu,
-                                                                  const double* __restrict__ bs, float* __restrict__ dx, int64_t ldd) {
-  __shared__ float mean[GN_MAX_GROUPS], rstd[GN_MAX_GROUPS], m1[GN_MAX_GROUPS], m2[GN_MAX_GROUPS];
-  const int G = C / cg;
-  const double count = (double)rows * cg;
-  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
-    m1[g] = (float)(bs[2 * g] / count);
-    m2[g] = (float)(bs[2 * g + 1] / count);
-  }
-  load_group_stats(sums, G, count, eps, mean, rstd);
-  const size_t total = (size_t)rows * C;
-  for (size_t i = blockIdx.x * (size_t)GN_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * GN_THREADS) {
-    const int r = (int)(i / C), c = (int)(i - (size_t)r * C);
-    const int g = c / cg;
-    const float gm = __ldg(gamma + c), rs = rstd[g];
-    float xh = (__ldg(x + (size_t)r * ldx + c) - mean[g]) * rs;
-    float dz = __ldg(gr + (size_t)r * ldg + c);
-    if (silu) dz *= silu_grad(gm * xh + __ldg(beta + c));
-    dx[(size_t)r * ldd + c] = rs * (dz * gm - m1[g] - xh * m2[g]);
-  }
-}
-
-static inline int gn_rows_per_cta(int rows) {
-  int per = (rows + 148 * 4 - 1) / (148 * 4);
-  return per < 8 ? 8 : per;
+static inline int gn_rows_per_cta(int rows, int C) {
+  GnMap m = gn_map(C >= 4 ? C : 4);
+  int per = (rows + 148 * 6 - 1) / (148 * 6);      // ~6 CTAs per SM
+  int min_rows = m.rl * 4;                         // at least 4 rows per row lane
+  return per < min_rows ? min_rows : per;
 }
 static inline int gn_grid(size_t n) {
   size_t b = (n + GN_THREADS - 1) / GN_THREADS;
   if (b > 148 * 16) b = 148 * 16;
   return b < 1 ? 1 : (int)b;
+}
+static inline bool gn_vec_ok(const float* x, int64_t ldx, int C, const float* g = nullptr, int64_t ldg = 0) {
+  bool ok = (C % 4 == 0) && (C <= 4 * GN_THREADS * GN_NCH) && (ldx % 4 == 0) && ((((uintptr_t)x) & 15) == 0);
+  if (g) ok = ok && (ldg % 4 == 0) && ((((uintptr_t)g) & 15) == 0);
+  return ok;
 }
 
 }  // namespace skp
@@ -220,8 +384,12 @@ extern "C" int skp_gn_stats(const float* x, int64_t ldx, int rows, int C, int gr
   SKP_REQUIRE(sums, "gn_stats: null sums");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups, st);
-  int per = gn_rows_per_cta(rows);
-  gn_stats_kernel<<<(rows + per - 1) / per, GN_THREADS, 0, st>>>(x, ldx, rows, C, C / groups, per, sums);
+  int per = gn_rows_per_cta(rows, C);
+  int grid = (rows + per - 1) / per;
+  if (gn_vec_ok(x, ldx, C))
+    gn_reduce_kernel<0><<<grid, GN_THREADS, 0, st>>>(x, ldx, nullptr, 0, rows, C, C / groups, nullptr, 0.f, nullptr, nullptr, 0, per, sums);
+  else
+    gn_stats_scalar_kernel<<<grid, GN_THREADS, 0, st>>>(x, ldx, rows, C, C / groups, per, sums);
   SKP_CHECK_LAUNCH("gn_stats");
   return SKP_OK;
 }
@@ -232,9 +400,19 @@ extern "C" int skp_gn_apply(const float* x, int64_t ldx, int rows, int C, int gr
   SKP_GN_CHECK("gn_apply");
   SKP_REQUIRE(sums && gamma && beta && (y || (hi && lo)), "gn_apply: null pointer");
   SKP_REQUIRE(!hi || (Kpad >= C && Kpad % 64 == 0), "gn_apply: Kpad=%d must be a multiple of 64 >= C", Kpad);
-  size_t total = (size_t)rows * (hi ? Kpad : C);
-  gn_apply_kernel<<<gn_grid(total), GN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, C / groups, sums, eps, gamma, beta, silu,
-                                                                          y, ldy, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = gn_vec_ok(x, ldx, C) && (!y || (ldy % 4 == 0 && ((((uintptr_t)y) & 15) == 0))) &&
+             (!hi || (((((uintptr_t)hi) | ((uintptr_t)lo)) & 7) == 0));
+  if (vec) {
+    int per = gn_rows_per_cta(rows, C);
+    gn_rowwise_kernel<0><<<(rows + per - 1) / per, GN_THREADS, 0, st>>>(x, ldx, nullptr, 0, rows, C, C / groups, sums, eps, gamma, beta,
+                                                                        silu, nullptr, per, y, ldy, (__nv_bfloat16*)hi,
+                                                                        (__nv_bfloat16*)lo, Kpad);
+  } else {
+    size_t total = (size_t)rows * (hi ? Kpad : C);
+    gn_apply_scalar_kernel<<<gn_grid(total), GN_THREADS, 0, st>>>(x, ldx, rows, C, C / groups, sums, eps, gamma, beta, silu, y, ldy,
+                                                                  (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad);
+  }
   SKP_CHECK_LAUNCH("gn_apply");
   return SKP_OK;
 }
@@ -263,12 +441,20 @@ extern "C" int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t l
   SKP_REQUIRE(g && sums && gamma && beta && bsums && dx, "gn_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * groups, st);
-  int per = gn_rows_per_cta(rows);
-  gn_bwd_reduce_kernel<<<(rows + per - 1) / per, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu,
-                                                                     per, bsums);
+  int per = gn_rows_per_cta(rows, C);
+  int grid = (rows + per - 1) / per;
+  const bool vec = gn_vec_ok(x, ldx, C, g, ldg) && (ldd % 4 == 0) && ((((uintptr_t)dx) & 15) == 0);
+  if (vec)
+    gn_reduce_kernel<1><<<grid, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, per, bsums);
+  else
+    gn_bwd_reduce_scalar_kernel<<<grid, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, per, bsums);
   SKP_CHECK_LAUNCH("gn_bwd_reduce");
-  gn_bwd_apply_kernel<<<gn_grid((size_t)rows * C), GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta,
-                                                                       silu, bsums, dx, ldd);
+  if (vec)
+    gn_rowwise_kernel<1><<<grid, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, bsums, per, dx, ldd,
+                                                      nullptr, nullptr, 0);
+  else
+    gn_bwd_apply_scalar_kernel<<<gn_grid((size_t)rows * C), GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta,
+                                                                                silu, bsums, dx, ldd);
   SKP_CHECK_LAUNCH("gn_bwd_apply");
   return SKP_OK;
 }
