@@ -179,6 +179,13 @@ int skp_affine_warp_bwd(const float* d_out, int B, int C, int H, int W, const fl
 int skp_soft_argmax(float* heatmaps, int T, int H, int W, const int64_t* peaks, float distance,
                     float* out, void* stream);
 
+/* Eval-time augmentation ensemble (eval.py:250-262): one pass does sum += unwarp(maps), num += unwarp(ones) for
+ * maps[K,H,W] under the inverse affine theta_inv (6-float DEVICE array); skp_ensemble_finalize: out = sum/num with
+ * 0/0 -> 0 (eval.py:333-336). */
+int skp_unwarp_accumulate(const float* maps, int K, int H, int W, const float* theta_inv, float* sum_samples,
+                          float* num_samples, void* stream);
+int skp_ensemble_finalize(const float* sum_samples, const float* num_samples, float* out, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------ optimiser (optimize.py:320,424)
  * torch.optim.Adam defaults (no weight decay / amsgrad); grad is scaled by grad_scale first (the
  * 1/world_size of the data-parallel mean, optimize.py:405-406). */

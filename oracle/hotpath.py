@@ -369,3 +369,32 @@ def synthetic_image(seed: int = 1, size: int = 512, blobs: int = 12, batch: int 
                             align_corners=False)[0]
         out.append((0.7 * img + 0.3 * low).clamp(0, 1))
     return torch.stack(out)
+
+
+# ----------------------------------------------------------------------------- "next" rows f2 / f3
+@torch.no_grad()
+def run_image_with_context_augmented(ldm, image, context, indices, controllers, thetas, noises=None, layers=(0, 1, 2, 3),
+                                     upscale_size: int = 512):
+    """eval.py:197-355 -- test-time augmentation ensemble: per iteration warp the image by theta, one captured forward
+    with the selected tokens at `upscale_size`, un-warp the maps and a ones mask, accumulate; sum/num with NaN -> 0.
+    ``image`` is [3,H,W]; ``thetas`` [iters,2,3] replace the reference's torch.rand draws (:238-243)."""
+    k = len(indices)
+    num = torch.zeros(k, upscale_size, upscale_size)
+    tot = torch.zeros(k, upscale_size, upscale_size)
+    for i in range(thetas.shape[0]):
+        th = thetas[i:i + 1]
+        aug = affine_warp(image[None], th)
+        maps = run_and_find_attn(ldm, aug, context, controllers, layers=layers, upsample_res=upscale_size,
+                                 indices=torch.as_tensor(indices), noise=None if noises is None else noises[i])
+        maps = torch.stack(maps)
+        num += affine_unwarp(torch.ones_like(maps), th).sum(dim=0)
+        tot += affine_unwarp(maps, th).sum(dim=0)
+    out = tot / num
+    out[out != out] = 0
+    return out
+
+
+def vote_top_k(indices_list: torch.Tensor, top_k: int) -> torch.Tensor:
+    """keypoint_regressor.py:101-106 -- most frequently selected token ids."""
+    idx, counts = torch.unique(indices_list, return_counts=True)
+    return idx[counts.argsort(descending=True)][:top_k]

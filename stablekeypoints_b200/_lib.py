@@ -57,6 +57,8 @@ _SIGNATURES: Dict[str, list] = {
     "skp_affine_warp": [_P, _I, _I, _I, _I, _P, _P, _P],
     "skp_affine_warp_bwd": [_P, _I, _I, _I, _I, _P, _P, _P],
     "skp_soft_argmax": [_P, _I, _I, _I, _P, _F, _P, _P],
+    "skp_unwarp_accumulate": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "skp_ensemble_finalize": [_P, _P, _P, _L, _P],
     "skp_adam_step": [_P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _P],
     "skp_adam_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }

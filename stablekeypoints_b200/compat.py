@@ -14,6 +14,8 @@ import sys
 import types
 
 _ALIASES = ("ptp_utils", "optimize", "optimize_token", "eval", "invertable_transform")
+# keypoint_regressor is NOT aliased wholesale (Stage 3/4 stay with the reference); use
+# stablekeypoints_b200.keypoint_regressor.find_best_indices explicitly or patch that one attribute.
 
 
 def install(package_name: str = "unsupervised_keypoints") -> None:

@@ -329,3 +329,53 @@ extern "C" int skp_adam_step_dev(float* param, const float* grad, float* exp_avg
   SKP_CHECK_LAUNCH("adam_dev");
   return SKP_OK;
 }
+
+// ------------------------------------------------------------------ eval-time augmentation ensemble (eval.py:250-262,333-336)
+namespace skp {
+// sum[k,p] += unwarp(maps[k])[p]; num[k,p] += unwarp(ones)[p]  (one pass instead of two grid_samples + two adds)
+__global__ void unwarp_accumulate_kernel(const float* __restrict__ maps, int K, int H, int W, const float* __restrict__ theta_inv,
+                                         float* __restrict__ sum, float* __restrict__ num) {
+  __shared__ float th[6];
+  if (threadIdx.x < 6) th[threadIdx.x] = theta_inv[threadIdx.x];
+  __syncthreads();
+  const int P = H * W;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+    const int y = pix / W, x = pix - y * W;
+    const BilinearTap t = affine_tap(th, y, x, H, W);
+    const bool xa = t.x0 >= 0 && t.x0 < W, xb = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+    const bool ya = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+    float ones = 0.f;
+    if (ya && xa) ones += t.w00;
+    if (ya && xb) ones += t.w01;
+    if (yb && xa) ones += t.w10;
+    if (yb && xb) ones += t.w11;
+    for (int k = 0; k < K; ++k) {
+      const size_t o = (size_t)k * P + pix;
+      sum[o] += sample_tap(maps + (size_t)k * P, t, H, W);
+      num[o] += ones;
+    }
+  }
+}
+// out = sum / num with 0/0 -> 0 (eval.py:333-336: NaNs replaced by 0)
+__global__ void ensemble_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ num, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = sum[i] / num[i];
+    out[i] = (v != v) ? 0.f : v;
+  }
+}
+}  // namespace skp
+
+extern "C" int skp_unwarp_accumulate(const float* maps, int K, int H, int W, const float* theta_inv, float* sum_samples,
+                                     float* num_samples, void* stream) {
+  SKP_REQUIRE(maps && theta_inv && sum_samples && num_samples && K > 0 && H > 0 && W > 0, "unwarp_accumulate: bad arguments");
+  unwarp_accumulate_kernel<<<grid_for((size_t)H * W, 256), 256, 0, (cudaStream_t)stream>>>(maps, K, H, W, theta_inv, sum_samples, num_samples);
+  SKP_CHECK_LAUNCH("unwarp_accumulate");
+  return SKP_OK;
+}
+
+extern "C" int skp_ensemble_finalize(const float* sum_samples, const float* num_samples, float* out, int64_t n, void* stream) {
+  SKP_REQUIRE(sum_samples && num_samples && out && n > 0, "ensemble_finalize: bad arguments");
+  ensemble_finalize_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>(sum_samples, num_samples, out, (size_t)n);
+  SKP_CHECK_LAUNCH("ensemble_finalize");
+  return SKP_OK;
+}

@@ -139,7 +139,9 @@ def find_pred_noise(ldm, image, context, noise_level=-1, device="cuda", noise=No
 def _fused_ok(ldm, controllers, upsample_res, indices) -> bool:
     if os.environ.get("SKP_CAPTURE_MODE", "fused") == "store":
         return False
-    return (upsample_res == -1 and indices is None and len(controllers) == 1
+    # upsample_res == R is the bilinear identity, so Stage 2 (keypoint_regressor.py:70-80) fuses too
+    same_res = upsample_res in (-1, ldm.unet.feature_upsample_res)
+    return (same_res and indices is None and len(controllers) == 1
             and all(type(c) is AttentionStore for c in controllers.values()))
 
 

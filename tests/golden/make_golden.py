@@ -12,6 +12,8 @@ Fixtures (all small, fp32/int64 .npz):
                     reference hook (ptp_utils.py:472-573) on the tiny same-topology UNet of
                     oracle/sd15.py: the 4 stored maps, collected maps, token indices, both losses,
                     d(loss)/d(context), plus the eval-shaped collect_maps and arg-max / soft-arg-max.
+  tiny_eval.npz     the eval-time augmentation ensemble (eval.py:197-355) run by the reference on the tiny pipeline,
+                    plus the Stage-2 vote (keypoint_regressor.py:101-106).
   post_unet.npz     model-free: reference collect_maps / find_top_k_gaussian / furthest_point_sampling /
                     sharpening_loss / equivariance_loss / find_max_pixel / pixel_from_weighted_avg /
                     RandomAffineWithInverse on seeded random stores (includes ties and border cases).
@@ -232,11 +234,39 @@ def make_post_unet(ref):
     print("post_unet.npz: sharp", float(sharp), "equiv", float(equiv), "fps", out["fps_s2.0"].tolist())
 
 
+def make_tiny_eval(ref):
+    """eval.py:197-355 run by the reference itself on the tiny pipeline (3 augmentation iterations, 3 tokens, 64^2)."""
+    from oracle import hotpath
+    pipe = tiny_pipeline()
+    image, context, noise_a, noise_b, _ = tiny_inputs()
+    g = torch.Generator().manual_seed(21)
+    noises = [noise_a, noise_b, torch.randn(noise_a.shape, generator=g)]
+    controllers = {torch.device("cpu"): ref.ptp_utils.AttentionStore()}
+    pipe.unet.register_forward_pre_hook(
+        lambda m, i: ref.ptp_utils.register_attention_control(m, controllers[i[0].device], feature_upsample_res=TINY["res"]))
+    indices = torch.tensor([5, 0, 9])
+    torch.manual_seed(77)
+    thetas = torch.cat([hotpath.sample_affine_params(1, degrees=30, scale=(0.9, 1.1), translate=(0.1, 0.1)) for _ in range(3)], 0)
+    torch.manual_seed(77)
+    with _FixedNoise(ref, noises):
+        out = ref.eval.run_image_with_context_augmented(pipe, image[0], context, indices, device="cpu", layers=[0, 1, 2, 3],
+                                                        augmentation_iterations=3, controllers=controllers, num_gpus=1,
+                                                        upscale_size=64)
+    res = {"indices": indices.numpy(), "thetas": thetas.numpy(), "noise_c": noises[2].numpy(), "ensemble": out.numpy(),
+           "keypoints": (ref.eval.find_max_pixel(out) / 64.0).numpy()}
+    votes = torch.tensor([3, 7, 7, 1, 3, 7, 9, 1, 1, 0, 3, 3])
+    idx, counts = torch.unique(votes, return_counts=True)
+    res["votes"], res["voted_top3"] = votes.numpy(), idx[counts.argsort(descending=True)][:3].numpy()
+    np.savez_compressed(os.path.join(HERE, "tiny_eval.npz"), **res)
+    print("tiny_eval.npz: ensemble", out.shape, "keypoints", res["keypoints"].tolist())
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "reference tree not present: fixtures can only be minted in the build container"
     torch.set_num_threads(8)
     ref = ref_shim.load()
     make_post_unet(ref)
     make_tiny_stage1(ref)
-    for f in ("tiny_stage1.npz", "post_unet.npz"):
+    make_tiny_eval(ref)
+    for f in ("tiny_stage1.npz", "post_unet.npz", "tiny_eval.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -215,3 +215,35 @@ def test_full_sd15_stage1_iteration_vs_oracle(full, precision, tol):
     print("candidate agreement:", int((cand == cand_gpu.cpu()).sum()), "/ 25")
     for k, v in errs.items():
         assert v < tol, (k, v)
+
+
+def test_tiny_eval_ensemble_matches_reference_golden(tiny):
+    """SURVEY 'next' row f2: eval.run_image_with_context_augmented (augment -> captured forward with K tokens at 64^2 ->
+    fused un-warp + accumulate -> sum/num) against the reference's own output; f3: the Stage-2 vote."""
+    from stablekeypoints_b200 import eval as skp_eval, keypoint_regressor
+    t, pipe = tiny
+    g = load_golden("tiny_eval.npz")
+    ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
+    noises = [torch.from_numpy(t["noise_a"]), torch.from_numpy(t["noise_b"]), torch.from_numpy(g["noise_c"])]
+    out = skp_eval.run_image_with_context_augmented(
+        ldm, torch.from_numpy(t["image"])[0], torch.from_numpy(t["context"]).cuda(), torch.from_numpy(g["indices"]),
+        layers=[0, 1, 2, 3], augmentation_iterations=3, controllers=controllers, num_gpus=1, upscale_size=64,
+        thetas=torch.from_numpy(g["thetas"]), noises=noises)
+    assert tuple(out.shape) == g["ensemble"].shape
+    assert rel_err(out.cpu(), g["ensemble"]) < 1e-3
+    assert np.array_equal((skp_eval.find_max_pixel(out) / 64.0).cpu().numpy(), g["keypoints"])
+    assert np.array_equal(keypoint_regressor.vote_top_k(torch.from_numpy(g["votes"]), 3).numpy(), g["voted_top3"])
+
+
+def test_find_best_indices_runs_on_synthetic_dataset(tiny):
+    """Stage 2 end to end on the tiny pipeline with the synthetic dataset (fused capture at upsample_res == R)."""
+    from stablekeypoints_b200 import keypoint_regressor
+    from stablekeypoints_b200.optimize import SyntheticKeypointDataset
+    t, pipe = tiny
+    ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
+    args = _args(top_k=TINY["top_k"], furthest_point_num_samples=TINY["num_candidates"], sigma=TINY["sigma"],
+                 dataset=SyntheticKeypointDataset(length=4, size=TINY["image_size"], blobs=6), dataset_name="synthetic",
+                 num_indices=4, feature_upsample_res=TINY["res"])
+    idx = keypoint_regressor.find_best_indices(ldm, torch.from_numpy(t["context"]).cuda(), args, controllers, 1)
+    assert idx.shape == (TINY["top_k"],) and len(set(idx.tolist())) == TINY["top_k"]
+    assert all(0 <= i < TINY["n_tokens"] for i in idx.tolist())

@@ -128,3 +128,19 @@ def test_tiny_stage1_iteration(tiny):
     p = torch.from_numpy(tiny["context"]).clone()
     hp.adam_step(p, torch.from_numpy(tiny["dcontext"]), torch.zeros_like(p), torch.zeros_like(p), 1)
     assert rel_err(p, tiny["context_after_adam"]) < 1e-6
+
+
+def test_tiny_eval_ensemble_and_vote():
+    """'next' rows f2/f3: oracle restatement vs the reference's own run_image_with_context_augmented / vote."""
+    g = load_golden("tiny_eval.npz")
+    t = load_golden("tiny_stage1.npz")
+    pipe = tiny_pipeline()
+    check_tiny_weights(pipe, t)
+    ldm, controllers, _ = hp.load_oracle_ldm(pipe, TINY["res"])
+    noises = [torch.from_numpy(t["noise_a"]), torch.from_numpy(t["noise_b"]), torch.from_numpy(g["noise_c"])]
+    out = hp.run_image_with_context_augmented(ldm, torch.from_numpy(t["image"])[0], torch.from_numpy(t["context"]),
+                                              torch.from_numpy(g["indices"]), controllers, torch.from_numpy(g["thetas"]),
+                                              noises, upscale_size=64)
+    assert rel_err(out, g["ensemble"]) < 2e-5
+    assert np.array_equal((hp.find_max_pixel(out) / 64.0).numpy(), g["keypoints"])
+    assert np.array_equal(hp.vote_top_k(torch.from_numpy(g["votes"]), 3).numpy(), g["voted_top3"])
