@@ -109,8 +109,7 @@ def main():
         out = torch.empty(m, nn, device=dev)
 
         def tc_only(a_hi=a_hi, a_lo=a_lo, fw=fw, out=out, m=m, nn=nn):
-            check(lib().skp_gemm_nt_tc(ptr(a_hi), ptr(a_lo), ptr(fw.w_split[0]), ptr(fw.w_split[1]), a_hi.shape[1], ptr(out),
-                                       out.stride(0), m, nn, 1.0, None, None, 0, stream()), "gemm")
+            ops.gemm_nt_presplit(a_hi, a_lo, m, fw.w_split, nn, out=out)
         add("gemm_nt_tc(kernel only)", f"{m}x{nn}x{k} {what}", tc_only, flops=2.0 * m * nn * k)
     # ---- attention core
     for (s, c) in [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]:

@@ -103,6 +103,9 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // power of two >= BN
+  static_assert(BN % 32 == 0 && BN <= 256, "BN must be a multiple of 32 up to 256");
+  static_assert(SMEM <= 227 * 1024, "stage ring does not fit shared memory");
 };
 
 // Implicit-GEMM 3x3 convolution (stride 1, zero padding 1) of a channels-last activation [H, W, Cin] (Cin % 64 == 0):
@@ -145,7 +148,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -258,7 +261,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(Cfg::TMEM_COLS));
   }
 }
 
@@ -465,22 +468,56 @@ extern "C" int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, in
   return SKP_OK;
 }
 
-static bool use_bn128(int M, int N) {
-  const long tiles128 = (long)((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
-  return tiles128 >= 120 && N >= 128;
+// ---- tile planner.  Two facts measured on B200 drive it: (1) with split-bf16 operands a CTA is fed by
+// its SM's share of L2 bandwidth (~42 B/clk), so bytes per k-block (128 + BN) * 256 B must be amortised over 6*BN MMA
+// cycles -> wide N tiles; (2) the grid should be a whole number of 148-CTA waves -> pick (BN, K-splits) by a cost model
+// instead of a fixed tile.
+struct TcPlan { int bn, splits; };
+
+static double plan_cost(int M, int N, int num_kb, int bn, int splits) {
+  const long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  const long ctas = tiles * splits;
+  const long waves = (ctas + 147) / 148;
+  const double active = ctas < 148 ? (double)ctas : 148.0;
+  const double bw_per_sm = 42.5 * 148.0 / active;                       // B/clk available to one CTA (L2 cap is chip-wide)
+  const double t_kb_mma = 6.0 * bn, t_kb_mem = (128.0 + bn) * 256.0 / (bw_per_sm > 120.0 ? 120.0 : bw_per_sm);
+  const double kb_per = (double)((num_kb + splits - 1) / splits);
+  const double t_cta = 3500.0 + kb_per * (t_kb_mma > t_kb_mem ? t_kb_mma : t_kb_mem) + 10.0 * bn;
+  double t = waves * t_cta;
+  if (splits > 1) t += 5000.0 + (double)M * N * 4.0 * (splits + 1) / 3000.0;   // extra launch + partial-sum traffic
+  return t;
+}
+
+static TcPlan plan_tiles(int M, int N, int Kpad, int forced_splits) {
+  static const int bns[] = {64, 96, 128, 160, 256};
+  static const int zs[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+  const int num_kb = Kpad / TC_BK;
+  TcPlan best{64, 1};
+  double best_t = 1e300;
+  for (int bn : bns)
+    for (int z : zs) {
+      if (forced_splits > 0 && z != forced_splits) continue;
+      if (z > 1 && num_kb / z < 2) continue;
+      double t = plan_cost(M, N, num_kb, bn, z);
+      if (t < best_t) { best_t = t; best = TcPlan{bn, z}; }
+    }
+  if (forced_splits > 0 && best_t == 1e300) best = TcPlan{64, forced_splits};
+  return best;
 }
 
 extern "C" int skp_gemm_nt_tc_plan(int M, int N, int Kpad) {
   if (M <= 0 || N <= 0 || Kpad <= 0) return 1;
-  const int bn = use_bn128(M, N) ? 128 : 64;
-  const long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
-  const int num_kb = Kpad / TC_BK;
-  long splits = 148 / tiles;            // fill the 148 SMs once
-  if (splits > num_kb / 4) splits = num_kb / 4;  // keep >= 4 k-blocks (256 of K) per split
-  if (splits > 32) splits = 32;
-  if (splits < 1) splits = 1;
-  return (int)splits;
+  return plan_tiles(M, N, Kpad, 0).splits;
 }
+
+#define SKP_TC_DISPATCH(FN, BNV, ...)                                   \
+  switch (BNV) {                                                        \
+    case 64:  return FN<64, 4>(__VA_ARGS__);                            \
+    case 96:  return FN<96, 3>(__VA_ARGS__);                            \
+    case 128: return FN<128, 3>(__VA_ARGS__);                           \
+    case 160: return FN<160, 3>(__VA_ARGS__);                           \
+    default:  return FN<256, 2>(__VA_ARGS__);                           \
+  }
 
 extern "C" int skp_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int Ho, int Wo, int stride, int pad,
                                    int Kpad, void* hi, void* lo, void* stream) {
@@ -506,9 +543,8 @@ extern "C" int skp_conv3x3_tc(const void* X_hi, const void* X_lo, int H, int W, 
   cudaStream_t st = (cudaStream_t)stream;
   if (splits < 1) splits = 1;
   SKP_REQUIRE(splits == 1 || splitk_ws != nullptr, "conv3x3_tc: split-K needs a workspace of splits*H*W*Cout floats");
-  if (use_bn128(H * W, Cout))
-    return launch_conv<128, 3>(X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st);
-  return launch_conv<64, 4>(X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st);
+  const TcPlan pl = plan_tiles(H * W, Cout, 9 * Cin, splits);
+  SKP_TC_DISPATCH(launch_conv, pl.bn, X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st)
 }
 
 extern "C" int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C,
@@ -521,7 +557,6 @@ extern "C" int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_
   cudaStream_t st = (cudaStream_t)stream;
   if (splits < 1) splits = 1;
   SKP_REQUIRE(splits == 1 || splitk_ws != nullptr, "gemm_nt_tc: split-K needs a workspace of splits*M*N floats");
-  if (use_bn128(M, N))
-    return launch_tc<128, 3>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, splits, splitk_ws, st);
-  return launch_tc<64, 4>(A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, splits, splitk_ws, st);
+  const TcPlan pl = plan_tiles(M, N, Kpad, splits);
+  SKP_TC_DISPATCH(launch_tc, pl.bn, A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, splits, splitk_ws, st)
 }
