@@ -101,6 +101,24 @@ int skp_cross_attn_bwd(const float* d_o, const float* q, const float* k, int64_t
                        float* dq, float* dk, float* dv, int S, int N, int heads, int d, float scale,
                        void* stream);
 
+/* ------------------------------------------------------------------ self-attention core (attn1 of every transformer block)
+ * The patched CrossAttention.forward runs the same lines for context=None (ptp_utils.py:480-506, is_cross == False):
+ * out = softmax(q k^T * scale) v per head with k,v projected from the layer's own tokens.  Flash-style (no [S,S]
+ * tensor in HBM), every contraction a split-bf16 (hi+lo, 3 MMAs, fp32 accumulate) tensor-core product so the
+ * captured maps downstream keep their 1e-3 budget.  q,k,v,o: [S, heads*d] fp32 with leading dims (q,k,v may be column
+ * slices of one [S, 3*heads*d] projection); d even, d <= 160.  planes is a workspace of 6*heads*S*DP bf16 with
+ * DP = skp_self_attn_dp(d) (the split operands; kept by the caller for the backward); lse[heads, S] receives the
+ * per-row log2-sum-exp. */
+int skp_self_attn_dp(int d);
+int skp_self_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                      float* o, int64_t ldo, float* lse, void* planes, int S, int heads, int d, float scale,
+                      void* stream);
+/* Backward: dq,dk,dv [S, heads*d] (leading dims given; fully written).  do_planes: workspace of 2*heads*S*DP bf16;
+ * dvec: workspace of heads*S floats (rowsum(dO * O)). */
+int skp_self_attn_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse,
+                      const void* planes, void* do_planes, float* dvec, float* dq, int64_t lddq, float* dk,
+                      int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale, void* stream);
+
 /* ------------------------------------------------------------------ attention-store ("capture")
  * ptp_utils.py:508-538: bicubic (align_corners=False, A=-0.75, clamped taps) upsample of the layer
  * input to R x R, to_q, q' k^T * scale, softmax over the TOKEN axis, stored as [heads, R*R, N].

@@ -122,6 +122,24 @@ def main():
         do = torch.randn_like(o)
         add("cross_attn_bwd", f"S{s} C{c} N{n}", lambda o=o, q=q, kv=kv, do=do: torch.autograd.grad(o, (q, kv), do, retain_graph=True),
             flops=8.0 * s * n * c)
+    # ---- self-attention core (split-bf16 flash kernels; algorithmic FLOPs 4*S^2*C fwd, 14*S^2*C bwd (7 contractions))
+    import torch.nn.functional as F
+    for (s, c) in [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]:
+        d = c // h
+        qkv = torch.randn(s, 3 * c, device=dev, generator=g).requires_grad_(True)
+        add("self_attn_fwd", f"S{s} C{c} d{d}", lambda qkv=qkv, d=d: ops.self_attn_core(qkv.detach(), h, d ** -0.5), flops=4.0 * s * s * c)
+        o = ops.self_attn_core(qkv, h, d ** -0.5)
+        do = torch.randn_like(o)
+        add("self_attn_bwd", f"S{s} C{c} d{d}", lambda o=o, qkv=qkv, do=do: torch.autograd.grad(o, qkv, do, retain_graph=True),
+            flops=14.0 * s * s * c)
+        q4 = qkv.detach().reshape(s, 3, h, d).permute(1, 2, 0, 3)
+        qq, kk, vv = (q4[i][None].contiguous().requires_grad_(True) for i in range(3))
+        add("torch_sdpa_fp32_fwd (library, for comparison)", f"S{s} C{c} d{d}",
+            lambda qq=qq, kk=kk, vv=vv: F.scaled_dot_product_attention(qq.detach(), kk.detach(), vv.detach()), flops=4.0 * s * s * c)
+        o2 = F.scaled_dot_product_attention(qq, kk, vv)
+        do2 = torch.randn_like(o2)
+        add("torch_sdpa_fp32_bwd (library, for comparison)", f"S{s} C{c} d{d}",
+            lambda o2=o2, qq=qq, kk=kk, vv=vv, do2=do2: torch.autograd.grad(o2, (qq, kk, vv), do2, retain_graph=True), flops=10.0 * s * s * c)
     # ---- losses / selection
     maps = torch.rand(n, r, r, device=dev, generator=g) ** 6
     maps_t = torch.rand(n, r, r, device=dev, generator=g) ** 6

@@ -759,9 +759,20 @@ static int launch_quad(CapParams& p, cudaStream_t st, bool* fits, bool need_grid
   return SKP_OK;
 }
 
+// skp_capture_row.cu: the row-per-CTA attn-store kernel (any R, s; needs the row + footprint to fit shared memory)
+int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled);
+
 template <bool STORE, bool BWD>
 static int launch(CapParams& p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (STORE && !BWD) {
+    static const bool row_off = getenv("SKP_CAPTURE_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_ROW")) == 0;
+    if (!row_off) {
+      bool handled = false;
+      int rr = capture_store_row(p.logits[0], p.out, p.heads, p.s[0], p.N, p.R, st, &handled);
+      if (rr != SKP_OK || handled) return rr;
+    }
+  }
   int Np4 = (p.N + 3) & ~3;
   p.Nf = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;
   p.Nb = p.N | 1;

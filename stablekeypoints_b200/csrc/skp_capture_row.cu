@@ -1,0 +1,207 @@
+// Attention-store kernel, row formulation (forward, STORE): ptp_utils.py:508-538 by linearity (see skp_capture.cu):
+//   probs[h, Y*R + X, :] = softmax_tokens( bicubic(logits[h])(Y, X, :) )
+// The 40 MB/layer store is the only HBM traffic that matters (logits <= 2.5 MB, L2-resident), so the kernel is built
+// around getting a full output row out of shared memory with as few instructions per element as possible:
+//
+//   CTA = (output row Y, head h), one thread per output pixel X.
+//   1. vertical pass   V[xs][n] = sum_j wy[j] * L[h, row_j, xs, n]   (s*N coalesced elements, 4 loads each), stored
+//      with 2 replicated halo columns on each side so the horizontal taps never clamp; per-column max/min over tokens.
+//   2. horizontal pass, thread = pixel: x_n = sum_i wx[i] * V[ix-1+i][n] with 128-bit shared loads (4 tokens per load;
+//      lanes of a warp share <= 6 distinct columns -> broadcast, conflict-free because the column stride is an odd
+//      number of float4), e_n = exp2(x_n - U) with U a per-pixel upper bound of max_n x_n built from the column
+//      max/min (no separate max sweep), e_n staged at [X][n] -- exactly the global layout of the row -- while the
+//      thread accumulates its own sum (no cross-thread reduction: the thread owns the whole token axis of its pixel).
+//   3. the thread rescales its pixel by 1/sum in place; then ONE bulk asynchronous copy (cp.async.bulk, the TMA
+//      engine) moves the contiguous R*N*4-byte row from shared memory to HBM.
+// ~12 instructions and ~0.1 shared-memory wavefronts per stored element, against 180 instructions for the tile kernel.
+// If U - max_n x_n is so loose that the sum underflows (pathological logits), the pixel is redone with the exact max.
+#include "skp_common.cuh"
+#include <math_constants.h>
+
+namespace skp {
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int ROW_MAX_THREADS = 256;
+
+__global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(const float* __restrict__ logits,
+                                                                            float* __restrict__ probs, int s, int N, int R,
+                                                                            int NV) {
+  extern __shared__ __align__(16) unsigned char row_smem[];
+  float* stage = reinterpret_cast<float*>(row_smem);                 // [R][N]  (the output row, global layout)
+  float* Vs = stage + (((size_t)R * N + 3) & ~(size_t)3);            // [s+4][NV]
+  float* vmax = Vs + (size_t)(s + 4) * NV;                           // [s+4]
+  float* vmin = vmax + (s + 4);                                      // [s+4]
+  const int Y = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const float scale = (float)s / (float)R;
+  const float LOG2E = 1.4426950408889634f;
+
+  // ---- 1. vertical pass
+  {
+    float ry = scale * (Y + 0.5f) - 0.5f, fy = floorf(ry);
+    float wy[4];
+    cubic_coeffs(ry - fy, wy);
+    int iy = (int)fy;
+    const float* rows[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = iy - 1 + j;
+      r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
+      rows[j] = logits + ((size_t)h * s + r) * s * N;
+    }
+    const int total = s * N;
+    for (int i = tid; i < total; i += NT) {
+      float v = wy[0] * __ldg(rows[0] + i);
+      v = fmaf(wy[1], __ldg(rows[1] + i), v);
+      v = fmaf(wy[2], __ldg(rows[2] + i), v);
+      v = fmaf(wy[3], __ldg(rows[3] + i), v);
+      int xs = i / N, n = i - xs * N;
+      Vs[(xs + 2) * NV + n] = v;
+      if (xs == 0) {
+        Vs[n] = v;
+        Vs[NV + n] = v;
+      }
+      if (xs == s - 1) {
+        Vs[(s + 2) * NV + n] = v;
+        Vs[(s + 3) * NV + n] = v;
+      }
+    }
+    // zero the token padding so the float4 loads of the last group read defined values
+    const int pad = NV - N;
+    for (int i = tid; i < (s + 4) * pad; i += NT) {
+      int c = i / pad, n = N + (i - c * pad);
+      Vs[c * NV + n] = 0.f;
+    }
+  }
+  __syncthreads();
+  // per-column max / min over tokens (one warp per column)
+  {
+    const int lane = tid & 31, w = tid >> 5, nw = NT >> 5;
+    for (int c = w; c < s + 4; c += nw) {
+      float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+      for (int n = lane; n < N; n += 32) {
+        float v = Vs[c * NV + n];
+        mx = fmaxf(mx, v);
+        mn = fminf(mn, v);
+      }
+      mx = warp_max(mx);
+      mn = -warp_max(-mn);
+      if (lane == 0) {
+        vmax[c] = mx;
+        vmin[c] = mn;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. + 3. horizontal pass, softmax over tokens, in-place normalisation
+  const int N4 = N >> 2;
+  for (int X = tid; X < R; X += NT) {
+    float rx = scale * (X + 0.5f) - 0.5f, fx = floorf(rx);
+    float wx[4];
+    cubic_coeffs(rx - fx, wx);
+    const int c0 = (int)fx + 1;   // column of tap 0 in the halo'd array (ix - 1 + 2)
+    float U = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wx[i] *= LOG2E;
+      U += wx[i] > 0.f ? wx[i] * vmax[c0 + i] : wx[i] * vmin[c0 + i];
+    }
+    const float4* v0 = reinterpret_cast<const float4*>(Vs + (size_t)c0 * NV);
+    const float4* v1 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 1) * NV);
+    const float4* v2 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 2) * NV);
+    const float4* v3 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 3) * NV);
+    float* orow = stage + (size_t)X * N;
+    float sum = 0.f;
+#pragma unroll 2
+    for (int g = 0; g < N4; ++g) {
+      float4 a = v0[g], b = v1[g], c = v2[g], d = v3[g];
+      float e0 = ex2_approx(fmaf(wx[3], d.x, fmaf(wx[2], c.x, fmaf(wx[1], b.x, fmaf(wx[0], a.x, -U)))));
+      float e1 = ex2_approx(fmaf(wx[3], d.y, fmaf(wx[2], c.y, fmaf(wx[1], b.y, fmaf(wx[0], a.y, -U)))));
+      float e2 = ex2_approx(fmaf(wx[3], d.z, fmaf(wx[2], c.z, fmaf(wx[1], b.z, fmaf(wx[0], a.z, -U)))));
+      float e3 = ex2_approx(fmaf(wx[3], d.w, fmaf(wx[2], c.w, fmaf(wx[1], b.w, fmaf(wx[0], a.w, -U)))));
+      orow[4 * g] = e0;
+      orow[4 * g + 1] = e1;
+      orow[4 * g + 2] = e2;
+      orow[4 * g + 3] = e3;
+      sum += (e0 + e1) + (e2 + e3);
+    }
+    for (int n = N4 * 4; n < N; ++n) {
+      float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                fmaf(wx[1], Vs[(c0 + 1) * NV + n], fmaf(wx[0], Vs[c0 * NV + n], -U))));
+      float e = ex2_approx(x);
+      orow[n] = e;
+      sum += e;
+    }
+    if (!(sum > 1e-30f) || !(sum < 1e30f)) {
+      // the bound was too loose (or not finite): redo this pixel with the exact max
+      float m = -CUDART_INF_F;
+      for (int n = 0; n < N; ++n) {
+        float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                  fmaf(wx[1], Vs[(c0 + 1) * NV + n], wx[0] * Vs[c0 * NV + n])));
+        orow[n] = x;
+        m = fmaxf(m, x);
+      }
+      sum = 0.f;
+      for (int n = 0; n < N; ++n) {
+        float e = exp2f(orow[n] - m);
+        orow[n] = e;
+        sum += e;
+      }
+    }
+    const float inv = 1.f / sum;
+#pragma unroll 4
+    for (int n = 0; n < N; ++n) orow[n] *= inv;
+  }
+  // ---- bulk store of the row: generic-proxy writes -> async proxy, then one thread drives the copy engine
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)((size_t)R * N * sizeof(float));
+    char* dst = reinterpret_cast<char*>(probs + ((size_t)h * R + Y) * R * N);
+    uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
+    for (uint32_t off = 0; off < bytes; off += 16384u) {
+      uint32_t n = bytes - off < 16384u ? bytes - off : 16384u;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src + off), "r"(n)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the engine's reads
+  }
+}
+
+// Returns SKP_OK with *handled = true when the row kernel ran; *handled = false when the shape does not fit it.
+int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (((size_t)R * N) % 4 != 0 || (reinterpret_cast<uintptr_t>(probs) & 15) != 0) return SKP_OK;   // 16-byte rows for the bulk copy
+  int Np4 = (N + 3) & ~3;
+  int NV = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;   // NV/4 odd: distinct columns land in distinct bank groups
+  size_t floats = (((size_t)R * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 2 * (size_t)(s + 4);
+  size_t bytes = floats * sizeof(float);
+  if (bytes > 200 * 1024) return SKP_OK;
+  static size_t configured = 0;
+  if (bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(capture_store_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("capture_store_row: smem attr: %s", cudaGetErrorString(e));
+      return SKP_ERR_LAUNCH;
+    }
+    cudaFuncSetAttribute(capture_store_row_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured = bytes;
+  }
+  int threads = ((R + 31) / 32) * 32;
+  if (threads > ROW_MAX_THREADS) threads = ROW_MAX_THREADS;
+  if (threads < 64) threads = 64;
+  dim3 grid(R, heads);
+  capture_store_row_kernel<<<grid, threads, bytes, st>>>(logits, probs, s, N, R, NV);
+  SKP_CHECK_LAUNCH("capture_store_row");
+  *handled = true;
+  return SKP_OK;
+}
+
+}  // namespace skp

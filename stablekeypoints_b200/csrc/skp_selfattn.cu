@@ -1,0 +1,701 @@
+// Self-attention core of the frozen SD1.5 trunk (diffusers CrossAttention with context=None: attn1 of every
+// BasicTransformerBlock; the patched forward runs the same code for it, ptp_utils.py:480-506
+// with is_cross == False):   out = softmax(q k^T * scale) v   per head, S = 64..4096 tokens, d = 40/80/160.
+//
+// The captured maps are a softmax of logits that pass through every one of these layers, and their parity budget is
+// 1e-3: plain bf16/fp16 tensor-core attention misses it (measured 7.6e-3 on d context).  So this is a flash-style
+// kernel (no [S,S] score tensor in HBM) whose every contraction is a SPLIT-bf16 product on the tensor cores:
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi);  a.b ~= hi.hi + hi.lo + lo.hi  (fp32 accumulate), which carries
+// ~16 mantissa bits through QK^T, PV and the five contractions of the backward.
+//
+//   sa_split_qkv_kernel : q,k,v fp32 -> six bf16 planes [heads][S][DP] (Q pre-scaled by scale*log2(e), zero padded)
+//   sa_fwd_kernel       : CTA = (q block of 16*NW rows, head); K/V tiles double-buffered with cp.async; S and P live in
+//                         registers (mma.sync m16n8k16 fragments), online softmax in base 2; writes O and the
+//                         log2-sum-exp per row
+//   sa_split_do_kernel  : dO fp32 -> 2 planes + D = rowsum(dO * O)
+//   sa_bwd_dq_kernel    : CTA = q block, loops over K/V tiles:  dQ = scale * (P o (dO V^T - D)) K
+//   sa_bwd_dkv_kernel   : CTA = kv block, loops over Q/dO tiles: dV = P^T dO,  dK = ln2 * (P o (dO V^T - D))^T Q'
+// Two backward kernels (7 contractions instead of 5) keep every accumulator in registers: no atomics, deterministic.
+#include "skp_common.cuh"
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+namespace skp {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+// D[16x8] += A[16x16] * B[16x8], bf16 operands, fp32 accumulate
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// split-bf16 product: c += ah*bh + ah*bl + al*bh (small terms first)
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                     uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma16816(c, al, bh0, bh1);
+  mma16816(c, ah, bl0, bl1);
+  mma16816(c, ah, bh0, bh1);
+}
+
+// (x, y) -> packed bf16 pairs hi and lo with x ~= hi.x + lo.x
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+constexpr int sa_pad(int dp) { return dp + 8; }        // smem row stride (elements): conflict-free ldmatrix
+constexpr int sa_bn(int dp) { return dp > 96 ? 32 : 64; }  // kv rows per staged tile
+
+// rows [row0, row0+ROWS) of a [S][DP] bf16 plane -> smem [ROWS][DP+8]; rows >= S are zero-filled
+template <int ROWS, int DP, int NT>
+__device__ __forceinline__ void sa_load_tile(bf16* smem, const bf16* __restrict__ plane, int row0, int S) {
+  constexpr int CH = DP / 8;
+  for (int i = threadIdx.x; i < ROWS * CH; i += NT) {
+    int r = i / CH, c = i - r * CH;
+    int gr = row0 + r;
+    bool ok = gr < S;
+    cp_async16(smem + r * sa_pad(DP) + c * 8, plane + (size_t)(ok ? gr : 0) * DP + c * 8, ok ? 16 : 0);
+  }
+}
+
+// A fragment (16 rows starting at r0, k columns k0..k0+15) of a row-major smem tile
+template <int DP>
+__device__ __forceinline__ void sa_ld_a(uint32_t (&a)[4], const bf16* tile, int r0, int k0, int lane) {
+  int r = r0 + (lane & 7) + ((lane >> 3) & 1) * 8, k = k0 + (lane >> 4) * 8;
+  ldsm4(a, smem_u32(tile + r * sa_pad(DP) + k));
+}
+// B fragments of TWO adjacent n-tiles (n0..n0+15) for one k16 step from a tile stored [n][k] (k contiguous):
+// b[0],b[1] -> n-tile 0, b[2],b[3] -> n-tile 1
+template <int DP>
+__device__ __forceinline__ void sa_ld_b_nk(uint32_t (&b)[4], const bf16* tile, int n0, int k0, int lane) {
+  int n = n0 + (lane & 7) + (lane >> 4) * 8, k = k0 + ((lane >> 3) & 1) * 8;
+  ldsm4(b, smem_u32(tile + n * sa_pad(DP) + k));
+}
+// same from a tile stored [k][n] (n contiguous), transposed on the fly
+template <int DP>
+__device__ __forceinline__ void sa_ld_b_kn(uint32_t (&b)[4], const bf16* tile, int k0, int n0, int lane) {
+  int k = k0 + (lane & 7) + ((lane >> 3) & 1) * 8, n = n0 + (lane >> 4) * 8;
+  ldsm4t(b, smem_u32(tile + k * sa_pad(DP) + n));
+}
+
+// ---------------------------------------------------------------------------------------------- operand split
+// planes: [6][heads][S][DP]  (Qh, Ql, Kh, Kl, Vh, Vl); Q is multiplied by qscale = scale*log2(e) before the split
+__global__ void sa_split_qkv_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
+                                    const float* __restrict__ v, int64_t ldv, bf16* __restrict__ planes, int S, int heads,
+                                    int d, int DP, float qscale) {
+  const int half = DP / 2;
+  int64_t total = (int64_t)3 * heads * S * half;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c2 = (int)(i % half);
+    int64_t t = i / half;
+    int row = (int)(t % S);
+    t /= S;
+    int h = (int)(t % heads), which = (int)(t / heads);
+    const float* src = which == 0 ? q + (size_t)row * ldq : which == 1 ? k + (size_t)row * ldk : v + (size_t)row * ldv;
+    src += h * d;
+    int c = 2 * c2;
+    float x = c < d ? __ldg(src + c) : 0.f, y = c + 1 < d ? __ldg(src + c + 1) : 0.f;
+    if (which == 0) {
+      x *= qscale;
+      y *= qscale;
+    }
+    uint32_t hi, lo;
+    split2(x, y, hi, lo);
+    size_t plane = (size_t)heads * S * DP;
+    size_t off = ((size_t)h * S + row) * DP + c;
+    *reinterpret_cast<uint32_t*>(planes + (2 * which) * plane + off) = hi;
+    *reinterpret_cast<uint32_t*>(planes + (2 * which + 1) * plane + off) = lo;
+  }
+}
+
+// do_planes: [2][heads][S][DP] (dOh, dOl);  dvec[heads][S] = sum_c dO[row, h*d+c] * O[row, h*d+c].  One warp per (h,row).
+__global__ void sa_split_do_kernel(const float* __restrict__ d_o, int64_t lddo, const float* __restrict__ o, int64_t ldo,
+                                   bf16* __restrict__ do_planes, float* __restrict__ dvec, int S, int heads, int d, int DP) {
+  int lane = threadIdx.x & 31;
+  int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  size_t plane = (size_t)heads * S * DP;
+  for (int64_t i = w; i < (int64_t)heads * S; i += nw) {
+    int h = (int)(i / S), row = (int)(i % S);
+    const float* g = d_o + (size_t)row * lddo + h * d;
+    const float* oo = o + (size_t)row * ldo + h * d;
+    float acc = 0.f;
+    for (int c = 2 * lane; c < DP; c += 64) {
+      float x = c < d ? __ldg(g + c) : 0.f, y = c + 1 < d ? __ldg(g + c + 1) : 0.f;
+      float ox = c < d ? __ldg(oo + c) : 0.f, oy = c + 1 < d ? __ldg(oo + c + 1) : 0.f;
+      acc = fmaf(x, ox, fmaf(y, oy, acc));
+      uint32_t hi, lo;
+      split2(x, y, hi, lo);
+      size_t off = ((size_t)h * S + row) * DP + c;
+      *reinterpret_cast<uint32_t*>(do_planes + off) = hi;
+      *reinterpret_cast<uint32_t*>(do_planes + plane + off) = lo;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dvec[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+template <int DP, int NW>
+__global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict__ planes, float* __restrict__ out,
+                                                         int64_t ldo, float* __restrict__ lse, int S, int heads, int d) {
+  constexpr int BM = 16 * NW, BN = sa_bn(DP), NT = NW * 32, LD = sa_pad(DP);
+  constexpr int NS = BN / 8;    // score n-tiles per warp row-block
+  constexpr int NO = DP / 8;    // output n-tiles
+  extern __shared__ __align__(16) unsigned char sa_smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(sa_smem);   // [2][BM][LD]
+  bf16* KVs = Qs + 2 * BM * LD;                   // [2 stages][4 planes: Kh Kl Vh Vl][BN][LD]
+  const int h = blockIdx.y, q0 = blockIdx.x * BM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const size_t plane = (size_t)heads * S * DP, hoff = (size_t)h * S * DP;
+
+  sa_load_tile<BM, DP, NT>(Qs, planes + hoff, q0, S);
+  sa_load_tile<BM, DP, NT>(Qs + BM * LD, planes + plane + hoff, q0, S);
+  const int ntiles = (S + BN - 1) / BN;
+  auto load_kv = [&](int j, int stage) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      sa_load_tile<BN, DP, NT>(KVs + (stage * 4 + p) * BN * LD, planes + (2 + p) * plane + hoff, j * BN, S);
+  };
+  load_kv(0, 0);
+  cp_async_commit();
+
+  float o[NO][4];
+#pragma unroll
+  for (int i = 0; i < NO; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+
+  for (int j = 0; j < ntiles; ++j) {
+    if (j + 1 < ntiles) {
+      load_kv(j + 1, (j + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const bf16* Kh = KVs + ((j & 1) * 4 + 0) * BN * LD;
+    const bf16* Kl = Kh + BN * LD;
+    const bf16* Vh = Kl + BN * LD;
+    const bf16* Vl = Vh + BN * LD;
+
+    float s[NS][4];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < DP / 16; ++ks) {
+      uint32_t qh[4], ql[4];
+      sa_ld_a<DP>(qh, Qs, warp * 16, ks * 16, lane);
+      sa_ld_a<DP>(ql, Qs + BM * LD, warp * 16, ks * 16, lane);
+#pragma unroll
+      for (int np = 0; np < NS / 2; ++np) {
+        uint32_t bh[4], bl[4];
+        sa_ld_b_nk<DP>(bh, Kh, np * 16, ks * 16, lane);
+        sa_ld_b_nk<DP>(bl, Kl, np * 16, ks * 16, lane);
+        mma3(s[2 * np], qh, ql, bh[0], bh[1], bl[0], bl[1]);
+        mma3(s[2 * np + 1], qh, ql, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+    if ((j + 1) * BN > S) {   // ragged last tile: columns >= S do not exist
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        int c = j * BN + i * 8 + 2 * t;
+        if (c >= S) s[i][0] = s[i][2] = -CUDART_INF_F;
+        if (c + 1 >= S) s[i][1] = s[i][3] = -CUDART_INF_F;
+      }
+    }
+    float t0 = -CUDART_INF_F, t1 = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      t0 = fmaxf(t0, fmaxf(s[i][0], s[i][1]));
+      t1 = fmaxf(t1, fmaxf(s[i][2], s[i][3]));
+    }
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+    float mn0 = fmaxf(m0, t0), mn1 = fmaxf(m1, t1);   // finite: every tile has at least one real column
+    float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    m0 = mn0;
+    m1 = mn1;
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      s[i][0] = exp2f(s[i][0] - mn0);
+      s[i][1] = exp2f(s[i][1] - mn0);
+      s[i][2] = exp2f(s[i][2] - mn1);
+      s[i][3] = exp2f(s[i][3] - mn1);
+      r0 += s[i][0] + s[i][1];
+      r1 += s[i][2] + s[i][3];
+    }
+    l0 = l0 * a0 + r0;
+    l1 = l1 * a1 + r1;
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+      o[i][0] *= a0;
+      o[i][1] *= a0;
+      o[i][2] *= a1;
+      o[i][3] *= a1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < BN / 16; ++kk) {
+      uint32_t ph[4], pl[4];
+      split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+      split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+      split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+      split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+      for (int np = 0; np < NO / 2; ++np) {
+        uint32_t vh[4], vl[4];
+        sa_ld_b_kn<DP>(vh, Vh, kk * 16, np * 16, lane);
+        sa_ld_b_kn<DP>(vl, Vl, kk * 16, np * 16, lane);
+        mma3(o[2 * np], ph, pl, vh[0], vh[1], vl[0], vl[1]);
+        mma3(o[2 * np + 1], ph, pl, vh[2], vh[3], vl[2], vl[3]);
+      }
+    }
+    __syncthreads();   // everyone is done with this stage before it is refilled
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
+#pragma unroll
+  for (int i = 0; i < NO; ++i) {
+    int c = i * 8 + 2 * t;
+    if (c < d) {   // d is even for every model this runs (checked on the host)
+      if (row0 < S) *reinterpret_cast<float2*>(out + (size_t)row0 * ldo + h * d + c) = make_float2(o[i][0] * i0, o[i][1] * i0);
+      if (row1 < S) *reinterpret_cast<float2*>(out + (size_t)row1 * ldo + h * d + c) = make_float2(o[i][2] * i1, o[i][3] * i1);
+    }
+  }
+  if (t == 0) {
+    if (row0 < S) lse[(size_t)h * S + row0] = m0 + log2f(l0);
+    if (row1 < S) lse[(size_t)h * S + row1] = m1 + log2f(l1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward: dQ
+template <int DP, int NW>
+__global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ do_planes,
+                                                            const float* __restrict__ lse, const float* __restrict__ dvec,
+                                                            float* __restrict__ dq, int64_t lddq, int S, int heads, int d,
+                                                            float scale) {
+  constexpr int BM = 16 * NW, BN = sa_bn(DP), NT = NW * 32, LD = sa_pad(DP);
+  constexpr int NS = BN / 8, NO = DP / 8;
+  extern __shared__ __align__(16) unsigned char sa_smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(sa_smem);   // [4 planes: Qh Ql dOh dOl][BM][LD]
+  bf16* KVs = Qs + 4 * BM * LD;                   // [2][4][BN][LD]
+  const int h = blockIdx.y, q0 = blockIdx.x * BM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const size_t plane = (size_t)heads * S * DP, hoff = (size_t)h * S * DP;
+
+  sa_load_tile<BM, DP, NT>(Qs, planes + hoff, q0, S);
+  sa_load_tile<BM, DP, NT>(Qs + BM * LD, planes + plane + hoff, q0, S);
+  sa_load_tile<BM, DP, NT>(Qs + 2 * BM * LD, do_planes + hoff, q0, S);
+  sa_load_tile<BM, DP, NT>(Qs + 3 * BM * LD, do_planes + plane + hoff, q0, S);
+  const int ntiles = (S + BN - 1) / BN;
+  auto load_kv = [&](int j, int stage) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      sa_load_tile<BN, DP, NT>(KVs + (stage * 4 + p) * BN * LD, planes + (2 + p) * plane + hoff, j * BN, S);
+  };
+  load_kv(0, 0);
+  cp_async_commit();
+
+  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
+  const float ls0 = row0 < S ? lse[(size_t)h * S + row0] : 0.f, ls1 = row1 < S ? lse[(size_t)h * S + row1] : 0.f;
+  const float dd0 = row0 < S ? dvec[(size_t)h * S + row0] : 0.f, dd1 = row1 < S ? dvec[(size_t)h * S + row1] : 0.f;
+
+  float acc[NO][4];
+#pragma unroll
+  for (int i = 0; i < NO; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  for (int j = 0; j < ntiles; ++j) {
+    if (j + 1 < ntiles) {
+      load_kv(j + 1, (j + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const bf16* Kh = KVs + ((j & 1) * 4 + 0) * BN * LD;
+    const bf16* Kl = Kh + BN * LD;
+    const bf16* Vh = Kl + BN * LD;
+    const bf16* Vl = Vh + BN * LD;
+
+    float s[NS][4], dp[NS][4];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < DP / 16; ++ks) {
+      uint32_t qh[4], ql[4], gh[4], gl[4];
+      sa_ld_a<DP>(qh, Qs, warp * 16, ks * 16, lane);
+      sa_ld_a<DP>(ql, Qs + BM * LD, warp * 16, ks * 16, lane);
+      sa_ld_a<DP>(gh, Qs + 2 * BM * LD, warp * 16, ks * 16, lane);
+      sa_ld_a<DP>(gl, Qs + 3 * BM * LD, warp * 16, ks * 16, lane);
+#pragma unroll
+      for (int np = 0; np < NS / 2; ++np) {
+        uint32_t bh[4], bl[4];
+        sa_ld_b_nk<DP>(bh, Kh, np * 16, ks * 16, lane);
+        sa_ld_b_nk<DP>(bl, Kl, np * 16, ks * 16, lane);
+        mma3(s[2 * np], qh, ql, bh[0], bh[1], bl[0], bl[1]);
+        mma3(s[2 * np + 1], qh, ql, bh[2], bh[3], bl[2], bl[3]);
+        sa_ld_b_nk<DP>(bh, Vh, np * 16, ks * 16, lane);
+        sa_ld_b_nk<DP>(bl, Vl, np * 16, ks * 16, lane);
+        mma3(dp[2 * np], gh, gl, bh[0], bh[1], bl[0], bl[1]);
+        mma3(dp[2 * np + 1], gh, gl, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+    // dS = P o (dP - D), P = exp2(S - lse); columns >= S contribute nothing
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      int c = j * BN + i * 8 + 2 * t;
+      float p0 = c < S ? exp2f(s[i][0] - ls0) : 0.f, p1 = c + 1 < S ? exp2f(s[i][1] - ls0) : 0.f;
+      float p2 = c < S ? exp2f(s[i][2] - ls1) : 0.f, p3 = c + 1 < S ? exp2f(s[i][3] - ls1) : 0.f;
+      s[i][0] = p0 * (dp[i][0] - dd0);
+      s[i][1] = p1 * (dp[i][1] - dd0);
+      s[i][2] = p2 * (dp[i][2] - dd1);
+      s[i][3] = p3 * (dp[i][3] - dd1);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BN / 16; ++kk) {
+      uint32_t ph[4], pl[4];
+      split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+      split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+      split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+      split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+      for (int np = 0; np < NO / 2; ++np) {
+        uint32_t kh[4], kl[4];
+        sa_ld_b_kn<DP>(kh, Kh, kk * 16, np * 16, lane);
+        sa_ld_b_kn<DP>(kl, Kl, kk * 16, np * 16, lane);
+        mma3(acc[2 * np], ph, pl, kh[0], kh[1], kl[0], kl[1]);
+        mma3(acc[2 * np + 1], ph, pl, kh[2], kh[3], kl[2], kl[3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < NO; ++i) {
+    int c = i * 8 + 2 * t;
+    if (c < d) {
+      if (row0 < S) *reinterpret_cast<float2*>(dq + (size_t)row0 * lddq + h * d + c) = make_float2(acc[i][0] * scale, acc[i][1] * scale);
+      if (row1 < S) *reinterpret_cast<float2*>(dq + (size_t)row1 * lddq + h * d + c) = make_float2(acc[i][2] * scale, acc[i][3] * scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward: dK, dV
+// CTA = 16*NW kv rows of one head; loops over Q/dO tiles of QT = 32 rows.  Everything is computed transposed
+// (S^T = K Q'^T, dP^T = V dO^T) so that P^T and dS^T come out of the MMA already in A-fragment layout.
+template <int DP, int NW>
+__global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ do_planes,
+                                                             const float* __restrict__ lse, const float* __restrict__ dvec,
+                                                             float* __restrict__ dk, int64_t lddk, float* __restrict__ dv,
+                                                             int64_t lddv, int S, int heads, int d) {
+  constexpr int BK = 16 * NW, QT = 32, NT = NW * 32, LD = sa_pad(DP);
+  constexpr int NS = QT / 8, NO = DP / 8;
+  extern __shared__ __align__(16) unsigned char sa_smem[];
+  bf16* Ks = reinterpret_cast<bf16*>(sa_smem);   // [4 planes: Kh Kl Vh Vl][BK][LD]
+  bf16* Qt = Ks + 4 * BK * LD;                    // [2 stages][4 planes: Qh Ql dOh dOl][QT][LD]
+  float* stat = reinterpret_cast<float*>(Qt + 2 * 4 * QT * LD);   // [2 stages][2: lse, D][QT]
+  const int h = blockIdx.y, k0 = blockIdx.x * BK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const size_t plane = (size_t)heads * S * DP, hoff = (size_t)h * S * DP;
+
+#pragma unroll
+  for (int p = 0; p < 4; ++p) sa_load_tile<BK, DP, NT>(Ks + p * BK * LD, planes + (2 + p) * plane + hoff, k0, S);
+  const int ntiles = (S + QT - 1) / QT;
+  auto load_q = [&](int j, int stage) {
+    bf16* base = Qt + stage * 4 * QT * LD;
+    sa_load_tile<QT, DP, NT>(base, planes + hoff, j * QT, S);
+    sa_load_tile<QT, DP, NT>(base + QT * LD, planes + plane + hoff, j * QT, S);
+    sa_load_tile<QT, DP, NT>(base + 2 * QT * LD, do_planes + hoff, j * QT, S);
+    sa_load_tile<QT, DP, NT>(base + 3 * QT * LD, do_planes + plane + hoff, j * QT, S);
+    for (int i = threadIdx.x; i < QT; i += NT) {   // plain stores: visible after the __syncthreads below
+      int r = j * QT + i;
+      stat[stage * 2 * QT + i] = r < S ? lse[(size_t)h * S + r] : CUDART_INF_F;   // +inf -> P = 0 for rows >= S
+      stat[stage * 2 * QT + QT + i] = r < S ? dvec[(size_t)h * S + r] : 0.f;
+    }
+  };
+  load_q(0, 0);
+  cp_async_commit();
+
+  float ak[NO][4], av[NO][4];
+#pragma unroll
+  for (int i = 0; i < NO; ++i) {
+    ak[i][0] = ak[i][1] = ak[i][2] = ak[i][3] = 0.f;
+    av[i][0] = av[i][1] = av[i][2] = av[i][3] = 0.f;
+  }
+  const int kr0 = k0 + warp * 16 + g, kr1 = kr0 + 8;
+  const bool kv0 = kr0 < S, kv1 = kr1 < S;
+
+  for (int j = 0; j < ntiles; ++j) {
+    if (j + 1 < ntiles) {
+      load_q(j + 1, (j + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const bf16* Qh = Qt + (j & 1) * 4 * QT * LD;
+    const bf16* Ql = Qh + QT * LD;
+    const bf16* Gh = Ql + QT * LD;
+    const bf16* Gl = Gh + QT * LD;
+    const float* ls = stat + (j & 1) * 2 * QT;
+    const float* dd = ls + QT;
+
+    float s[NS][4], dp[NS][4];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < DP / 16; ++ks) {
+      uint32_t kh[4], kl[4], vh[4], vl[4];
+      sa_ld_a<DP>(kh, Ks, warp * 16, ks * 16, lane);
+      sa_ld_a<DP>(kl, Ks + BK * LD, warp * 16, ks * 16, lane);
+      sa_ld_a<DP>(vh, Ks + 2 * BK * LD, warp * 16, ks * 16, lane);
+      sa_ld_a<DP>(vl, Ks + 3 * BK * LD, warp * 16, ks * 16, lane);
+#pragma unroll
+      for (int np = 0; np < NS / 2; ++np) {
+        uint32_t bh[4], bl[4];
+        sa_ld_b_nk<DP>(bh, Qh, np * 16, ks * 16, lane);
+        sa_ld_b_nk<DP>(bl, Ql, np * 16, ks * 16, lane);
+        mma3(s[2 * np], kh, kl, bh[0], bh[1], bl[0], bl[1]);
+        mma3(s[2 * np + 1], kh, kl, bh[2], bh[3], bl[2], bl[3]);
+        sa_ld_b_nk<DP>(bh, Gh, np * 16, ks * 16, lane);
+        sa_ld_b_nk<DP>(bl, Gl, np * 16, ks * 16, lane);
+        mma3(dp[2 * np], vh, vl, bh[0], bh[1], bl[0], bl[1]);
+        mma3(dp[2 * np + 1], vh, vl, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+    // P^T (kept in s) and dS^T (kept in dp); kv rows >= S are not real keys
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      int c = i * 8 + 2 * t;
+      float lc0 = ls[c], lc1 = ls[c + 1], dc0 = dd[c], dc1 = dd[c + 1];
+      float p0 = kv0 ? exp2f(s[i][0] - lc0) : 0.f, p1 = kv0 ? exp2f(s[i][1] - lc1) : 0.f;
+      float p2 = kv1 ? exp2f(s[i][2] - lc0) : 0.f, p3 = kv1 ? exp2f(s[i][3] - lc1) : 0.f;
+      s[i][0] = p0;
+      s[i][1] = p1;
+      s[i][2] = p2;
+      s[i][3] = p3;
+      dp[i][0] = p0 * (dp[i][0] - dc0);
+      dp[i][1] = p1 * (dp[i][1] - dc1);
+      dp[i][2] = p2 * (dp[i][2] - dc0);
+      dp[i][3] = p3 * (dp[i][3] - dc1);
+    }
+#pragma unroll
+    for (int kk = 0; kk < QT / 16; ++kk) {
+      uint32_t ph[4], pl[4], sh[4], sl[4];
+      split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+      split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+      split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+      split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+      split2(dp[2 * kk][0], dp[2 * kk][1], sh[0], sl[0]);
+      split2(dp[2 * kk][2], dp[2 * kk][3], sh[1], sl[1]);
+      split2(dp[2 * kk + 1][0], dp[2 * kk + 1][1], sh[2], sl[2]);
+      split2(dp[2 * kk + 1][2], dp[2 * kk + 1][3], sh[3], sl[3]);
+#pragma unroll
+      for (int np = 0; np < NO / 2; ++np) {
+        uint32_t bh[4], bl[4];
+        sa_ld_b_kn<DP>(bh, Gh, kk * 16, np * 16, lane);
+        sa_ld_b_kn<DP>(bl, Gl, kk * 16, np * 16, lane);
+        mma3(av[2 * np], ph, pl, bh[0], bh[1], bl[0], bl[1]);
+        mma3(av[2 * np + 1], ph, pl, bh[2], bh[3], bl[2], bl[3]);
+        sa_ld_b_kn<DP>(bh, Qh, kk * 16, np * 16, lane);
+        sa_ld_b_kn<DP>(bl, Ql, kk * 16, np * 16, lane);
+        mma3(ak[2 * np], sh, sl, bh[0], bh[1], bl[0], bl[1]);
+        mma3(ak[2 * np + 1], sh, sl, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+    __syncthreads();
+  }
+  const float ln2 = 0.6931471805599453f;   // Q' carries scale*log2(e): dK = dS^T (scale Q) = ln2 * dS^T Q'
+#pragma unroll
+  for (int i = 0; i < NO; ++i) {
+    int c = i * 8 + 2 * t;
+    if (c < d) {
+      if (kv0) {
+        *reinterpret_cast<float2*>(dk + (size_t)kr0 * lddk + h * d + c) = make_float2(ak[i][0] * ln2, ak[i][1] * ln2);
+        *reinterpret_cast<float2*>(dv + (size_t)kr0 * lddv + h * d + c) = make_float2(av[i][0], av[i][1]);
+      }
+      if (kv1) {
+        *reinterpret_cast<float2*>(dk + (size_t)kr1 * lddk + h * d + c) = make_float2(ak[i][2] * ln2, ak[i][3] * ln2);
+        *reinterpret_cast<float2*>(dv + (size_t)kr1 * lddv + h * d + c) = make_float2(av[i][2], av[i][3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int sa_dp(int d) {
+  const int opts[] = {16, 32, 48, 80, 160};
+  for (int o : opts)
+    if (d <= o) return o;
+  return 0;
+}
+
+template <int DP, int NW>
+static size_t sa_fwd_smem() { return (size_t)(2 * 16 * NW + 2 * 4 * sa_bn(DP)) * sa_pad(DP) * sizeof(bf16); }
+template <int DP, int NW>
+static size_t sa_dq_smem() { return (size_t)(4 * 16 * NW + 2 * 4 * sa_bn(DP)) * sa_pad(DP) * sizeof(bf16); }
+template <int DP, int NW>
+static size_t sa_dkv_smem() { return (size_t)(4 * 16 * NW + 2 * 4 * 32) * sa_pad(DP) * sizeof(bf16) + 2 * 2 * 32 * sizeof(float); }
+
+template <int DP, int NW>
+static cudaError_t sa_launch_fwd(const bf16* planes, float* o, int64_t ldo, float* lse, int S, int heads, int d, cudaStream_t st) {
+  size_t smem = sa_fwd_smem<DP, NW>();
+  static bool configured = false;   // once per instantiation (not a stream operation: legal under graph capture too)
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sa_fwd_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((S + 16 * NW - 1) / (16 * NW), heads);
+  sa_fwd_kernel<DP, NW><<<grid, NW * 32, smem, st>>>(planes, o, ldo, lse, S, heads, d);
+  return cudaSuccess;
+}
+template <int DP, int NW>
+static cudaError_t sa_launch_bwd(const bf16* planes, const bf16* do_planes, const float* lse, const float* dvec, float* dq,
+                                 int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d,
+                                 float scale, cudaStream_t st) {
+  size_t s1 = sa_dq_smem<DP, NW>(), s2 = sa_dkv_smem<DP, NW>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sa_bwd_dq_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sa_bwd_dkv_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((S + 16 * NW - 1) / (16 * NW), heads);
+  sa_bwd_dq_kernel<DP, NW><<<grid, NW * 32, s1, st>>>(planes, do_planes, lse, dvec, dq, lddq, S, heads, d, scale);
+  sa_bwd_dkv_kernel<DP, NW><<<grid, NW * 32, s2, st>>>(planes, do_planes, lse, dvec, dk, lddk, dv, lddv, S, heads, d);
+  return cudaSuccess;
+}
+
+#define SA_DISPATCH(DPV, NWV, CALL)                                  \
+  do {                                                               \
+    if (NWV == 4) {                                                  \
+      switch (DPV) {                                                 \
+        case 16: err = CALL(16, 4); break;                           \
+        case 32: err = CALL(32, 4); break;                           \
+        case 48: err = CALL(48, 4); break;                           \
+        case 80: err = CALL(80, 4); break;                           \
+        default: err = CALL(160, 4); break;                          \
+      }                                                              \
+    } else {                                                         \
+      switch (DPV) {                                                 \
+        case 16: err = CALL(16, 2); break;                           \
+        case 32: err = CALL(32, 2); break;                           \
+        case 48: err = CALL(48, 2); break;                           \
+        case 80: err = CALL(80, 2); break;                           \
+        default: err = CALL(160, 2); break;                          \
+      }                                                              \
+    }                                                                \
+  } while (0)
+
+}  // namespace skp
+
+using namespace skp;
+
+extern "C" int skp_self_attn_dp(int d) { return sa_dp(d); }
+
+extern "C" int skp_self_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                 float* o, int64_t ldo, float* lse, void* planes, int S, int heads, int d, float scale,
+                                 void* stream) {
+  SKP_REQUIRE(q && k && v && o && lse && planes, "skp_self_attn_fwd: null pointer");
+  SKP_REQUIRE(S > 0 && heads > 0 && d > 0 && d % 2 == 0, "skp_self_attn_fwd: bad sizes S=%d heads=%d d=%d (d must be even)", S, heads, d);
+  const int DP = sa_dp(d);
+  if (DP == 0) {
+    set_error("skp_self_attn_fwd: head dim %d > 160 unsupported", d);
+    return SKP_ERR_UNSUPPORTED;
+  }
+  SKP_REQUIRE(ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0, "skp_self_attn_fwd: o must be 8-byte aligned with even ld");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)3 * heads * S * (DP / 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sa_split_qkv_kernel<<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, (bf16*)planes, S, heads, d, DP, scale * 1.4426950408889634f);
+  SKP_CHECK_LAUNCH("sa_split_qkv_kernel");
+  const int NW = S >= 1024 ? 4 : 2;
+  cudaError_t err = cudaSuccess;
+#define SA_FWD(DPV, NWV) sa_launch_fwd<DPV, NWV>((const bf16*)planes, o, ldo, lse, S, heads, d, st)
+  SA_DISPATCH(DP, NW, SA_FWD);
+#undef SA_FWD
+  if (err != cudaSuccess) {
+    set_error("skp_self_attn_fwd: %s", cudaGetErrorString(err));
+    return SKP_ERR_LAUNCH;
+  }
+  SKP_CHECK_LAUNCH("sa_fwd_kernel");
+  return SKP_OK;
+}
+
+extern "C" int skp_self_attn_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse,
+                                 const void* planes, void* do_planes, float* dvec, float* dq, int64_t lddq, float* dk,
+                                 int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale, void* stream) {
+  SKP_REQUIRE(d_o && o && lse && planes && do_planes && dvec && dq && dk && dv, "skp_self_attn_bwd: null pointer");
+  SKP_REQUIRE(S > 0 && heads > 0 && d > 0 && d % 2 == 0, "skp_self_attn_bwd: bad sizes S=%d heads=%d d=%d", S, heads, d);
+  const int DP = sa_dp(d);
+  if (DP == 0) {
+    set_error("skp_self_attn_bwd: head dim %d > 160 unsupported", d);
+    return SKP_ERR_UNSUPPORTED;
+  }
+  SKP_REQUIRE(lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 && ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
+                                                                  reinterpret_cast<uintptr_t>(dv)) & 7) == 0,
+              "skp_self_attn_bwd: dq/dk/dv must be 8-byte aligned with even ld");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t warps = (int64_t)heads * S;
+  int blocks = (int)((warps + 7) / 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sa_split_do_kernel<<<blocks, 256, 0, st>>>(d_o, lddo, o, ldo, (bf16*)do_planes, dvec, S, heads, d, DP);
+  SKP_CHECK_LAUNCH("sa_split_do_kernel");
+  const int NW = S >= 1024 ? 4 : 2;
+  cudaError_t err = cudaSuccess;
+#define SA_BWD(DPV, NWV) \
+  sa_launch_bwd<DPV, NWV>((const bf16*)planes, (const bf16*)do_planes, lse, dvec, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st)
+  SA_DISPATCH(DP, NW, SA_BWD);
+#undef SA_BWD
+  if (err != cudaSuccess) {
+    set_error("skp_self_attn_bwd: %s", cudaGetErrorString(err));
+    return SKP_ERR_LAUNCH;
+  }
+  SKP_CHECK_LAUNCH("sa_bwd kernels");
+  count_launch(1);
+  return SKP_OK;
+}

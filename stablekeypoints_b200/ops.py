@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import check, int_array, lib, ptr, ptr_array, require_cuda, stream
+from ._lib import SkpError, check, int_array, lib, ptr, ptr_array, require_cuda, stream
 
 # "tc": tcgen05 split-bf16 tensor-core GEMM (default); "simt": exact-fp32 FMA GEMM.
 GEMM_IMPL = os.environ.get("SKP_GEMM_IMPL", "tc")
@@ -386,6 +386,54 @@ class _CrossAttnCore(torch.autograd.Function):
 def cross_attn_core(q, k, v, heads: int, scale: float, want_logits: bool = False):
     """(out[S,C], scaled logits[h,S,N]) = softmax(q k^T scale) v per head."""
     return _CrossAttnCore.apply(q, k, v, heads, scale, want_logits)
+
+
+# ----------------------------------------------------------------------------- self-attention core
+SELF_ATTN_MAX_D = 160
+
+
+class _SelfAttnCore(torch.autograd.Function):
+    """softmax(q k^T scale) v per head from the packed projection qkv[S, 3C] (columns q | k | v, head-major inside
+    each): flash-style split-bf16 tensor-core kernels (skp_selfattn.cu); the split operands are kept for backward."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads: int, scale: float):
+        require_cuda(qkv)
+        qkv = _f32c(qkv)
+        s, c3 = qkv.shape
+        c = c3 // 3
+        d = c // heads
+        dp = int(lib().skp_self_attn_dp(d))
+        if dp == 0 or d % 2:
+            raise SkpError(f"self-attention head dim {d} unsupported (even, <= {SELF_ATTN_MAX_D})")
+        o = torch.empty(s, c, dtype=torch.float32, device=qkv.device)
+        lse = torch.empty(heads, s, dtype=torch.float32, device=qkv.device)
+        planes = torch.empty(6 * heads * s * dp, dtype=torch.bfloat16, device=qkv.device)
+        e = qkv.element_size()
+        check(lib().skp_self_attn_fwd(qkv.data_ptr(), c3, qkv.data_ptr() + c * e, c3, qkv.data_ptr() + 2 * c * e, c3,
+                                      ptr(o), c, ptr(lse), ptr(planes), s, heads, d, scale, stream()), "skp_self_attn_fwd")
+        ctx.save_for_backward(o, lse, planes)
+        ctx.meta = (s, c, heads, d, dp, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        o, lse, planes = ctx.saved_tensors
+        s, c, heads, d, dp, scale = ctx.meta
+        d_o = _f32c(d_o)
+        do_planes = torch.empty(2 * heads * s * dp, dtype=torch.bfloat16, device=o.device)
+        dvec = torch.empty(heads, s, dtype=torch.float32, device=o.device)
+        dqkv = torch.empty(s, 3 * c, dtype=torch.float32, device=o.device)
+        base = dqkv.data_ptr()
+        check(lib().skp_self_attn_bwd(ptr(d_o), c, ptr(o), c, ptr(lse), ptr(planes), ptr(do_planes), ptr(dvec),
+                                      base, 3 * c, base + 4 * c, 3 * c, base + 8 * c, 3 * c, s, heads, d, scale, stream()),
+              "skp_self_attn_bwd")
+        return dqkv, None, None
+
+
+def self_attn_core(qkv: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
+    """out[S, C] = softmax(q k^T scale) v per head, qkv = [S, 3C] packed projection (attn1, ptp_utils.py:480-506)."""
+    return _SelfAttnCore.apply(qkv, heads, scale)
 
 
 # ----------------------------------------------------------------------------- capture (attention store)

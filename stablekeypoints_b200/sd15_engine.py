@@ -177,13 +177,15 @@ def synthetic_state_dict(shapes: Dict[str, tuple], device, seed: int, attn_gain:
     return sd
 
 
-# ----------------------------------------------------------------------------- self-attention core (not on the named path)
-SELF_ATTN_DTYPE = os.environ.get("SKP_SELF_ATTN", "fp32")   # "fp32": torch mem-efficient fp32 kernel; "fp16": flash fp16
+# ----------------------------------------------------------------------------- self-attention core
+# "skp" (default): libskp_b200's flash-style split-bf16 tensor-core kernels (skp_selfattn.cu) for every attn1 layer;
+# "fp32" / "fp16": torch SDPA, kept for A/B measurements only (fp16 fails the 1e-3 parity budget).
+SELF_ATTN_DTYPE = os.environ.get("SKP_SELF_ATTN", "skp")
 
 
 def _self_attention_core(q, k, v):
-    """softmax(q k^T / sqrt(d)) v of the self-attention layers (attn1) and the VAE mid-block attention: library SDPA.
-    fp16 runs the flash kernel (fp32 accumulation, 11-bit operands) ~18x faster than the fp32 kernel at S=4096."""
+    """Library SDPA: the A/B alternative for attn1 and, for now, the VAE mid-block attention (one head of 512 channels,
+    wider than the 160 the flash kernel keeps in registers)."""
     if SELF_ATTN_DTYPE == "fp16":
         return F.scaled_dot_product_attention(q.half(), k.half(), v.half()).float()
     return F.scaled_dot_product_attention(q, k, v)
@@ -428,10 +430,14 @@ class UNetEngine:
         t = f"{p}.transformer_blocks.0"
         hdn = ops.gn_linear(x, w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], self.cfg.norm_num_groups, 1e-6, False,
                             self._fw[f"{p}.proj_in"], w[f"{p}.proj_in.bias"])
-        # attn1 (self-attention): projections on the tcgen05 GEMM, softmax(QK^T)V on torch SDPA
+        # attn1 (self-attention): projections on the tcgen05 GEMM, softmax(QK^T)V on the split-bf16 flash kernels
         y = F.layer_norm(hdn, (c,), w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"])
-        qkv = ops.frozen_linear(y, self._fw[f"{t}.attn1.qkv"]).reshape(s, 3, heads, c // heads).permute(1, 2, 0, 3)
-        o = _self_attention_core(qkv[0][None], qkv[1][None], qkv[2][None])[0].permute(1, 0, 2).reshape(s, c)
+        qkv = ops.frozen_linear(y, self._fw[f"{t}.attn1.qkv"])
+        if SELF_ATTN_DTYPE == "skp":
+            o = ops.self_attn_core(qkv, heads, (c // heads) ** -0.5)
+        else:
+            qkv = qkv.reshape(s, 3, heads, c // heads).permute(1, 2, 0, 3)
+            o = _self_attention_core(qkv[0][None], qkv[1][None], qkv[2][None])[0].permute(1, 0, 2).reshape(s, c)
         hdn = ops.frozen_linear(o, self._fw[f"{t}.attn1.to_out.0"], w[f"{t}.attn1.to_out.0.bias"], residual=hdn)
         # attn2 (cross-attention + capture)
         y = F.layer_norm(hdn, (c,), w[f"{t}.norm2.weight"], w[f"{t}.norm2.bias"])

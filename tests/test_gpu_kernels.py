@@ -159,6 +159,31 @@ def test_cross_attn_fwd_bwd(ops, s, n, heads, d):
     assert rel_err(kvc.grad.cpu(), kvr.grad) < 2e-5
 
 
+# ----------------------------------------------------------------------------- self-attention (attn1)
+@pytest.mark.parametrize("s,heads,d", [(4096, 8, 40), (1024, 8, 80), (256, 8, 160), (64, 8, 160), (16, 4, 8), (100, 2, 16),
+                                       (4, 4, 32), (1100, 3, 24), (77, 2, 48)])
+def test_self_attn_fwd_bwd(ops, s, heads, d):
+    """Flash-style split-bf16 kernels vs float64 attention of the same packed [S, 3C] projection (fp32-grade: the
+    softmax sits upstream of every captured map).  Ragged S, padded d and every tile shape are covered."""
+    g = torch.Generator().manual_seed(s + heads + d)
+    c = heads * d
+    qkv = torch.randn(s, 3 * c, generator=g, dtype=torch.float64) * 1.5
+    do = torch.randn(s, c, generator=g, dtype=torch.float64)
+    scale = d ** -0.5
+    ref_in = qkv.clone().requires_grad_(True)
+    q, k, v = (ref_in[:, i * c:(i + 1) * c].reshape(s, heads, d).permute(1, 0, 2) for i in range(3))
+    p = torch.softmax(q @ k.transpose(1, 2) * scale, dim=-1)
+    o_ref = (p @ v).permute(1, 0, 2).reshape(s, c)
+    (o_ref * do).sum().backward()
+    x = cu(qkv.float()).requires_grad_(True)
+    o = ops.self_attn_core(x, heads, scale)
+    (o * cu(do.float())).sum().backward()
+    errs = [rel_err(o.detach().cpu(), o_ref.detach())]
+    errs += [rel_err(x.grad[:, i * c:(i + 1) * c].cpu(), ref_in.grad[:, i * c:(i + 1) * c]) for i in range(3)]   # dq, dk, dv
+    print(f"self-attn S={s} h={heads} d={d}: rel err o/dq/dk/dv = {errs}")
+    assert errs[0] < 5e-5 and max(errs[1:]) < 1e-4, errs
+
+
 # ----------------------------------------------------------------------------- capture
 def _capture_ref(logits, res):
     """softmax_tokens(bicubic_pixels(low-res logits)) -> [h, res*res, N]  (linearity form of ptp_utils.py:513-536)."""
