@@ -119,6 +119,19 @@ int skp_self_attn_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ld
                       const void* planes, void* do_planes, float* dvec, float* dq, int64_t lddq, float* dk,
                       int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale, void* stream);
 
+/* Cross-attention core on the same split-bf16 tensor-core kernels (S queries, N << S keys): the tensor-core
+ * replacement of skp_cross_attn_fwd/bwd.  logits (nullable) receives the scaled scores [heads, S, N] of a captured
+ * layer; lse[heads, S]; q_planes: 2*heads*S*DP bf16, kv_planes: 4*heads*N*DP bf16 (kept for the backward).
+ * Backward: d_logits_extra (nullable, [heads, S, N]) is added to d(sim); dk/dv [N, heads*d] MUST be zero-initialised
+ * (the query axis is split over CTAs and accumulated atomically); do_planes: 2*heads*S*DP bf16; dvec: heads*S floats. */
+int skp_cross_attn_tc_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                          float* o, int64_t ldo, float* lse, float* logits, void* q_planes, void* kv_planes, int S,
+                          int N, int heads, int d, float scale, void* stream);
+int skp_cross_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse,
+                          const void* q_planes, const void* kv_planes, void* do_planes, float* dvec,
+                          const float* d_logits_extra, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                          int64_t lddv, int S, int N, int heads, int d, float scale, void* stream);
+
 /* ------------------------------------------------------------------ attention-store ("capture")
  * ptp_utils.py:508-538: bicubic (align_corners=False, A=-0.75, clamped taps) upsample of the layer
  * input to R x R, to_q, q' k^T * scale, softmax over the TOKEN axis, stored as [heads, R*R, N].

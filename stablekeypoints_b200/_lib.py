@@ -42,6 +42,8 @@ _SIGNATURES: Dict[str, list] = {
     "skp_self_attn_dp": [_I],
     "skp_self_attn_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _F, _P],
     "skp_self_attn_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P],
+    "skp_cross_attn_tc_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "skp_cross_attn_tc_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P],
     "skp_capture_store_fwd": [_P, _P, _I, _I, _I, _I, _P],
     "skp_capture_store_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "skp_capture_mean_fwd": [_P, _P, _I, _P, _I, _I, _I, _P],

@@ -105,21 +105,27 @@ __device__ __forceinline__ void sa_ld_b_kn(uint32_t (&b)[4], const bf16* tile, i
 }
 
 // ---------------------------------------------------------------------------------------------- operand split
-// planes: [6][heads][S][DP]  (Qh, Ql, Kh, Kl, Vh, Vl); Q is multiplied by qscale = scale*log2(e) before the split
+// qp: [2][heads][Sq][DP] (Qh, Ql);  kvp: [4][heads][Skv][DP] (Kh, Kl, Vh, Vl).  Q is multiplied by qscale = scale*log2(e)
+// before the split; columns >= d are zero.
 __global__ void sa_split_qkv_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
-                                    const float* __restrict__ v, int64_t ldv, bf16* __restrict__ planes, int S, int heads,
-                                    int d, int DP, float qscale) {
+                                    const float* __restrict__ v, int64_t ldv, bf16* __restrict__ qp, bf16* __restrict__ kvp,
+                                    int Sq, int Skv, int heads, int d, int DP, float qscale) {
   const int half = DP / 2;
-  int64_t total = (int64_t)3 * heads * S * half;
+  const int64_t nq = (int64_t)heads * Sq, nkv = (int64_t)heads * Skv;
+  const int64_t total = (nq + 2 * nkv) * half;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c2 = (int)(i % half);
+    int c = 2 * (int)(i % half);
     int64_t t = i / half;
-    int row = (int)(t % S);
-    t /= S;
-    int h = (int)(t % heads), which = (int)(t / heads);
+    int which = 0, S = Sq;
+    if (t >= nq) {
+      t -= nq;
+      which = 1 + (int)(t / nkv);
+      t %= nkv;
+      S = Skv;
+    }
+    int h = (int)(t / S), row = (int)(t % S);
     const float* src = which == 0 ? q + (size_t)row * ldq : which == 1 ? k + (size_t)row * ldk : v + (size_t)row * ldv;
     src += h * d;
-    int c = 2 * c2;
     float x = c < d ? __ldg(src + c) : 0.f, y = c + 1 < d ? __ldg(src + c + 1) : 0.f;
     if (which == 0) {
       x *= qscale;
@@ -129,8 +135,9 @@ __global__ void sa_split_qkv_kernel(const float* __restrict__ q, int64_t ldq, co
     split2(x, y, hi, lo);
     size_t plane = (size_t)heads * S * DP;
     size_t off = ((size_t)h * S + row) * DP + c;
-    *reinterpret_cast<uint32_t*>(planes + (2 * which) * plane + off) = hi;
-    *reinterpret_cast<uint32_t*>(planes + (2 * which + 1) * plane + off) = lo;
+    bf16* dst = which == 0 ? qp : kvp + (size_t)(2 * (which - 1)) * plane;
+    *reinterpret_cast<uint32_t*>(dst + off) = hi;
+    *reinterpret_cast<uint32_t*>(dst + plane + off) = lo;
   }
 }
 
@@ -163,8 +170,9 @@ __global__ void sa_split_do_kernel(const float* __restrict__ d_o, int64_t lddo, 
 
 // ---------------------------------------------------------------------------------------------- forward
 template <int DP, int NW>
-__global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict__ planes, float* __restrict__ out,
-                                                         int64_t ldo, float* __restrict__ lse, int S, int heads, int d) {
+__global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ kvp,
+                                                         float* __restrict__ out, int64_t ldo, float* __restrict__ lse,
+                                                         float* __restrict__ lg_out, int Sq, int Skv, int heads, int d) {
   constexpr int BM = 16 * NW, BN = sa_bn(DP), NT = NW * 32, LD = sa_pad(DP);
   constexpr int NS = BN / 8;    // score n-tiles per warp row-block
   constexpr int NO = DP / 8;    // output n-tiles
@@ -173,15 +181,17 @@ __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict_
   bf16* KVs = Qs + 2 * BM * LD;                   // [2 stages][4 planes: Kh Kl Vh Vl][BN][LD]
   const int h = blockIdx.y, q0 = blockIdx.x * BM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const size_t plane = (size_t)heads * S * DP, hoff = (size_t)h * S * DP;
+  const size_t qplane = (size_t)heads * Sq * DP, qoff = (size_t)h * Sq * DP;
+  const size_t plane = (size_t)heads * Skv * DP, hoff = (size_t)h * Skv * DP;
+  const int S = Skv;   // key/value count: masks and tile loop
 
-  sa_load_tile<BM, DP, NT>(Qs, planes + hoff, q0, S);
-  sa_load_tile<BM, DP, NT>(Qs + BM * LD, planes + plane + hoff, q0, S);
+  sa_load_tile<BM, DP, NT>(Qs, qp + qoff, q0, Sq);
+  sa_load_tile<BM, DP, NT>(Qs + BM * LD, qp + qplane + qoff, q0, Sq);
   const int ntiles = (S + BN - 1) / BN;
   auto load_kv = [&](int j, int stage) {
 #pragma unroll
     for (int p = 0; p < 4; ++p)
-      sa_load_tile<BN, DP, NT>(KVs + (stage * 4 + p) * BN * LD, planes + (2 + p) * plane + hoff, j * BN, S);
+      sa_load_tile<BN, DP, NT>(KVs + (stage * 4 + p) * BN * LD, kvp + p * plane + hoff, j * BN, S);
   };
   load_kv(0, 0);
   cp_async_commit();
@@ -220,6 +230,24 @@ __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict_
         sa_ld_b_nk<DP>(bl, Kl, np * 16, ks * 16, lane);
         mma3(s[2 * np], qh, ql, bh[0], bh[1], bl[0], bl[1]);
         mma3(s[2 * np + 1], qh, ql, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+    if (lg_out != nullptr) {   // scaled logits (natural units) for the capture kernels: s holds logits * log2(e)
+      const float ln2 = 0.6931471805599453f;
+      const int ra = q0 + warp * 16 + g, rb = ra + 8;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        int c = j * BN + i * 8 + 2 * t;
+        if (ra < Sq) {
+          float* dst = lg_out + ((size_t)h * Sq + ra) * S + c;
+          if (c < S) dst[0] = s[i][0] * ln2;
+          if (c + 1 < S) dst[1] = s[i][1] * ln2;
+        }
+        if (rb < Sq) {
+          float* dst = lg_out + ((size_t)h * Sq + rb) * S + c;
+          if (c < S) dst[0] = s[i][2] * ln2;
+          if (c + 1 < S) dst[1] = s[i][3] * ln2;
+        }
       }
     }
     if ((j + 1) * BN > S) {   // ragged last tile: columns >= S do not exist
@@ -291,22 +319,23 @@ __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict_
   for (int i = 0; i < NO; ++i) {
     int c = i * 8 + 2 * t;
     if (c < d) {   // d is even for every model this runs (checked on the host)
-      if (row0 < S) *reinterpret_cast<float2*>(out + (size_t)row0 * ldo + h * d + c) = make_float2(o[i][0] * i0, o[i][1] * i0);
-      if (row1 < S) *reinterpret_cast<float2*>(out + (size_t)row1 * ldo + h * d + c) = make_float2(o[i][2] * i1, o[i][3] * i1);
+      if (row0 < Sq) *reinterpret_cast<float2*>(out + (size_t)row0 * ldo + h * d + c) = make_float2(o[i][0] * i0, o[i][1] * i0);
+      if (row1 < Sq) *reinterpret_cast<float2*>(out + (size_t)row1 * ldo + h * d + c) = make_float2(o[i][2] * i1, o[i][3] * i1);
     }
   }
   if (t == 0) {
-    if (row0 < S) lse[(size_t)h * S + row0] = m0 + log2f(l0);
-    if (row1 < S) lse[(size_t)h * S + row1] = m1 + log2f(l1);
+    if (row0 < Sq) lse[(size_t)h * Sq + row0] = m0 + log2f(l0);
+    if (row1 < Sq) lse[(size_t)h * Sq + row1] = m1 + log2f(l1);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- backward: dQ
 template <int DP, int NW>
-__global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ do_planes,
-                                                            const float* __restrict__ lse, const float* __restrict__ dvec,
-                                                            float* __restrict__ dq, int64_t lddq, int S, int heads, int d,
-                                                            float scale) {
+__global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ kvp,
+                                                            const bf16* __restrict__ do_planes, const float* __restrict__ lse,
+                                                            const float* __restrict__ dvec, const float* __restrict__ extra,
+                                                            float* __restrict__ dq, int64_t lddq, int Sq, int Skv, int heads,
+                                                            int d, float scale) {
   constexpr int BM = 16 * NW, BN = sa_bn(DP), NT = NW * 32, LD = sa_pad(DP);
   constexpr int NS = BN / 8, NO = DP / 8;
   extern __shared__ __align__(16) unsigned char sa_smem[];
@@ -314,24 +343,26 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restri
   bf16* KVs = Qs + 4 * BM * LD;                   // [2][4][BN][LD]
   const int h = blockIdx.y, q0 = blockIdx.x * BM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const size_t plane = (size_t)heads * S * DP, hoff = (size_t)h * S * DP;
+  const size_t qplane = (size_t)heads * Sq * DP, qoff = (size_t)h * Sq * DP;
+  const size_t plane = (size_t)heads * Skv * DP, hoff = (size_t)h * Skv * DP;
+  const int S = Skv;
 
-  sa_load_tile<BM, DP, NT>(Qs, planes + hoff, q0, S);
-  sa_load_tile<BM, DP, NT>(Qs + BM * LD, planes + plane + hoff, q0, S);
-  sa_load_tile<BM, DP, NT>(Qs + 2 * BM * LD, do_planes + hoff, q0, S);
-  sa_load_tile<BM, DP, NT>(Qs + 3 * BM * LD, do_planes + plane + hoff, q0, S);
+  sa_load_tile<BM, DP, NT>(Qs, qp + qoff, q0, Sq);
+  sa_load_tile<BM, DP, NT>(Qs + BM * LD, qp + qplane + qoff, q0, Sq);
+  sa_load_tile<BM, DP, NT>(Qs + 2 * BM * LD, do_planes + qoff, q0, Sq);
+  sa_load_tile<BM, DP, NT>(Qs + 3 * BM * LD, do_planes + qplane + qoff, q0, Sq);
   const int ntiles = (S + BN - 1) / BN;
   auto load_kv = [&](int j, int stage) {
 #pragma unroll
     for (int p = 0; p < 4; ++p)
-      sa_load_tile<BN, DP, NT>(KVs + (stage * 4 + p) * BN * LD, planes + (2 + p) * plane + hoff, j * BN, S);
+      sa_load_tile<BN, DP, NT>(KVs + (stage * 4 + p) * BN * LD, kvp + p * plane + hoff, j * BN, S);
   };
   load_kv(0, 0);
   cp_async_commit();
 
   const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
-  const float ls0 = row0 < S ? lse[(size_t)h * S + row0] : 0.f, ls1 = row1 < S ? lse[(size_t)h * S + row1] : 0.f;
-  const float dd0 = row0 < S ? dvec[(size_t)h * S + row0] : 0.f, dd1 = row1 < S ? dvec[(size_t)h * S + row1] : 0.f;
+  const float ls0 = row0 < Sq ? lse[(size_t)h * Sq + row0] : 0.f, ls1 = row1 < Sq ? lse[(size_t)h * Sq + row1] : 0.f;
+  const float dd0 = row0 < Sq ? dvec[(size_t)h * Sq + row0] : 0.f, dd1 = row1 < Sq ? dvec[(size_t)h * Sq + row1] : 0.f;
 
   float acc[NO][4];
 #pragma unroll
@@ -387,6 +418,18 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restri
       s[i][1] = p1 * (dp[i][1] - dd0);
       s[i][2] = p2 * (dp[i][2] - dd1);
       s[i][3] = p3 * (dp[i][3] - dd1);
+      if (extra != nullptr) {   // gradient arriving directly on the scaled logits (captured layers)
+        if (row0 < Sq) {
+          const float* e = extra + ((size_t)h * Sq + row0) * S + c;
+          if (c < S) s[i][0] += __ldg(e);
+          if (c + 1 < S) s[i][1] += __ldg(e + 1);
+        }
+        if (row1 < Sq) {
+          const float* e = extra + ((size_t)h * Sq + row1) * S + c;
+          if (c < S) s[i][2] += __ldg(e);
+          if (c + 1 < S) s[i][3] += __ldg(e + 1);
+        }
+      }
     }
 #pragma unroll
     for (int kk = 0; kk < BN / 16; ++kk) {
@@ -410,8 +453,8 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restri
   for (int i = 0; i < NO; ++i) {
     int c = i * 8 + 2 * t;
     if (c < d) {
-      if (row0 < S) *reinterpret_cast<float2*>(dq + (size_t)row0 * lddq + h * d + c) = make_float2(acc[i][0] * scale, acc[i][1] * scale);
-      if (row1 < S) *reinterpret_cast<float2*>(dq + (size_t)row1 * lddq + h * d + c) = make_float2(acc[i][2] * scale, acc[i][3] * scale);
+      if (row0 < Sq) *reinterpret_cast<float2*>(dq + (size_t)row0 * lddq + h * d + c) = make_float2(acc[i][0] * scale, acc[i][1] * scale);
+      if (row1 < Sq) *reinterpret_cast<float2*>(dq + (size_t)row1 * lddq + h * d + c) = make_float2(acc[i][2] * scale, acc[i][3] * scale);
     }
   }
 }
@@ -420,10 +463,11 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restri
 // CTA = 16*NW kv rows of one head; loops over Q/dO tiles of QT = 32 rows.  Everything is computed transposed
 // (S^T = K Q'^T, dP^T = V dO^T) so that P^T and dS^T come out of the MMA already in A-fragment layout.
 template <int DP, int NW>
-__global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ do_planes,
-                                                             const float* __restrict__ lse, const float* __restrict__ dvec,
+__global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ kvp,
+                                                             const bf16* __restrict__ do_planes, const float* __restrict__ lse,
+                                                             const float* __restrict__ dvec, const float* __restrict__ extra,
                                                              float* __restrict__ dk, int64_t lddk, float* __restrict__ dv,
-                                                             int64_t lddv, int S, int heads, int d) {
+                                                             int64_t lddv, int Sq, int Skv, int heads, int d) {
   constexpr int BK = 16 * NW, QT = 32, NT = NW * 32, LD = sa_pad(DP);
   constexpr int NS = QT / 8, NO = DP / 8;
   extern __shared__ __align__(16) unsigned char sa_smem[];
@@ -432,24 +476,29 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restr
   float* stat = reinterpret_cast<float*>(Qt + 2 * 4 * QT * LD);   // [2 stages][2: lse, D][QT]
   const int h = blockIdx.y, k0 = blockIdx.x * BK;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const size_t plane = (size_t)heads * S * DP, hoff = (size_t)h * S * DP;
+  const size_t qplane = (size_t)heads * Sq * DP, qoff = (size_t)h * Sq * DP;
+  const size_t plane = (size_t)heads * Skv * DP, hoff = (size_t)h * Skv * DP;
+  const int S = Skv;
 
 #pragma unroll
-  for (int p = 0; p < 4; ++p) sa_load_tile<BK, DP, NT>(Ks + p * BK * LD, planes + (2 + p) * plane + hoff, k0, S);
-  const int ntiles = (S + QT - 1) / QT;
+  for (int p = 0; p < 4; ++p) sa_load_tile<BK, DP, NT>(Ks + p * BK * LD, kvp + p * plane + hoff, k0, S);
+  // gridDim.z CTAs share the query axis (cross-attention: few keys, many queries); each takes a contiguous tile range
+  const int ntq = (Sq + QT - 1) / QT;
+  const int per = (ntq + gridDim.z - 1) / gridDim.z;
+  const int jt0 = blockIdx.z * per, jt1 = min(ntq, jt0 + per);
   auto load_q = [&](int j, int stage) {
     bf16* base = Qt + stage * 4 * QT * LD;
-    sa_load_tile<QT, DP, NT>(base, planes + hoff, j * QT, S);
-    sa_load_tile<QT, DP, NT>(base + QT * LD, planes + plane + hoff, j * QT, S);
-    sa_load_tile<QT, DP, NT>(base + 2 * QT * LD, do_planes + hoff, j * QT, S);
-    sa_load_tile<QT, DP, NT>(base + 3 * QT * LD, do_planes + plane + hoff, j * QT, S);
+    sa_load_tile<QT, DP, NT>(base, qp + qoff, j * QT, Sq);
+    sa_load_tile<QT, DP, NT>(base + QT * LD, qp + qplane + qoff, j * QT, Sq);
+    sa_load_tile<QT, DP, NT>(base + 2 * QT * LD, do_planes + qoff, j * QT, Sq);
+    sa_load_tile<QT, DP, NT>(base + 3 * QT * LD, do_planes + qplane + qoff, j * QT, Sq);
     for (int i = threadIdx.x; i < QT; i += NT) {   // plain stores: visible after the __syncthreads below
       int r = j * QT + i;
-      stat[stage * 2 * QT + i] = r < S ? lse[(size_t)h * S + r] : CUDART_INF_F;   // +inf -> P = 0 for rows >= S
-      stat[stage * 2 * QT + QT + i] = r < S ? dvec[(size_t)h * S + r] : 0.f;
+      stat[stage * 2 * QT + i] = r < Sq ? lse[(size_t)h * Sq + r] : CUDART_INF_F;   // +inf -> P = 0 for rows >= Sq
+      stat[stage * 2 * QT + QT + i] = r < Sq ? dvec[(size_t)h * Sq + r] : 0.f;
     }
   };
-  load_q(0, 0);
+  if (jt0 < jt1) load_q(jt0, 0);
   cp_async_commit();
 
   float ak[NO][4], av[NO][4];
@@ -461,9 +510,10 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restr
   const int kr0 = k0 + warp * 16 + g, kr1 = kr0 + 8;
   const bool kv0 = kr0 < S, kv1 = kr1 < S;
 
-  for (int j = 0; j < ntiles; ++j) {
-    if (j + 1 < ntiles) {
-      load_q(j + 1, (j + 1) & 1);
+  for (int jj = jt0; jj < jt1; ++jj) {
+    const int j = jj - jt0;   // stage parity
+    if (jj + 1 < jt1) {
+      load_q(jj + 1, (j + 1) & 1);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -518,6 +568,17 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restr
       dp[i][1] = p1 * (dp[i][1] - dc1);
       dp[i][2] = p2 * (dp[i][2] - dc0);
       dp[i][3] = p3 * (dp[i][3] - dc1);
+      if (extra != nullptr) {   // extra[h, q, kv] read transposed: this thread's (kv row, q column) elements
+        const int qa = jj * QT + c, qb = qa + 1;
+        if (kv0) {
+          if (qa < Sq) dp[i][0] += __ldg(extra + ((size_t)h * Sq + qa) * S + kr0);
+          if (qb < Sq) dp[i][1] += __ldg(extra + ((size_t)h * Sq + qb) * S + kr0);
+        }
+        if (kv1) {
+          if (qa < Sq) dp[i][2] += __ldg(extra + ((size_t)h * Sq + qa) * S + kr1);
+          if (qb < Sq) dp[i][3] += __ldg(extra + ((size_t)h * Sq + qb) * S + kr1);
+        }
+      }
     }
 #pragma unroll
     for (int kk = 0; kk < QT / 16; ++kk) {
@@ -545,18 +606,40 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restr
     }
     __syncthreads();
   }
+  cp_async_wait<0>();   // a CTA with an empty query range still owns in-flight K/V copies
   const float ln2 = 0.6931471805599453f;   // Q' carries scale*log2(e): dK = dS^T (scale Q) = ln2 * dS^T Q'
+  if (gridDim.z == 1) {
 #pragma unroll
-  for (int i = 0; i < NO; ++i) {
-    int c = i * 8 + 2 * t;
-    if (c < d) {
-      if (kv0) {
-        *reinterpret_cast<float2*>(dk + (size_t)kr0 * lddk + h * d + c) = make_float2(ak[i][0] * ln2, ak[i][1] * ln2);
-        *reinterpret_cast<float2*>(dv + (size_t)kr0 * lddv + h * d + c) = make_float2(av[i][0], av[i][1]);
+    for (int i = 0; i < NO; ++i) {
+      int c = i * 8 + 2 * t;
+      if (c < d) {
+        if (kv0) {
+          *reinterpret_cast<float2*>(dk + (size_t)kr0 * lddk + h * d + c) = make_float2(ak[i][0] * ln2, ak[i][1] * ln2);
+          *reinterpret_cast<float2*>(dv + (size_t)kr0 * lddv + h * d + c) = make_float2(av[i][0], av[i][1]);
+        }
+        if (kv1) {
+          *reinterpret_cast<float2*>(dk + (size_t)kr1 * lddk + h * d + c) = make_float2(ak[i][2] * ln2, ak[i][3] * ln2);
+          *reinterpret_cast<float2*>(dv + (size_t)kr1 * lddv + h * d + c) = make_float2(av[i][2], av[i][3]);
+        }
       }
-      if (kv1) {
-        *reinterpret_cast<float2*>(dk + (size_t)kr1 * lddk + h * d + c) = make_float2(ak[i][2] * ln2, ak[i][3] * ln2);
-        *reinterpret_cast<float2*>(dv + (size_t)kr1 * lddv + h * d + c) = make_float2(av[i][2], av[i][3]);
+    }
+  } else {   // query axis split over CTAs: accumulate into the zero-initialised outputs
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+      int c = i * 8 + 2 * t;
+      if (c < d) {
+        if (kv0) {
+          float* a = dk + (size_t)kr0 * lddk + h * d + c;
+          float* b = dv + (size_t)kr0 * lddv + h * d + c;
+          atomicAdd(a, ak[i][0] * ln2); atomicAdd(a + 1, ak[i][1] * ln2);
+          atomicAdd(b, av[i][0]); atomicAdd(b + 1, av[i][1]);
+        }
+        if (kv1) {
+          float* a = dk + (size_t)kr1 * lddk + h * d + c;
+          float* b = dv + (size_t)kr1 * lddv + h * d + c;
+          atomicAdd(a, ak[i][2] * ln2); atomicAdd(a + 1, ak[i][3] * ln2);
+          atomicAdd(b, av[i][2]); atomicAdd(b + 1, av[i][3]);
+        }
       }
     }
   }
@@ -578,7 +661,8 @@ template <int DP, int NW>
 static size_t sa_dkv_smem() { return (size_t)(4 * 16 * NW + 2 * 4 * 32) * sa_pad(DP) * sizeof(bf16) + 2 * 2 * 32 * sizeof(float); }
 
 template <int DP, int NW>
-static cudaError_t sa_launch_fwd(const bf16* planes, float* o, int64_t ldo, float* lse, int S, int heads, int d, cudaStream_t st) {
+static cudaError_t sa_launch_fwd(const bf16* qp, const bf16* kvp, float* o, int64_t ldo, float* lse, float* lg_out, int Sq,
+                                 int Skv, int heads, int d, cudaStream_t st) {
   size_t smem = sa_fwd_smem<DP, NW>();
   static bool configured = false;   // once per instantiation (not a stream operation: legal under graph capture too)
   if (!configured) {
@@ -586,26 +670,38 @@ static cudaError_t sa_launch_fwd(const bf16* planes, float* o, int64_t ldo, floa
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((S + 16 * NW - 1) / (16 * NW), heads);
-  sa_fwd_kernel<DP, NW><<<grid, NW * 32, smem, st>>>(planes, o, ldo, lse, S, heads, d);
+  dim3 grid((Sq + 16 * NW - 1) / (16 * NW), heads);
+  sa_fwd_kernel<DP, NW><<<grid, NW * 32, smem, st>>>(qp, kvp, o, ldo, lse, lg_out, Sq, Skv, heads, d);
   return cudaSuccess;
 }
 template <int DP, int NW>
-static cudaError_t sa_launch_bwd(const bf16* planes, const bf16* do_planes, const float* lse, const float* dvec, float* dq,
-                                 int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d,
-                                 float scale, cudaStream_t st) {
-  size_t s1 = sa_dq_smem<DP, NW>(), s2 = sa_dkv_smem<DP, NW>();
+static cudaError_t sa_launch_dq(const bf16* qp, const bf16* kvp, const bf16* do_planes, const float* lse, const float* dvec,
+                                const float* extra, float* dq, int64_t lddq, int Sq, int Skv, int heads, int d, float scale,
+                                cudaStream_t st) {
+  size_t smem = sa_dq_smem<DP, NW>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sa_bwd_dq_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sa_bwd_dkv_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+    cudaError_t e = cudaFuncSetAttribute(sa_bwd_dq_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((S + 16 * NW - 1) / (16 * NW), heads);
-  sa_bwd_dq_kernel<DP, NW><<<grid, NW * 32, s1, st>>>(planes, do_planes, lse, dvec, dq, lddq, S, heads, d, scale);
-  sa_bwd_dkv_kernel<DP, NW><<<grid, NW * 32, s2, st>>>(planes, do_planes, lse, dvec, dk, lddk, dv, lddv, S, heads, d);
+  dim3 grid((Sq + 16 * NW - 1) / (16 * NW), heads);
+  sa_bwd_dq_kernel<DP, NW><<<grid, NW * 32, smem, st>>>(qp, kvp, do_planes, lse, dvec, extra, dq, lddq, Sq, Skv, heads, d, scale);
+  return cudaSuccess;
+}
+template <int DP, int NW>
+static cudaError_t sa_launch_dkv(const bf16* qp, const bf16* kvp, const bf16* do_planes, const float* lse, const float* dvec,
+                                 const float* extra, float* dk, int64_t lddk, float* dv, int64_t lddv, int Sq, int Skv,
+                                 int heads, int d, int qsplit, cudaStream_t st) {
+  size_t smem = sa_dkv_smem<DP, NW>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sa_bwd_dkv_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((Skv + 16 * NW - 1) / (16 * NW), heads, qsplit);
+  sa_bwd_dkv_kernel<DP, NW><<<grid, NW * 32, smem, st>>>(qp, kvp, do_planes, lse, dvec, extra, dk, lddk, dv, lddv, Sq, Skv, heads, d);
   return cudaSuccess;
 }
 
@@ -630,6 +726,88 @@ static cudaError_t sa_launch_bwd(const bf16* planes, const bf16* do_planes, cons
     }                                                                \
   } while (0)
 
+static int sa_check(const char* who, int Sq, int Skv, int heads, int d, int* DP) {
+  SKP_REQUIRE(Sq > 0 && Skv > 0 && heads > 0 && d > 0 && d % 2 == 0, "%s: bad sizes Sq=%d Skv=%d heads=%d d=%d (d must be even)", who,
+              Sq, Skv, heads, d);
+  *DP = sa_dp(d);
+  if (*DP == 0) {
+    set_error("%s: head dim %d > 160 unsupported", who, d);
+    return SKP_ERR_UNSUPPORTED;
+  }
+  return SKP_OK;
+}
+
+static int sa_forward(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, float* o, int64_t ldo,
+                      float* lse, float* lg_out, bf16* qp, bf16* kvp, int Sq, int Skv, int heads, int d, float scale,
+                      cudaStream_t st) {
+  int DP;
+  int rc = sa_check("attn_flash_fwd", Sq, Skv, heads, d, &DP);
+  if (rc) return rc;
+  SKP_REQUIRE(q && k && v && o && lse && qp && kvp, "attn_flash_fwd: null pointer");
+  SKP_REQUIRE(ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0, "attn_flash_fwd: o must be 8-byte aligned with even ld");
+  int64_t total = (int64_t)heads * (Sq + 2 * (int64_t)Skv) * (DP / 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sa_split_qkv_kernel<<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, qp, kvp, Sq, Skv, heads, d, DP, scale * 1.4426950408889634f);
+  SKP_CHECK_LAUNCH("sa_split_qkv_kernel");
+  const int NW = Sq >= 1024 ? 4 : 2;
+  cudaError_t err = cudaSuccess;
+#define SA_FWD(DPV, NWV) sa_launch_fwd<DPV, NWV>(qp, kvp, o, ldo, lse, lg_out, Sq, Skv, heads, d, st)
+  SA_DISPATCH(DP, NW, SA_FWD);
+#undef SA_FWD
+  if (err != cudaSuccess) {
+    set_error("attn_flash_fwd: %s", cudaGetErrorString(err));
+    return SKP_ERR_LAUNCH;
+  }
+  SKP_CHECK_LAUNCH("sa_fwd_kernel");
+  return SKP_OK;
+}
+
+static int sa_backward(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse, const bf16* qp,
+                       const bf16* kvp, bf16* do_planes, float* dvec, const float* extra, float* dq, int64_t lddq, float* dk,
+                       int64_t lddk, float* dv, int64_t lddv, int Sq, int Skv, int heads, int d, float scale, bool may_split,
+                       cudaStream_t st) {
+  int DP;
+  int rc = sa_check("attn_flash_bwd", Sq, Skv, heads, d, &DP);
+  if (rc) return rc;
+  SKP_REQUIRE(d_o && o && lse && qp && kvp && do_planes && dvec && dq && dk && dv, "attn_flash_bwd: null pointer");
+  SKP_REQUIRE(lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 && ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
+                                                                  reinterpret_cast<uintptr_t>(dv)) & 7) == 0,
+              "attn_flash_bwd: dq/dk/dv must be 8-byte aligned with even ld");
+  int64_t warps = (int64_t)heads * Sq;
+  int blocks = (int)((warps + 7) / 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sa_split_do_kernel<<<blocks, 256, 0, st>>>(d_o, lddo, o, ldo, do_planes, dvec, Sq, heads, d, DP);
+  SKP_CHECK_LAUNCH("sa_split_do_kernel");
+  cudaError_t err = cudaSuccess;
+  const int NWq = Sq >= 1024 ? 4 : 2;
+#define SA_DQ(DPV, NWV) sa_launch_dq<DPV, NWV>(qp, kvp, do_planes, lse, dvec, extra, dq, lddq, Sq, Skv, heads, d, scale, st)
+  SA_DISPATCH(DP, NWq, SA_DQ);
+#undef SA_DQ
+  if (err != cudaSuccess) {
+    set_error("attn_flash_bwd(dq): %s", cudaGetErrorString(err));
+    return SKP_ERR_LAUNCH;
+  }
+  SKP_CHECK_LAUNCH("sa_bwd_dq_kernel");
+  const int NWk = Skv >= 1024 ? 4 : 2;
+  int qsplit = 1;
+  if (may_split) {   // few keys, many queries: share the query axis so that ~2 CTAs per SM exist
+    int ctas = ((Skv + 16 * NWk - 1) / (16 * NWk)) * heads, ntq = (Sq + 31) / 32;
+    qsplit = (2 * 148 + ctas - 1) / ctas;
+    if (qsplit > ntq) qsplit = ntq;
+    if (qsplit < 1) qsplit = 1;
+  }
+#define SA_DKV(DPV, NWV) sa_launch_dkv<DPV, NWV>(qp, kvp, do_planes, lse, dvec, extra, dk, lddk, dv, lddv, Sq, Skv, heads, d, qsplit, st)
+  SA_DISPATCH(DP, NWk, SA_DKV);
+#undef SA_DKV
+  if (err != cudaSuccess) {
+    set_error("attn_flash_bwd(dkv): %s", cudaGetErrorString(err));
+    return SKP_ERR_LAUNCH;
+  }
+  SKP_CHECK_LAUNCH("sa_bwd_dkv_kernel");
+  return SKP_OK;
+}
+
 }  // namespace skp
 
 using namespace skp;
@@ -639,63 +817,34 @@ extern "C" int skp_self_attn_dp(int d) { return sa_dp(d); }
 extern "C" int skp_self_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                                  float* o, int64_t ldo, float* lse, void* planes, int S, int heads, int d, float scale,
                                  void* stream) {
-  SKP_REQUIRE(q && k && v && o && lse && planes, "skp_self_attn_fwd: null pointer");
-  SKP_REQUIRE(S > 0 && heads > 0 && d > 0 && d % 2 == 0, "skp_self_attn_fwd: bad sizes S=%d heads=%d d=%d (d must be even)", S, heads, d);
+  SKP_REQUIRE(planes != nullptr && S > 0 && heads > 0, "skp_self_attn_fwd: null workspace / bad sizes");
   const int DP = sa_dp(d);
-  if (DP == 0) {
-    set_error("skp_self_attn_fwd: head dim %d > 160 unsupported", d);
-    return SKP_ERR_UNSUPPORTED;
-  }
-  SKP_REQUIRE(ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0, "skp_self_attn_fwd: o must be 8-byte aligned with even ld");
-  cudaStream_t st = (cudaStream_t)stream;
-  int64_t total = (int64_t)3 * heads * S * (DP / 2);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  sa_split_qkv_kernel<<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, (bf16*)planes, S, heads, d, DP, scale * 1.4426950408889634f);
-  SKP_CHECK_LAUNCH("sa_split_qkv_kernel");
-  const int NW = S >= 1024 ? 4 : 2;
-  cudaError_t err = cudaSuccess;
-#define SA_FWD(DPV, NWV) sa_launch_fwd<DPV, NWV>((const bf16*)planes, o, ldo, lse, S, heads, d, st)
-  SA_DISPATCH(DP, NW, SA_FWD);
-#undef SA_FWD
-  if (err != cudaSuccess) {
-    set_error("skp_self_attn_fwd: %s", cudaGetErrorString(err));
-    return SKP_ERR_LAUNCH;
-  }
-  SKP_CHECK_LAUNCH("sa_fwd_kernel");
-  return SKP_OK;
+  bf16* qp = (bf16*)planes;
+  return sa_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, nullptr, qp, qp + (size_t)2 * heads * S * DP, S, S, heads, d, scale,
+                    (cudaStream_t)stream);
 }
 
 extern "C" int skp_self_attn_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse,
                                  const void* planes, void* do_planes, float* dvec, float* dq, int64_t lddq, float* dk,
                                  int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale, void* stream) {
-  SKP_REQUIRE(d_o && o && lse && planes && do_planes && dvec && dq && dk && dv, "skp_self_attn_bwd: null pointer");
-  SKP_REQUIRE(S > 0 && heads > 0 && d > 0 && d % 2 == 0, "skp_self_attn_bwd: bad sizes S=%d heads=%d d=%d", S, heads, d);
+  SKP_REQUIRE(planes != nullptr && S > 0 && heads > 0, "skp_self_attn_bwd: null workspace / bad sizes");
   const int DP = sa_dp(d);
-  if (DP == 0) {
-    set_error("skp_self_attn_bwd: head dim %d > 160 unsupported", d);
-    return SKP_ERR_UNSUPPORTED;
-  }
-  SKP_REQUIRE(lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 && ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
-                                                                  reinterpret_cast<uintptr_t>(dv)) & 7) == 0,
-              "skp_self_attn_bwd: dq/dk/dv must be 8-byte aligned with even ld");
-  cudaStream_t st = (cudaStream_t)stream;
-  int64_t warps = (int64_t)heads * S;
-  int blocks = (int)((warps + 7) / 8);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  sa_split_do_kernel<<<blocks, 256, 0, st>>>(d_o, lddo, o, ldo, (bf16*)do_planes, dvec, S, heads, d, DP);
-  SKP_CHECK_LAUNCH("sa_split_do_kernel");
-  const int NW = S >= 1024 ? 4 : 2;
-  cudaError_t err = cudaSuccess;
-#define SA_BWD(DPV, NWV) \
-  sa_launch_bwd<DPV, NWV>((const bf16*)planes, (const bf16*)do_planes, lse, dvec, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st)
-  SA_DISPATCH(DP, NW, SA_BWD);
-#undef SA_BWD
-  if (err != cudaSuccess) {
-    set_error("skp_self_attn_bwd: %s", cudaGetErrorString(err));
-    return SKP_ERR_LAUNCH;
-  }
-  SKP_CHECK_LAUNCH("sa_bwd kernels");
-  count_launch(1);
-  return SKP_OK;
+  const bf16* qp = (const bf16*)planes;
+  return sa_backward(d_o, lddo, o, ldo, lse, qp, qp + (size_t)2 * heads * S * DP, (bf16*)do_planes, dvec, nullptr, dq, lddq, dk,
+                     lddk, dv, lddv, S, S, heads, d, scale, false, (cudaStream_t)stream);
+}
+
+extern "C" int skp_cross_attn_tc_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                     float* o, int64_t ldo, float* lse, float* logits, void* q_planes, void* kv_planes, int S,
+                                     int N, int heads, int d, float scale, void* stream) {
+  return sa_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, logits, (bf16*)q_planes, (bf16*)kv_planes, S, N, heads, d, scale,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int skp_cross_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse,
+                                     const void* q_planes, const void* kv_planes, void* do_planes, float* dvec,
+                                     const float* d_logits_extra, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                                     int64_t lddv, int S, int N, int heads, int d, float scale, void* stream) {
+  return sa_backward(d_o, lddo, o, ldo, lse, (const bf16*)q_planes, (const bf16*)kv_planes, (bf16*)do_planes, dvec,
+                     d_logits_extra, dq, lddq, dk, lddk, dv, lddv, S, N, heads, d, scale, true, (cudaStream_t)stream);
 }

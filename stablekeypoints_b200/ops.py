@@ -383,8 +383,66 @@ class _CrossAttnCore(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
-def cross_attn_core(q, k, v, heads: int, scale: float, want_logits: bool = False):
-    """(out[S,C], scaled logits[h,S,N]) = softmax(q k^T scale) v per head."""
+class _CrossAttnTC(torch.autograd.Function):
+    """Same contract as _CrossAttnCore on the flash-style split-bf16 tensor-core kernels (skp_selfattn.cu): no [h,S,N]
+    tensor unless the layer is captured (want_logits), log-sum-exp saved instead of the probabilities."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float, want_logits: bool):
+        require_cuda(q, k, v)
+        q = _f32c(q)
+        assert k.stride(1) == 1 and v.stride(1) == 1 and k.dtype == torch.float32 and v.dtype == torch.float32
+        s, c = q.shape
+        n = k.shape[0]
+        d = c // heads
+        dp = int(lib().skp_self_attn_dp(d))
+        if dp == 0 or d % 2:
+            raise SkpError(f"cross-attention head dim {d} unsupported on the tensor-core path (even, <= {SELF_ATTN_MAX_D})")
+        dev = q.device
+        o = torch.empty_like(q)
+        lse = torch.empty(heads, s, dtype=torch.float32, device=dev)
+        logits = torch.empty(heads, s, n, dtype=torch.float32, device=dev) if want_logits else None
+        qp = torch.empty(2 * heads * s * dp, dtype=torch.bfloat16, device=dev)
+        kvp = torch.empty(4 * heads * n * dp, dtype=torch.bfloat16, device=dev)
+        check(lib().skp_cross_attn_tc_fwd(ptr(q), c, ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), c, ptr(lse), ptr(logits),
+                                          ptr(qp), ptr(kvp), s, n, heads, d, scale, stream()), "skp_cross_attn_tc_fwd")
+        ctx.save_for_backward(o, lse, qp, kvp)
+        ctx.meta = (s, n, c, heads, d, dp, scale)
+        if logits is None:
+            logits = torch.empty(0, dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(logits)
+        return o, logits
+
+    @staticmethod
+    def backward(ctx, d_o, d_logits):
+        o, lse, qp, kvp = ctx.saved_tensors
+        s, n, c, heads, d, dp, scale = ctx.meta
+        dev = o.device
+        if d_o is None:
+            d_o = torch.zeros_like(o)
+        d_o = _f32c(d_o)
+        extra = _f32c(d_logits) if d_logits is not None else None
+        do_planes = torch.empty(2 * heads * s * dp, dtype=torch.bfloat16, device=dev)
+        dvec = torch.empty(heads, s, dtype=torch.float32, device=dev)
+        dq = torch.empty(s, c, dtype=torch.float32, device=dev)
+        dkv = torch.zeros(2, n, c, dtype=torch.float32, device=dev)
+        check(lib().skp_cross_attn_tc_bwd(ptr(d_o), c, ptr(o), c, ptr(lse), ptr(qp), ptr(kvp), ptr(do_planes), ptr(dvec),
+                                          ptr(extra), ptr(dq), c, ptr(dkv[0]), c, ptr(dkv[1]), c, s, n, heads, d, scale,
+                                          stream()), "skp_cross_attn_tc_bwd")
+        return dq, dkv[0], dkv[1], None, None, None
+
+
+# "tc": split-bf16 tensor-core kernels (default); "simt": the exact-fp32 FMA kernels of skp_attn.cu
+CROSS_ATTN_IMPL = os.environ.get("SKP_CROSS_ATTN", "tc")
+
+
+def cross_attn_core(q, k, v, heads: int, scale: float, want_logits: bool = False, impl: Optional[str] = None):
+    """(out[S,C], scaled logits[h,S,N]) = softmax(q k^T scale) v per head.  The logits tensor is only meaningful when
+    want_logits (captured layers); the tensor-core path returns an empty tensor otherwise."""
+    impl = impl or CROSS_ATTN_IMPL
+    d = q.shape[1] // heads
+    if impl == "tc" and d % 2 == 0 and d <= SELF_ATTN_MAX_D:
+        return _CrossAttnTC.apply(q, k, v, heads, scale, want_logits)
     return _CrossAttnCore.apply(q, k, v, heads, scale, want_logits)
 
 
