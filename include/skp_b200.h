@@ -86,6 +86,20 @@ int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t ldg, int row
                const double* sums, float eps, const float* gamma, const float* beta, int silu, double* bsums,
                float* dx, int64_t ldd, void* stream);
 
+/* ------------------------------------------------------------------ LayerNorm / GEGLU of the transformer blocks
+ * diffusers BasicTransformerBlock: norm1/2/3 feed attn1.qkv, attn2.to_q (ptp_utils.py:483) and
+ * ff.net.0.proj; GEGLU = a * gelu(gate) (exact erf) feeds ff.net.2.  Each is fused with the split-bf16 operand write of
+ * the projection that follows: hi/lo[rows, Kpad] bf16 (Kpad >= C, multiple of 64, zero padded).  C % 4 == 0.
+ * stats[rows, 2] receives (mean, rstd) per row for skp_ln_bwd: dx = d/dx of LayerNorm given g = d/dy (gamma frozen). */
+int skp_ln_split_fwd(const float* x, int64_t ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                     void* hi, void* lo, int Kpad, float* stats, void* stream);
+int skp_ln_bwd(const float* x, int64_t ldx, const float* g, int64_t ldg, int rows, int C, const float* gamma,
+               const float* stats, float* dx, int64_t lddx, void* stream);
+/* proj[rows, 2H] = (a | gate): hi/lo = split(a * gelu(gate));  bwd: dproj[rows, 2H] from g = d/d(a * gelu(gate)). */
+int skp_geglu_split_fwd(const float* proj, int64_t ld, int rows, int H, void* hi, void* lo, int Kpad, void* stream);
+int skp_geglu_bwd(const float* proj, int64_t ld, const float* g, int64_t ldg, int rows, int H, float* dproj, int64_t ldd,
+                  void* stream);
+
 /* ------------------------------------------------------------------ cross-attention core
  * ptp_utils.py:493-506: sim = q k^T * scale; attn = softmax(sim, -1); out = attn v, per head.
  * q,o: [S, heads*d] (ld = heads*d); k,v: [N, heads*d] with leading dims ldk/ldv (slices of the batched

@@ -1,0 +1,16 @@
+#!/bin/bash
+# session 2, call 3: fused LN/GEGLU ops, leaner row attn-store kernel, per-shape GEMM table, ncu of the S=4096 flash fwd
+mkdir -p gpurun_out
+echo "== kernel tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py -q -k "ln_linear or geglu or capture" --timeout 400 2>&1 | tail -5 | cut -c1-250
+echo "== kernel bench"; timeout 300 python scripts/kernel_bench.py --only capture_store_fwd 2>&1 | cut -c1-260
+echo "== full-size parity"; timeout 1200 python -m pytest tests/test_gpu_pipeline.py -q -s -k "full" --timeout 1000 2>&1 | grep -E "full-size|passed|failed|Error|assert" | cut -c1-300 | tail -20
+echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r_bench.json 2> gpurun_out/r_bench.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r_bench.json').read().strip().splitlines()[-1])
+print({k:d.get(k) for k in ('value','ms_per_step','e2e','early_exit_images_per_s_1gpu','roofline','gpu_launches')})
+PY
+echo "== shapes"; timeout 600 python scripts/profile_step.py --shapes gpurun_out/r_shapes.json --table gpurun_out/r_step_table.json 2>&1 | cut -c1-160 | tail -110
+echo "== ncu set full"
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"sa_fwd_kernel<48" --launch-skip 3 -c 1 -o gpurun_out/r_sa_fwd python scripts/kernel_bench.py --only self_attn_fwd --reps 1 > gpurun_out/r_ncu2.log 2>&1; tail -2 gpurun_out/r_ncu2.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:capture_store_row --launch-skip 3 -c 1 -o gpurun_out/r_store_row python scripts/kernel_bench.py --only capture_store_fwd --reps 1 > gpurun_out/r_ncu1.log 2>&1; tail -2 gpurun_out/r_ncu1.log
+ls -la gpurun_out/*.ncu-rep

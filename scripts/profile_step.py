@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--table", default="")
 ap.add_argument("--tokens", type=int, default=77)
 ap.add_argument("--early-exit", action="store_true")
+ap.add_argument("--shapes", default="", help="write a per-(entry point, problem shape) table of one eager step (CUDA events)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 ldm, controllers, _ = optimize_token.load_ldm("cuda:0", "synthetic:0", feature_upsample_res=128, attn_gain=4.0, precision="fp32")
@@ -37,6 +38,16 @@ rid = torch.cuda.nvtx.range_start("skp_step")   # start/end range: process-wide 
 step()
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_end(rid)
+if a.shapes:
+    from stablekeypoints_b200 import _lib
+    _lib.start_profile()
+    step()
+    prof = _lib.stop_profile(by_shape=True)
+    rows = sorted(({"call": k, "calls": len(v), "ms": round(sum(v), 4), "us_each": round(1e3 * sum(v) / len(v), 2)} for k, v in prof.items()),
+                  key=lambda r: -r["ms"])
+    json.dump(rows, open(a.shapes, "w"), indent=1)
+    for r in rows[:60]:
+        print(f"{r['ms']:9.3f} ms  x{r['calls']:4d}  {r['us_each']:9.2f} us  {r['call']}")
 if a.table:
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:

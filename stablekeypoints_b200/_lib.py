@@ -37,6 +37,10 @@ _SIGNATURES: Dict[str, list] = {
     "skp_gn_apply": [_P, _L, _I, _I, _I, _P, _F, _P, _P, _I, _P, _L, _P, _P, _I, _P],
     "skp_gn_im2col3x3_split": [_P, _L, _I, _I, _I, _I, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "skp_gn_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _I, _P, _P, _L, _P],
+    "skp_ln_split_fwd": [_P, _L, _I, _I, _P, _P, _F, _P, _P, _I, _P, _P],
+    "skp_ln_bwd": [_P, _L, _P, _L, _I, _I, _P, _P, _P, _L, _P],
+    "skp_geglu_split_fwd": [_P, _L, _I, _I, _P, _P, _I, _P],
+    "skp_geglu_bwd": [_P, _L, _P, _L, _I, _I, _P, _L, _P],
     "skp_cross_attn_fwd": [_P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_cross_attn_bwd": [_P, _P, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_self_attn_dp": [_I],
@@ -97,10 +101,23 @@ class _Profiled:
             s.record()
             rc = fn(*args)
             e.record()
-            _profile.append((name, s, e))
+            _profile.append((name, s, e, _shape_key(name, args)))
             return rc
 
         return wrapped
+
+
+def _shape_key(name, args):
+    """Problem shape of the GEMM-like entry points (scripts/profile_step.py --shapes)."""
+    if name == "skp_gemm_nt_tc":
+        return "M%d N%d K%d split%d" % (args[7], args[8], args[4], args[13])
+    if name == "skp_conv3x3_tc":
+        return "H%d W%d Cin%d Cout%d split%d" % (args[2], args[3], args[4], args[9], args[14])
+    if name in ("skp_self_attn_fwd", "skp_self_attn_bwd"):
+        return "S%d h%d d%d" % (args[-5], args[-4], args[-3])
+    if name in ("skp_cross_attn_tc_fwd", "skp_cross_attn_tc_bwd"):
+        return "S%d N%d h%d d%d" % (args[-6], args[-5], args[-4], args[-3])
+    return ""
 
 
 def start_profile() -> None:
@@ -108,14 +125,15 @@ def start_profile() -> None:
     _profile = []
 
 
-def stop_profile() -> Dict[str, list]:
-    """Returns {kernel entry point: [ms per call]} and disables profiling."""
+def stop_profile(by_shape: bool = False) -> Dict[str, list]:
+    """Returns {kernel entry point: [ms per call]} (keys get the problem shape appended when by_shape) and disables
+    profiling."""
     global _profile
     rec, _profile = _profile or [], None
     torch.cuda.synchronize()
     out: Dict[str, list] = {}
-    for name, s, e in rec:
-        out.setdefault(name, []).append(s.elapsed_time(e))
+    for name, s, e, key in rec:
+        out.setdefault(f"{name} {key}".strip() if by_shape else name, []).append(s.elapsed_time(e))
     return out
 
 

@@ -4,12 +4,12 @@
 // around getting a full output row out of shared memory with as few instructions per element as possible:
 //
 //   CTA = (output row Y, head h), one thread per output pixel X.
-//   1. vertical pass   V[xs][n] = sum_j wy[j] * L[h, row_j, xs, n]   (s*N coalesced elements, 4 loads each), stored
-//      with 2 replicated halo columns on each side so the horizontal taps never clamp; per-column max/min over tokens.
+//   1. vertical pass   V[xs][n] = sum_j wy[j] * L[h, row_j, xs, n]   (thread = column x 4 tokens, one 128-bit shared
+//      store), with 2 replicated halo columns on each side so the horizontal taps never clamp; M = max |V| of the row.
 //   2. horizontal pass, thread = pixel: x_n = sum_i wx[i] * V[ix-1+i][n] with 128-bit shared loads (4 tokens per load;
 //      lanes of a warp share <= 6 distinct columns -> broadcast, conflict-free because the column stride is an odd
-//      number of float4), e_n = exp2(x_n - U) with U a per-pixel upper bound of max_n x_n built from the column
-//      max/min (no separate max sweep), e_n staged at [X][n] -- exactly the global layout of the row -- while the
+//      number of float4), e_n = exp2(x_n - U) with U = M * sum_i |wx[i]| an upper bound of max_n x_n (no max sweep;
+//      softmax is shift-invariant and fp32 keeps its relative precision), e_n staged at [X][n] -- exactly the global layout of the row -- while the
 //      thread accumulates its own sum (no cross-thread reduction: the thread owns the whole token axis of its pixel).
 //   3. the thread rescales its pixel by 1/sum in place; then ONE bulk asynchronous copy (cp.async.bulk, the TMA
 //      engine) moves the contiguous R*N*4-byte row from shared memory to HBM.
@@ -34,14 +34,14 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
   extern __shared__ __align__(16) unsigned char row_smem[];
   float* stage = reinterpret_cast<float*>(row_smem);                 // [R][N]  (the output row, global layout)
   float* Vs = stage + (((size_t)R * N + 3) & ~(size_t)3);            // [s+4][NV]
-  float* vmax = Vs + (size_t)(s + 4) * NV;                           // [s+4]
-  float* vmin = vmax + (s + 4);                                      // [s+4]
+  float* red = Vs + (size_t)(s + 4) * NV;                            // [32] per-warp max |V|
   const int Y = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, NT = blockDim.x;
   const float scale = (float)s / (float)R;
   const float LOG2E = 1.4426950408889634f;
 
-  // ---- 1. vertical pass
+  // ---- 1. vertical pass: thread = (low-res column xs, group of 4 tokens); one 128-bit shared store per item
+  float amax = 0.f;
   {
     float ry = scale * (Y + 0.5f) - 0.5f, fy = floorf(ry);
     float wy[4];
@@ -54,50 +54,44 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
       r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
       rows[j] = logits + ((size_t)h * s + r) * s * N;
     }
-    const int total = s * N;
-    for (int i = tid; i < total; i += NT) {
-      float v = wy[0] * __ldg(rows[0] + i);
-      v = fmaf(wy[1], __ldg(rows[1] + i), v);
-      v = fmaf(wy[2], __ldg(rows[2] + i), v);
-      v = fmaf(wy[3], __ldg(rows[3] + i), v);
-      int xs = i / N, n = i - xs * N;
-      Vs[(xs + 2) * NV + n] = v;
-      if (xs == 0) {
-        Vs[n] = v;
-        Vs[NV + n] = v;
+    const int NV4 = NV >> 2, items = s * NV4;
+    const float inv_nv4 = 1.f / (float)NV4;
+    for (int i = tid; i < items; i += NT) {
+      int xs = (int)((i + 0.5f) * inv_nv4);          // i / NV4 (exact: the quotient is never within 0.5/NV4 of an integer)
+      int n0 = (i - xs * NV4) << 2;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int n = n0 + k;
+        float a = 0.f;
+        if (n < N) {
+          int o = xs * N + n;
+          a = wy[0] * __ldg(rows[0] + o);
+          a = fmaf(wy[1], __ldg(rows[1] + o), a);
+          a = fmaf(wy[2], __ldg(rows[2] + o), a);
+          a = fmaf(wy[3], __ldg(rows[3] + o), a);
+          amax = fmaxf(amax, fabsf(a));
+        }
+        v[k] = a;   // token padding = 0
+      }
+      float4 q = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(Vs + (xs + 2) * NV + n0) = q;
+      if (xs == 0) {            // replicated halo columns: the horizontal taps never clamp
+        *reinterpret_cast<float4*>(Vs + n0) = q;
+        *reinterpret_cast<float4*>(Vs + NV + n0) = q;
       }
       if (xs == s - 1) {
-        Vs[(s + 2) * NV + n] = v;
-        Vs[(s + 3) * NV + n] = v;
+        *reinterpret_cast<float4*>(Vs + (s + 2) * NV + n0) = q;
+        *reinterpret_cast<float4*>(Vs + (s + 3) * NV + n0) = q;
       }
     }
-    // zero the token padding so the float4 loads of the last group read defined values
-    const int pad = NV - N;
-    for (int i = tid; i < (s + 4) * pad; i += NT) {
-      int c = i / pad, n = N + (i - c * pad);
-      Vs[c * NV + n] = 0.f;
-    }
+    amax = warp_max(amax);
+    if ((tid & 31) == 0) red[tid >> 5] = amax;
   }
   __syncthreads();
-  // per-column max / min over tokens (one warp per column)
-  {
-    const int lane = tid & 31, w = tid >> 5, nw = NT >> 5;
-    for (int c = w; c < s + 4; c += nw) {
-      float mx = -CUDART_INF_F, mn = CUDART_INF_F;
-      for (int n = lane; n < N; n += 32) {
-        float v = Vs[c * NV + n];
-        mx = fmaxf(mx, v);
-        mn = fminf(mn, v);
-      }
-      mx = warp_max(mx);
-      mn = -warp_max(-mn);
-      if (lane == 0) {
-        vmax[c] = mx;
-        vmin[c] = mn;
-      }
-    }
-  }
-  __syncthreads();
+  // M = max |V| over the row's footprint: x_n = sum_i wx[i] V_i[n] <= (sum_i |wx[i]|) * M for every token
+  float M = 0.f;
+  for (int w = 0; w < (NT >> 5); ++w) M = fmaxf(M, red[w]);
 
   // ---- 2. + 3. horizontal pass, softmax over tokens, in-place normalisation
   const int N4 = N >> 2;
@@ -110,15 +104,16 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       wx[i] *= LOG2E;
-      U += wx[i] > 0.f ? wx[i] * vmax[c0 + i] : wx[i] * vmin[c0 + i];
+      U += fabsf(wx[i]);
     }
+    U *= M;
     const float4* v0 = reinterpret_cast<const float4*>(Vs + (size_t)c0 * NV);
     const float4* v1 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 1) * NV);
     const float4* v2 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 2) * NV);
     const float4* v3 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 3) * NV);
     float* orow = stage + (size_t)X * N;
     float sum = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int g = 0; g < N4; ++g) {
       float4 a = v0[g], b = v1[g], c = v2[g], d = v3[g];
       float e0 = ex2_approx(fmaf(wx[3], d.x, fmaf(wx[2], c.x, fmaf(wx[1], b.x, fmaf(wx[0], a.x, -U)))));
@@ -155,7 +150,7 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
       }
     }
     const float inv = 1.f / sum;
-#pragma unroll 4
+#pragma unroll 8
     for (int n = 0; n < N; ++n) orow[n] *= inv;
   }
   // ---- bulk store of the row: generic-proxy writes -> async proxy, then one thread drives the copy engine
@@ -181,7 +176,7 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
   if (((size_t)R * N) % 4 != 0 || (reinterpret_cast<uintptr_t>(probs) & 15) != 0) return SKP_OK;   // 16-byte rows for the bulk copy
   int Np4 = (N + 3) & ~3;
   int NV = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;   // NV/4 odd: distinct columns land in distinct bank groups
-  size_t floats = (((size_t)R * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 2 * (size_t)(s + 4);
+  size_t floats = (((size_t)R * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 32;
   size_t bytes = floats * sizeof(float);
   if (bytes > 200 * 1024) return SKP_OK;
   static size_t configured = 0;

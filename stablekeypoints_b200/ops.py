@@ -332,6 +332,80 @@ def gn_linear(x2d, gamma, beta, groups, eps, silu, fw: FrozenWeight, bias=None, 
     return _GNLinear.apply(x2d, residual, gamma, beta, fw, bias, groups, eps, silu)
 
 
+# ----------------------------------------------------------------------------- LayerNorm / GEGLU fused into the projection
+class _LNLinear(torch.autograd.Function):
+    """y = LayerNorm(x) W^T + bias (+ residual) (BasicTransformerBlock norm1/2/3 -> qkv / to_q / ff.net.0.proj): the
+    normalised rows are written straight as the split-bf16 A operand (skp_rowops.cu)."""
+
+    @staticmethod
+    def forward(ctx, x2d, residual, gamma, beta, fw: FrozenWeight, bias, eps):
+        x2d = _f32c(x2d)
+        rows, c = x2d.shape
+        kp = _pad64(c)
+        hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=x2d.device)
+        lo = torch.empty(rows, kp, dtype=torch.bfloat16, device=x2d.device)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=x2d.device)
+        check(lib().skp_ln_split_fwd(ptr(x2d), x2d.stride(0), rows, c, ptr(gamma), ptr(beta), eps, ptr(hi), ptr(lo), kp, ptr(stats),
+                                     stream()), "skp_ln_split_fwd")
+        ctx.save_for_backward(x2d, stats, gamma)
+        ctx.meta = (fw, residual is not None)
+        return gemm_nt_presplit(hi, lo, rows, fw.w_split, fw.out_features, bias, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, stats, gamma = ctx.saved_tensors
+        fw, has_res = ctx.meta
+        dy = _f32c(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            d_act = gemm_nt(dy, fw.wt, fw.wt_split)
+            dx = torch.empty_like(x2d)
+            check(lib().skp_ln_bwd(ptr(x2d), x2d.stride(0), ptr(d_act), d_act.stride(0), x2d.shape[0], x2d.shape[1], ptr(gamma),
+                                   ptr(stats), ptr(dx), dx.stride(0), stream()), "skp_ln_bwd")
+        dres = dy if (has_res and ctx.needs_input_grad[1]) else None
+        return (dx, dres) + (None,) * 5
+
+
+def ln_linear(x2d, gamma, beta, fw: FrozenWeight, bias=None, residual=None, eps: float = 1e-5):
+    return _LNLinear.apply(x2d, residual, gamma, beta, fw, bias, eps)
+
+
+class _GegluLinear(torch.autograd.Function):
+    """y = (a * gelu(gate)) W^T + bias (+ residual) with proj = (a | gate) (diffusers GEGLU + ff.net.2): the gated
+    activation only exists as the split-bf16 A operand."""
+
+    @staticmethod
+    def forward(ctx, proj, residual, fw: FrozenWeight, bias):
+        proj = _f32c(proj)
+        rows, h2 = proj.shape
+        h = h2 // 2
+        kp = _pad64(h)
+        hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=proj.device)
+        lo = torch.empty(rows, kp, dtype=torch.bfloat16, device=proj.device)
+        check(lib().skp_geglu_split_fwd(ptr(proj), proj.stride(0), rows, h, ptr(hi), ptr(lo), kp, stream()), "skp_geglu_split_fwd")
+        ctx.save_for_backward(proj)
+        ctx.meta = (fw, residual is not None)
+        return gemm_nt_presplit(hi, lo, rows, fw.w_split, fw.out_features, bias, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (proj,) = ctx.saved_tensors
+        fw, has_res = ctx.meta
+        dy = _f32c(dy)
+        dproj = None
+        if ctx.needs_input_grad[0]:
+            d_act = gemm_nt(dy, fw.wt, fw.wt_split)
+            dproj = torch.empty_like(proj)
+            check(lib().skp_geglu_bwd(ptr(proj), proj.stride(0), ptr(d_act), d_act.stride(0), proj.shape[0], proj.shape[1] // 2,
+                                      ptr(dproj), dproj.stride(0), stream()), "skp_geglu_bwd")
+        dres = dy if (has_res and ctx.needs_input_grad[1]) else None
+        return dproj, dres, None, None
+
+
+def geglu_linear(proj, fw: FrozenWeight, bias=None, residual=None):
+    return _GegluLinear.apply(proj, residual, fw, bias)
+
+
 def group_norm_cl(x2d, gamma, beta, groups, eps, silu=False):
     """Plain act(GroupNorm(x)) -> fp32 [rows, C] (forward only; used by tests and no-grad paths)."""
     x2d = _f32c(x2d)

@@ -183,6 +183,10 @@ def synthetic_state_dict(shapes: Dict[str, tuple], device, seed: int, attn_gain:
 SELF_ATTN_DTYPE = os.environ.get("SKP_SELF_ATTN", "skp")
 
 
+# LayerNorm / GEGLU fused into the operand split of the projection that follows (skp_rowops.cu); "0" = torch ops (A/B)
+FUSED_ROWOPS = os.environ.get("SKP_FUSED_ROWOPS", "1") != "0"
+
+
 def _self_attention_core(q, k, v):
     """Library SDPA: the A/B alternative for attn1 and, for now, the VAE mid-block attention (one head of 512 channels,
     wider than the 160 the flash kernel keeps in registers)."""
@@ -363,8 +367,9 @@ class UNetEngine:
         o = o.permute(1, 0, 2).reshape(s, c)
         return F.linear(o, w[f"{p}.to_out.0.weight"], w[f"{p}.to_out.0.bias"])
 
-    def _cross_attention(self, p, y, resid, kv_all, state):
-        """attn2 (ptp_utils.py:480-541) on the hand-written kernels; returns resid + to_out(attn(y, ctx))."""
+    def _cross_attention(self, p, y, resid, kv_all, state, norm=None):
+        """attn2 (ptp_utils.py:480-541) on the hand-written kernels; returns resid + to_out(attn(y, ctx)).
+        norm = (gamma, beta): y is the un-normalised hidden state and LayerNorm is fused into to_q's operand."""
         layer = self._layer_by_prefix[p]
         c, heads = layer.channels, self.cfg.heads
         d = c // heads
@@ -374,7 +379,12 @@ class UNetEngine:
         ctl = self.controller
         capture = (ctl is not None and layer.in_up and s <= self.max_capture_tokens
                    and state["captured"] < self.max_captures)
-        q = ops.frozen_linear(y, self._fw[f"{p}.to_q"])
+        if norm is not None and FUSED_ROWOPS:
+            q = ops.ln_linear(y, norm[0], norm[1], self._fw[f"{p}.to_q"])
+        else:
+            if norm is not None:
+                y = F.layer_norm(y, (c,), norm[0], norm[1])
+            q = ops.frozen_linear(y, self._fw[f"{p}.to_q"])
         o, logits = ops.cross_attn_core(q, k, v, heads, d ** -0.5, want_logits=capture)
         if capture:
             state["captured"] += 1
@@ -430,22 +440,29 @@ class UNetEngine:
         t = f"{p}.transformer_blocks.0"
         hdn = ops.gn_linear(x, w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], self.cfg.norm_num_groups, 1e-6, False,
                             self._fw[f"{p}.proj_in"], w[f"{p}.proj_in.bias"])
-        # attn1 (self-attention): projections on the tcgen05 GEMM, softmax(QK^T)V on the split-bf16 flash kernels
-        y = F.layer_norm(hdn, (c,), w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"])
-        qkv = ops.frozen_linear(y, self._fw[f"{t}.attn1.qkv"])
+        # attn1 (self-attention): LayerNorm fused into the qkv projection's operand, projections on the tcgen05 GEMM,
+        # softmax(QK^T)V on the split-bf16 flash kernels
+        if FUSED_ROWOPS:
+            qkv = ops.ln_linear(hdn, w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"], self._fw[f"{t}.attn1.qkv"])
+        else:
+            qkv = ops.frozen_linear(F.layer_norm(hdn, (c,), w[f"{t}.norm1.weight"], w[f"{t}.norm1.bias"]), self._fw[f"{t}.attn1.qkv"])
         if SELF_ATTN_DTYPE == "skp":
             o = ops.self_attn_core(qkv, heads, (c // heads) ** -0.5)
         else:
             qkv = qkv.reshape(s, 3, heads, c // heads).permute(1, 2, 0, 3)
             o = _self_attention_core(qkv[0][None], qkv[1][None], qkv[2][None])[0].permute(1, 0, 2).reshape(s, c)
         hdn = ops.frozen_linear(o, self._fw[f"{t}.attn1.to_out.0"], w[f"{t}.attn1.to_out.0.bias"], residual=hdn)
-        # attn2 (cross-attention + capture)
-        y = F.layer_norm(hdn, (c,), w[f"{t}.norm2.weight"], w[f"{t}.norm2.bias"])
-        hdn = self._cross_attention(f"{t}.attn2", y, hdn, kv_all, state)
-        # GEGLU feed-forward
-        y = F.layer_norm(hdn, (c,), w[f"{t}.norm3.weight"], w[f"{t}.norm3.bias"])
-        a, gate = ops.frozen_linear(y, self._fw[f"{t}.ff.net.0.proj"], w[f"{t}.ff.net.0.proj.bias"]).chunk(2, dim=-1)
-        hdn = ops.frozen_linear(a * F.gelu(gate), self._fw[f"{t}.ff.net.2"], w[f"{t}.ff.net.2.bias"], residual=hdn)
+        # attn2 (cross-attention + capture): norm2 fused into to_q's operand
+        hdn = self._cross_attention(f"{t}.attn2", hdn, hdn, kv_all, state, norm=(w[f"{t}.norm2.weight"], w[f"{t}.norm2.bias"]))
+        # GEGLU feed-forward: norm3 fused into ff.net.0.proj's operand, a*gelu(gate) into ff.net.2's
+        if FUSED_ROWOPS:
+            proj = ops.ln_linear(hdn, w[f"{t}.norm3.weight"], w[f"{t}.norm3.bias"], self._fw[f"{t}.ff.net.0.proj"],
+                                 w[f"{t}.ff.net.0.proj.bias"])
+            hdn = ops.geglu_linear(proj, self._fw[f"{t}.ff.net.2"], w[f"{t}.ff.net.2.bias"], residual=hdn)
+        else:
+            y = F.layer_norm(hdn, (c,), w[f"{t}.norm3.weight"], w[f"{t}.norm3.bias"])
+            a, gate = ops.frozen_linear(y, self._fw[f"{t}.ff.net.0.proj"], w[f"{t}.ff.net.0.proj.bias"]).chunk(2, dim=-1)
+            hdn = ops.frozen_linear(a * F.gelu(gate), self._fw[f"{t}.ff.net.2"], w[f"{t}.ff.net.2.bias"], residual=hdn)
         return ops.frozen_linear(hdn, self._fw[f"{p}.proj_out"], w[f"{p}.proj_out.bias"], residual=x)
 
     def _forward_cl(self, sample, tb, kv_all, state):

@@ -124,6 +124,47 @@ def test_groupnorm_fused_ops_vs_torch(ops, h, w, c, cout, groups, silu):
     assert rel_err(x1.grad.cpu(), cl(g1)) < 10 * tol
 
 
+# ----------------------------------------------------------------------------- LayerNorm / GEGLU fused projections
+@pytest.mark.parametrize("rows,c,n_out", [(4096, 320, 960), (256, 1280, 1280), (64, 1280, 10240), (16, 32, 48), (100, 64, 40)])
+def test_ln_linear_fwd_bwd(ops, rows, c, n_out):
+    g = torch.Generator().manual_seed(rows + c)
+    x = torch.randn(rows, c, generator=g) * 2 + 0.3
+    gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g)
+    w = torch.randn(n_out, c, generator=g) / c ** 0.5
+    b = torch.randn(n_out, generator=g)
+    res = torch.randn(rows, n_out, generator=g)
+    dy = torch.randn(rows, n_out, generator=g)
+    xr = x.double().requires_grad_(True)
+    yr = F.linear(F.layer_norm(xr, (c,), gamma.double(), beta.double()), w.double(), b.double()) + res.double()
+    yr.backward(dy.double())
+    xc = cu(x).requires_grad_(True)
+    y = ops.ln_linear(xc, cu(gamma), cu(beta), ops.FrozenWeight(cu(w)), cu(b), residual=cu(res))
+    y.backward(cu(dy))
+    tol = 3e-5 * max(1.0, (c / 1024) ** 0.5)
+    assert rel_err(y.detach().cpu(), yr.detach()) < tol
+    assert rel_err(xc.grad.cpu(), xr.grad) < 4 * tol
+
+
+@pytest.mark.parametrize("rows,h,n_out", [(4096, 1280, 320), (256, 5120, 1280), (16, 128, 32), (100, 64, 24)])
+def test_geglu_linear_fwd_bwd(ops, rows, h, n_out):
+    g = torch.Generator().manual_seed(rows + h)
+    proj = torch.randn(rows, 2 * h, generator=g) * 1.5
+    w = torch.randn(n_out, h, generator=g) / h ** 0.5
+    b = torch.randn(n_out, generator=g)
+    res = torch.randn(rows, n_out, generator=g)
+    dy = torch.randn(rows, n_out, generator=g)
+    pr = proj.double().requires_grad_(True)
+    a, gate = pr.chunk(2, dim=-1)
+    yr = F.linear(a * F.gelu(gate), w.double(), b.double()) + res.double()
+    yr.backward(dy.double())
+    pc = cu(proj).requires_grad_(True)
+    y = ops.geglu_linear(pc, ops.FrozenWeight(cu(w)), cu(b), residual=cu(res))
+    y.backward(cu(dy))
+    tol = 3e-5 * max(1.0, (h / 1024) ** 0.5)
+    assert rel_err(y.detach().cpu(), yr.detach()) < tol
+    assert rel_err(pc.grad.cpu(), pr.grad) < 4 * tol
+
+
 # ----------------------------------------------------------------------------- cross-attention core
 def _attn_ref(q, k, v, heads, scale, extra_w=None):
     s, c = q.shape
