@@ -3,14 +3,14 @@
 // The 40 MB/layer store is the only HBM traffic that matters (logits <= 2.5 MB, L2-resident), so the kernel is built
 // around getting a full output row out of shared memory with as few instructions per element as possible:
 //
-//   CTA = (output row Y, head h), one thread per output pixel X.
+//   CTA = (output row Y, head h), two threads per output pixel X (each owns half of the token axis).
 //   1. vertical pass   V[xs][n] = sum_j wy[j] * L[h, row_j, xs, n]   (thread = column x 4 tokens, one 128-bit shared
 //      store), with 2 replicated halo columns on each side so the horizontal taps never clamp; M = max |V| of the row.
 //   2. horizontal pass, thread = pixel: x_n = sum_i wx[i] * V[ix-1+i][n] with 128-bit shared loads (4 tokens per load;
 //      lanes of a warp share <= 6 distinct columns -> broadcast, conflict-free because the column stride is an odd
 //      number of float4), e_n = exp2(x_n - U) with U = M * sum_i |wx[i]| an upper bound of max_n x_n (no max sweep;
 //      softmax is shift-invariant and fp32 keeps its relative precision), e_n staged at [X][n] -- exactly the global layout of the row -- while the
-//      thread accumulates its own sum (no cross-thread reduction: the thread owns the whole token axis of its pixel).
+//      thread accumulates the sum of its token slice (the two slices of a pixel meet through one shared float each).
 //   3. the thread rescales its pixel by 1/sum in place; then ONE bulk asynchronous copy (cp.async.bulk, the TMA
 //      engine) moves the contiguous R*N*4-byte row from shared memory to HBM.
 // ~12 instructions and ~0.1 shared-memory wavefronts per stored element, against 180 instructions for the tile kernel.
@@ -26,15 +26,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-constexpr int ROW_MAX_THREADS = 256;
+constexpr int ROW_MAX_THREADS = 512;
 
 __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(const float* __restrict__ logits,
                                                                             float* __restrict__ probs, int s, int N, int R,
-                                                                            int NV) {
+                                                                            int NV, int P, int TS) {
   extern __shared__ __align__(16) unsigned char row_smem[];
   float* stage = reinterpret_cast<float*>(row_smem);                 // [R][N]  (the output row, global layout)
   float* Vs = stage + (((size_t)R * N + 3) & ~(size_t)3);            // [s+4][NV]
   float* red = Vs + (size_t)(s + 4) * NV;                            // [32] per-warp max |V|
+  float* psum = red + 32;                                            // [TS][P] partial softmax sums
   const int Y = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, NT = blockDim.x;
   const float scale = (float)s / (float)R;
@@ -93,65 +94,86 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
   float M = 0.f;
   for (int w = 0; w < (NT >> 5); ++w) M = fmaxf(M, red[w]);
 
-  // ---- 2. + 3. horizontal pass, softmax over tokens, in-place normalisation
+  // ---- 2. + 3. horizontal pass, softmax over tokens, in-place normalisation.
+  // P pixel lanes x TS token slices: thread = (pixel X, slice of the token axis); slices meet through psum[].
   const int N4 = N >> 2;
-  for (int X = tid; X < R; X += NT) {
-    float rx = scale * (X + 0.5f) - 0.5f, fx = floorf(rx);
-    float wx[4];
-    cubic_coeffs(rx - fx, wx);
-    const int c0 = (int)fx + 1;   // column of tap 0 in the halo'd array (ix - 1 + 2)
-    float U = 0.f;
+  const int X_lane = tid % P, part = tid / P;
+  const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;      // float4 token groups of this slice
+  const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;     // the last slice also takes the N % 4 tail
+  for (int X0 = 0; X0 < R; X0 += P) {
+    const int X = X0 + X_lane;
+    const bool live = X < R;
+    float wx[4] = {0.f, 0.f, 0.f, 0.f};
+    int c0 = 1;
+    float U = 0.f, sum = 0.f;
+    float* orow = stage + (size_t)(live ? X : 0) * N;
+    if (live) {
+      float rx = scale * (X + 0.5f) - 0.5f, fx = floorf(rx);
+      cubic_coeffs(rx - fx, wx);
+      c0 = (int)fx + 1;   // column of tap 0 in the halo'd array (ix - 1 + 2)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      wx[i] *= LOG2E;
-      U += fabsf(wx[i]);
-    }
-    U *= M;
-    const float4* v0 = reinterpret_cast<const float4*>(Vs + (size_t)c0 * NV);
-    const float4* v1 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 1) * NV);
-    const float4* v2 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 2) * NV);
-    const float4* v3 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 3) * NV);
-    float* orow = stage + (size_t)X * N;
-    float sum = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        wx[i] *= LOG2E;
+        U += fabsf(wx[i]);
+      }
+      U *= M;
+      const float4* v0 = reinterpret_cast<const float4*>(Vs + (size_t)c0 * NV);
+      const float4* v1 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 1) * NV);
+      const float4* v2 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 2) * NV);
+      const float4* v3 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 3) * NV);
 #pragma unroll 4
-    for (int g = 0; g < N4; ++g) {
-      float4 a = v0[g], b = v1[g], c = v2[g], d = v3[g];
-      float e0 = ex2_approx(fmaf(wx[3], d.x, fmaf(wx[2], c.x, fmaf(wx[1], b.x, fmaf(wx[0], a.x, -U)))));
-      float e1 = ex2_approx(fmaf(wx[3], d.y, fmaf(wx[2], c.y, fmaf(wx[1], b.y, fmaf(wx[0], a.y, -U)))));
-      float e2 = ex2_approx(fmaf(wx[3], d.z, fmaf(wx[2], c.z, fmaf(wx[1], b.z, fmaf(wx[0], a.z, -U)))));
-      float e3 = ex2_approx(fmaf(wx[3], d.w, fmaf(wx[2], c.w, fmaf(wx[1], b.w, fmaf(wx[0], a.w, -U)))));
-      orow[4 * g] = e0;
-      orow[4 * g + 1] = e1;
-      orow[4 * g + 2] = e2;
-      orow[4 * g + 3] = e3;
-      sum += (e0 + e1) + (e2 + e3);
-    }
-    for (int n = N4 * 4; n < N; ++n) {
-      float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
-                fmaf(wx[1], Vs[(c0 + 1) * NV + n], fmaf(wx[0], Vs[c0 * NV + n], -U))));
-      float e = ex2_approx(x);
-      orow[n] = e;
-      sum += e;
-    }
-    if (!(sum > 1e-30f) || !(sum < 1e30f)) {
-      // the bound was too loose (or not finite): redo this pixel with the exact max
-      float m = -CUDART_INF_F;
-      for (int n = 0; n < N; ++n) {
-        float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
-                  fmaf(wx[1], Vs[(c0 + 1) * NV + n], wx[0] * Vs[c0 * NV + n])));
-        orow[n] = x;
-        m = fmaxf(m, x);
+      for (int g = g0; g < g1; ++g) {
+        float4 a = v0[g], b = v1[g], c = v2[g], d = v3[g];
+        float e0 = ex2_approx(fmaf(wx[3], d.x, fmaf(wx[2], c.x, fmaf(wx[1], b.x, fmaf(wx[0], a.x, -U)))));
+        float e1 = ex2_approx(fmaf(wx[3], d.y, fmaf(wx[2], c.y, fmaf(wx[1], b.y, fmaf(wx[0], a.y, -U)))));
+        float e2 = ex2_approx(fmaf(wx[3], d.z, fmaf(wx[2], c.z, fmaf(wx[1], b.z, fmaf(wx[0], a.z, -U)))));
+        float e3 = ex2_approx(fmaf(wx[3], d.w, fmaf(wx[2], c.w, fmaf(wx[1], b.w, fmaf(wx[0], a.w, -U)))));
+        orow[4 * g] = e0;
+        orow[4 * g + 1] = e1;
+        orow[4 * g + 2] = e2;
+        orow[4 * g + 3] = e3;
+        sum += (e0 + e1) + (e2 + e3);
       }
-      sum = 0.f;
-      for (int n = 0; n < N; ++n) {
-        float e = exp2f(orow[n] - m);
-        orow[n] = e;
-        sum += e;
-      }
+      if (part == TS - 1)
+        for (int n = N4 * 4; n < N; ++n) {
+          float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                    fmaf(wx[1], Vs[(c0 + 1) * NV + n], fmaf(wx[0], Vs[c0 * NV + n], -U))));
+          float e = ex2_approx(x);
+          orow[n] = e;
+          sum += e;
+        }
+      psum[part * P + X_lane] = sum;
     }
-    const float inv = 1.f / sum;
+    __syncthreads();
+    if (live) {
+      float total = 0.f;
+      for (int q = 0; q < TS; ++q) total += psum[q * P + X_lane];
+      if (!(total > 1e-30f) || !(total < 1e30f)) {
+        // the bound was too loose (or not finite): slice 0 redoes the whole pixel with the exact max, the others stand by
+        if (part == 0) {
+          float m = -CUDART_INF_F;
+          for (int n = 0; n < N; ++n) {
+            float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                      fmaf(wx[1], Vs[(c0 + 1) * NV + n], wx[0] * Vs[c0 * NV + n])));
+            orow[n] = x;
+            m = fmaxf(m, x);
+          }
+          float t = 0.f;
+          for (int n = 0; n < N; ++n) {
+            float e = exp2f(orow[n] - m);
+            orow[n] = e;
+            t += e;
+          }
+          const float inv = 1.f / t;
+          for (int n = 0; n < N; ++n) orow[n] *= inv;
+        }
+      } else {
+        const float inv = 1.f / total;
 #pragma unroll 8
-    for (int n = 0; n < N; ++n) orow[n] *= inv;
+        for (int n = n_lo; n < n_hi; ++n) orow[n] *= inv;
+      }
+    }
+    __syncthreads();   // psum is reused by the next pixel block
   }
   // ---- bulk store of the row: generic-proxy writes -> async proxy, then one thread drives the copy engine
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -176,7 +198,10 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
   if (((size_t)R * N) % 4 != 0 || (reinterpret_cast<uintptr_t>(probs) & 15) != 0) return SKP_OK;   // 16-byte rows for the bulk copy
   int Np4 = (N + 3) & ~3;
   int NV = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;   // NV/4 odd: distinct columns land in distinct bank groups
-  size_t floats = (((size_t)R * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 32;
+  int P = ((R + 31) / 32) * 32;                // pixel lanes (whole warps)
+  if (P > 256) P = 256;
+  const int TS = (N >= 16) ? 2 : 1;            // token slices per pixel: 2 x the warps to hide the LDS->FMA->EX2->STS chain
+  size_t floats = (((size_t)R * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 32 + (size_t)TS * P;
   size_t bytes = floats * sizeof(float);
   if (bytes > 200 * 1024) return SKP_OK;
   static size_t configured = 0;
@@ -189,11 +214,8 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
     cudaFuncSetAttribute(capture_store_row_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = bytes;
   }
-  int threads = ((R + 31) / 32) * 32;
-  if (threads > ROW_MAX_THREADS) threads = ROW_MAX_THREADS;
-  if (threads < 64) threads = 64;
   dim3 grid(R, heads);
-  capture_store_row_kernel<<<grid, threads, bytes, st>>>(logits, probs, s, N, R, NV);
+  capture_store_row_kernel<<<grid, P * TS, bytes, st>>>(logits, probs, s, N, R, NV, P, TS);
   SKP_CHECK_LAUNCH("capture_store_row");
   *handled = true;
   return SKP_OK;

@@ -104,6 +104,83 @@ __device__ __forceinline__ void sa_ld_b_kn(uint32_t (&b)[4], const bf16* tile, i
   ldsm4t(b, smem_u32(tile + k * sa_pad(DP) + n));
 }
 
+// Split-bf16 product of one A fragment pair (hi, lo) with CNT pairs of n-tiles: acc[2i], acc[2i+1] += A . B_i.
+// The three terms are issued term-by-term ACROSS the accumulators (small terms first), so consecutive MMAs never
+// depend on each other: 2*CNT independent tensor instructions sit between two updates of the same accumulator.
+template <int CNT>
+__device__ __forceinline__ void mma3_multi(float (*acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[CNT][4], const uint32_t (&bl)[CNT][4]) {
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    mma16816(acc[2 * i], al, bh[i][0], bh[i][1]);
+    mma16816(acc[2 * i + 1], al, bh[i][2], bh[i][3]);
+  }
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    mma16816(acc[2 * i], ah, bl[i][0], bl[i][1]);
+    mma16816(acc[2 * i + 1], ah, bl[i][2], bl[i][3]);
+  }
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    mma16816(acc[2 * i], ah, bh[i][0], bh[i][1]);
+    mma16816(acc[2 * i + 1], ah, bh[i][2], bh[i][3]);
+  }
+}
+// acc[0 .. 2*PAIRS) += A . B for B tiles stored [n][k] (n0 = first n, k0 = k offset), in chunks of <= 4 pairs
+template <int DP, int PAIRS>
+__device__ __forceinline__ void mma3_nk(float (*acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const bf16* Bh,
+                                        const bf16* Bl, int k0, int lane) {
+#pragma unroll
+  for (int c = 0; c < PAIRS; c += 4) {
+    constexpr int FULL = 4;
+    if (c + FULL <= PAIRS) {
+      uint32_t bh[4][4], bl[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sa_ld_b_nk<DP>(bh[i], Bh, (c + i) * 16, k0, lane);
+        sa_ld_b_nk<DP>(bl[i], Bl, (c + i) * 16, k0, lane);
+      }
+      mma3_multi<4>(acc + 2 * c, ah, al, bh, bl);
+    } else {
+      constexpr int REM = PAIRS % 4 == 0 ? 4 : PAIRS % 4;
+      uint32_t bh[REM][4], bl[REM][4];
+#pragma unroll
+      for (int i = 0; i < REM; ++i) {
+        sa_ld_b_nk<DP>(bh[i], Bh, (c + i) * 16, k0, lane);
+        sa_ld_b_nk<DP>(bl[i], Bl, (c + i) * 16, k0, lane);
+      }
+      mma3_multi<REM>(acc + 2 * c, ah, al, bh, bl);
+    }
+  }
+}
+// same for B tiles stored [k][n] (transposed on the fly): k0 = first k row, n runs over 16*PAIRS columns
+template <int DP, int PAIRS>
+__device__ __forceinline__ void mma3_kn(float (*acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const bf16* Bh,
+                                        const bf16* Bl, int k0, int lane) {
+#pragma unroll
+  for (int c = 0; c < PAIRS; c += 4) {
+    constexpr int FULL = 4;
+    if (c + FULL <= PAIRS) {
+      uint32_t bh[4][4], bl[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sa_ld_b_kn<DP>(bh[i], Bh, k0, (c + i) * 16, lane);
+        sa_ld_b_kn<DP>(bl[i], Bl, k0, (c + i) * 16, lane);
+      }
+      mma3_multi<4>(acc + 2 * c, ah, al, bh, bl);
+    } else {
+      constexpr int REM = PAIRS % 4 == 0 ? 4 : PAIRS % 4;
+      uint32_t bh[REM][4], bl[REM][4];
+#pragma unroll
+      for (int i = 0; i < REM; ++i) {
+        sa_ld_b_kn<DP>(bh[i], Bh, k0, (c + i) * 16, lane);
+        sa_ld_b_kn<DP>(bl[i], Bl, k0, (c + i) * 16, lane);
+      }
+      mma3_multi<REM>(acc + 2 * c, ah, al, bh, bl);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- operand split
 // qp: [2][heads][Sq][DP] (Qh, Ql);  kvp: [4][heads][Skv][DP] (Kh, Kl, Vh, Vl).  Q is multiplied by qscale = scale*log2(e)
 // before the split; columns >= d are zero.
@@ -223,14 +300,7 @@ __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict_
       uint32_t qh[4], ql[4];
       sa_ld_a<DP>(qh, Qs, warp * 16, ks * 16, lane);
       sa_ld_a<DP>(ql, Qs + BM * LD, warp * 16, ks * 16, lane);
-#pragma unroll
-      for (int np = 0; np < NS / 2; ++np) {
-        uint32_t bh[4], bl[4];
-        sa_ld_b_nk<DP>(bh, Kh, np * 16, ks * 16, lane);
-        sa_ld_b_nk<DP>(bl, Kl, np * 16, ks * 16, lane);
-        mma3(s[2 * np], qh, ql, bh[0], bh[1], bl[0], bl[1]);
-        mma3(s[2 * np + 1], qh, ql, bh[2], bh[3], bl[2], bl[3]);
-      }
+      mma3_nk<DP, NS / 2>(s, qh, ql, Kh, Kl, ks * 16, lane);
     }
     if (lg_out != nullptr) {   // scaled logits (natural units) for the capture kernels: s holds logits * log2(e)
       const float ln2 = 0.6931471805599453f;
@@ -298,14 +368,7 @@ __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict_
       split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
       split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
       split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
-#pragma unroll
-      for (int np = 0; np < NO / 2; ++np) {
-        uint32_t vh[4], vl[4];
-        sa_ld_b_kn<DP>(vh, Vh, kk * 16, np * 16, lane);
-        sa_ld_b_kn<DP>(vl, Vl, kk * 16, np * 16, lane);
-        mma3(o[2 * np], ph, pl, vh[0], vh[1], vl[0], vl[1]);
-        mma3(o[2 * np + 1], ph, pl, vh[2], vh[3], vl[2], vl[3]);
-      }
+      mma3_kn<DP, NO / 2>(o, ph, pl, Vh, Vl, kk * 16, lane);
     }
     __syncthreads();   // everyone is done with this stage before it is refilled
   }
@@ -395,18 +458,8 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restri
       sa_ld_a<DP>(ql, Qs + BM * LD, warp * 16, ks * 16, lane);
       sa_ld_a<DP>(gh, Qs + 2 * BM * LD, warp * 16, ks * 16, lane);
       sa_ld_a<DP>(gl, Qs + 3 * BM * LD, warp * 16, ks * 16, lane);
-#pragma unroll
-      for (int np = 0; np < NS / 2; ++np) {
-        uint32_t bh[4], bl[4];
-        sa_ld_b_nk<DP>(bh, Kh, np * 16, ks * 16, lane);
-        sa_ld_b_nk<DP>(bl, Kl, np * 16, ks * 16, lane);
-        mma3(s[2 * np], qh, ql, bh[0], bh[1], bl[0], bl[1]);
-        mma3(s[2 * np + 1], qh, ql, bh[2], bh[3], bl[2], bl[3]);
-        sa_ld_b_nk<DP>(bh, Vh, np * 16, ks * 16, lane);
-        sa_ld_b_nk<DP>(bl, Vl, np * 16, ks * 16, lane);
-        mma3(dp[2 * np], gh, gl, bh[0], bh[1], bl[0], bl[1]);
-        mma3(dp[2 * np + 1], gh, gl, bh[2], bh[3], bl[2], bl[3]);
-      }
+      mma3_nk<DP, NS / 2>(s, qh, ql, Kh, Kl, ks * 16, lane);
+      mma3_nk<DP, NS / 2>(dp, gh, gl, Vh, Vl, ks * 16, lane);
     }
     // dS = P o (dP - D), P = exp2(S - lse); columns >= S contribute nothing
 #pragma unroll
@@ -438,14 +491,7 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restri
       split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
       split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
       split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
-#pragma unroll
-      for (int np = 0; np < NO / 2; ++np) {
-        uint32_t kh[4], kl[4];
-        sa_ld_b_kn<DP>(kh, Kh, kk * 16, np * 16, lane);
-        sa_ld_b_kn<DP>(kl, Kl, kk * 16, np * 16, lane);
-        mma3(acc[2 * np], ph, pl, kh[0], kh[1], kl[0], kl[1]);
-        mma3(acc[2 * np + 1], ph, pl, kh[2], kh[3], kl[2], kl[3]);
-      }
+      mma3_kn<DP, NO / 2>(acc, ph, pl, Kh, Kl, kk * 16, lane);
     }
     __syncthreads();
   }
@@ -540,18 +586,8 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restr
       sa_ld_a<DP>(kl, Ks + BK * LD, warp * 16, ks * 16, lane);
       sa_ld_a<DP>(vh, Ks + 2 * BK * LD, warp * 16, ks * 16, lane);
       sa_ld_a<DP>(vl, Ks + 3 * BK * LD, warp * 16, ks * 16, lane);
-#pragma unroll
-      for (int np = 0; np < NS / 2; ++np) {
-        uint32_t bh[4], bl[4];
-        sa_ld_b_nk<DP>(bh, Qh, np * 16, ks * 16, lane);
-        sa_ld_b_nk<DP>(bl, Ql, np * 16, ks * 16, lane);
-        mma3(s[2 * np], kh, kl, bh[0], bh[1], bl[0], bl[1]);
-        mma3(s[2 * np + 1], kh, kl, bh[2], bh[3], bl[2], bl[3]);
-        sa_ld_b_nk<DP>(bh, Gh, np * 16, ks * 16, lane);
-        sa_ld_b_nk<DP>(bl, Gl, np * 16, ks * 16, lane);
-        mma3(dp[2 * np], vh, vl, bh[0], bh[1], bl[0], bl[1]);
-        mma3(dp[2 * np + 1], vh, vl, bh[2], bh[3], bl[2], bl[3]);
-      }
+      mma3_nk<DP, NS / 2>(s, kh, kl, Qh, Ql, ks * 16, lane);
+      mma3_nk<DP, NS / 2>(dp, vh, vl, Gh, Gl, ks * 16, lane);
     }
     // P^T (kept in s) and dS^T (kept in dp); kv rows >= S are not real keys
 #pragma unroll
@@ -591,18 +627,8 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restr
       split2(dp[2 * kk][2], dp[2 * kk][3], sh[1], sl[1]);
       split2(dp[2 * kk + 1][0], dp[2 * kk + 1][1], sh[2], sl[2]);
       split2(dp[2 * kk + 1][2], dp[2 * kk + 1][3], sh[3], sl[3]);
-#pragma unroll
-      for (int np = 0; np < NO / 2; ++np) {
-        uint32_t bh[4], bl[4];
-        sa_ld_b_kn<DP>(bh, Gh, kk * 16, np * 16, lane);
-        sa_ld_b_kn<DP>(bl, Gl, kk * 16, np * 16, lane);
-        mma3(av[2 * np], ph, pl, bh[0], bh[1], bl[0], bl[1]);
-        mma3(av[2 * np + 1], ph, pl, bh[2], bh[3], bl[2], bl[3]);
-        sa_ld_b_kn<DP>(bh, Qh, kk * 16, np * 16, lane);
-        sa_ld_b_kn<DP>(bl, Ql, kk * 16, np * 16, lane);
-        mma3(ak[2 * np], sh, sl, bh[0], bh[1], bl[0], bl[1]);
-        mma3(ak[2 * np + 1], sh, sl, bh[2], bh[3], bl[2], bl[3]);
-      }
+      mma3_kn<DP, NO / 2>(av, ph, pl, Gh, Gl, kk * 16, lane);
+      mma3_kn<DP, NO / 2>(ak, sh, sl, Qh, Ql, kk * 16, lane);
     }
     __syncthreads();
   }
