@@ -51,6 +51,8 @@ int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, int cols_pad,
 /* splits > 1 runs split-K over blockIdx.z (partial sums in splitk_ws[splits*M*N], then one reduce+epilogue
  * kernel); skp_gemm_nt_tc_plan returns the split count that fills the 148 SMs for a given problem. */
 int skp_gemm_nt_tc_plan(int M, int N, int Kpad);
+/* Tuning hook: force the N tile (64/96/128/160/256; 0 = planner) of skp_gemm_nt_tc / skp_conv3x3_tc (scripts/gemm_sweep.py). */
+void skp_gemm_tc_force_bn(int bn);
 int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad,
                    float* C, int64_t ldc, int M, int N, float alpha, const float* bias,
                    const float* residual, int64_t ldr, int splits, float* splitk_ws, void* stream);
@@ -99,6 +101,11 @@ int skp_ln_bwd(const float* x, int64_t ldx, const float* g, int64_t ldg, int row
 int skp_geglu_split_fwd(const float* proj, int64_t ld, int rows, int H, void* hi, void* lo, int Kpad, void* stream);
 int skp_geglu_bwd(const float* proj, int64_t ld, const float* g, int64_t ldg, int rows, int H, float* dproj, int64_t ldd,
                   void* stream);
+
+/* hi/lo[rows, Kpad] = split-bf16( softmax(x[rows, cols], -1) ), cols % 4 == 0: the probability operand of the dense
+ * (two-GEMM) attention used for the VAE mid-block AttentionBlock (one head of 512 channels; diffusers AutoencoderKL
+ * encoder, reached from ptp_utils.py:299-302). */
+int skp_softmax_split_fwd(const float* x, int64_t ldx, int rows, int cols, void* hi, void* lo, int Kpad, void* stream);
 
 /* ------------------------------------------------------------------ cross-attention core
  * ptp_utils.py:493-506: sim = q k^T * scale; attn = softmax(sim, -1); out = attn v, per head.

@@ -30,6 +30,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_gemm_nt_simt": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P, _P, _L, _P],
     "skp_split_bf16": [_P, _L, _I, _I, _I, _P, _P, _P],
     "skp_gemm_nt_tc_plan": [_I, _I, _I],
+    "skp_gemm_tc_force_bn": [_I],
     "skp_gemm_nt_tc": [_P, _P, _P, _P, _I, _P, _L, _I, _I, _F, _P, _P, _L, _I, _P, _P],
     "skp_im2col3x3_split": [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "skp_conv3x3_tc": [_P, _P, _I, _I, _I, _P, _P, _P, _L, _I, _F, _P, _P, _L, _I, _P, _P],
@@ -41,6 +42,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_ln_bwd": [_P, _L, _P, _L, _I, _I, _P, _P, _P, _L, _P],
     "skp_geglu_split_fwd": [_P, _L, _I, _I, _P, _P, _I, _P],
     "skp_geglu_bwd": [_P, _L, _P, _L, _I, _I, _P, _L, _P],
+    "skp_softmax_split_fwd": [_P, _L, _I, _I, _P, _P, _I, _P],
     "skp_cross_attn_fwd": [_P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_cross_attn_bwd": [_P, _P, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_self_attn_dp": [_I],
@@ -71,7 +73,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_adam_step": [_P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _P],
     "skp_adam_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }
-_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64}
+_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None}
 
 
 def declared_symbols() -> List[str]:

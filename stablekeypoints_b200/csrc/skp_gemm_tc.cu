@@ -474,6 +474,18 @@ extern "C" int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, in
 // instead of a fixed tile.
 struct TcPlan { int bn, splits; };
 
+// Measured-best (BN, K-splits) for the GEMM / implicit-conv problems of the SD1.5 trunk at 512^2 (scripts/gemm_sweep.py on
+// B200, L2 flushed); anything else falls through to the cost model below.  Key: (M, N, K padded to 64).
+struct TunedEntry { int conv, M, N, K; TcPlan plan; };
+static const TunedEntry kTuned[] = {
+#include "skp_gemm_tuned.inc"
+    {0, 0, 0, 0, {0, 0}}};
+static const TcPlan* tuned_plan(bool /*conv: informational*/, int M, int N, int Kpad) {
+  for (const TunedEntry* e = kTuned; e->M != 0; ++e)
+    if (e->M == M && e->N == N && e->K == Kpad) return &e->plan;   // K = 9*Cin never collides with a projection's K
+  return nullptr;
+}
+
 static double plan_cost(int M, int N, int num_kb, int bn, int splits) {
   const long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
   const long ctas = tiles * splits;
@@ -488,14 +500,21 @@ static double plan_cost(int M, int N, int num_kb, int bn, int splits) {
   return t;
 }
 
-static TcPlan plan_tiles(int M, int N, int Kpad, int forced_splits) {
+static int g_force_bn = 0;   // tuning hook (scripts/gemm_sweep.py): 0 = planner's choice
+
+static TcPlan plan_tiles(int M, int N, int Kpad, int forced_splits, bool conv = false) {
   static const int bns[] = {64, 96, 128, 160, 256};
   static const int zs[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
   const int num_kb = Kpad / TC_BK;
   TcPlan best{64, 1};
   double best_t = 1e300;
+  if (g_force_bn == 0) {   // the caller may pass back the split count this planner gave it: keep the tuned tile then
+    const TcPlan* t = tuned_plan(conv, M, N, Kpad);
+    if (t != nullptr && (forced_splits == 0 || forced_splits == t->splits) && (t->splits == 1 || num_kb / t->splits >= 2)) return *t;
+  }
   for (int bn : bns)
     for (int z : zs) {
+      if (g_force_bn > 0 && bn != g_force_bn) continue;
       if (forced_splits > 0 && z != forced_splits) continue;
       if (z > 1 && num_kb / z < 2) continue;
       double t = plan_cost(M, N, num_kb, bn, z);
@@ -504,6 +523,8 @@ static TcPlan plan_tiles(int M, int N, int Kpad, int forced_splits) {
   if (forced_splits > 0 && best_t == 1e300) best = TcPlan{64, forced_splits};
   return best;
 }
+
+extern "C" void skp_gemm_tc_force_bn(int bn) { g_force_bn = bn; }
 
 extern "C" int skp_gemm_nt_tc_plan(int M, int N, int Kpad) {
   if (M <= 0 || N <= 0 || Kpad <= 0) return 1;
@@ -543,7 +564,7 @@ extern "C" int skp_conv3x3_tc(const void* X_hi, const void* X_lo, int H, int W, 
   cudaStream_t st = (cudaStream_t)stream;
   if (splits < 1) splits = 1;
   SKP_REQUIRE(splits == 1 || splitk_ws != nullptr, "conv3x3_tc: split-K needs a workspace of splits*H*W*Cout floats");
-  const TcPlan pl = plan_tiles(H * W, Cout, 9 * Cin, splits);
+  const TcPlan pl = plan_tiles(H * W, Cout, 9 * Cin, splits, true);
   SKP_TC_DISPATCH(launch_conv, pl.bn, X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st)
 }
 

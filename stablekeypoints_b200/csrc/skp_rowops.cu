@@ -134,6 +134,42 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const float* __restrict_
   }
 }
 
+// x[rows, cols] -> hi/lo[rows, Kpad] = split(softmax(x, -1)).  One CTA per row, three sweeps (max, sum, write) over a row
+// that stays in L1/L2.  Used by the dense (GEMM-formulated) attention of the VAE mid block: one head of 512 channels.
+__global__ void __launch_bounds__(256) softmax_split_kernel(const float* __restrict__ x, int64_t ldx, int cols,
+                                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Kpad) {
+  __shared__ float red[32];
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)blockIdx.x * ldx);
+  const int C4 = cols >> 2, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float m = -3.0e38f;
+  for (int i = threadIdx.x; i < C4; i += 256) {
+    float4 v = __ldg(xr + i);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  m = warp_max(m);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < C4; i += 256) {
+    float4 v = __ldg(xr + i);
+    sum += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+  }
+  const float inv = 1.f / block_sum(sum, red);
+  const size_t base = (size_t)blockIdx.x * Kpad;
+  for (int i = threadIdx.x; i < (Kpad >> 2); i += 256) {
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < C4) {
+      float4 v = __ldg(xr + i);
+      y = make_float4(__expf(v.x - m) * inv, __expf(v.y - m) * inv, __expf(v.z - m) * inv, __expf(v.w - m) * inv);
+    }
+    split_store4(hi, lo, base + 4 * (size_t)i, y.x, y.y, y.z, y.w);
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace skp
@@ -186,5 +222,14 @@ extern "C" int skp_geglu_bwd(const float* proj, int64_t ld, const float* g, int6
   if (blocks > 148 * 16) blocks = 148 * 16;
   geglu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(proj, ld, g, ldg, rows, H, dproj, ldd);
   SKP_CHECK_LAUNCH("geglu_bwd_kernel");
+  return SKP_OK;
+}
+
+extern "C" int skp_softmax_split_fwd(const float* x, int64_t ldx, int rows, int cols, void* hi, void* lo, int Kpad, void* stream) {
+  SKP_REQUIRE(x && hi && lo, "skp_softmax_split_fwd: null pointer");
+  SKP_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && Kpad >= cols && Kpad % 4 == 0 && ldx % 4 == 0 && aligned16(x),
+              "skp_softmax_split_fwd: bad sizes rows=%d cols=%d Kpad=%d", rows, cols, Kpad);
+  softmax_split_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, ldx, cols, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad);
+  SKP_CHECK_LAUNCH("softmax_split_kernel");
   return SKP_OK;
 }

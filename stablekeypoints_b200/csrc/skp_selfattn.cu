@@ -69,18 +69,38 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
+// exp2 on the SFU (2 ulp): arguments are <= 0 (or -inf -> 0) everywhere it is used
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int sa_pad(int dp) { return dp + 8; }        // smem row stride (elements): conflict-free ldmatrix
 constexpr int sa_bn(int dp) { return dp > 96 ? 32 : 64; }  // kv rows per staged tile
 
-// rows [row0, row0+ROWS) of a [S][DP] bf16 plane -> smem [ROWS][DP+8]; rows >= S are zero-filled
+// rows [row0, row0+ROWS) of a [S][DP] bf16 plane -> smem [ROWS][DP+8]; rows >= S are zero-filled.
+// NT/ROWS threads share a row and walk its 16-byte chunks, so a thread's row (and its bounds check) is loop-invariant.
 template <int ROWS, int DP, int NT>
 __device__ __forceinline__ void sa_load_tile(bf16* smem, const bf16* __restrict__ plane, int row0, int S) {
   constexpr int CH = DP / 8;
-  for (int i = threadIdx.x; i < ROWS * CH; i += NT) {
-    int r = i / CH, c = i - r * CH;
-    int gr = row0 + r;
-    bool ok = gr < S;
-    cp_async16(smem + r * sa_pad(DP) + c * 8, plane + (size_t)(ok ? gr : 0) * DP + c * 8, ok ? 16 : 0);
+  if constexpr (NT >= ROWS && NT % ROWS == 0) {
+    constexpr int TPR = NT / ROWS;
+    const int r = threadIdx.x / TPR, sub = threadIdx.x % TPR;
+    const int gr = row0 + r;
+    const bool ok = gr < S;
+    const bf16* src = plane + (size_t)(ok ? gr : 0) * DP;
+    bf16* dst = smem + r * sa_pad(DP);
+    const int bytes = ok ? 16 : 0;
+#pragma unroll
+    for (int c = sub; c < CH; c += TPR) cp_async16(dst + c * 8, src + c * 8, bytes);
+  } else {
+    for (int i = threadIdx.x; i < ROWS * CH; i += NT) {
+      int r = i / CH, c = i - r * CH;
+      int gr = row0 + r;
+      bool ok = gr < S;
+      cp_async16(smem + r * sa_pad(DP) + c * 8, plane + (size_t)(ok ? gr : 0) * DP + c * 8, ok ? 16 : 0);
+    }
   }
 }
 
@@ -246,11 +266,11 @@ __global__ void sa_split_do_kernel(const float* __restrict__ d_o, int64_t lddo, 
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-template <int DP, int NW>
+template <int DP, int NW, int BN>
 __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ kvp,
                                                          float* __restrict__ out, int64_t ldo, float* __restrict__ lse,
                                                          float* __restrict__ lg_out, int Sq, int Skv, int heads, int d) {
-  constexpr int BM = 16 * NW, BN = sa_bn(DP), NT = NW * 32, LD = sa_pad(DP);
+  constexpr int BM = 16 * NW, NT = NW * 32, LD = sa_pad(DP);
   constexpr int NS = BN / 8;    // score n-tiles per warp row-block
   constexpr int NO = DP / 8;    // output n-tiles
   extern __shared__ __align__(16) unsigned char sa_smem[];
@@ -339,16 +359,16 @@ __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict_
     t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
     t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
     float mn0 = fmaxf(m0, t0), mn1 = fmaxf(m1, t1);   // finite: every tile has at least one real column
-    float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    float a0 = ex2f(m0 - mn0), a1 = ex2f(m1 - mn1);
     m0 = mn0;
     m1 = mn1;
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-      s[i][0] = exp2f(s[i][0] - mn0);
-      s[i][1] = exp2f(s[i][1] - mn0);
-      s[i][2] = exp2f(s[i][2] - mn1);
-      s[i][3] = exp2f(s[i][3] - mn1);
+      s[i][0] = ex2f(s[i][0] - mn0);
+      s[i][1] = ex2f(s[i][1] - mn0);
+      s[i][2] = ex2f(s[i][2] - mn1);
+      s[i][3] = ex2f(s[i][3] - mn1);
       r0 += s[i][0] + s[i][1];
       r1 += s[i][2] + s[i][3];
     }
@@ -393,13 +413,13 @@ __global__ void __launch_bounds__(NW * 32) sa_fwd_kernel(const bf16* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------- backward: dQ
-template <int DP, int NW>
+template <int DP, int NW, int BN>
 __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restrict__ qp, const bf16* __restrict__ kvp,
                                                             const bf16* __restrict__ do_planes, const float* __restrict__ lse,
                                                             const float* __restrict__ dvec, const float* __restrict__ extra,
                                                             float* __restrict__ dq, int64_t lddq, int Sq, int Skv, int heads,
                                                             int d, float scale) {
-  constexpr int BM = 16 * NW, BN = sa_bn(DP), NT = NW * 32, LD = sa_pad(DP);
+  constexpr int BM = 16 * NW, NT = NW * 32, LD = sa_pad(DP);
   constexpr int NS = BN / 8, NO = DP / 8;
   extern __shared__ __align__(16) unsigned char sa_smem[];
   bf16* Qs = reinterpret_cast<bf16*>(sa_smem);   // [4 planes: Qh Ql dOh dOl][BM][LD]
@@ -465,8 +485,8 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dq_kernel(const bf16* __restri
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       int c = j * BN + i * 8 + 2 * t;
-      float p0 = c < S ? exp2f(s[i][0] - ls0) : 0.f, p1 = c + 1 < S ? exp2f(s[i][1] - ls0) : 0.f;
-      float p2 = c < S ? exp2f(s[i][2] - ls1) : 0.f, p3 = c + 1 < S ? exp2f(s[i][3] - ls1) : 0.f;
+      float p0 = c < S ? ex2f(s[i][0] - ls0) : 0.f, p1 = c + 1 < S ? ex2f(s[i][1] - ls0) : 0.f;
+      float p2 = c < S ? ex2f(s[i][2] - ls1) : 0.f, p3 = c + 1 < S ? ex2f(s[i][3] - ls1) : 0.f;
       s[i][0] = p0 * (dp[i][0] - dd0);
       s[i][1] = p1 * (dp[i][1] - dd0);
       s[i][2] = p2 * (dp[i][2] - dd1);
@@ -594,8 +614,8 @@ __global__ void __launch_bounds__(NW * 32) sa_bwd_dkv_kernel(const bf16* __restr
     for (int i = 0; i < NS; ++i) {
       int c = i * 8 + 2 * t;
       float lc0 = ls[c], lc1 = ls[c + 1], dc0 = dd[c], dc1 = dd[c + 1];
-      float p0 = kv0 ? exp2f(s[i][0] - lc0) : 0.f, p1 = kv0 ? exp2f(s[i][1] - lc1) : 0.f;
-      float p2 = kv1 ? exp2f(s[i][2] - lc0) : 0.f, p3 = kv1 ? exp2f(s[i][3] - lc1) : 0.f;
+      float p0 = kv0 ? ex2f(s[i][0] - lc0) : 0.f, p1 = kv0 ? ex2f(s[i][1] - lc1) : 0.f;
+      float p2 = kv1 ? ex2f(s[i][2] - lc0) : 0.f, p3 = kv1 ? ex2f(s[i][3] - lc1) : 0.f;
       s[i][0] = p0;
       s[i][1] = p1;
       s[i][2] = p2;
@@ -679,10 +699,13 @@ static int sa_dp(int d) {
   return 0;
 }
 
+// kv rows per staged tile of the q-block kernels: 64 unless that would leave fewer than two CTAs per SM
+constexpr int sa_bn_fwd(int dp, int nw) { return sa_bn(dp); }
+constexpr int sa_bn_dq(int dp, int nw) { return (nw >= 8 && sa_bn(dp) > 32) ? 32 : sa_bn(dp); }
 template <int DP, int NW>
-static size_t sa_fwd_smem() { return (size_t)(2 * 16 * NW + 2 * 4 * sa_bn(DP)) * sa_pad(DP) * sizeof(bf16); }
+static size_t sa_fwd_smem() { return (size_t)(2 * 16 * NW + 2 * 4 * sa_bn_fwd(DP, NW)) * sa_pad(DP) * sizeof(bf16); }
 template <int DP, int NW>
-static size_t sa_dq_smem() { return (size_t)(4 * 16 * NW + 2 * 4 * sa_bn(DP)) * sa_pad(DP) * sizeof(bf16); }
+static size_t sa_dq_smem() { return (size_t)(4 * 16 * NW + 2 * 4 * sa_bn_dq(DP, NW)) * sa_pad(DP) * sizeof(bf16); }
 template <int DP, int NW>
 static size_t sa_dkv_smem() { return (size_t)(4 * 16 * NW + 2 * 4 * 32) * sa_pad(DP) * sizeof(bf16) + 2 * 2 * 32 * sizeof(float); }
 
@@ -692,12 +715,12 @@ static cudaError_t sa_launch_fwd(const bf16* qp, const bf16* kvp, float* o, int6
   size_t smem = sa_fwd_smem<DP, NW>();
   static bool configured = false;   // once per instantiation (not a stream operation: legal under graph capture too)
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sa_fwd_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sa_fwd_kernel<DP, NW, sa_bn_fwd(DP, NW)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((Sq + 16 * NW - 1) / (16 * NW), heads);
-  sa_fwd_kernel<DP, NW><<<grid, NW * 32, smem, st>>>(qp, kvp, o, ldo, lse, lg_out, Sq, Skv, heads, d);
+  sa_fwd_kernel<DP, NW, sa_bn_fwd(DP, NW)><<<grid, NW * 32, smem, st>>>(qp, kvp, o, ldo, lse, lg_out, Sq, Skv, heads, d);
   return cudaSuccess;
 }
 template <int DP, int NW>
@@ -707,12 +730,12 @@ static cudaError_t sa_launch_dq(const bf16* qp, const bf16* kvp, const bf16* do_
   size_t smem = sa_dq_smem<DP, NW>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sa_bwd_dq_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sa_bwd_dq_kernel<DP, NW, sa_bn_dq(DP, NW)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((Sq + 16 * NW - 1) / (16 * NW), heads);
-  sa_bwd_dq_kernel<DP, NW><<<grid, NW * 32, smem, st>>>(qp, kvp, do_planes, lse, dvec, extra, dq, lddq, Sq, Skv, heads, d, scale);
+  sa_bwd_dq_kernel<DP, NW, sa_bn_dq(DP, NW)><<<grid, NW * 32, smem, st>>>(qp, kvp, do_planes, lse, dvec, extra, dq, lddq, Sq, Skv, heads, d, scale);
   return cudaSuccess;
 }
 template <int DP, int NW>
@@ -733,7 +756,9 @@ static cudaError_t sa_launch_dkv(const bf16* qp, const bf16* kvp, const bf16* do
 
 #define SA_DISPATCH(DPV, NWV, CALL)                                  \
   do {                                                               \
-    if (NWV == 4) {                                                  \
+    if (NWV == 8 && DPV == 48) err = CALL(48, 8);                    \
+    else if (NWV == 8 && DPV == 80) err = CALL(80, 8);               \
+    else if (NWV >= 4) {                                             \
       switch (DPV) {                                                 \
         case 16: err = CALL(16, 4); break;                           \
         case 32: err = CALL(32, 4); break;                           \
@@ -751,6 +776,10 @@ static cudaError_t sa_launch_dkv(const bf16* qp, const bf16* kvp, const bf16* do
       }                                                              \
     }                                                                \
   } while (0)
+
+// warps per CTA (16 query / key rows each): enough CTAs to fill the 148 SMs, and for long sequences 8 warps so that the
+// grid is ONE wave of two CTAs per SM (512 four-warp CTAs at three per SM are 1.15 waves: the tail doubles the time)
+static int sa_warps(int rows) { return rows >= 2048 ? 8 : rows >= 1024 ? 4 : 2; }
 
 static int sa_check(const char* who, int Sq, int Skv, int heads, int d, int* DP) {
   SKP_REQUIRE(Sq > 0 && Skv > 0 && heads > 0 && d > 0 && d % 2 == 0, "%s: bad sizes Sq=%d Skv=%d heads=%d d=%d (d must be even)", who,
@@ -776,7 +805,7 @@ static int sa_forward(const float* q, int64_t ldq, const float* k, int64_t ldk, 
   if (blocks > 148 * 16) blocks = 148 * 16;
   sa_split_qkv_kernel<<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, qp, kvp, Sq, Skv, heads, d, DP, scale * 1.4426950408889634f);
   SKP_CHECK_LAUNCH("sa_split_qkv_kernel");
-  const int NW = Sq >= 1024 ? 4 : 2;
+  const int NW = sa_warps(Sq);
   cudaError_t err = cudaSuccess;
 #define SA_FWD(DPV, NWV) sa_launch_fwd<DPV, NWV>(qp, kvp, o, ldo, lse, lg_out, Sq, Skv, heads, d, st)
   SA_DISPATCH(DP, NW, SA_FWD);
@@ -806,7 +835,7 @@ static int sa_backward(const float* d_o, int64_t lddo, const float* o, int64_t l
   sa_split_do_kernel<<<blocks, 256, 0, st>>>(d_o, lddo, o, ldo, do_planes, dvec, Sq, heads, d, DP);
   SKP_CHECK_LAUNCH("sa_split_do_kernel");
   cudaError_t err = cudaSuccess;
-  const int NWq = Sq >= 1024 ? 4 : 2;
+  const int NWq = sa_warps(Sq);
 #define SA_DQ(DPV, NWV) sa_launch_dq<DPV, NWV>(qp, kvp, do_planes, lse, dvec, extra, dq, lddq, Sq, Skv, heads, d, scale, st)
   SA_DISPATCH(DP, NWq, SA_DQ);
 #undef SA_DQ
@@ -815,7 +844,7 @@ static int sa_backward(const float* d_o, int64_t lddo, const float* o, int64_t l
     return SKP_ERR_LAUNCH;
   }
   SKP_CHECK_LAUNCH("sa_bwd_dq_kernel");
-  const int NWk = Skv >= 1024 ? 4 : 2;
+  const int NWk = sa_warps(Skv);
   int qsplit = 1;
   if (may_split) {   // few keys, many queries: share the query axis so that ~2 CTAs per SM exist
     int ctas = ((Skv + 16 * NWk - 1) / (16 * NWk)) * heads, ntq = (Sq + 31) / 32;

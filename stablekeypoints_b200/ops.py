@@ -406,6 +406,24 @@ def geglu_linear(proj, fw: FrozenWeight, bias=None, residual=None):
     return _GegluLinear.apply(proj, residual, fw, bias)
 
 
+def dense_attention(q, k, v, scale: float) -> torch.Tensor:
+    """Single-head softmax(q k^T scale) v for wide heads (VAE mid block: d = 512), forward only: two tcgen05 split-bf16
+    GEMMs around a fused softmax+operand-split kernel.  q, k, v: [S, d] fp32 (row stride free)."""
+    require_cuda(q, k, v)
+    s_q, d = q.shape
+    s_k = k.shape[0]
+    if s_k % 4:
+        raise SkpError("dense_attention needs a key count that is a multiple of 4")
+    scores = gemm_nt(q, k, split_bf16(k), alpha=scale)                    # [s_q, s_k]
+    kp = _pad64(s_k)
+    p_hi = torch.empty(s_q, kp, dtype=torch.bfloat16, device=q.device)
+    p_lo = torch.empty(s_q, kp, dtype=torch.bfloat16, device=q.device)
+    check(lib().skp_softmax_split_fwd(ptr(scores), scores.stride(0), s_q, s_k, ptr(p_hi), ptr(p_lo), kp, stream()),
+          "skp_softmax_split_fwd")
+    vt = v.t().contiguous()                                               # [d, s_k]: K-major B operand of P v
+    return gemm_nt_presplit(p_hi, p_lo, s_q, split_bf16(vt), d)
+
+
 def group_norm_cl(x2d, gamma, beta, groups, eps, silu=False):
     """Plain act(GroupNorm(x)) -> fp32 [rows, C] (forward only; used by tests and no-grad paths)."""
     x2d = _f32c(x2d)

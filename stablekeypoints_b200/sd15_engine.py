@@ -671,7 +671,10 @@ class VAEEncoderEngine:
         qkv = ops.gn_linear(x, w[f"{a}.group_norm.weight"], w[f"{a}.group_norm.bias"], cfg.norm_num_groups, 1e-6, False,
                             self._fw[f"{a}.qkv"], self._qkv_bias)
         q, k, v = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
-        o = _self_attention_core(q[None, None], k[None, None], v[None, None])[0, 0]
+        if SELF_ATTN_DTYPE == "skp" and x.shape[0] % 4 == 0:
+            o = ops.dense_attention(q, k, v, c ** -0.5)     # one head of c channels: two GEMMs + fused softmax/split
+        else:
+            o = _self_attention_core(q[None, None], k[None, None], v[None, None])[0, 0]
         x = ops.frozen_linear(o, self._fw[f"{a}.proj_attn"], w[f"{a}.proj_attn.bias"], residual=x)
         x = self._resnet_cl("encoder.mid_block.resnets.1", x, h, wd)
         x, _, _ = ops.gn_conv3x3(x, h, wd, w["encoder.conv_norm_out.weight"], w["encoder.conv_norm_out.bias"],

@@ -236,6 +236,18 @@ def test_self_attn_fwd_bwd(ops, s, heads, d):
     assert errs[0] < 5e-5 and max(errs[1:]) < 1e-4, errs
 
 
+@pytest.mark.parametrize("s,d", [(4096, 512), (256, 32), (100, 24)])
+def test_dense_attention_vs_float64(ops, s, d):
+    """VAE mid-block attention (one wide head) as two split-bf16 GEMMs around the fused softmax/operand-split kernel."""
+    g = torch.Generator().manual_seed(s + d)
+    qkv = torch.randn(s, 3 * d, generator=g, dtype=torch.float64)
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    want = torch.softmax(q @ k.t() * d ** -0.5, -1) @ v
+    x = cu(qkv.float())
+    got = ops.dense_attention(x[:, :d], x[:, d:2 * d], x[:, 2 * d:], d ** -0.5)
+    assert rel_err(got.cpu(), want) < 5e-5
+
+
 # ----------------------------------------------------------------------------- capture
 def _capture_ref(logits, res):
     """softmax_tokens(bicubic_pixels(low-res logits)) -> [h, res*res, N]  (linearity form of ptp_utils.py:513-536)."""
