@@ -27,8 +27,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 constexpr int ROW_MAX_THREADS = 512;
+constexpr int ROWS_PER_CTA = 2;   // consecutive output rows per CTA: the per-pixel horizontal setup is shared
 
-__global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(const float* __restrict__ logits,
+__global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(const float* __restrict__ logits,
                                                                             float* __restrict__ probs, int s, int N, int R,
                                                                             int NV, int P, int TS) {
   extern __shared__ __align__(16) unsigned char row_smem[];
@@ -36,11 +37,32 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
   float* Vs = stage + (((size_t)R * N + 3) & ~(size_t)3);            // [s+4][NV]
   float* red = Vs + (size_t)(s + 4) * NV;                            // [32] per-warp max |V|
   float* psum = red + 32;                                            // [TS][P] partial softmax sums
-  const int Y = blockIdx.x, h = blockIdx.y;
+  const int h = blockIdx.y;
   const int tid = threadIdx.x, NT = blockDim.x;
   const float scale = (float)s / (float)R;
   const float LOG2E = 1.4426950408889634f;
+  // P pixel lanes x TS token slices: thread = (pixel X, slice of the token axis); slices meet through psum[].
+  const int N4 = N >> 2;
+  const int X_lane = tid % P, part = tid / P;
+  const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;      // float4 token groups of this slice
+  const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;     // the last slice also takes the N % 4 tail
+  // horizontal taps of this thread's pixel in the first pixel block: the same for every row this CTA produces
+  float pwx[4] = {0.f, 0.f, 0.f, 0.f}, psabs = 0.f;
+  int pc0 = 1;
+  if (X_lane < R) {
+    float rx = scale * (X_lane + 0.5f) - 0.5f, fx = floorf(rx);
+    cubic_coeffs(rx - fx, pwx);
+    pc0 = (int)fx + 1;   // column of tap 0 in the halo'd array (ix - 1 + 2)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pwx[i] *= LOG2E;
+      psabs += fabsf(pwx[i]);
+    }
+  }
 
+  for (int rr = 0; rr < ROWS_PER_CTA; ++rr) {
+  const int Y = blockIdx.x * ROWS_PER_CTA + rr;
+  if (Y >= R) break;
   // ---- 1. vertical pass: thread = (low-res column xs, group of 4 tokens); one 128-bit shared store per item
   float amax = 0.f;
   {
@@ -89,17 +111,13 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
     amax = warp_max(amax);
     if ((tid & 31) == 0) red[tid >> 5] = amax;
   }
+  if (rr > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging is free again
   __syncthreads();
   // M = max |V| over the row's footprint: x_n = sum_i wx[i] V_i[n] <= (sum_i |wx[i]|) * M for every token
   float M = 0.f;
   for (int w = 0; w < (NT >> 5); ++w) M = fmaxf(M, red[w]);
 
   // ---- 2. + 3. horizontal pass, softmax over tokens, in-place normalisation.
-  // P pixel lanes x TS token slices: thread = (pixel X, slice of the token axis); slices meet through psum[].
-  const int N4 = N >> 2;
-  const int X_lane = tid % P, part = tid / P;
-  const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;      // float4 token groups of this slice
-  const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;     // the last slice also takes the N % 4 tail
   for (int X0 = 0; X0 < R; X0 += P) {
     const int X = X0 + X_lane;
     const bool live = X < R;
@@ -108,15 +126,22 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
     float U = 0.f, sum = 0.f;
     float* orow = stage + (size_t)(live ? X : 0) * N;
     if (live) {
-      float rx = scale * (X + 0.5f) - 0.5f, fx = floorf(rx);
-      cubic_coeffs(rx - fx, wx);
-      c0 = (int)fx + 1;   // column of tap 0 in the halo'd array (ix - 1 + 2)
+      if (X0 == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        wx[i] *= LOG2E;
-        U += fabsf(wx[i]);
+        for (int i = 0; i < 4; ++i) wx[i] = pwx[i];
+        c0 = pc0;
+        U = psabs * M;
+      } else {
+        float rx = scale * (X + 0.5f) - 0.5f, fx = floorf(rx);
+        cubic_coeffs(rx - fx, wx);
+        c0 = (int)fx + 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          wx[i] *= LOG2E;
+          U += fabsf(wx[i]);
+        }
+        U *= M;
       }
-      U *= M;
       const float4* v0 = reinterpret_cast<const float4*>(Vs + (size_t)c0 * NV);
       const float4* v1 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 1) * NV);
       const float4* v2 = reinterpret_cast<const float4*>(Vs + (size_t)(c0 + 2) * NV);
@@ -188,8 +213,9 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS) capture_store_row_kernel(cons
                    : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the engine's reads
   }
+  }   // rows of this CTA
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the engine's reads
 }
 
 // Returns SKP_OK with *handled = true when the row kernel ran; *handled = false when the shape does not fit it.
@@ -214,7 +240,7 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
     cudaFuncSetAttribute(capture_store_row_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = bytes;
   }
-  dim3 grid(R, heads);
+  dim3 grid((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA, heads);
   capture_store_row_kernel<<<grid, P * TS, bytes, st>>>(logits, probs, s, N, R, NV, P, TS);
   SKP_CHECK_LAUNCH("capture_store_row");
   *handled = true;
