@@ -2,6 +2,7 @@
 :157-206, optimize_embedding :269-452) on the B200 kernels, one process per GPU."""
 from __future__ import annotations
 
+import os
 import time
 from typing import Optional
 
@@ -80,16 +81,33 @@ def stage1_losses(attn_map, attn_map_t, theta, *, top_k=10, num_candidates=25, s
 
 
 def stage1_iteration(ldm, controllers, image, context, transform: RandomAffineWithInverse, args, *, accum: int = 1,
-                     theta=None, theta_inv=None, noise_a=None, noise_b=None, forced_indices=None, from_where=None):
+                     theta=None, theta_inv=None, noise_a=None, noise_b=None, forced_indices=None, from_where=None,
+                     side_stream: Optional["torch.cuda.Stream"] = None):
     """optimize.py:341-422 for one rank: two captured forwards, selection, loss = w_e*equiv + w_s*sharp, / accum,
-    backward into ``context`` (its .grad accumulates)."""
+    backward into ``context`` (its .grad accumulates).
+
+    side_stream: the two captured forwards (original / warped image) only share the K|V projection of the embedding, and
+    at one image per rank most of their kernels are far too small to fill 148 SMs.  With a side stream the warped
+    image's forward (and, through autograd's stream tracking, its backward) runs concurrently with the original's."""
     kw = dict(layers=args.layers, noise_level=args.noise_level, from_where=from_where, upsample_res=-1,
               device=args.device, controllers=controllers)
     dev = ldm.unet.device
     image = image.to(dev, non_blocking=True) if isinstance(image, torch.Tensor) else image
-    attn_maps = ptp_utils.run_and_find_attn(ldm, image, context, noise=noise_a, **kw)
-    transformed_img = transform(image, theta=theta)
-    attn_maps_t = ptp_utils.run_and_find_attn(ldm, transformed_img, context, noise=noise_b, **kw)
+    if side_stream is None or not isinstance(image, torch.Tensor):
+        attn_maps = ptp_utils.run_and_find_attn(ldm, image, context, noise=noise_a, **kw)
+        transformed_img = transform(image, theta=theta)
+        attn_maps_t = ptp_utils.run_and_find_attn(ldm, transformed_img, context, noise=noise_b, **kw)
+    else:
+        main = torch.cuda.current_stream()
+        transformed_img = transform(image, theta=theta)
+        ldm.unet.project_context(context)            # shared K|V projection: once, before the fork (both forwards hit the cache)
+        side_stream.wait_stream(main)
+        attn_maps = ptp_utils.run_and_find_attn(ldm, image, context, noise=noise_a, **kw)
+        with torch.cuda.stream(side_stream):
+            attn_maps_t = ptp_utils.run_and_find_attn(ldm, transformed_img, context, noise=noise_b, **kw)
+        main.wait_stream(side_stream)
+        for t in attn_maps_t:                        # produced on the side stream, consumed (and freed) on the main one
+            t.record_stream(main)
     idx, sharp, equiv = stage1_losses(attn_maps[0], attn_maps_t[0], transform.last_params["theta"], top_k=args.top_k,
                                       num_candidates=args.furthest_point_num_samples, sigma=args.sigma,
                                       num_subjects=args.num_subjects, top_k_strategy=args.top_k_strategy,
@@ -171,10 +189,13 @@ class Stage1Graph:
         self.out = None
         self.graph = None
         self._warmup = warmup
+        # second stream inside the graph: the two forwards / backwards of a step overlap (SKP_TWO_STREAM=0 disables)
+        self.side = torch.cuda.Stream(device=dev) if os.environ.get("SKP_TWO_STREAM", "1") != "0" else None
 
     def _step(self):
         out = stage1_iteration(self.ldm, self.controllers, self.image, self.context, self.transform, self.args,
-                               theta=self.theta, theta_inv=self.theta_inv, from_where=self.from_where)
+                               theta=self.theta, theta_inv=self.theta_inv, from_where=self.from_where,
+                               side_stream=self.side)
         self.optimizer.step()
         self.optimizer.zero_grad()
         return out
