@@ -82,24 +82,31 @@ def stage1_losses(attn_map, attn_map_t, theta, *, top_k=10, num_candidates=25, s
 
 def stage1_iteration(ldm, controllers, image, context, transform: RandomAffineWithInverse, args, *, accum: int = 1,
                      theta=None, theta_inv=None, noise_a=None, noise_b=None, forced_indices=None, from_where=None,
-                     side_stream: Optional["torch.cuda.Stream"] = None):
+                     side_stream: Optional["torch.cuda.Stream"] = None, latents=None):
     """optimize.py:341-422 for one rank: two captured forwards, selection, loss = w_e*equiv + w_s*sharp, / accum,
     backward into ``context`` (its .grad accumulates).
 
     side_stream: the two captured forwards (original / warped image) only share the K|V projection of the embedding, and
     at one image per rank most of their kernels are far too small to fill 148 SMs.  With a side stream the warped
-    image's forward (and, through autograd's stream tracking, its backward) runs concurrently with the original's."""
+    image's forward (and, through autograd's stream tracking, its backward) runs concurrently with the original's.
+    latents = (latent, latent_of_warped_image): VAE encodes done ahead of time (Stage1Graph's prefetch stage); `image`
+    is ignored, `theta` / `theta_inv` must be the warp those latents were made with."""
     kw = dict(layers=args.layers, noise_level=args.noise_level, from_where=from_where, upsample_res=-1,
               device=args.device, controllers=controllers)
     dev = ldm.unet.device
-    image = image.to(dev, non_blocking=True) if isinstance(image, torch.Tensor) else image
+    if latents is not None:
+        image, transformed_pre = latents       # 4-channel tensors pass through image2latent (ptp_utils.py:293-298 contract)
+        transform.last_params = {"theta": theta}
+    else:
+        transformed_pre = None
+        image = image.to(dev, non_blocking=True) if isinstance(image, torch.Tensor) else image
     if side_stream is None or not isinstance(image, torch.Tensor):
         attn_maps = ptp_utils.run_and_find_attn(ldm, image, context, noise=noise_a, **kw)
-        transformed_img = transform(image, theta=theta)
+        transformed_img = transform(image, theta=theta) if transformed_pre is None else transformed_pre
         attn_maps_t = ptp_utils.run_and_find_attn(ldm, transformed_img, context, noise=noise_b, **kw)
     else:
         main = torch.cuda.current_stream()
-        transformed_img = transform(image, theta=theta)
+        transformed_img = transform(image, theta=theta) if transformed_pre is None else transformed_pre
         ldm.unet.project_context(context)            # shared K|V projection: once, before the fork (both forwards hit the cache)
         side_stream.wait_stream(main)
         attn_maps = ptp_utils.run_and_find_attn(ldm, image, context, noise=noise_a, **kw)
@@ -191,11 +198,59 @@ class Stage1Graph:
         self._warmup = warmup
         # second stream inside the graph: the two forwards / backwards of a step overlap (SKP_TWO_STREAM=0 disables)
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("SKP_TWO_STREAM", "1") != "0" else None
+        # VAE prefetch (SKP_VAE_PREFETCH=0 disables): the two VAE encodes of an image do not depend on the embedding, so the
+        # graph of step i encodes the image of step i+1 on a third stream while the UNet work of step i -- mostly kernels
+        # too small to fill the GPU -- runs on the other two.  One-step software pipeline: replay() returns the losses of
+        # the image given to the PREVIOUS set_inputs(); prime() fills the pipeline, flush() drains it.
+        self.prefetch = (os.environ.get("SKP_VAE_PREFETCH", "1") != "0" and len(image_shape) == 4 and image_shape[1] == 3
+                         and getattr(ldm, "vae", None) is not None)
+        if self.prefetch:
+            lat_shape = (2, 4, image_shape[2] // 8, image_shape[3] // 8)
+            self.vae_stream = torch.cuda.Stream(device=dev)
+            self.lat_next = torch.zeros(lat_shape, device=dev)          # [latent(image), latent(warped image)] of the NEXT step
+            self.lat_cur = torch.zeros(lat_shape, device=dev)
+            self.theta_next, self.theta_inv_next = torch.zeros_like(self.theta), torch.zeros_like(self.theta_inv)
+            self.theta_cur, self.theta_inv_cur = torch.zeros_like(self.theta), torch.zeros_like(self.theta_inv)
+
+    @property
+    def latency(self) -> int:
+        """Steps between set_inputs(image) and the replay() that returns that image's losses."""
+        return 1 if self.prefetch else 0
+
+    def _encode_next(self):
+        """Prefetch stage: VAE-encode the input image and its warp by the input theta into the pipeline registers
+        (no grad; ptp_utils.py:289-304, invertable_transform.py:38-70)."""
+        with torch.no_grad():
+            self.theta_next.copy_(self.theta)
+            self.theta_inv_next.copy_(self.theta_inv)
+            warped = self.transform(self.image, theta=self.theta)
+            self.lat_next[0:1].copy_(ptp_utils.image2latent(self.ldm, self.image, self.args.device))
+            self.lat_next[1:2].copy_(ptp_utils.image2latent(self.ldm, warped, self.args.device))
+
+    def prime(self):
+        """Fill the pipeline with the image / theta last given to set_inputs (eager, outside the graph)."""
+        if self.prefetch:
+            self._encode_next()
+        return self
 
     def _step(self):
-        out = stage1_iteration(self.ldm, self.controllers, self.image, self.context, self.transform, self.args,
-                               theta=self.theta, theta_inv=self.theta_inv, from_where=self.from_where,
-                               side_stream=self.side)
+        if not self.prefetch:
+            out = stage1_iteration(self.ldm, self.controllers, self.image, self.context, self.transform, self.args,
+                                   theta=self.theta, theta_inv=self.theta_inv, from_where=self.from_where,
+                                   side_stream=self.side)
+        else:
+            main = torch.cuda.current_stream()
+            with torch.no_grad():          # roll the pipeline registers: what was prefetched becomes this step's input
+                self.lat_cur.copy_(self.lat_next)
+                self.theta_cur.copy_(self.theta_next)
+                self.theta_inv_cur.copy_(self.theta_inv_next)
+            self.vae_stream.wait_stream(main)
+            with torch.cuda.stream(self.vae_stream):
+                self._encode_next()
+            out = stage1_iteration(self.ldm, self.controllers, None, self.context, self.transform, self.args,
+                                   theta=self.theta_cur, theta_inv=self.theta_inv_cur, from_where=self.from_where,
+                                   side_stream=self.side, latents=(self.lat_cur[0:1], self.lat_cur[1:2]))
+            main.wait_stream(self.vae_stream)
         self.optimizer.step()
         self.optimizer.zero_grad()
         return out
@@ -230,6 +285,7 @@ class Stage1Graph:
         return self
 
     def replay(self):
+        """Replays the step.  With the VAE prefetch the returned losses belong to the image of the previous set_inputs()."""
         self.graph.replay()
         return self.out
 

@@ -122,6 +122,8 @@ def test_tiny_cuda_graph_step_equals_eager_step(tiny, monkeypatch):
             runner = optimize.Stage1Graph(ldm, controllers, ctx, opt, args, image_shape=tuple(image.shape))
             runner.set_inputs(image, theta)
             runner.capture()
+            runner.set_inputs(image, theta)
+            runner.prime()                 # VAE prefetch pipeline (same image every step here, so step i == eager step i)
             for _ in range(3):
                 runner.set_inputs(image, theta)
                 losses.append(float(runner.replay()["loss"]))
