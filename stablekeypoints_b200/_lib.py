@@ -119,6 +119,14 @@ def _shape_key(name, args):
         return "S%d h%d d%d" % (args[-5], args[-4], args[-3])
     if name in ("skp_cross_attn_tc_fwd", "skp_cross_attn_tc_bwd"):
         return "S%d N%d h%d d%d" % (args[-6], args[-5], args[-4], args[-3])
+    if name in ("skp_gn_stats", "skp_gn_apply"):
+        return "rows%d C%d" % (args[2], args[3])
+    if name == "skp_gn_bwd":
+        return "rows%d C%d" % (args[4], args[5])
+    if name == "skp_split_bf16":
+        return "rows%d cols%d" % (args[2], args[3])
+    if name == "skp_ln_split_fwd":
+        return "rows%d C%d" % (args[2], args[3])
     return ""
 
 

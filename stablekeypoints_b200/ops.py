@@ -178,7 +178,14 @@ class _FrozenConv3x3(torch.autograd.Function):
             elif stride == 1 and pad == 1:
                 hi, lo = im2col3x3_split(dy, ho, wo, h, w, 1, 1)
                 dx = gemm_nt_presplit(hi, lo, h * w, fcw.dgrad_split, fcw.cin)
-            else:  # the three strided down-samplers: cuDNN dgrad on an NCHW view
+            elif stride == 2 and pad == 1 and h == 2 * ho and w == 2 * wo and _implicit_ok(w, fcw.cout):
+                # the UNet down-samplers: a stride-2 convolution's input gradient is the stride-1 input gradient of the
+                # zero-stuffed output gradient (dyz[2o] = dy[o]) -> same implicit-GEMM kernel, no library call
+                dyz = torch.zeros(h, w, fcw.cout, dtype=torch.float32, device=dy.device)
+                dyz[::2, ::2] = dy.reshape(ho, wo, fcw.cout)
+                hi, lo = split_bf16(dyz.reshape(h * w, fcw.cout))
+                dx = conv3x3_implicit(hi, lo, h, w, fcw.dgrad_split, fcw.cin)
+            else:  # odd geometries only (not reached by SD1.5): cuDNN dgrad on an NCHW view
                 g = dy.reshape(1, ho, wo, fcw.cout).permute(0, 3, 1, 2)
                 # the geometry is "rows/cols beyond the image read zero": the padded extent that makes (ho, wo) exact
                 hp_, wp_ = (ho - 1) * stride + 3 - pad, (wo - 1) * stride + 3 - pad
@@ -621,6 +628,11 @@ def capture_store(logits: torch.Tensor, res: int) -> torch.Tensor:
     return _CaptureStore.apply(logits, res)
 
 
+# forward of the fused capture+collect: "fused" = one tile kernel over all (layer, head) slices; "store" = row attn-store
+# kernel per layer + collect mean (A/B measured in scripts/kernel_bench.py; the backward is the fused kernel either way)
+CAPTURE_MEAN_FWD = os.environ.get("SKP_CAPTURE_MEAN_FWD", "fused")
+
+
 class _CaptureMean(torch.autograd.Function):
     @staticmethod
     def forward(ctx, res: int, *logits):
@@ -629,8 +641,17 @@ class _CaptureMean(torch.autograd.Function):
         h, _, n = logits[0].shape
         sides = [_side(l) for l in logits]
         maps = torch.empty(n, res, res, dtype=torch.float32, device=logits[0].device)
-        check(lib().skp_capture_mean_fwd(ptr_array(logits), int_array(sides), len(logits), ptr(maps), h, n, res, stream()),
-              "skp_capture_mean_fwd")
+        if CAPTURE_MEAN_FWD == "store" and h * res * res * n * 4 * len(logits) <= (1 << 30):
+            # forward through the row attn-store kernel + the collect mean: the per-layer probabilities make a round trip
+            # through L2 (161 MB at N=77) but both kernels run near their memory roofline, which beats the fused tile kernel
+            stored = [torch.empty(h, res * res, n, dtype=torch.float32, device=maps.device) for _ in logits]
+            for lg, sd, pr in zip(logits, sides, stored):
+                check(lib().skp_capture_store_fwd(ptr(lg), ptr(pr), h, sd, n, res, stream()), "skp_capture_store_fwd")
+            check(lib().skp_collect_maps_fwd(ptr_array(stored), len(stored), h, res, n, None, 0, res, None, ptr(maps), stream()),
+                  "skp_collect_maps_fwd")
+        else:
+            check(lib().skp_capture_mean_fwd(ptr_array(logits), int_array(sides), len(logits), ptr(maps), h, n, res, stream()),
+                  "skp_capture_mean_fwd")
         ctx.save_for_backward(*logits)
         ctx.res, ctx.sides = res, sides
         return maps
