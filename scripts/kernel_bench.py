@@ -80,10 +80,10 @@ def main():
             bytes_=store_bytes + 2 * lg.numel() * 4)
     lgs = [torch.randn(h, s * s, n, device=dev, generator=g) * 3 for s in (16, 16, 16, 32)]
     mean_bytes = sum(l.numel() for l in lgs) * 4 + n * r * r * 4
-    add("capture_mean_fwd", f"4 layers N{n} R{r}", lambda: ops.capture_mean(lgs, r), bytes_=mean_bytes)
-    ops.CAPTURE_MEAN_FWD = "store"
-    add("capture_mean_fwd(store+collect)", f"4 layers N{n} R{r}", lambda: ops.capture_mean(lgs, r), bytes_=mean_bytes)
     ops.CAPTURE_MEAN_FWD = "fused"
+    add("capture_mean_fwd(fused tile kernel)", f"4 layers N{n} R{r}", lambda: ops.capture_mean(lgs, r), bytes_=mean_bytes)
+    ops.CAPTURE_MEAN_FWD = "store"
+    add("capture_mean_fwd(store+collect, default)", f"4 layers N{n} R{r}", lambda: ops.capture_mean(lgs, r), bytes_=mean_bytes)
     lgr = [l.clone().requires_grad_(True) for l in lgs]
     mp = ops.capture_mean(lgr, r)
     dm = torch.randn_like(mp)

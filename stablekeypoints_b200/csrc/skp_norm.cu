@@ -82,12 +82,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_reduce_kernel(const float* __re
   const GnMap mp = gn_map(C);
   const int cx = threadIdx.x % mp.tpr, ry = threadIdx.x / mp.tpr;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-  if (ry < mp.rl) {
+  const bool same_group4 = (cg % 4) == 0;   // the 4 channels of a chunk share a group
 #pragma unroll
-    for (int k = 0; k < GN_NCH; ++k) {
-      const int c = (cx + k * mp.tpr) * 4;
-      if (c >= C) break;
-      float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < GN_NCH; ++k) {
+    if ((k * mp.tpr) * 4 >= C) break;       // uniform over the CTA
+    const int c = (cx + k * mp.tpr) * 4;
+    const bool valid = ry < mp.rl && c < C;
+    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
       float sc[4], sh[4], gm[4];
       if (MODE == 1) {
 #pragma unroll
@@ -117,11 +119,27 @@ __global__ void __launch_bounds__(GN_THREADS) gn_reduce_kernel(const float* __re
           }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int g = (c + j) / cg;
-        atomicAdd(&sg[2 * g], a1[j]);
-        atomicAdd(&sg[2 * g + 1], a2[j]);
+    }
+    // Warp-segmented reduction by group before touching shared memory: lanes of a warp cover a handful of groups, so
+    // one leader per (warp, group) issues the shared atomic instead of every thread (256 threads hammering <= 64
+    // addresses serialised for ~10 us on the small UNet activations).
+    const int lane = threadIdx.x & 31;
+    const int npass = same_group4 ? 1 : 4;
+    for (int j = 0; j < npass; ++j) {
+      float v1 = same_group4 ? (a1[0] + a1[1]) + (a1[2] + a1[3]) : a1[j];
+      float v2 = same_group4 ? (a2[0] + a2[1]) + (a2[2] + a2[3]) : a2[j];
+      const int key = valid ? (c + j) / cg : -1;
+      unsigned remaining = __ballot_sync(0xffffffffu, key >= 0);
+      while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int gk = __shfl_sync(0xffffffffu, key, leader);
+        const bool mine = key == gk;
+        const float s1 = warp_sum(mine ? v1 : 0.f), s2 = warp_sum(mine ? v2 : 0.f);
+        if (lane == leader) {
+          atomicAdd(&sg[2 * gk], s1);
+          atomicAdd(&sg[2 * gk + 1], s2);
+        }
+        remaining &= ~__ballot_sync(0xffffffffu, mine);
       }
     }
   }

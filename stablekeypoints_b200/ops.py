@@ -630,7 +630,7 @@ def capture_store(logits: torch.Tensor, res: int) -> torch.Tensor:
 
 # forward of the fused capture+collect: "fused" = one tile kernel over all (layer, head) slices; "store" = row attn-store
 # kernel per layer + collect mean (A/B measured in scripts/kernel_bench.py; the backward is the fused kernel either way)
-CAPTURE_MEAN_FWD = os.environ.get("SKP_CAPTURE_MEAN_FWD", "fused")
+CAPTURE_MEAN_FWD = os.environ.get("SKP_CAPTURE_MEAN_FWD", "store")
 
 
 class _CaptureMean(torch.autograd.Function):
