@@ -29,6 +29,7 @@ typedef enum {
 } skp_status;
 
 #define SKP_MAX_LAYERS 8
+#define SKP_GN_REPL 8
 
 int skp_version(void);
 const char* skp_last_error(void);
@@ -72,11 +73,12 @@ int skp_conv3x3_tc(const void* X_hi, const void* X_lo, int H, int W, int Cin, co
 
 /* ------------------------------------------------------------------ GroupNorm (+SiLU) of the frozen trunk
  * Channels-last activations x[rows = H*W, C] (row stride ldx), `groups` groups of C/groups channels (diffusers
- * ResnetBlock2D / Transformer2DModel norms).  sums[2*groups] (fp64: sum, sum of squares) is
- * written by skp_gn_stats and consumed by the others.  The normalised tensor is never stored on its own:
+ * ResnetBlock2D / Transformer2DModel norms).  sums[SKP_GN_REPL][2*groups] (fp64: sum, sum of
+ * squares; CTA b accumulates into replica b % SKP_GN_REPL, consumers add the replicas) is written by skp_gn_stats and
+ * consumed by the others.  The normalised tensor is never stored on its own:
  * skp_gn_apply emits fp32 y[rows, C] and/or the split-bf16 K-major operand [rows, Kpad] of a following 1x1
  * projection; skp_gn_im2col3x3_split emits the split-bf16 3x3 im2col operand of a following convolution.
- * skp_gn_bwd: dx = d(loss)/dx from g = d(loss)/dy (gamma, beta frozen); bsums[2*groups] is fp64 workspace. */
+ * skp_gn_bwd: dx = d(loss)/dx from g = d(loss)/dy (gamma, beta frozen); bsums[SKP_GN_REPL][2*groups] is fp64 workspace. */
 int skp_gn_stats(const float* x, int64_t ldx, int rows, int C, int groups, double* sums, void* stream);
 int skp_gn_apply(const float* x, int64_t ldx, int rows, int C, int groups, const double* sums, float eps,
                  const float* gamma, const float* beta, int silu, float* y, int64_t ldy, void* hi, void* lo,

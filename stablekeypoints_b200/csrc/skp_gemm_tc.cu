@@ -265,31 +265,70 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   }
 }
 
+// 4 columns per thread: one 128-bit load, two 64-bit stores (cols_pad is a multiple of 64; VEC: x rows are 16-byte aligned)
+template <bool VEC>
 __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, int cols_pad,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  size_t total = (size_t)rows * cols_pad;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int r = (int)(i / cols_pad), c = (int)(i - (size_t)r * cols_pad);
-    float v = (c < cols) ? x[(size_t)r * ld + c] : 0.f;
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[i] = h;
-    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  const int q = cols_pad >> 2;
+  const long total = (long)rows * q;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / q), c = (int)(i - (long)r * q) << 2;
+    const float* src = x + (size_t)r * ld + c;
+    float v[4];
+    if (VEC && c + 3 < cols) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (c + j < cols) ? __ldg(src + j) : 0.f;
+    }
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+    const size_t o = (size_t)r * cols_pad + c;
+    *reinterpret_cast<uint2*>(hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
   }
 }
 
-// out[m,n] = alpha * sum_z ws[z][m][n] + bias[n] + residual[m][n]
+// out[m,n] = alpha * sum_z ws[z][m][n] + bias[n] + residual[m][n];  VEC: N % 4 == 0 and every row 16-byte aligned
+template <bool VEC>
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float* __restrict__ C, int64_t ldc,
                                      float alpha, const float* __restrict__ bias, const float* __restrict__ residual,
                                      int64_t ldr) {
-  size_t total = (size_t)M * N;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int m = (int)(i / N), n = (int)(i - (size_t)m * N);
-    float a = 0.f;
-    for (int z = 0; z < splits; ++z) a += ws[(size_t)z * total + i];
-    a *= alpha;
-    if (bias) a += bias[n];
-    if (residual) a += residual[(size_t)m * ldr + n];
-    C[(size_t)m * ldc + n] = a;
+  const size_t total = (size_t)M * N;
+  if (VEC) {
+    const int q = N >> 2;
+    const long tq = (long)M * q;
+    const float4* w4 = reinterpret_cast<const float4*>(ws);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < tq; i += (long)gridDim.x * blockDim.x) {
+      const int m = (int)(i / q), n = (int)(i - (long)m * q) << 2;
+      float4 a = __ldg(w4 + i);
+      for (int z = 1; z < splits; ++z) {
+        const float4 t = __ldg(w4 + (size_t)z * tq + i);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (residual) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(residual + (size_t)m * ldr + n));
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = a;
+    }
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+      float a = 0.f;
+      for (int z = 0; z < splits; ++z) a += ws[(size_t)z * total + i];
+      a *= alpha;
+      if (bias) a += bias[n];
+      if (residual) a += residual[(size_t)m * ldr + n];
+      C[(size_t)m * ldc + n] = a;
+    }
   }
 }
 
@@ -385,6 +424,17 @@ static int make_map_3d(CUtensorMap* m, const void* ptr, int H, int W, int C, int
   return SKP_OK;
 }
 
+static void launch_splitk_reduce(const float* ws, int zs, int M, int N, float* C, int64_t ldc, float alpha, const float* bias,
+                                 const float* residual, int64_t ldr, cudaStream_t st) {
+  const bool vec = (N % 4 == 0) && (ldc % 4 == 0) && ((((uintptr_t)C) & 15) == 0) && ((((uintptr_t)ws) & 15) == 0) &&
+                   (!bias || (((uintptr_t)bias) & 15) == 0) && (!residual || ((ldr % 4 == 0) && (((uintptr_t)residual) & 15) == 0));
+  size_t items = vec ? (size_t)M * N / 4 : (size_t)M * N;
+  int blocks = (int)((items + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (vec) splitk_reduce_kernel<true><<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+  else splitk_reduce_kernel<false><<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+}
+
 template <int BN, int STAGES>
 static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin, const void* B_hi, const void* B_lo, float* C,
                        int64_t ldc, int N, float alpha, const float* bias, const float* residual, int64_t ldr, int splits, float* ws,
@@ -414,10 +464,7 @@ static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin
                                                                           bias, residual, ldr, ws, cg);
   SKP_CHECK_LAUNCH("conv3x3_tc");
   if (zs > 1) {
-    size_t total = (size_t)M * N;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+    launch_splitk_reduce(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr, st);
     SKP_CHECK_LAUNCH("splitk_reduce");
   }
   return SKP_OK;
@@ -444,10 +491,7 @@ static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const
                                                                            alpha, bias, residual, ldr, ws, ConvGeom{});
   SKP_CHECK_LAUNCH("gemm_nt_tc");
   if (zs > 1) {
-    size_t total = (size_t)M * N;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+    launch_splitk_reduce(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr, st);
     SKP_CHECK_LAUNCH("splitk_reduce");
   }
   return SKP_OK;
@@ -460,10 +504,13 @@ using namespace skp;
 extern "C" int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, int cols_pad, void* hi, void* lo, void* stream) {
   SKP_REQUIRE(x && hi && lo && rows > 0 && cols > 0, "split_bf16: bad arguments");
   SKP_REQUIRE(cols_pad >= cols && cols_pad % TC_BK == 0, "split_bf16: cols_pad=%d must be a multiple of 64 >= cols", cols_pad);
-  size_t total = (size_t)rows * cols_pad;
+  SKP_REQUIRE(((((uintptr_t)hi) | ((uintptr_t)lo)) & 7) == 0, "split_bf16: hi/lo must be 8-byte aligned");
+  size_t total = (size_t)rows * (cols_pad / 4);
   size_t b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
-  split_bf16_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  const bool vec = (ld % 4 == 0) && ((((uintptr_t)x) & 15) == 0);
+  if (vec) split_bf16_kernel<true><<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  else split_bf16_kernel<false><<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   SKP_CHECK_LAUNCH("split_bf16");
   return SKP_OK;
 }

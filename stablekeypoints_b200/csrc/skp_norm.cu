@@ -18,6 +18,8 @@ namespace skp {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_GROUPS = 64;
 constexpr int GN_NCH = 3;   // 4-channel chunks per thread -> C <= 4 * 256 * 3 = 3072
+constexpr int GN_REPL = 8;  // replicas of the fp64 (sum, sumsq) accumulators: CTA b adds into replica b % 8 (8x less
+                            // same-address atomic contention), consumers add the replicas up
 
 __device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
 __device__ __forceinline__ float silu_grad(float z) {
@@ -40,8 +42,14 @@ __host__ __device__ inline GnMap gn_map(int C) {
 // per-group (mean, rstd) from the fp64 sums into shared memory
 __device__ __forceinline__ void load_group_stats(const double* __restrict__ sums, int G, double count, float eps, float* mean, float* rstd) {
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double m = sums[2 * g] / count;
-    double var = sums[2 * g + 1] / count - m * m;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < GN_REPL; ++r) {
+      s1 += sums[r * 2 * G + 2 * g];
+      s2 += sums[r * 2 * G + 2 * g + 1];
+    }
+    double m = s1 / count;
+    double var = s2 / count - m * m;
     if (var < 0.0) var = 0.0;
     mean[g] = (float)m;
     rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
@@ -144,7 +152,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_reduce_kernel(const float* __re
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(out + i, (double)sg[i]);
+  double* dst = out + (size_t)(blockIdx.x % GN_REPL) * 2 * G;
+  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) atomicAdd(dst + i, (double)sg[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ apply
@@ -162,8 +171,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_rowwise_kernel(const float* __r
   const double count = (double)rows * cg;
   if (MODE == 1)
     for (int g = threadIdx.x; g < G; g += GN_THREADS) {
-      m1[g] = (float)(bs[2 * g] / count);
-      m2[g] = (float)(bs[2 * g + 1] / count);
+      double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < GN_REPL; ++r) {
+        b1 += bs[r * 2 * G + 2 * g];
+        b2 += bs[r * 2 * G + 2 * g + 1];
+      }
+      m1[g] = (float)(b1 / count);
+      m2[g] = (float)(b2 / count);
     }
   load_group_stats(sums, G, count, eps, mean, rstd);
   const GnMap mp = gn_map(C);
@@ -303,8 +318,13 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_scalar_kernel(const f
   const int G = C / cg;
   const double count = (double)rows * cg;
   for (int g = threadIdx.x; g < G; g += GN_THREADS) {
-    m1[g] = (float)(bs[2 * g] / count);
-    m2[g] = (float)(bs[2 * g + 1] / count);
+    double b1 = 0.0, b2 = 0.0;
+    for (int r = 0; r < GN_REPL; ++r) {
+      b1 += bs[r * 2 * G + 2 * g];
+      b2 += bs[r * 2 * G + 2 * g + 1];
+    }
+    m1[g] = (float)(b1 / count);
+    m2[g] = (float)(b2 / count);
   }
   load_group_stats(sums, G, count, eps, mean, rstd);
   const size_t total = (size_t)rows * C;
@@ -372,10 +392,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_im2col3x3_split_kernel(const fl
   }
 }
 
-static inline int gn_rows_per_cta(int rows, int C) {
+// Rows per CTA.  Large activations (VAE): ~6 CTAs per SM so enough loads are in flight.  Small ones (the UNet at one image
+// per rank is 0.1-5 MB per tensor): few rows per thread -- the kernels are latency-bound, and for the reductions the grid
+// is capped so that the fp64 global atomics of the CTAs do not pile up on the same 64 addresses.
+static inline int gn_rows_per_cta(int rows, int C, bool reduce = false) {
   GnMap m = gn_map(C >= 4 ? C : 4);
-  int per = (rows + 148 * 6 - 1) / (148 * 6);      // ~6 CTAs per SM
-  int min_rows = m.rl * 4;                         // at least 4 rows per row lane
+  const bool small = (size_t)rows * C < ((size_t)4 << 20);
+  int per = (rows + 148 * 6 - 1) / (148 * 6);
+  if (small && reduce) per = (rows + 295) / 296;
+  int min_rows = m.rl * (small ? (reduce ? 2 : 1) : 4);
   return per < min_rows ? min_rows : per;
 }
 static inline int gn_grid(size_t n) {
@@ -401,8 +426,8 @@ extern "C" int skp_gn_stats(const float* x, int64_t ldx, int rows, int C, int gr
   SKP_GN_CHECK("gn_stats");
   SKP_REQUIRE(sums, "gn_stats: null sums");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups, st);
-  int per = gn_rows_per_cta(rows, C);
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * GN_REPL, st);
+  int per = gn_rows_per_cta(rows, C, true);
   int grid = (rows + per - 1) / per;
   if (gn_vec_ok(x, ldx, C))
     gn_reduce_kernel<0><<<grid, GN_THREADS, 0, st>>>(x, ldx, nullptr, 0, rows, C, C / groups, nullptr, 0.f, nullptr, nullptr, 0, per, sums);
@@ -458,9 +483,10 @@ extern "C" int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t l
   SKP_GN_CHECK("gn_bwd");
   SKP_REQUIRE(g && sums && gamma && beta && bsums && dx, "gn_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * groups, st);
-  int per = gn_rows_per_cta(rows, C);
+  cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * groups * GN_REPL, st);
+  int per = gn_rows_per_cta(rows, C, true);
   int grid = (rows + per - 1) / per;
+  const int per_rw = gn_rows_per_cta(rows, C, false), grid_rw = (rows + per_rw - 1) / per_rw;
   const bool vec = gn_vec_ok(x, ldx, C, g, ldg) && (ldd % 4 == 0) && ((((uintptr_t)dx) & 15) == 0);
   if (vec)
     gn_reduce_kernel<1><<<grid, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, per, bsums);
@@ -468,8 +494,8 @@ extern "C" int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t l
     gn_bwd_reduce_scalar_kernel<<<grid, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, per, bsums);
   SKP_CHECK_LAUNCH("gn_bwd_reduce");
   if (vec)
-    gn_rowwise_kernel<1><<<grid, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, bsums, per, dx, ldd,
-                                                      nullptr, nullptr, 0);
+    gn_rowwise_kernel<1><<<grid_rw, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, bsums, per_rw, dx,
+                                                         ldd, nullptr, nullptr, 0);
   else
     gn_bwd_apply_scalar_kernel<<<gn_grid((size_t)rows * C), GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta,
                                                                                 silu, bsums, dx, ldd);

@@ -9,7 +9,7 @@
 
 namespace skp {
 
-constexpr int ROW_WARPS = 8;   // rows per CTA
+constexpr int ROW_WARPS = 4;   // rows per CTA (one warp each)
 
 __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float a, float b, float c, float d) {
   __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, d);
@@ -19,7 +19,11 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* hi, __nv_bfloat16* l
   *reinterpret_cast<uint2*>(lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
 }
 
+constexpr int LN_MAXCH = 10;   // float4 chunks a lane keeps in registers: rows of up to 1280 channels are read from L2 ONCE
+
 // x[rows, C] (C % 4 == 0) -> hi/lo[rows, Kpad] = split(LayerNorm(x) * gamma + beta); stats[row] = (mean, rstd)
+// CACHED: C <= 1280, the row lives in registers between the three sweeps (mean, variance, normalise).
+template <bool CACHED>
 __global__ void __launch_bounds__(ROW_WARPS * 32) ln_split_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   float eps, __nv_bfloat16* __restrict__ hi,
@@ -28,37 +32,74 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_split_kernel(const float* _
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
   const int C4 = C >> 2;
+  float4 v[LN_MAXCH];
   float s = 0.f;
-  for (int i = lane; i < C4; i += 32) {
-    float4 v = __ldg(xr + i);
-    s += (v.x + v.y) + (v.z + v.w);
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < LN_MAXCH; ++k) {
+      const int i = lane + 32 * k;
+      v[k] = i < C4 ? __ldg(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  } else {
+    for (int i = lane; i < C4; i += 32) {
+      float4 t = __ldg(xr + i);
+      s += (t.x + t.y) + (t.z + t.w);
+    }
   }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
-  for (int i = lane; i < C4; i += 32) {
-    float4 v = __ldg(xr + i);
-    float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < LN_MAXCH; ++k)
+      if (lane + 32 * k < C4) {
+        float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+  } else {
+    for (int i = lane; i < C4; i += 32) {
+      float4 t = __ldg(xr + i);
+      float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
   if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   const size_t base = (size_t)row * Kpad;
-  for (int i = lane; i < (Kpad >> 2); i += 32) {
-    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < C4) {
-      float4 v = __ldg(xr + i), g = __ldg(g4 + i), b = __ldg(b4 + i);
-      y.x = fmaf((v.x - mean) * rstd, g.x, b.x);
-      y.y = fmaf((v.y - mean) * rstd, g.y, b.y);
-      y.z = fmaf((v.z - mean) * rstd, g.z, b.z);
-      y.w = fmaf((v.w - mean) * rstd, g.w, b.w);
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < LN_MAXCH + 2; ++k) {     // + the zero padding up to Kpad (< 64 columns past C)
+      const int i = lane + 32 * k;
+      if (i >= (Kpad >> 2)) break;
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < LN_MAXCH && i < C4) {
+        const float4 t = v[k < LN_MAXCH ? k : 0], g = __ldg(g4 + i), b = __ldg(b4 + i);
+        y.x = fmaf((t.x - mean) * rstd, g.x, b.x);
+        y.y = fmaf((t.y - mean) * rstd, g.y, b.y);
+        y.z = fmaf((t.z - mean) * rstd, g.z, b.z);
+        y.w = fmaf((t.w - mean) * rstd, g.w, b.w);
+      }
+      split_store4(hi, lo, base + 4 * (size_t)i, y.x, y.y, y.z, y.w);
     }
-    split_store4(hi, lo, base + 4 * (size_t)i, y.x, y.y, y.z, y.w);
+  } else {
+    for (int i = lane; i < (Kpad >> 2); i += 32) {
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < C4) {
+        float4 t = __ldg(xr + i), g = __ldg(g4 + i), b = __ldg(b4 + i);
+        y.x = fmaf((t.x - mean) * rstd, g.x, b.x);
+        y.y = fmaf((t.y - mean) * rstd, g.y, b.y);
+        y.z = fmaf((t.z - mean) * rstd, g.z, b.z);
+        y.w = fmaf((t.w - mean) * rstd, g.w, b.w);
+      }
+      split_store4(hi, lo, base + 4 * (size_t)i, y.x, y.y, y.z, y.w);
+    }
   }
 }
 
 // dx = rstd * (a - mean(a) - xhat * mean(a * xhat)),  a = g * gamma,  xhat = (x - mean) * rstd
+template <bool CACHED>
 __global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g,
                                                                 int64_t ldg, int rows, int C, const float* __restrict__ gamma,
                                                                 const float2* __restrict__ stats, float* __restrict__ dx,
@@ -70,22 +111,48 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln_bwd_kernel(const float* __r
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float2 st = stats[row];
   const int C4 = C >> 2;
+  float4 xh[LN_MAXCH], av[LN_MAXCH];   // CACHED: xhat and a = g * gamma of this lane's chunks
   float s1 = 0.f, s2 = 0.f;
-  for (int i = lane; i < C4; i += 32) {
-    float4 v = __ldg(xr + i), gg = __ldg(gr + i), w = __ldg(g4 + i);
-    float a0 = gg.x * w.x, a1 = gg.y * w.y, a2 = gg.z * w.z, a3 = gg.w * w.w;
-    s1 += (a0 + a1) + (a2 + a3);
-    s2 += a0 * ((v.x - st.x) * st.y) + a1 * ((v.y - st.x) * st.y) + a2 * ((v.z - st.x) * st.y) + a3 * ((v.w - st.x) * st.y);
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < LN_MAXCH; ++k) {
+      const int i = lane + 32 * k;
+      xh[k] = av[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < C4) {
+        const float4 v = __ldg(xr + i), gg = __ldg(gr + i), w = __ldg(g4 + i);
+        xh[k] = make_float4((v.x - st.x) * st.y, (v.y - st.x) * st.y, (v.z - st.x) * st.y, (v.w - st.x) * st.y);
+        av[k] = make_float4(gg.x * w.x, gg.y * w.y, gg.z * w.z, gg.w * w.w);
+        s1 += (av[k].x + av[k].y) + (av[k].z + av[k].w);
+        s2 += av[k].x * xh[k].x + av[k].y * xh[k].y + av[k].z * xh[k].z + av[k].w * xh[k].w;
+      }
+    }
+  } else {
+    for (int i = lane; i < C4; i += 32) {
+      float4 v = __ldg(xr + i), gg = __ldg(gr + i), w = __ldg(g4 + i);
+      float a0 = gg.x * w.x, a1 = gg.y * w.y, a2 = gg.z * w.z, a3 = gg.w * w.w;
+      s1 += (a0 + a1) + (a2 + a3);
+      s2 += a0 * ((v.x - st.x) * st.y) + a1 * ((v.y - st.x) * st.y) + a2 * ((v.z - st.x) * st.y) + a3 * ((v.w - st.x) * st.y);
+    }
   }
   const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
   float4* dr = reinterpret_cast<float4*>(dx + (size_t)row * lddx);
-  for (int i = lane; i < C4; i += 32) {
-    float4 v = __ldg(xr + i), gg = __ldg(gr + i), w = __ldg(g4 + i), o;
-    o.x = st.y * (gg.x * w.x - m1 - (v.x - st.x) * st.y * m2);
-    o.y = st.y * (gg.y * w.y - m1 - (v.y - st.x) * st.y * m2);
-    o.z = st.y * (gg.z * w.z - m1 - (v.z - st.x) * st.y * m2);
-    o.w = st.y * (gg.w * w.w - m1 - (v.w - st.x) * st.y * m2);
-    dr[i] = o;
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < LN_MAXCH; ++k) {
+      const int i = lane + 32 * k;
+      if (i < C4)
+        dr[i] = make_float4(st.y * (av[k].x - m1 - xh[k].x * m2), st.y * (av[k].y - m1 - xh[k].y * m2),
+                            st.y * (av[k].z - m1 - xh[k].z * m2), st.y * (av[k].w - m1 - xh[k].w * m2));
+    }
+  } else {
+    for (int i = lane; i < C4; i += 32) {
+      float4 v = __ldg(xr + i), gg = __ldg(gr + i), w = __ldg(g4 + i), o;
+      o.x = st.y * (gg.x * w.x - m1 - (v.x - st.x) * st.y * m2);
+      o.y = st.y * (gg.y * w.y - m1 - (v.y - st.x) * st.y * m2);
+      o.z = st.y * (gg.z * w.z - m1 - (v.z - st.x) * st.y * m2);
+      o.w = st.y * (gg.w * w.w - m1 - (v.w - st.x) * st.y * m2);
+      dr[i] = o;
+    }
   }
 }
 
@@ -183,8 +250,13 @@ extern "C" int skp_ln_split_fwd(const float* x, int64_t ldx, int rows, int C, co
   SKP_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(beta) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
                   (reinterpret_cast<uintptr_t>(lo) & 7) == 0 && (stats == nullptr || (reinterpret_cast<uintptr_t>(stats) & 7) == 0),
               "skp_ln_split_fwd: misaligned pointer");
-  ln_split_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      x, ldx, rows, C, gamma, beta, eps, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad, reinterpret_cast<float2*>(stats));
+  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  if (C <= 128 * LN_MAXCH)
+    ln_split_kernel<true><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, gamma, beta, eps, (__nv_bfloat16*)hi,
+                                                                             (__nv_bfloat16*)lo, Kpad, reinterpret_cast<float2*>(stats));
+  else
+    ln_split_kernel<false><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, gamma, beta, eps, (__nv_bfloat16*)hi,
+                                                                              (__nv_bfloat16*)lo, Kpad, reinterpret_cast<float2*>(stats));
   SKP_CHECK_LAUNCH("ln_split_kernel");
   return SKP_OK;
 }
@@ -195,8 +267,13 @@ extern "C" int skp_ln_bwd(const float* x, int64_t ldx, const float* g, int64_t l
   SKP_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldg % 4 == 0 && lddx % 4 == 0, "skp_ln_bwd: bad sizes rows=%d C=%d", rows, C);
   SKP_REQUIRE(aligned16(x) && aligned16(g) && aligned16(gamma) && aligned16(dx) && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
               "skp_ln_bwd: misaligned pointer");
-  ln_bwd_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      x, ldx, g, ldg, rows, C, gamma, reinterpret_cast<const float2*>(stats), dx, lddx);
+  const int grid = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  if (C <= 128 * LN_MAXCH)
+    ln_bwd_kernel<true><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, g, ldg, rows, C, gamma,
+                                                                           reinterpret_cast<const float2*>(stats), dx, lddx);
+  else
+    ln_bwd_kernel<false><<<grid, ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, g, ldg, rows, C, gamma,
+                                                                            reinterpret_cast<const float2*>(stats), dx, lddx);
   SKP_CHECK_LAUNCH("ln_bwd_kernel");
   return SKP_OK;
 }

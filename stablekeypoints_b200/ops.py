@@ -230,8 +230,11 @@ def frozen_linear(x: torch.Tensor, fw: FrozenWeight, bias: Optional[torch.Tensor
 
 
 # ----------------------------------------------------------------------------- GroupNorm(+SiLU) fused into what follows
+GN_REPL = 8   # replicas of the fp64 accumulators (skp_norm.cu GN_REPL; include/skp_b200.h)
+
+
 def _gn_stats(x2d: torch.Tensor, groups: int) -> torch.Tensor:
-    sums = torch.empty(2 * groups, dtype=torch.float64, device=x2d.device)
+    sums = torch.empty(2 * groups * GN_REPL, dtype=torch.float64, device=x2d.device)
     check(lib().skp_gn_stats(ptr(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], groups, ptr(sums), stream()), "skp_gn_stats")
     return sums
 
@@ -239,7 +242,7 @@ def _gn_stats(x2d: torch.Tensor, groups: int) -> torch.Tensor:
 def _gn_backward(x2d, g, sums, gamma, beta, groups, eps, silu):
     g = _f32c(g)
     dx = torch.empty_like(x2d)
-    bs = torch.empty(2 * groups, dtype=torch.float64, device=x2d.device)
+    bs = torch.empty(2 * groups * GN_REPL, dtype=torch.float64, device=x2d.device)
     check(lib().skp_gn_bwd(ptr(x2d), x2d.stride(0), ptr(g), g.stride(0), x2d.shape[0], x2d.shape[1], groups, ptr(sums), eps,
                            ptr(gamma), ptr(beta), int(silu), ptr(bs), ptr(dx), dx.stride(0), stream()), "skp_gn_bwd")
     return dx
