@@ -334,46 +334,71 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
 
 // 3x3 im2col of a channels-last activation x[H*W, C] (row stride ldx) straight into the split-bf16 K-major operand:
 // row = output pixel, column = tap*C + c, zero outside the image and in the K padding.  One warp per (pixel, tap).
+__device__ __forceinline__ void store_split4_bf16(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t o, float4 v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  *reinterpret_cast<uint2*>(hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+}
+
+// Wide channels (C % 4 == 0, 16-byte aligned rows): one warp per output pixel, the 9 taps of a 128-channel slab are
+// loaded back to back (9 independent 128-bit loads in flight per lane) before they are converted and stored.
 __global__ void im2col3x3_split_kernel(const float* __restrict__ x, int64_t ldx, int H, int W, int C, int Ho, int Wo,
                                        int stride, int pad, int Kpad, __nv_bfloat16* __restrict__ hi,
                                        __nv_bfloat16* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  const long items = (long)Ho * Wo * 9;
-  const bool vec = (C & 3) == 0 && (ldx & 3) == 0 && ((((uintptr_t)x) & 15) == 0);
-  for (long it = warp; it < items; it += nwarps) {
-    const int tap = (int)(it % 9);
-    const long row = it / 9;
+  const long pixels = (long)Ho * Wo;
+  for (long row = warp; row < pixels; row += nwarps) {
     const int oy = (int)(row / Wo), ox = (int)(row - (long)oy * Wo);
-    const int iy = oy * stride + tap / 3 - pad, ix = ox * stride + tap % 3 - pad;
-    const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
-    const float* src = x + ((size_t)(inside ? iy : 0) * W + (inside ? ix : 0)) * ldx;
-    const size_t dst = (size_t)row * Kpad + (size_t)tap * C;
-    if (vec) {
-      for (int c = lane * 4; c < C; c += 128) {
-        float4 v = inside ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
-        __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
-        __nv_bfloat162 la = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
-        __nv_bfloat162 lb = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
-        uint2 hv = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
-        uint2 lv = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
-        *reinterpret_cast<uint2*>(hi + dst + c) = hv;
-        *reinterpret_cast<uint2*>(lo + dst + c) = lv;
-      }
-    } else {
-      for (int c = lane; c < C; c += 32) {
-        float v = inside ? src[c] : 0.f;
-        __nv_bfloat16 h = __float2bfloat16_rn(v);
-        hi[dst + c] = h;
-        lo[dst + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    const float* src[9];
+    bool inside[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = oy * stride + tap / 3 - pad, ix = ox * stride + tap % 3 - pad;
+      inside[tap] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      src[tap] = x + ((size_t)(inside[tap] ? iy : 0) * W + (inside[tap] ? ix : 0)) * ldx;
+    }
+    const size_t dst = (size_t)row * Kpad;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 v[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+        v[tap] = inside[tap] ? __ldg(reinterpret_cast<const float4*>(src[tap] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) store_split4_bf16(hi, lo, dst + (size_t)tap * C + c, v[tap]);
+    }
+    for (int c = 9 * C + lane * 4; c < Kpad; c += 128) store_split4_bf16(hi, lo, dst + c, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
+// Any channel count (the 3- and 4-channel conv_in of VAE / UNet): one thread per (output pixel, pair of K columns).
+__global__ void im2col3x3_split_generic_kernel(const float* __restrict__ x, int64_t ldx, int H, int W, int C, int Ho, int Wo,
+                                               int stride, int pad, int Kpad, __nv_bfloat16* __restrict__ hi,
+                                               __nv_bfloat16* __restrict__ lo) {
+  const int half = Kpad >> 1;
+  const long total = (long)Ho * Wo * half;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long row = i / half;
+    const int k0 = (int)(i - row * half) << 1;
+    const int oy = (int)(row / Wo), ox = (int)(row - (long)oy * Wo);
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = k0 + j;
+      v[j] = 0.f;
+      if (k < 9 * C) {
+        const int tap = k / C, c = k - tap * C;
+        const int iy = oy * stride + tap / 3 - pad, ix = ox * stride + tap % 3 - pad;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[j] = __ldg(x + ((size_t)iy * W + ix) * ldx + c);
       }
     }
-    if (tap == 8)
-      for (int c = 9 * C + lane; c < Kpad; c += 32) {
-        hi[(size_t)row * Kpad + c] = __float2bfloat16_rn(0.f);
-        lo[(size_t)row * Kpad + c] = __float2bfloat16_rn(0.f);
-      }
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+    float2 f = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(v[0] - f.x, v[1] - f.y);
+    *reinterpret_cast<__nv_bfloat162*>(hi + (size_t)row * Kpad + k0) = h;
+    *reinterpret_cast<__nv_bfloat162*>(lo + (size_t)row * Kpad + k0) = l;
   }
 }
 
@@ -591,11 +616,18 @@ extern "C" int skp_im2col3x3_split(const float* x, int64_t ldx, int H, int W, in
                                    int Kpad, void* hi, void* lo, void* stream) {
   SKP_REQUIRE(x && hi && lo && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && stride > 0, "im2col3x3_split: bad arguments");
   SKP_REQUIRE(Kpad >= 9 * C && Kpad % TC_BK == 0, "im2col3x3_split: Kpad=%d must be a multiple of 64 >= 9*C", Kpad);
-  long items = (long)Ho * Wo * 9;
-  long blocks = (items * 32 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col3x3_split_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, H, W, C, Ho, Wo, stride, pad, Kpad,
-                                                                       (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  const bool vec = (C & 3) == 0 && (ldx & 3) == 0 && ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)hi) | ((uintptr_t)lo)) & 7) == 0;
+  if (vec && C >= 32) {
+    long blocks = ((long)Ho * Wo * 32 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    im2col3x3_split_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, H, W, C, Ho, Wo, stride, pad, Kpad,
+                                                                         (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  } else {
+    long blocks = ((long)Ho * Wo * (Kpad / 2) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    im2col3x3_split_generic_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, H, W, C, Ho, Wo, stride, pad, Kpad,
+                                                                                 (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  }
   SKP_CHECK_LAUNCH("im2col3x3_split");
   return SKP_OK;
 }
