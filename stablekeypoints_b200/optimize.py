@@ -362,8 +362,11 @@ def optimize_embedding(ldm, args, controllers, num_gpus, context=None,
             dist.broadcast(context, src=0)
     context = context.to(dev).detach().clone().contiguous()
     context.requires_grad = True
-    optimizer = EmbeddingOptimizer(context, lr=args.lr)
     accum = max(1, args.batch_size // (num_gpus * world))
+    # one image per optimizer step per rank (the reference's default batch_size == num_gpus): replay the whole step as
+    # ONE 3-stream CUDA graph (Stage1Graph); gradient accumulation (B//G > 1) keeps the eager loop
+    use_graph = accum == 1 and getattr(args, "cuda_graph", os.environ.get("SKP_LOOP_GRAPH", "1") != "0")
+    optimizer = EmbeddingOptimizer(context, lr=args.lr, capturable=bool(use_graph))
     start = it_start = time.time()
     running = {"equiv": 0.0, "sharp": 0.0, "total": 0.0}
     sampler = None
@@ -373,20 +376,49 @@ def optimize_embedding(ldm, args, controllers, num_gpus, context=None,
     loader = torch.utils.data.DataLoader(dataset, batch_size=num_gpus, shuffle=sampler is None, sampler=sampler,
                                          drop_last=True, pin_memory=True)
     it = iter(loader)
-    for iteration in range(int(int(args.num_steps) * accum)):
+
+    def next_batch():
+        nonlocal it
         try:
-            batch = next(it)
+            return next(it)
         except StopIteration:
             it = iter(loader)
-            batch = next(it)
-        out = stage1_iteration(ldm, controllers, batch["img"], context, transform, args, accum=accum,
-                               from_where=from_where)
+            return next(it)
+
+    graph = None
+    n_iters = int(int(args.num_steps) * accum)
+    if use_graph and n_iters > 0:
+        first = next_batch()
+        graph = Stage1Graph(ldm, controllers, context, optimizer, args, image_shape=tuple(first["img"].shape),
+                            from_where=from_where)
+        graph.transform = transform
+        graph.set_inputs(first["img"], transform.sample_theta(first["img"].shape[0]))
+        graph.capture()            # warm-up steps are rolled back (optimizer state and embedding restored)
+        graph.prime()              # fill the VAE prefetch stage with the first image
+    for iteration in range(n_iters):
+        if graph is not None:
+            if graph.latency == 1:
+                # VAE prefetch: feed the NEXT image (its encodes overlap this step); replay() trains on the current one
+                if iteration + 1 < n_iters:
+                    nxt = next_batch()
+                    graph.set_inputs(nxt["img"], transform.sample_theta(nxt["img"].shape[0]))
+            else:
+                cur = first if iteration == 0 else next_batch()
+                if iteration > 0:
+                    graph.set_inputs(cur["img"], transform.sample_theta(cur["img"].shape[0]))
+            out = graph.replay()
+            out = {k: v.clone() for k, v in out.items() if k in ("loss", "sharp", "equiv")}
+        else:
+            batch = next_batch()
+            out = stage1_iteration(ldm, controllers, batch["img"], context, transform, args, accum=accum,
+                                   from_where=from_where)
         running["equiv"] += out["equiv"] / accum * args.equivariance_attn_loss_weight
         running["sharp"] += out["sharp"] / accum * args.sharpening_loss_weight
         running["total"] += out["loss"] / accum
         if (iteration + 1) % accum == 0:
-            optimizer.step()
-            optimizer.zero_grad()
+            if graph is None:              # the graph holds the all-reduce + Adam update itself
+                optimizer.step()
+                optimizer.zero_grad()
             ldm.unet.invalidate_context_cache()
             if rank == 0:
                 msg = {"loss": float(running["total"]), "running_equivariance_attn_loss": float(running["equiv"]),

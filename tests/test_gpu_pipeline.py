@@ -249,3 +249,33 @@ def test_find_best_indices_runs_on_synthetic_dataset(tiny):
     idx = keypoint_regressor.find_best_indices(ldm, torch.from_numpy(t["context"]).cuda(), args, controllers, 1)
     assert idx.shape == (TINY["top_k"],) and len(set(idx.tolist())) == TINY["top_k"]
     assert all(0 <= i < TINY["n_tokens"] for i in idx.tolist())
+
+
+def test_optimize_embedding_graph_loop_matches_eager_loop(tiny, monkeypatch):
+    """The drop-in entry point (optimize.py:269-452): the default loop replays one 3-stream CUDA graph per optimizer step
+    (VAE prefetch of the next image included); it must walk the same images / warps and land on the same embedding as
+    the eager loop (fixed noise, so the two differ only by fp32 summation order)."""
+    import itertools
+    from stablekeypoints_b200 import optimize
+    g, pipe = tiny
+    ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
+    results = []
+    for use_graph in (False, True):
+        noises = itertools.cycle([torch.from_numpy(g["noise_a"]).cuda(), torch.from_numpy(g["noise_b"]).cuda()])
+        monkeypatch.setattr(torch, "randn_like", lambda t, *a, _n=noises, **k: next(_n).clone())
+        torch.manual_seed(11)                      # the host-side theta draws (invertable_transform.py:42-57)
+        args = _args(top_k=TINY["top_k"], furthest_point_num_samples=TINY["num_candidates"], sigma=TINY["sigma"],
+                     dataset=optimize.SyntheticKeypointDataset(length=4, size=TINY["image_size"], seed=5, blobs=6),
+                     dataset_name="synthetic", augment_degrees=15, augment_scale=(0.8, 1.0), augment_translate=(0.25, 0.25),
+                     num_tokens=TINY["n_tokens"], lr=5e-3, batch_size=1, num_steps=4, cuda_graph=use_graph, wandb=False)
+        ctx0 = torch.from_numpy(g["context"]).cuda()
+        # shuffle=True in the loader: fix the order so both runs see the same images
+        monkeypatch.setattr(torch.utils.data, "DataLoader",
+                            lambda ds, **kw: [{"img": ds[i]["img"][None]} for i in range(len(ds))])
+        out = optimize.optimize_embedding(ldm, args, controllers, 1, context=ctx0)
+        results.append(out.clone())
+    eager, graph = results
+    assert eager.shape == graph.shape == (1, TINY["n_tokens"], ldm.unet.cfg.cross_attention_dim)
+    assert float((eager - torch.from_numpy(g["context"]).cuda()).abs().max()) > 1e-3          # it did train
+    assert float((graph - eager).abs().mean() / eager.abs().mean()) < 2e-4
+    assert rel_err(graph.cpu(), eager.cpu()) < 3e-2
