@@ -142,6 +142,18 @@ int skp_self_attn_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ld
                       const void* planes, void* do_planes, float* dvec, float* dq, int64_t lddq, float* dk,
                       int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale, void* stream);
 
+/* Long-sequence self-attention forward on tcgen05 (QK^T and PV as tcgen05.mma with TMEM accumulators, operands by TMA,
+ * P handed from the softmax warps to the tensor core through 128B-swizzled shared memory; same split-bf16 numerics).
+ * Needs S % 128 == 0 and even d <= 64; workspace = skp_self_attn_tc_workspace(S, heads, d) bytes (0 = shape not
+ * eligible), 128-byte aligned.  lse as in skp_self_attn_fwd; the backward is skp_self_attn_bwd on planes made by
+ * skp_self_attn_split (6*heads*S*DP bf16). */
+int64_t skp_self_attn_tc_workspace(int S, int heads, int d);
+int skp_self_attn_tc_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                         float* o, int64_t ldo, float* lse, void* workspace, int S, int heads, int d, float scale,
+                         void* stream);
+int skp_self_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        void* planes, int S, int heads, int d, float scale, void* stream);
+
 /* Cross-attention core on the same split-bf16 tensor-core kernels (S queries, N << S keys): the tensor-core
  * replacement of skp_cross_attn_fwd/bwd.  logits (nullable) receives the scaled scores [heads, S, N] of a captured
  * layer; lse[heads, S]; q_planes: 2*heads*S*DP bf16, kv_planes: 4*heads*N*DP bf16 (kept for the backward).

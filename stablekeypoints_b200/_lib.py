@@ -46,6 +46,9 @@ _SIGNATURES: Dict[str, list] = {
     "skp_cross_attn_fwd": [_P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_cross_attn_bwd": [_P, _P, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_self_attn_dp": [_I],
+    "skp_self_attn_tc_workspace": [_I, _I, _I],
+    "skp_self_attn_tc_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _F, _P],
+    "skp_self_attn_split": [_P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _F, _P],
     "skp_self_attn_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _F, _P],
     "skp_self_attn_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P],
     "skp_cross_attn_tc_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
@@ -73,7 +76,8 @@ _SIGNATURES: Dict[str, list] = {
     "skp_adam_step": [_P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _P],
     "skp_adam_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }
-_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None}
+_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None,
+            "skp_self_attn_tc_workspace": C.c_int64}
 
 
 def declared_symbols() -> List[str]:

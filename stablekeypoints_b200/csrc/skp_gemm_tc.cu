@@ -13,89 +13,13 @@
 //                              releases the stage and finally signals the epilogue
 //   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 (one accumulator row per thread), alpha/bias/residual,
 //                              vectorised global stores
-#include "skp_common.cuh"
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include "skp_tc.cuh"
 
 namespace skp {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_THREADS = 192;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups 1024 B apart (SBO), LBO unused (=1).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
-  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-  return d;
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 template <int BN, int STAGES>
 struct TcCfg {
@@ -421,7 +345,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, const void* ptr, int rows, int kpad, int box_rows) {
+int tc_make_map(CUtensorMap* m, const void* ptr, int rows, int kpad, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("gemm_nt_tc: cuTensorMapEncodeTiled entry point unavailable"); return SKP_ERR_DRIVER; }
   cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
@@ -477,8 +401,8 @@ static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin
   int rc;
   if ((rc = make_map_3d(&ta_hi, X_hi, H, W, Cin, cg.BW, cg.BH))) return rc;
   if ((rc = make_map_3d(&ta_lo, X_lo, H, W, Cin, cg.BW, cg.BH))) return rc;
-  if ((rc = make_map(&tb_hi, B_hi, N, Kpad, BN))) return rc;
-  if ((rc = make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
+  if ((rc = tc_make_map(&tb_hi, B_hi, N, Kpad, BN))) return rc;
+  if ((rc = tc_make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
   cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
   const int num_kb = Kpad / TC_BK;
@@ -502,10 +426,10 @@ static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const
   using Cfg = TcCfg<BN, STAGES>;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_map(&ta_hi, A_hi, M, Kpad, TC_BM))) return rc;
-  if ((rc = make_map(&ta_lo, A_lo, M, Kpad, TC_BM))) return rc;
-  if ((rc = make_map(&tb_hi, B_hi, N, Kpad, BN))) return rc;
-  if ((rc = make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
+  if ((rc = tc_make_map(&ta_hi, A_hi, M, Kpad, TC_BM))) return rc;
+  if ((rc = tc_make_map(&ta_lo, A_lo, M, Kpad, TC_BM))) return rc;
+  if ((rc = tc_make_map(&tb_hi, B_hi, N, Kpad, BN))) return rc;
+  if ((rc = tc_make_map(&tb_lo, B_lo, N, Kpad, BN))) return rc;
   cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) { set_error("gemm_nt_tc: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
   const int num_kb = Kpad / TC_BK;

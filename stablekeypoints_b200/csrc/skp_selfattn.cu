@@ -903,3 +903,24 @@ extern "C" int skp_cross_attn_tc_bwd(const float* d_o, int64_t lddo, const float
   return sa_backward(d_o, lddo, o, ldo, lse, (const bf16*)q_planes, (const bf16*)kv_planes, (bf16*)do_planes, dvec,
                      d_logits_extra, dq, lddq, dk, lddk, dv, lddv, S, N, heads, d, scale, true, (cudaStream_t)stream);
 }
+
+/* Operand split only (the planes skp_self_attn_bwd needs) -- used when the forward ran on the tcgen05 kernel
+ * (skp_attn_tc.cu), which keeps its own operand layout. */
+extern "C" int skp_self_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                   void* planes, int S, int heads, int d, float scale, void* stream) {
+  SKP_REQUIRE(q && k && v && planes && S > 0 && heads > 0 && d > 0 && d % 2 == 0, "skp_self_attn_split: bad arguments");
+  const int DP = sa_dp(d);
+  if (DP == 0) {
+    set_error("skp_self_attn_split: head dim %d > 160 unsupported", d);
+    return SKP_ERR_UNSUPPORTED;
+  }
+  bf16* qp = (bf16*)planes;
+  bf16* kvp = qp + (size_t)2 * heads * S * DP;
+  int64_t total = (int64_t)heads * 3 * S * (DP / 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sa_split_qkv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, qp, kvp, S, S, heads, d, DP,
+                                                               scale * 1.4426950408889634f);
+  SKP_CHECK_LAUNCH("sa_split_qkv_kernel");
+  return SKP_OK;
+}

@@ -552,9 +552,16 @@ def cross_attn_core(q, k, v, heads: int, scale: float, want_logits: bool = False
 SELF_ATTN_MAX_D = 160
 
 
+# long sequences (S % 128 == 0, d <= 64): forward on the tcgen05/TMEM kernel of skp_attn_tc.cu ("0" = mma.sync kernels only)
+SELF_ATTN_TC = os.environ.get("SKP_SELF_ATTN_TC", "1") != "0"
+SELF_ATTN_TC_MIN_S = 1024
+
+
 class _SelfAttnCore(torch.autograd.Function):
     """softmax(q k^T scale) v per head from the packed projection qkv[S, 3C] (columns q | k | v, head-major inside
-    each): flash-style split-bf16 tensor-core kernels (skp_selfattn.cu); the split operands are kept for backward."""
+    each): flash-style split-bf16 tensor-core kernels.  Forward: tcgen05 kernel (skp_attn_tc.cu) for long sequences,
+    mma.sync kernel (skp_selfattn.cu) otherwise; backward: mma.sync kernels on split operand planes (kept from the
+    forward, or re-made from qkv when the forward ran on tcgen05)."""
 
     @staticmethod
     def forward(ctx, qkv, heads: int, scale: float):
@@ -568,19 +575,36 @@ class _SelfAttnCore(torch.autograd.Function):
             raise SkpError(f"self-attention head dim {d} unsupported (even, <= {SELF_ATTN_MAX_D})")
         o = torch.empty(s, c, dtype=torch.float32, device=qkv.device)
         lse = torch.empty(heads, s, dtype=torch.float32, device=qkv.device)
-        planes = torch.empty(6 * heads * s * dp, dtype=torch.bfloat16, device=qkv.device)
         e = qkv.element_size()
-        check(lib().skp_self_attn_fwd(qkv.data_ptr(), c3, qkv.data_ptr() + c * e, c3, qkv.data_ptr() + 2 * c * e, c3,
-                                      ptr(o), c, ptr(lse), ptr(planes), s, heads, d, scale, stream()), "skp_self_attn_fwd")
-        ctx.save_for_backward(o, lse, planes)
+        qp, kp, vp = qkv.data_ptr(), qkv.data_ptr() + c * e, qkv.data_ptr() + 2 * c * e
+        ws_bytes = int(lib().skp_self_attn_tc_workspace(s, heads, d)) if (SELF_ATTN_TC and s >= SELF_ATTN_TC_MIN_S) else 0
+        if ws_bytes > 0:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device)
+            check(lib().skp_self_attn_tc_fwd(qp, c3, kp, c3, vp, c3, ptr(o), c, ptr(lse), ptr(ws), s, heads, d, scale, stream()),
+                  "skp_self_attn_tc_fwd")
+            ctx.save_for_backward(o, lse, qkv)
+            ctx.tc = True
+        else:
+            planes = torch.empty(6 * heads * s * dp, dtype=torch.bfloat16, device=qkv.device)
+            check(lib().skp_self_attn_fwd(qp, c3, kp, c3, vp, c3, ptr(o), c, ptr(lse), ptr(planes), s, heads, d, scale, stream()),
+                  "skp_self_attn_fwd")
+            ctx.save_for_backward(o, lse, planes)
+            ctx.tc = False
         ctx.meta = (s, c, heads, d, dp, scale)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
-        o, lse, planes = ctx.saved_tensors
+        o, lse, third = ctx.saved_tensors
         s, c, heads, d, dp, scale = ctx.meta
         d_o = _f32c(d_o)
+        if ctx.tc:        # the tcgen05 forward keeps its own operand layout: make the mma.sync planes from qkv now
+            qkv, e, c3 = third, third.element_size(), 3 * c
+            planes = torch.empty(6 * heads * s * dp, dtype=torch.bfloat16, device=o.device)
+            check(lib().skp_self_attn_split(qkv.data_ptr(), c3, qkv.data_ptr() + c * e, c3, qkv.data_ptr() + 2 * c * e, c3,
+                                            ptr(planes), s, heads, d, scale, stream()), "skp_self_attn_split")
+        else:
+            planes = third
         do_planes = torch.empty(2 * heads * s * dp, dtype=torch.bfloat16, device=o.device)
         dvec = torch.empty(heads, s, dtype=torch.float32, device=o.device)
         dqkv = torch.empty(s, 3 * c, dtype=torch.float32, device=o.device)

@@ -213,8 +213,12 @@ def test_cross_attn_fwd_bwd(ops, s, n, heads, d, impl, tol):
 
 # ----------------------------------------------------------------------------- self-attention (attn1)
 @pytest.mark.parametrize("s,heads,d", [(4096, 8, 40), (1024, 8, 80), (256, 8, 160), (64, 8, 160), (16, 4, 8), (100, 2, 16),
-                                       (4, 4, 32), (1100, 3, 24), (77, 2, 48)])
-def test_self_attn_fwd_bwd(ops, s, heads, d):
+                                       (4, 4, 32), (1100, 3, 24), (77, 2, 48), (128, 2, 16), (256, 3, 64), (1024, 4, 32),
+                                       (384, 2, 48)])
+@pytest.mark.parametrize("tc", [True, False])
+def test_self_attn_fwd_bwd(ops, s, heads, d, tc, monkeypatch):
+    monkeypatch.setattr(ops, "SELF_ATTN_TC", tc)            # tcgen05 forward (eligible shapes only) vs mma.sync forward
+    monkeypatch.setattr(ops, "SELF_ATTN_TC_MIN_S", 128)
     """Flash-style split-bf16 kernels vs float64 attention of the same packed [S, 3C] projection (fp32-grade: the
     softmax sits upstream of every captured map).  Ragged S, padded d and every tile shape are covered."""
     g = torch.Generator().manual_seed(s + heads + d)
