@@ -19,23 +19,23 @@ __device__ __forceinline__ float gaussian_target(int y, int x, const int64_t* __
   return g / (float)num;
 }
 
-__global__ void __launch_bounds__(1024) sharpen_fwd_kernel(const float* __restrict__ maps, int H, int W,
-                                                           const int64_t* __restrict__ sel, int K,
-                                                           const int64_t* __restrict__ peaks, int num, float denom,
-                                                           float* __restrict__ loss) {
+// Multi-CTA reduction: each CTA adds its share of the mean into the zero-initialised device scalar (the loss sits on
+// the serial part of the step between the two forwards' join and the backward, so one 1024-thread CTA cost 170 us).
+__global__ void __launch_bounds__(256) sharpen_fwd_kernel(const float* __restrict__ maps, int H, int W,
+                                                          const int64_t* __restrict__ sel, int K,
+                                                          const int64_t* __restrict__ peaks, int num, float denom,
+                                                          float* __restrict__ loss) {
   __shared__ float red[32];
   const int P = H * W;
   float acc = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float* m = maps + (size_t)sel[k] * P;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-      int y = i / W, x = i - y * W;
-      float d = m[i] - gaussian_target(y, x, peaks, num, K, k, H, W, denom);
-      acc = fmaf(d, d, acc);
-    }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * P; i += gridDim.x * blockDim.x) {
+    int k = i / P, pix = i - k * P;
+    int y = pix / W, x = pix - y * W;
+    float d = maps[(size_t)sel[k] * P + pix] - gaussian_target(y, x, peaks, num, K, k, H, W, denom);
+    acc = fmaf(d, d, acc);
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) *loss = acc / ((float)K * (float)P);
+  if (threadIdx.x == 0) atomicAdd(loss, acc / ((float)K * (float)P));
 }
 
 __global__ void sharpen_bwd_kernel(const float* __restrict__ maps, int H, int W, const int64_t* __restrict__ sel, int K,
@@ -87,16 +87,16 @@ __device__ __forceinline__ float sample_tap(const float* __restrict__ m, const B
   return v;
 }
 
-__global__ void __launch_bounds__(1024) equiv_fwd_kernel(const float* __restrict__ maps, const float* __restrict__ maps_t,
-                                                         int H, int W, const int64_t* __restrict__ sel, int K,
-                                                         const float* __restrict__ theta_inv, float* __restrict__ loss) {
+__global__ void __launch_bounds__(256) equiv_fwd_kernel(const float* __restrict__ maps, const float* __restrict__ maps_t,
+                                                        int H, int W, const int64_t* __restrict__ sel, int K,
+                                                        const float* __restrict__ theta_inv, float* __restrict__ loss) {
   __shared__ float red[32];
   __shared__ float th[6];
   if (threadIdx.x < 6) th[threadIdx.x] = theta_inv[threadIdx.x];
   __syncthreads();
   const int P = H * W;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
     int y = i / W, x = i - y * W;
     BilinearTap t = affine_tap(th, y, x, H, W);
     for (int k = 0; k < K; ++k) {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(1024) equiv_fwd_kernel(const float* __restrict
     }
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) *loss = acc / ((float)K * (float)P);
+  if (threadIdx.x == 0) atomicAdd(loss, acc / ((float)K * (float)P));
 }
 
 __global__ void equiv_bwd_kernel(const float* __restrict__ maps, const float* __restrict__ maps_t, int H, int W,
@@ -252,7 +252,8 @@ extern "C" int skp_sharpen_loss_fwd(const float* maps, int H, int W, const int64
                                     int num, float sigma, float* loss, void* stream) {
   SKP_REQUIRE(maps && sel && peaks && loss && H > 0 && W > 0 && K > 0 && num > 0 && sigma > 0.f, "sharpen_loss_fwd: bad arguments");
   float denom = (float)(2.0 * (double)sigma * (double)sigma);
-  sharpen_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(maps, H, W, sel, K, peaks, num, denom, loss);
+  cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
+  sharpen_fwd_kernel<<<grid_for((size_t)K * H * W, 256), 256, 0, (cudaStream_t)stream>>>(maps, H, W, sel, K, peaks, num, denom, loss);
   SKP_CHECK_LAUNCH("sharpen_fwd");
   return SKP_OK;
 }
@@ -270,7 +271,8 @@ extern "C" int skp_sharpen_loss_bwd(const float* maps, int H, int W, const int64
 extern "C" int skp_equivariance_loss_fwd(const float* maps, const float* maps_t, int H, int W, const int64_t* sel, int K,
                                          const float* theta_inv, float* loss, void* stream) {
   SKP_REQUIRE(maps && maps_t && sel && theta_inv && loss && H > 0 && W > 0 && K > 0, "equivariance_loss_fwd: bad arguments");
-  equiv_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(maps, maps_t, H, W, sel, K, theta_inv, loss);
+  cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
+  equiv_fwd_kernel<<<grid_for((size_t)H * W, 256), 256, 0, (cudaStream_t)stream>>>(maps, maps_t, H, W, sel, K, theta_inv, loss);
   SKP_CHECK_LAUNCH("equiv_fwd");
   return SKP_OK;
 }

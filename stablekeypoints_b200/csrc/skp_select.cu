@@ -165,21 +165,35 @@ __global__ void fps_kernel(const int64_t* __restrict__ peaks, int H, int W, cons
     lx[c] = __fdiv_rn((float)(pk % W) + 0.5f, (float)H);
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x >= 32) return;
+  // One warp; every reduction reproduces the serial loop's "first strict maximum": larger value wins, ties go to the
+  // smaller (i, j) pair / candidate slot -- exactly the element the reference's Python loops keep.
+  const int lane = threadIdx.x;
   float best = -1.f;
-  int bi = 0, bj = 1;
-  for (int i = 0; i < n_cand; ++i)
-    for (int j = i + 1; j < n_cand; ++j) {
-      float d = fps_dist(ly, lx, i, j);
-      if (d > best) { best = d; bi = i; bj = j; }
+  int bp = 0x7fffffff;
+  for (int p = lane; p < n_cand * n_cand; p += 32) {
+    const int i = p / n_cand, j = p - i * n_cand;
+    if (j > i) {
+      const float dd = fps_dist(ly, lx, i, j);
+      if (dd > best) { best = dd; bp = p; }
     }
-  int n = 0;
-  chosen[n++] = bi;
-  chosen[n++] = bj;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+    if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; }
+  }
+  int n = 2;
+  if (lane == 0) {
+    chosen[0] = bp == 0x7fffffff ? 0 : bp / n_cand;
+    chosen[1] = bp == 0x7fffffff ? 1 : bp % n_cand;
+  }
+  __syncwarp();
   for (int it = 0; it < top_k - 2; ++it) {
     float bmin = -1.f;
-    int pick = -1;
-    for (int c = 0; c < n_cand; ++c) {
+    int pick = 0x7fffffff;
+    for (int c = lane; c < n_cand; c += 32) {
       // the reference skips by token VALUE (`i.item() in selected_indices`), so duplicate tokens are skipped too
       bool used = false;
       for (int k = 0; k < n; ++k) used |= (cand[chosen[k]] == cand[c]);
@@ -188,10 +202,20 @@ __global__ void fps_kernel(const int64_t* __restrict__ peaks, int H, int W, cons
       for (int k = 0; k < n; ++k) mn = fminf(mn, fps_dist(ly, lx, c, chosen[k]));
       if (mn > bmin) { bmin = mn; pick = c; }
     }
-    if (pick >= 0) chosen[n++] = pick;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, bmin, o);
+      const int op = __shfl_xor_sync(0xffffffffu, pick, o);
+      if (ob > bmin || (ob == bmin && op < pick)) { bmin = ob; pick = op; }
+    }
+    if (pick != 0x7fffffff) {
+      if (lane == 0) chosen[n] = pick;
+      ++n;
+    }
+    __syncwarp();
   }
-  for (int k = 0; k < n; ++k) out[k] = cand[chosen[k]];
-  *n_out = n;
+  for (int k = lane; k < n; k += 32) out[k] = cand[chosen[k]];
+  if (lane == 0) *n_out = n;
 }
 
 }  // namespace skp
