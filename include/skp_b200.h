@@ -80,6 +80,10 @@ int skp_conv3x3_tc(const void* X_hi, const void* X_lo, int H, int W, int Cin, co
  * projection; skp_gn_im2col3x3_split emits the split-bf16 3x3 im2col operand of a following convolution.
  * skp_gn_bwd: dx = d(loss)/dx from g = d(loss)/dy (gamma, beta frozen); bsums[SKP_GN_REPL][2*groups] is fp64 workspace. */
 int skp_gn_stats(const float* x, int64_t ldx, int rows, int C, int groups, double* sums, void* stream);
+/* skp_gn_stats + skp_gn_apply in one call; small activations take ONE launch (one CTA per group: no atomics, no memset). */
+int skp_gn_fwd(const float* x, int64_t ldx, int rows, int C, int groups, float eps, const float* gamma,
+               const float* beta, int silu, float* y, int64_t ldy, void* hi, void* lo, int Kpad, double* sums,
+               void* stream);
 int skp_gn_apply(const float* x, int64_t ldx, int rows, int C, int groups, const double* sums, float eps,
                  const float* gamma, const float* beta, int silu, float* y, int64_t ldy, void* hi, void* lo,
                  int Kpad, void* stream);

@@ -35,6 +35,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_im2col3x3_split": [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "skp_conv3x3_tc": [_P, _P, _I, _I, _I, _P, _P, _P, _L, _I, _F, _P, _P, _L, _I, _P, _P],
     "skp_gn_stats": [_P, _L, _I, _I, _I, _P, _P],
+    "skp_gn_fwd": [_P, _L, _I, _I, _I, _F, _P, _P, _I, _P, _L, _P, _P, _I, _P, _P],
     "skp_gn_apply": [_P, _L, _I, _I, _I, _P, _F, _P, _P, _I, _P, _L, _P, _P, _I, _P],
     "skp_gn_im2col3x3_split": [_P, _L, _I, _I, _I, _I, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "skp_gn_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _I, _P, _P, _L, _P],

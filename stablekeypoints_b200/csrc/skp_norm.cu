@@ -12,6 +12,7 @@
 // path runs through (ptp_utils.py:227-229, 299-302).
 #include "skp_common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace skp {
 
@@ -392,6 +393,140 @@ __global__ void __launch_bounds__(GN_THREADS) gn_im2col3x3_split_kernel(const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------------ one CTA per group
+// Small activations (the UNet at one image per rank: 64..4096 rows): statistics AND normalisation in ONE launch, one CTA per
+// group -- no atomics, no memset, no second kernel.  The CTA sweeps its [rows x cg] slab twice (the second sweep hits L1/L2).
+// Thread = (channel pair, row lane).  The (sum, sumsq) pair is still published (replica 0; the others zeroed) for the backward.
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_group_fwd_kernel(const float* __restrict__ x, int64_t ldx, int rows, int C, int cg,
+                                                                  float eps, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, int silu, float* __restrict__ y,
+                                                                  int64_t ldy, __nv_bfloat16* __restrict__ hi,
+                                                                  __nv_bfloat16* __restrict__ lo, int Kpad, double* __restrict__ sums) {
+  __shared__ double red[GN_THREADS / 32];
+  const int g = blockIdx.x, G = gridDim.x, c0 = g * cg;
+  const int PP = cg >> 1, RL = GN_THREADS / PP;
+  const int p = threadIdx.x % PP, ry = threadIdx.x / PP;
+  const bool active = ry < RL;
+  const float* xc = x + c0 + 2 * p;
+  float s = 0.f, ss = 0.f;
+  if (active)
+    for (int r = ry; r < rows; r += RL) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(xc + (size_t)r * ldx));
+      s += v.x + v.y;
+      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+    }
+  const double S = block_sum_d((double)s, red), SS = block_sum_d((double)ss, red);
+  const double count = (double)rows * cg;
+  const double md = S / count;
+  double var = SS / count - md * md;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)md, rstd = (float)(1.0 / sqrt(var + (double)eps));
+  if (threadIdx.x < 2 * GN_REPL) {   // replica 0 carries the sums, the rest must read as zero
+    const int r = threadIdx.x >> 1, w = threadIdx.x & 1;
+    sums[(size_t)r * 2 * G + 2 * g + w] = r == 0 ? (w == 0 ? S : SS) : 0.0;
+  }
+  if (active) {
+    const float g0 = __ldg(gamma + c0 + 2 * p), g1 = __ldg(gamma + c0 + 2 * p + 1);
+    const float sc0 = rstd * g0, sc1 = rstd * g1;
+    const float sh0 = fmaf(-mean, sc0, __ldg(beta + c0 + 2 * p)), sh1 = fmaf(-mean, sc1, __ldg(beta + c0 + 2 * p + 1));
+    for (int r = ry; r < rows; r += RL) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(xc + (size_t)r * ldx));
+      float z0 = fmaf(v.x, sc0, sh0), z1 = fmaf(v.y, sc1, sh1);
+      if (silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
+      if (y) *reinterpret_cast<float2*>(y + (size_t)r * ldy + c0 + 2 * p) = make_float2(z0, z1);
+      if (hi) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
+        const float2 f = __bfloat1622float2(h);
+        const size_t o = (size_t)r * Kpad + c0 + 2 * p;
+        *reinterpret_cast<__nv_bfloat162*>(hi + o) = h;
+        *reinterpret_cast<__nv_bfloat162*>(lo + o) = __floats2bfloat162_rn(z0 - f.x, z1 - f.y);
+      }
+    }
+  }
+  if (hi && Kpad > C && g == G - 1) {   // zero the K padding of the operand
+    const int padp = (Kpad - C) >> 1;
+    for (int i = threadIdx.x; i < rows * padp; i += GN_THREADS) {
+      const int r = i / padp, c = C + 2 * (i - r * padp);
+      *reinterpret_cast<uint32_t*>(hi + (size_t)r * Kpad + c) = 0u;
+      *reinterpret_cast<uint32_t*>(lo + (size_t)r * Kpad + c) = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_group_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gr,
+                                                                  int64_t ldg, int rows, int C, int cg,
+                                                                  const double* __restrict__ sums, float eps,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  int silu, float* __restrict__ dx, int64_t ldd) {
+  __shared__ double red[GN_THREADS / 32];
+  __shared__ float st[2];
+  const int g = blockIdx.x, G = gridDim.x, c0 = g * cg;
+  const double count = (double)rows * cg;
+  if (threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < GN_REPL; ++r) {
+      s1 += sums[(size_t)r * 2 * G + 2 * g];
+      s2 += sums[(size_t)r * 2 * G + 2 * g + 1];
+    }
+    const double m = s1 / count;
+    double var = s2 / count - m * m;
+    if (var < 0.0) var = 0.0;
+    st[0] = (float)m;
+    st[1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float mean = st[0], rstd = st[1];
+  const int PP = cg >> 1, RL = GN_THREADS / PP;
+  const int p = threadIdx.x % PP, ry = threadIdx.x / PP;
+  const bool active = ry < RL;
+  const int c = c0 + 2 * p;
+  float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (active) { g0 = __ldg(gamma + c); g1 = __ldg(gamma + c + 1); b0 = __ldg(beta + c); b1 = __ldg(beta + c + 1); }
+  const float sc = rstd, sh = -mean * rstd;
+  float a1 = 0.f, a2 = 0.f;
+  if (active)
+    for (int r = ry; r < rows; r += RL) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(x + (size_t)r * ldx + c));
+      const float2 gv = __ldg(reinterpret_cast<const float2*>(gr + (size_t)r * ldg + c));
+      const float xh0 = fmaf(v.x, sc, sh), xh1 = fmaf(v.y, sc, sh);
+      float dz0 = gv.x, dz1 = gv.y;
+      if (silu) { dz0 *= silu_grad(fmaf(g0, xh0, b0)); dz1 *= silu_grad(fmaf(g1, xh1, b1)); }
+      const float d0 = dz0 * g0, d1 = dz1 * g1;
+      a1 += d0 + d1;
+      a2 = fmaf(d0, xh0, fmaf(d1, xh1, a2));
+    }
+  const double A1 = block_sum_d((double)a1, red), A2 = block_sum_d((double)a2, red);
+  const float m1 = (float)(A1 / count), m2 = (float)(A2 / count);
+  if (active)
+    for (int r = ry; r < rows; r += RL) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(x + (size_t)r * ldx + c));
+      const float2 gv = __ldg(reinterpret_cast<const float2*>(gr + (size_t)r * ldg + c));
+      const float xh0 = fmaf(v.x, sc, sh), xh1 = fmaf(v.y, sc, sh);
+      float dz0 = gv.x, dz1 = gv.y;
+      if (silu) { dz0 *= silu_grad(fmaf(g0, xh0, b0)); dz1 *= silu_grad(fmaf(g1, xh1, b1)); }
+      *reinterpret_cast<float2*>(dx + (size_t)r * ldd + c) =
+          make_float2(sc * (dz0 * g0 - m1 - xh0 * m2), sc * (dz1 * g1 - m1 - xh1 * m2));
+    }
+}
+
+// the one-CTA-per-group kernels take even group widths up to 512 channels and slabs of at most 48K elements
+static inline bool gn_group_ok(int rows, int C, int groups, const float* x, int64_t ldx) {
+  const int cg = C / groups;
+  return (cg % 2 == 0) && cg <= 2 * GN_THREADS && (size_t)rows * cg <= 49152 && (ldx % 2 == 0) && ((((uintptr_t)x) & 7) == 0);
+}
+
 // Rows per CTA.  Large activations (VAE): ~6 CTAs per SM so enough loads are in flight.  Small ones (the UNet at one image
 // per rank is 0.1-5 MB per tensor): few rows per thread -- the kernels are latency-bound, and for the reductions the grid
 // is capped so that the fp64 global atomics of the CTAs do not pile up on the same 64 addresses.
@@ -460,6 +595,25 @@ extern "C" int skp_gn_apply(const float* x, int64_t ldx, int rows, int C, int gr
   return SKP_OK;
 }
 
+extern "C" int skp_gn_fwd(const float* x, int64_t ldx, int rows, int C, int groups, float eps, const float* gamma,
+                          const float* beta, int silu, float* y, int64_t ldy, void* hi, void* lo, int Kpad, double* sums,
+                          void* stream) {
+  SKP_GN_CHECK("gn_fwd");
+  SKP_REQUIRE(sums && gamma && beta && (y || (hi && lo)), "gn_fwd: null pointer");
+  SKP_REQUIRE(!hi || (Kpad >= C && Kpad % 64 == 0), "gn_fwd: Kpad=%d must be a multiple of 64 >= C", Kpad);
+  static const bool group_off = getenv("SKP_GN_GROUP") != nullptr && atoi(getenv("SKP_GN_GROUP")) == 0;
+  if (!group_off && gn_group_ok(rows, C, groups, x, ldx) && (!y || (ldy % 2 == 0 && ((((uintptr_t)y) & 7) == 0))) &&
+      (!hi || (((((uintptr_t)hi) | ((uintptr_t)lo)) & 3) == 0))) {
+    gn_group_fwd_kernel<<<groups, GN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, C / groups, eps, gamma, beta, silu, y, ldy,
+                                                                        (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad, sums);
+    SKP_CHECK_LAUNCH("gn_group_fwd");
+    return SKP_OK;
+  }
+  int rc = skp_gn_stats(x, ldx, rows, C, groups, sums, stream);
+  if (rc != SKP_OK) return rc;
+  return skp_gn_apply(x, ldx, rows, C, groups, sums, eps, gamma, beta, silu, y, ldy, hi, lo, Kpad, stream);
+}
+
 extern "C" int skp_gn_im2col3x3_split(const float* x, int64_t ldx, int H, int W, int C, int groups, const double* sums, float eps,
                                       const float* gamma, const float* beta, int silu, int Ho, int Wo, int stride, int pad,
                                       int Kpad, void* hi, void* lo, void* stream) {
@@ -483,6 +637,13 @@ extern "C" int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t l
   SKP_GN_CHECK("gn_bwd");
   SKP_REQUIRE(g && sums && gamma && beta && bsums && dx, "gn_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool group_off = getenv("SKP_GN_GROUP") != nullptr && atoi(getenv("SKP_GN_GROUP")) == 0;
+  if (!group_off && gn_group_ok(rows, C, groups, x, ldx) && (ldg % 2 == 0) && (ldd % 2 == 0) &&
+      (((((uintptr_t)g) | ((uintptr_t)dx)) & 7) == 0)) {
+    gn_group_bwd_kernel<<<groups, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, dx, ldd);
+    SKP_CHECK_LAUNCH("gn_group_bwd");
+    return SKP_OK;
+  }
   cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * groups * GN_REPL, st);
   int per = gn_rows_per_cta(rows, C, true);
   int grid = (rows + per - 1) / per;

@@ -239,6 +239,15 @@ def _gn_stats(x2d: torch.Tensor, groups: int) -> torch.Tensor:
     return sums
 
 
+def _gn_fwd(x2d, groups, eps, gamma, beta, silu, y, hi, lo, kp) -> torch.Tensor:
+    """Statistics + act(GroupNorm(x)) into fp32 y and/or the split-bf16 operand (hi, lo) [rows, kp]; returns the fp64 sums
+    the backward needs.  Small activations take one launch (one CTA per group), large ones stats + apply."""
+    sums = torch.empty(2 * groups * GN_REPL, dtype=torch.float64, device=x2d.device)
+    check(lib().skp_gn_fwd(ptr(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], groups, eps, ptr(gamma), ptr(beta), int(silu),
+                           ptr(y), y.stride(0) if y is not None else 0, ptr(hi), ptr(lo), kp, ptr(sums), stream()), "skp_gn_fwd")
+    return sums
+
+
 def _gn_backward(x2d, g, sums, gamma, beta, groups, eps, silu):
     g = _f32c(g)
     dx = torch.empty_like(x2d)
@@ -256,16 +265,16 @@ class _GNConv3x3(torch.autograd.Function):
     def forward(ctx, x2d, residual, gamma, beta, fcw: FrozenConv3x3, bias, groups, eps, silu, h, w, stride, pad, ho, wo):
         x2d = _f32c(x2d)
         c = x2d.shape[1]
-        sums = _gn_stats(x2d, groups)
-        ctx.save_for_backward(x2d, sums, gamma, beta)
         ctx.meta = (fcw, groups, eps, silu, h, w, stride, pad, ho, wo, residual is not None)
         if stride == 1 and pad == 1 and _implicit_ok(w, c):
             # normalised activation written ONCE as split-bf16 channels-last; the conv reads it through shifted TMA boxes
             hi = torch.empty(h * w, c, dtype=torch.bfloat16, device=x2d.device)
             lo = torch.empty(h * w, c, dtype=torch.bfloat16, device=x2d.device)
-            check(lib().skp_gn_apply(ptr(x2d), x2d.stride(0), h * w, c, groups, ptr(sums), eps, ptr(gamma), ptr(beta), int(silu),
-                                     None, 0, ptr(hi), ptr(lo), c, stream()), "skp_gn_apply")
+            sums = _gn_fwd(x2d, groups, eps, gamma, beta, silu, None, hi, lo, c)
+            ctx.save_for_backward(x2d, sums, gamma, beta)
             return conv3x3_implicit(hi, lo, h, w, fcw.fwd_split, fcw.cout, bias, residual)
+        sums = _gn_stats(x2d, groups)
+        ctx.save_for_backward(x2d, sums, gamma, beta)
         kp = _pad64(9 * c)
         hi = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
         lo = torch.empty(ho * wo, kp, dtype=torch.bfloat16, device=x2d.device)
@@ -315,12 +324,10 @@ class _GNLinear(torch.autograd.Function):
     def forward(ctx, x2d, residual, gamma, beta, fw: FrozenWeight, bias, groups, eps, silu):
         x2d = _f32c(x2d)
         rows, c = x2d.shape
-        sums = _gn_stats(x2d, groups)
         kp = _pad64(c)
         hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=x2d.device)
         lo = torch.empty(rows, kp, dtype=torch.bfloat16, device=x2d.device)
-        check(lib().skp_gn_apply(ptr(x2d), x2d.stride(0), rows, c, groups, ptr(sums), eps, ptr(gamma), ptr(beta), int(silu),
-                                 None, 0, ptr(hi), ptr(lo), kp, stream()), "skp_gn_apply")
+        sums = _gn_fwd(x2d, groups, eps, gamma, beta, silu, None, hi, lo, kp)
         ctx.save_for_backward(x2d, sums, gamma, beta)
         ctx.meta = (fw, groups, eps, silu, residual is not None)
         return gemm_nt_presplit(hi, lo, rows, fw.w_split, fw.out_features, bias, residual)
@@ -437,10 +444,8 @@ def dense_attention(q, k, v, scale: float) -> torch.Tensor:
 def group_norm_cl(x2d, gamma, beta, groups, eps, silu=False):
     """Plain act(GroupNorm(x)) -> fp32 [rows, C] (forward only; used by tests and no-grad paths)."""
     x2d = _f32c(x2d)
-    sums = _gn_stats(x2d, groups)
     y = torch.empty_like(x2d)
-    check(lib().skp_gn_apply(ptr(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], groups, ptr(sums), eps, ptr(gamma), ptr(beta),
-                             int(silu), ptr(y), y.stride(0), None, None, 0, stream()), "skp_gn_apply")
+    _gn_fwd(x2d, groups, eps, gamma, beta, silu, y, None, None, 0)
     return y
 
 
