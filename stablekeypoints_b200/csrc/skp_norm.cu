@@ -422,10 +422,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_fwd_kernel(const float* _
   const float* xc = x + c0 + 2 * p;
   float s = 0.f, ss = 0.f;
   if (active)
-    for (int r = ry; r < rows; r += RL) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(xc + (size_t)r * ldx));
-      s += v.x + v.y;
-      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+    for (int r = ry; r < rows; r += 4 * RL) {   // 4 independent loads in flight per thread
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (r + u * RL < rows) ? __ldg(reinterpret_cast<const float2*>(xc + (size_t)(r + u * RL) * ldx)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s += v[u].x + v[u].y;
+        ss = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, ss));
+      }
     }
   const double S = block_sum_d((double)s, red), SS = block_sum_d((double)ss, red);
   const double count = (double)rows * cg;
@@ -441,17 +447,25 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_fwd_kernel(const float* _
     const float g0 = __ldg(gamma + c0 + 2 * p), g1 = __ldg(gamma + c0 + 2 * p + 1);
     const float sc0 = rstd * g0, sc1 = rstd * g1;
     const float sh0 = fmaf(-mean, sc0, __ldg(beta + c0 + 2 * p)), sh1 = fmaf(-mean, sc1, __ldg(beta + c0 + 2 * p + 1));
-    for (int r = ry; r < rows; r += RL) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(xc + (size_t)r * ldx));
-      float z0 = fmaf(v.x, sc0, sh0), z1 = fmaf(v.y, sc1, sh1);
-      if (silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
-      if (y) *reinterpret_cast<float2*>(y + (size_t)r * ldy + c0 + 2 * p) = make_float2(z0, z1);
-      if (hi) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
-        const float2 f = __bfloat1622float2(h);
-        const size_t o = (size_t)r * Kpad + c0 + 2 * p;
-        *reinterpret_cast<__nv_bfloat162*>(hi + o) = h;
-        *reinterpret_cast<__nv_bfloat162*>(lo + o) = __floats2bfloat162_rn(z0 - f.x, z1 - f.y);
+    for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (r0 + u * RL < rows) ? __ldg(reinterpret_cast<const float2*>(xc + (size_t)(r0 + u * RL) * ldx)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * RL;
+        if (r >= rows) break;
+        float z0 = fmaf(v[u].x, sc0, sh0), z1 = fmaf(v[u].y, sc1, sh1);
+        if (silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
+        if (y) *reinterpret_cast<float2*>(y + (size_t)r * ldy + c0 + 2 * p) = make_float2(z0, z1);
+        if (hi) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
+          const float2 f = __bfloat1622float2(h);
+          const size_t o = (size_t)r * Kpad + c0 + 2 * p;
+          *reinterpret_cast<__nv_bfloat162*>(hi + o) = h;
+          *reinterpret_cast<__nv_bfloat162*>(lo + o) = __floats2bfloat162_rn(z0 - f.x, z1 - f.y);
+        }
       }
     }
   }
@@ -497,34 +511,53 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_bwd_kernel(const float* _
   const float sc = rstd, sh = -mean * rstd;
   float a1 = 0.f, a2 = 0.f;
   if (active)
-    for (int r = ry; r < rows; r += RL) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(x + (size_t)r * ldx + c));
-      const float2 gv = __ldg(reinterpret_cast<const float2*>(gr + (size_t)r * ldg + c));
-      const float xh0 = fmaf(v.x, sc, sh), xh1 = fmaf(v.y, sc, sh);
-      float dz0 = gv.x, dz1 = gv.y;
-      if (silu) { dz0 *= silu_grad(fmaf(g0, xh0, b0)); dz1 *= silu_grad(fmaf(g1, xh1, b1)); }
-      const float d0 = dz0 * g0, d1 = dz1 * g1;
-      a1 += d0 + d1;
-      a2 = fmaf(d0, xh0, fmaf(d1, xh1, a2));
+    for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+      float2 v[4], gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = r0 + u * RL < rows;
+        v[u] = ok ? __ldg(reinterpret_cast<const float2*>(x + (size_t)(r0 + u * RL) * ldx + c)) : make_float2(0.f, 0.f);
+        gv[u] = ok ? __ldg(reinterpret_cast<const float2*>(gr + (size_t)(r0 + u * RL) * ldg + c)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float xh0 = fmaf(v[u].x, sc, sh), xh1 = fmaf(v[u].y, sc, sh);
+        float dz0 = gv[u].x, dz1 = gv[u].y;     // rows past the end carry g = 0 and contribute nothing
+        if (silu) { dz0 *= silu_grad(fmaf(g0, xh0, b0)); dz1 *= silu_grad(fmaf(g1, xh1, b1)); }
+        const float d0 = dz0 * g0, d1 = dz1 * g1;
+        a1 += d0 + d1;
+        a2 = fmaf(d0, xh0, fmaf(d1, xh1, a2));
+      }
     }
   const double A1 = block_sum_d((double)a1, red), A2 = block_sum_d((double)a2, red);
   const float m1 = (float)(A1 / count), m2 = (float)(A2 / count);
   if (active)
-    for (int r = ry; r < rows; r += RL) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(x + (size_t)r * ldx + c));
-      const float2 gv = __ldg(reinterpret_cast<const float2*>(gr + (size_t)r * ldg + c));
-      const float xh0 = fmaf(v.x, sc, sh), xh1 = fmaf(v.y, sc, sh);
-      float dz0 = gv.x, dz1 = gv.y;
-      if (silu) { dz0 *= silu_grad(fmaf(g0, xh0, b0)); dz1 *= silu_grad(fmaf(g1, xh1, b1)); }
-      *reinterpret_cast<float2*>(dx + (size_t)r * ldd + c) =
-          make_float2(sc * (dz0 * g0 - m1 - xh0 * m2), sc * (dz1 * g1 - m1 - xh1 * m2));
+    for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+      float2 v[4], gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = r0 + u * RL < rows;
+        v[u] = ok ? __ldg(reinterpret_cast<const float2*>(x + (size_t)(r0 + u * RL) * ldx + c)) : make_float2(0.f, 0.f);
+        gv[u] = ok ? __ldg(reinterpret_cast<const float2*>(gr + (size_t)(r0 + u * RL) * ldg + c)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * RL;
+        if (r >= rows) break;
+        const float xh0 = fmaf(v[u].x, sc, sh), xh1 = fmaf(v[u].y, sc, sh);
+        float dz0 = gv[u].x, dz1 = gv[u].y;
+        if (silu) { dz0 *= silu_grad(fmaf(g0, xh0, b0)); dz1 *= silu_grad(fmaf(g1, xh1, b1)); }
+        *reinterpret_cast<float2*>(dx + (size_t)r * ldd + c) =
+            make_float2(sc * (dz0 * g0 - m1 - xh0 * m2), sc * (dz1 * g1 - m1 - xh1 * m2));
+      }
     }
 }
 
-// the one-CTA-per-group kernels take even group widths up to 512 channels and slabs of at most 48K elements
+// the one-CTA-per-group kernels take even group widths up to 512 channels and slabs of at most 20K elements (beyond
+// that 32 CTAs are too few: measured 29 us per GroupNorm against 15 us for the two-kernel path)
 static inline bool gn_group_ok(int rows, int C, int groups, const float* x, int64_t ldx) {
   const int cg = C / groups;
-  return (cg % 2 == 0) && cg <= 2 * GN_THREADS && (size_t)rows * cg <= 49152 && (ldx % 2 == 0) && ((((uintptr_t)x) & 7) == 0);
+  return (cg % 2 == 0) && cg <= 2 * GN_THREADS && (size_t)rows * cg <= 20480 && (ldx % 2 == 0) && ((((uintptr_t)x) & 7) == 0);
 }
 
 // Rows per CTA.  Large activations (VAE): ~6 CTAs per SM so enough loads are in flight.  Small ones (the UNet at one image
