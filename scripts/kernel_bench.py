@@ -78,6 +78,11 @@ def main():
         pr = ops.capture_store(lgr, r)
         add("capture_store_bwd", f"h8 s{s} N{n} R{r}", lambda pr=pr, dp=dp: torch.autograd.grad(pr, lgr, dp, retain_graph=True),
             bytes_=store_bytes + 2 * lg.numel() * 4)
+    # BASELINE cfg5: SDXL-shaped capture (20 heads, 32x32 layer, R=256): a 404 MB store per layer, larger than L2
+    lg5 = torch.randn(20, 32 * 32, n, device=dev, generator=g) * 3
+    add("capture_store_fwd (cfg5: SDXL-shaped)", f"h20 s32 N{n} R256", lambda: ops.capture_store(lg5, 256),
+        bytes_=20 * 256 * 256 * n * 4 + lg5.numel() * 4)
+    del lg5
     lgs = [torch.randn(h, s * s, n, device=dev, generator=g) * 3 for s in (16, 16, 16, 32)]
     mean_bytes = sum(l.numel() for l in lgs) * 4 + n * r * r * 4
     ops.CAPTURE_MEAN_FWD = "fused"

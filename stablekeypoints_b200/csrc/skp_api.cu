@@ -2,6 +2,7 @@
 #include "skp_common.cuh"
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace skp {
 
@@ -16,6 +17,11 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("SKP_PDL") != nullptr && atoi(getenv("SKP_PDL")) == 0);
+  return on;
+}
 
 }  // namespace skp
 

@@ -56,6 +56,31 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with skp::launch_pdl may be scheduled while its predecessor on the
+// stream is still draining; it must call pdl_wait() before its first global-memory access (the wait returns once the
+// predecessor has completed and flushed), and calls pdl_launch_dependents() at its top so that ITS successor may be
+// scheduled early too.  Everything before pdl_wait() (barrier init, TMEM allocation, index set-up) overlaps the
+// predecessor's tail.  With several thousand 5-15 us launches per step this launch latency is a visible share.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // skp_api.cu: SKP_PDL != "0"
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // PyTorch upsample_bicubic2d coefficients (A = -0.75), align_corners=False.
 __device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
   const float A = -0.75f;

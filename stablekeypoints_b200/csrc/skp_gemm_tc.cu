@@ -47,6 +47,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   float* C, int64_t ldc, int M, int N, int num_kb_total, int kb_per_split, float alpha,
                   const float* bias, const float* residual, int64_t ldr, float* __restrict__ splitk_ws, ConvGeom cg) {
   using Cfg = TcCfg<BN, STAGES>;
+  pdl_launch_dependents();
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb); partial sums go to splitk_ws[z][M][N] (reduced afterwards)
   const int kb0 = blockIdx.z * kb_per_split;
   const int num_kb = min(kb_per_split, num_kb_total - kb0);
@@ -79,6 +80,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_wait();   // barriers / TMEM are set up: from here on global memory written by the predecessor is touched
 
   if (warp == 0) {
     if (lane == 0) {
@@ -193,8 +195,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 template <bool VEC>
 __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, int cols_pad,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_launch_dependents();
   const int q = cols_pad >> 2;
   const long total = (long)rows * q;
+  pdl_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int r = (int)(i / q), c = (int)(i - (long)r * q) << 2;
     const float* src = x + (size_t)r * ld + c;
@@ -220,7 +224,9 @@ template <bool VEC>
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float* __restrict__ C, int64_t ldc,
                                      float alpha, const float* __restrict__ bias, const float* __restrict__ residual,
                                      int64_t ldr) {
+  pdl_launch_dependents();
   const size_t total = (size_t)M * N;
+  pdl_wait();
   if (VEC) {
     const int q = N >> 2;
     const long tq = (long)M * q;
@@ -380,8 +386,8 @@ static void launch_splitk_reduce(const float* ws, int zs, int M, int N, float* C
   size_t items = vec ? (size_t)M * N / 4 : (size_t)M * N;
   int blocks = (int)((items + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (vec) splitk_reduce_kernel<true><<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
-  else splitk_reduce_kernel<false><<<blocks, 256, 0, st>>>(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+  if (vec) launch_pdl(splitk_reduce_kernel<true>, dim3(blocks), dim3(256), 0, st, ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
+  else launch_pdl(splitk_reduce_kernel<false>, dim3(blocks), dim3(256), 0, st, ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
 }
 
 template <int BN, int STAGES>
@@ -409,8 +415,8 @@ static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin
   const int per = (num_kb + splits - 1) / splits;
   const int zs = (num_kb + per - 1) / per;
   dim3 grid((N + BN - 1) / BN, tiles_y * cg.tiles_x, zs);
-  gemm_nt_tc_kernel<BN, STAGES, true><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, num_kb, per, alpha,
-                                                                          bias, residual, ldr, ws, cg);
+  launch_pdl(gemm_nt_tc_kernel<BN, STAGES, true>, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N,
+             num_kb, per, alpha, bias, residual, ldr, ws, cg);
   SKP_CHECK_LAUNCH("conv3x3_tc");
   if (zs > 1) {
     launch_splitk_reduce(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr, st);
@@ -436,8 +442,8 @@ static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const
   const int per = (num_kb + splits - 1) / splits;
   const int zs = (num_kb + per - 1) / per;  // every z gets >= 1 k-block
   dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM, zs);
-  gemm_nt_tc_kernel<BN, STAGES, false><<<grid, TC_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N, num_kb, per,
-                                                                           alpha, bias, residual, ldr, ws, ConvGeom{});
+  launch_pdl(gemm_nt_tc_kernel<BN, STAGES, false>, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N,
+             num_kb, per, alpha, bias, residual, ldr, ws, ConvGeom{});
   SKP_CHECK_LAUNCH("gemm_nt_tc");
   if (zs > 1) {
     launch_splitk_reduce(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr, st);
@@ -458,8 +464,8 @@ extern "C" int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, in
   size_t b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
   const bool vec = (ld % 4 == 0) && ((((uintptr_t)x) & 15) == 0);
-  if (vec) split_bf16_kernel<true><<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
-  else split_bf16_kernel<false><<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  if (vec) launch_pdl(split_bf16_kernel<true>, dim3((unsigned)b), dim3(256), 0, (cudaStream_t)stream, x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  else launch_pdl(split_bf16_kernel<false>, dim3((unsigned)b), dim3(256), 0, (cudaStream_t)stream, x, ld, rows, cols, cols_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   SKP_CHECK_LAUNCH("split_bf16");
   return SKP_OK;
 }

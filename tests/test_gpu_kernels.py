@@ -262,7 +262,8 @@ def _capture_ref(logits, res):
 
 
 @pytest.mark.parametrize("heads,s,n,res", [(8, 16, 77, 128), (8, 32, 77, 128), (4, 4, 12, 16), (8, 16, 500, 128),
-                                            (8, 8, 100, 64), (2, 16, 20, 24), (8, 32, 16, 16)])
+                                            (8, 8, 100, 64), (2, 16, 20, 24), (8, 32, 16, 16), (8, 16, 100, 128),
+                                            (3, 32, 77, 256), (2, 16, 13, 40)])
 def test_capture_store_fwd_bwd(ops, heads, s, n, res):
     g = torch.Generator().manual_seed(heads + s + n)
     logits = torch.randn(heads, s * s, n, generator=g) * 3
