@@ -19,7 +19,8 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 bool pdl_enabled() {
-  static const bool on = !(getenv("SKP_PDL") != nullptr && atoi(getenv("SKP_PDL")) == 0);
+  // measured on B200 inside the 3-stream step graph: no gain (36.04 vs 36.07 images/s), so the attribute is opt-in
+  static const bool on = getenv("SKP_PDL") != nullptr && atoi(getenv("SKP_PDL")) != 0;
   return on;
 }
 

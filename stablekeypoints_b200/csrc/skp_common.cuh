@@ -64,7 +64,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-bool pdl_enabled();   // skp_api.cu: SKP_PDL != "0"
+bool pdl_enabled();   // skp_api.cu: SKP_PDL=1 (opt-in; no measurable gain inside the step graph)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
