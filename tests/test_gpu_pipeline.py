@@ -279,3 +279,32 @@ def test_optimize_embedding_graph_loop_matches_eager_loop(tiny, monkeypatch):
     assert float((eager - torch.from_numpy(g["context"]).cuda()).abs().max()) > 1e-3          # it did train
     assert float((graph - eager).abs().mean() / eager.abs().mean()) < 2e-4
     assert rel_err(graph.cpu(), eager.cpu()) < 3e-2
+
+
+@pytest.mark.parametrize("n_tokens,res", [(100, 16), (500, 16), (77, 32)])
+def test_tiny_stage1_other_token_counts_vs_oracle(tiny, n_tokens, res):
+    """The reference's other token counts (notebook N=100, CLI default N=500) and another map size, tiny model, against
+    the CPU oracle run live: exercises the even-N / large-N paths of the attn-store and attention kernels (N=500 rows do
+    not fit the row kernel's shared memory -> tile kernel; 500 keys -> 8 key tiles in the cross-attention kernels)."""
+    from oracle import hotpath as hp
+    from stablekeypoints_b200 import optimize
+    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+    g, pipe = tiny
+    gen = torch.Generator().manual_seed(1000 + n_tokens + res)
+    context = torch.randn(1, n_tokens, pipe.unet.cfg.cross_attention_dim, generator=gen)
+    na, nb = torch.randn(1, 4, 16, 16, generator=gen), torch.randn(1, 4, 16, 16, generator=gen)
+    image = torch.from_numpy(g["image"])
+    theta = hp.affine_theta(-7.0, 0.85, -0.1, 0.12)
+    ldm_o, ctl_o, _ = hp.load_oracle_ldm(pipe, res)
+    ctx_o = context.clone().requires_grad_(True)
+    ref = hp.stage1_iteration(ldm_o, ctl_o, image, ctx_o, theta, na, nb, top_k=4, num_candidates=8, sigma=1.5)
+    ldm, controllers, _ = _product_ldm(pipe, res)
+    ctx = context.clone().cuda().requires_grad_(True)
+    args = _args(top_k=4, furthest_point_num_samples=8, sigma=1.5)
+    out = optimize.stage1_iteration(ldm, controllers, image, ctx, RandomAffineWithInverse(), args, theta=theta, noise_a=na,
+                                    noise_b=nb, forced_indices=ref["indices"])
+    errs = {"maps": rel_err(out["maps"].cpu(), ref["maps"]), "maps_t": rel_err(out["maps_t"].cpu(), ref["maps_t"]),
+            "loss": rel_err(out["loss"].cpu(), ref["loss"]), "dcontext": rel_err(ctx.grad.cpu(), ctx_o.grad)}
+    print(f"[tiny, N={n_tokens}, R={res}] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    assert out["maps"].shape == (n_tokens, res, res)
+    assert all(v < 1e-3 for v in errs.values()), errs
