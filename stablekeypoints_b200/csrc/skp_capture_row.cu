@@ -31,10 +31,10 @@ constexpr int ROWS_PER_CTA = 2;   // consecutive output rows per CTA: the per-pi
 
 __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(const float* __restrict__ logits,
                                                                             float* __restrict__ probs, int s, int N, int R,
-                                                                            int NV, int P, int TS) {
+                                                                            int NV, int P, int TS, int XB) {
   extern __shared__ __align__(16) unsigned char row_smem[];
-  float* stage = reinterpret_cast<float*>(row_smem);                 // [R][N]  (the output row, global layout)
-  float* Vs = stage + (((size_t)R * N + 3) & ~(size_t)3);            // [s+4][NV]
+  float* stage = reinterpret_cast<float*>(row_smem);                 // [XB][N]  (this CTA's pixels of the output row, global layout)
+  float* Vs = stage + (((size_t)XB * N + 3) & ~(size_t)3);           // [s+4][NV]
   float* red = Vs + (size_t)(s + 4) * NV;                            // [32] per-warp max |V|
   float* psum = red + 32;                                            // [TS][P] partial softmax sums
   const int h = blockIdx.y;
@@ -44,13 +44,15 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
   // P pixel lanes x TS token slices: thread = (pixel X, slice of the token axis); slices meet through psum[].
   const int N4 = N >> 2;
   const int X_lane = tid % P, part = tid / P;
+  // pixels [xb0, xb1) of the row belong to this CTA (blockIdx.z): wide token axes (N = 500) do not fit a whole row
+  const int xb0 = blockIdx.z * XB, xb1 = min(R, xb0 + XB);
   const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;      // float4 token groups of this slice
   const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;     // the last slice also takes the N % 4 tail
   // horizontal taps of this thread's pixel in the first pixel block: the same for every row this CTA produces
   float pwx[4] = {0.f, 0.f, 0.f, 0.f}, psabs = 0.f;
   int pc0 = 1;
-  if (X_lane < R) {
-    float rx = scale * (X_lane + 0.5f) - 0.5f, fx = floorf(rx);
+  if (xb0 + X_lane < xb1) {
+    float rx = scale * (xb0 + X_lane + 0.5f) - 0.5f, fx = floorf(rx);
     cubic_coeffs(rx - fx, pwx);
     pc0 = (int)fx + 1;   // column of tap 0 in the halo'd array (ix - 1 + 2)
 #pragma unroll
@@ -118,15 +120,15 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
   for (int w = 0; w < (NT >> 5); ++w) M = fmaxf(M, red[w]);
 
   // ---- 2. + 3. horizontal pass, softmax over tokens, in-place normalisation.
-  for (int X0 = 0; X0 < R; X0 += P) {
+  for (int X0 = xb0; X0 < xb1; X0 += P) {
     const int X = X0 + X_lane;
-    const bool live = X < R;
+    const bool live = X < xb1;
     float wx[4] = {0.f, 0.f, 0.f, 0.f};
     int c0 = 1;
     float U = 0.f, sum = 0.f;
-    float* orow = stage + (size_t)(live ? X : 0) * N;
+    float* orow = stage + (size_t)(live ? X - xb0 : 0) * N;
     if (live) {
-      if (X0 == 0) {
+      if (X0 == xb0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) wx[i] = pwx[i];
         c0 = pc0;
@@ -204,8 +206,8 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
-    const uint32_t bytes = (uint32_t)((size_t)R * N * sizeof(float));
-    char* dst = reinterpret_cast<char*>(probs + ((size_t)h * R + Y) * R * N);
+    const uint32_t bytes = (uint32_t)((size_t)(xb1 - xb0) * N * sizeof(float));
+    char* dst = reinterpret_cast<char*>(probs + (((size_t)h * R + Y) * R + xb0) * N);
     uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
     for (uint32_t off = 0; off < bytes; off += 16384u) {
       uint32_t n = bytes - off < 16384u ? bytes - off : 16384u;
@@ -224,10 +226,19 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
   if (((size_t)R * N) % 4 != 0 || (reinterpret_cast<uintptr_t>(probs) & 15) != 0) return SKP_OK;   // 16-byte rows for the bulk copy
   int Np4 = (N + 3) & ~3;
   int NV = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;   // NV/4 odd: distinct columns land in distinct bank groups
-  int P = ((R + 31) / 32) * 32;                // pixel lanes (whole warps)
+  // pixels per CTA: the whole row when it fits ~100 KB of staging (4 CTAs per SM at N = 77), else the largest multiple of
+  // 32 (>= 4) pixels that does -- each x-block is still one contiguous, 16-byte aligned chunk of the row
+  int XB = R;
+  if ((size_t)R * N * sizeof(float) > 100 * 1024) {
+    XB = (int)((96 * 1024) / ((size_t)N * sizeof(float)));
+    XB = XB >= 32 ? (XB / 32) * 32 : (XB / 4) * 4;
+    if (XB < 4) return SKP_OK;
+  }
+  if (((size_t)XB * N) % 4 != 0) return SKP_OK;
+  int P = ((XB + 31) / 32) * 32;               // pixel lanes (whole warps)
   if (P > 256) P = 256;
   const int TS = (N >= 16) ? 2 : 1;            // token slices per pixel: 2 x the warps to hide the LDS->FMA->EX2->STS chain
-  size_t floats = (((size_t)R * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 32 + (size_t)TS * P;
+  size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 32 + (size_t)TS * P;
   size_t bytes = floats * sizeof(float);
   if (bytes > 200 * 1024) return SKP_OK;
   static size_t configured = 0;
@@ -240,8 +251,8 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
     cudaFuncSetAttribute(capture_store_row_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = bytes;
   }
-  dim3 grid((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA, heads);
-  capture_store_row_kernel<<<grid, P * TS, bytes, st>>>(logits, probs, s, N, R, NV, P, TS);
+  dim3 grid((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA, heads, (R + XB - 1) / XB);
+  capture_store_row_kernel<<<grid, P * TS, bytes, st>>>(logits, probs, s, N, R, NV, P, TS, XB);
   SKP_CHECK_LAUNCH("capture_store_row");
   *handled = true;
   return SKP_OK;

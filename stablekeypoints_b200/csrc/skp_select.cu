@@ -136,10 +136,14 @@ __global__ void __launch_bounds__(1024) argsort_topk_kernel(const float* __restr
   __syncthreads();
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
     float v = sc[i];
+    const bool vn = v != v;
     int rank = 0;
     for (int j = 0; j < T; ++j) {
       float u = sc[j];
-      rank += (u < v) || (u == v && j < i);
+      const bool un = u != u;
+      // total order (NaN last, like torch.argsort; ties by index): the ranks are a permutation, so every out[] slot is
+      // written even for degenerate scores and no stale index can reach the loss kernels
+      rank += (u < v) || (vn && !un) || ((u == v || (un && vn)) && j < i);
     }
     if (rank < top_k) out[rank] = i;
   }
