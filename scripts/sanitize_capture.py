@@ -1,3 +1,5 @@
+"""compute-sanitizer target: the attn-store / fused capture forwards at N=500 and N=77 (all four captured-layer shapes).
+    compute-sanitizer --tool memcheck python scripts/sanitize_capture.py"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
