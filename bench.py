@@ -363,7 +363,24 @@ def attn_store_roofline(a, dev):
     ms = sum(times) / len(times)
     algo = heads * r * r * n * 4 + heads * s * s * n * 4
     ach = algo / (ms * 1e-3) / 1e9
-    return {"kernel": "skp_capture_store_fwd (attn-store, C=1280 layer: h=8, s=16 -> R=%d, N=%d)" % (r, n), "bound": "hbm",
+    # BASELINE cfg5 (SDXL-shaped capture: 20 heads, 32x32 layer, R=256): a 404 MB store that does not fit the 126 MB L2
+    lg5 = torch.randn(20, 32 * 32, n, device=dev) * 3
+    t5 = []
+    for i in range(6):
+        flush.fill_(float(i))
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        ops.capture_store(lg5, 256)
+        en.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            t5.append(st.elapsed_time(en))
+    ms5 = sum(t5) / len(t5)
+    algo5 = 20 * 256 * 256 * n * 4 + lg5.numel() * 4
+    cfg5 = {"shape": "h=20, s=32 -> R=256, N=%d (BASELINE cfg5, SDXL-shaped)" % n, "achieved": round(algo5 / (ms5 * 1e-3) / 1e9, 1),
+            "frac": round(algo5 / (ms5 * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": algo5, "ms_per_launch": round(ms5, 5)}
+    del lg5
+    return {"kernel": "skp_capture_store_fwd (attn-store, C=1280 layer: h=8, s=16 -> R=%d, N=%d)" % (r, n), "bound": "hbm", "cfg5": cfg5,
             "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(ach / peak, 4),
             "traffic": ATTN_STORE_DRAM_TRAFFIC if (n, r) == (77, 128) else None, "traffic_note": ATTN_STORE_TRAFFIC_NOTE,
             "algorithmic_bytes": algo, "ms_per_launch": round(ms, 5), "l2": "flushed (512 MiB fill) between launches"}
