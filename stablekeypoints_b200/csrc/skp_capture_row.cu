@@ -19,6 +19,7 @@
 // If U - max_n x_n is so loose that the sum underflows (pathological logits), the pixel is redone with the exact max.
 #include "skp_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace skp {
 
@@ -239,7 +240,9 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
   if (((size_t)XB * N) % 4 != 0) return SKP_OK;
   int P = ((XB + 31) / 32) * 32;               // pixel lanes (whole warps)
   if (P > 256) P = 256;
-  const int TS = (N >= 16) ? 2 : 1;            // token slices per pixel: 2 x the warps to hide the LDS->FMA->EX2->STS chain
+  int TS = (N >= 16) ? 2 : 1;                  // token slices per pixel: 2 x the warps to hide the LDS->FMA->EX2->STS chain
+  static const int ts_env = getenv("SKP_ROW_TS") ? atoi(getenv("SKP_ROW_TS")) : 0;   // tuning knob (1, 2 or 4)
+  if (ts_env > 0 && N >= 8 * ts_env && P * ts_env <= ROW_MAX_THREADS) TS = ts_env;
   size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 32 + (size_t)TS * P;
   size_t bytes = floats * sizeof(float);
   if (bytes > 200 * 1024) return SKP_OK;
