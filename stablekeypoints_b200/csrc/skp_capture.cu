@@ -761,6 +761,8 @@ static int launch_quad(CapParams& p, cudaStream_t st, bool* fits, bool need_grid
 
 // skp_capture_row.cu: the row-per-CTA attn-store kernel (any R, s; needs the row + footprint to fit shared memory)
 int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled);
+int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
+                         cudaStream_t st, bool* handled);
 
 template <bool STORE, bool BWD>
 static int launch(CapParams& p, void* stream) {
@@ -852,6 +854,24 @@ extern "C" int skp_capture_mean_bwd(const float* const* logits, const int* s, in
                                     float* const* d_logits, int heads, int N, int R, void* stream) {
   SKP_REQUIRE(logits != nullptr && s != nullptr && d_maps != nullptr && d_logits != nullptr,
               "capture_mean_bwd: null pointer");
+  {   // row formulation (skp_capture_row.cu), one launch per layer; SKP_CAPTURE_BWD_ROW=0 keeps the tile kernel
+    static const bool row_on = !(getenv("SKP_CAPTURE_BWD_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_BWD_ROW")) == 0);
+    if (row_on && n_layers >= 1 && n_layers <= SKP_MAX_LAYERS && heads > 0 && N > 0 && R > 0) {
+      bool all = true;
+      for (int l = 0; l < n_layers && all; ++l) {
+        if (logits[l] == nullptr || d_logits[l] == nullptr || s[l] <= 0) { all = false; break; }
+        bool handled = false;
+        int rr = capture_mean_row_bwd(logits[l], d_maps, d_logits[l], heads, s[l], N, R, 1.f / (float)(n_layers * heads),
+                                      (cudaStream_t)stream, &handled);
+        if (rr != SKP_OK) return rr;
+        if (!handled) {
+          SKP_REQUIRE(l == 0, "capture_mean_bwd: layer %d does not fit the row kernel after earlier layers were accumulated", l);
+          all = false;
+        }
+      }
+      if (all) return SKP_OK;
+    }
+  }
   CapParams p{};
   int rc = fill(p, logits, d_logits, s, n_layers, heads, N, R);
   if (rc) return rc;

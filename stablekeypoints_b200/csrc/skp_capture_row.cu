@@ -223,6 +223,231 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the engine's reads
 }
 
+// ------------------------------------------------------------------------------------------------ backward (fused mean)
+// d_logits[l][h, ys, xs, n] += bicubic^T( p o (g - <p, g>) ),  g[n] = w * d_maps[n, Y, X],  p = softmax_tokens(bicubic(logits)):
+// the input gradient of  maps = mean_{l,h} softmax_tokens(bicubic(logits[l][h]))  (ptp_utils.py:508-538 + optimize.py:50-75).
+// Same row formulation as the forward: CTA = (output row Y, head h, x-block); the probabilities are recomputed, the
+// gradient of the scores replaces them in the staging tile, and the TRANSPOSED bicubic is applied as a gather
+// (thread = (low-res column, token) sums the <= 4*F pixels whose taps touch that column: no shared atomics), then the
+// four vertical taps are scattered with coalesced global atomics (4*s*N per CTA, lanes = consecutive tokens).
+__global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kernel(const float* __restrict__ logits,
+                                                                               const float* __restrict__ d_maps,
+                                                                               float* __restrict__ d_logits, int s, int N, int R,
+                                                                               int NV, int P, int TS, int XB, float w) {
+  extern __shared__ __align__(16) unsigned char row_smem[];
+  float* stage = reinterpret_cast<float*>(row_smem);                 // [XB][N]  e_n, then dS_n
+  float* Vs = stage + (((size_t)XB * N + 3) & ~(size_t)3);           // [s+4][NV] vertically interpolated logits
+  float* dVs = Vs + (size_t)(s + 4) * NV;                            // [s+4][NV] gradient wrt Vs
+  float* red = dVs + (size_t)(s + 4) * NV;                           // [32]
+  float* psum = red + 32;                                            // [2][TS][P]  partial (sum e, sum e*g)
+  float* wtab = psum + 2 * TS * P;                                   // [XB][4] raw horizontal weights
+  int* c0tab = reinterpret_cast<int*>(wtab + 4 * XB);                // [XB]    first halo'd column of the pixel's taps
+  int* xrange = c0tab + XB;                                          // [s+4][2] pixel range (local) touching a column
+  const int Y = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const float scale = (float)s / (float)R;
+  const float LOG2E = 1.4426950408889634f;
+  const int N4 = N >> 2;
+  const int X_lane = tid % P, part = tid / P;
+  const int xb0 = blockIdx.z * XB, xb1 = min(R, xb0 + XB), nx = xb1 - xb0;
+  const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;
+  const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;
+
+  // per-pixel tap tables (raw weights: the transposed stencil needs them un-scaled)
+  for (int i = tid; i < nx; i += NT) {
+    float rx = scale * (xb0 + i + 0.5f) - 0.5f, fx = floorf(rx);
+    float cw[4];
+    cubic_coeffs(rx - fx, cw);
+    wtab[4 * i] = cw[0]; wtab[4 * i + 1] = cw[1]; wtab[4 * i + 2] = cw[2]; wtab[4 * i + 3] = cw[3];
+    c0tab[i] = (int)fx + 1;
+  }
+  // vertical weights / rows of this output row
+  float wy[4];
+  int rowj[4];
+  {
+    float ry = scale * (Y + 0.5f) - 0.5f, fy = floorf(ry);
+    cubic_coeffs(ry - fy, wy);
+    const int iy = (int)fy;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = iy - 1 + j;
+      rowj[j] = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
+    }
+  }
+  // ---- 1. vertical pass (as the forward)
+  float amax = 0.f;
+  {
+    const float* rows[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rows[j] = logits + ((size_t)h * s + rowj[j]) * s * N;
+    const int NV4 = NV >> 2, items = s * NV4;
+    const float inv_nv4 = 1.f / (float)NV4;
+    for (int i = tid; i < items; i += NT) {
+      int xs = (int)((i + 0.5f) * inv_nv4);
+      int n0 = (i - xs * NV4) << 2;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int n = n0 + k;
+        float a = 0.f;
+        if (n < N) {
+          int o = xs * N + n;
+          a = wy[0] * __ldg(rows[0] + o);
+          a = fmaf(wy[1], __ldg(rows[1] + o), a);
+          a = fmaf(wy[2], __ldg(rows[2] + o), a);
+          a = fmaf(wy[3], __ldg(rows[3] + o), a);
+          amax = fmaxf(amax, fabsf(a));
+        }
+        v[k] = a;
+      }
+      float4 q = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(Vs + (xs + 2) * NV + n0) = q;
+      if (xs == 0) {
+        *reinterpret_cast<float4*>(Vs + n0) = q;
+        *reinterpret_cast<float4*>(Vs + NV + n0) = q;
+      }
+      if (xs == s - 1) {
+        *reinterpret_cast<float4*>(Vs + (s + 2) * NV + n0) = q;
+        *reinterpret_cast<float4*>(Vs + (s + 3) * NV + n0) = q;
+      }
+    }
+    amax = warp_max(amax);
+    if ((tid & 31) == 0) red[tid >> 5] = amax;
+  }
+  __syncthreads();
+  // pixel range of every halo'd column (c0tab is non-decreasing in X): pixels with c0 <= c <= c0 + 3
+  for (int c = tid; c < s + 4; c += NT) {
+    int lo = nx, hi = -1;
+    for (int i = 0; i < nx; ++i) {
+      const int d = c - c0tab[i];
+      if (d >= 0 && d <= 3) { lo = min(lo, i); hi = i; }
+    }
+    xrange[2 * c] = lo;
+    xrange[2 * c + 1] = hi;
+  }
+  float M = 0.f;
+  for (int q = 0; q < (NT >> 5); ++q) M = fmaxf(M, red[q]);
+
+  // ---- 2. horizontal pass: e_n staged, partial (sum e, sum e*g) per token slice; g read coalesced over X from d_maps
+  for (int X0 = 0; X0 < nx; X0 += P) {
+    const int xi = X0 + X_lane;           // local pixel
+    const bool live = xi < nx;
+    const int X = xb0 + xi;
+    float wx[4] = {0.f, 0.f, 0.f, 0.f};
+    int c0 = 1;
+    float U = 0.f, s1 = 0.f, s2 = 0.f;
+    float* orow = stage + (size_t)(live ? xi : 0) * N;
+    const float* grow = d_maps + (size_t)Y * R + (live ? X : 0);     // + n*R*R per token
+    if (live) {
+      c0 = c0tab[xi];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        wx[i] = wtab[4 * xi + i] * LOG2E;
+        U += fabsf(wx[i]);
+      }
+      U *= M;
+      for (int n = n_lo; n < n_hi; ++n) {
+        float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                  fmaf(wx[1], Vs[(c0 + 1) * NV + n], fmaf(wx[0], Vs[c0 * NV + n], -U))));
+        float e = ex2_approx(x);
+        orow[n] = e;
+        s1 += e;
+        s2 = fmaf(e, __ldg(grow + (size_t)n * R * R), s2);
+      }
+      psum[part * P + X_lane] = s1;
+      psum[(TS + part) * P + X_lane] = s2;
+    }
+    __syncthreads();
+    if (live) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int q = 0; q < TS; ++q) {
+        t1 += psum[q * P + X_lane];
+        t2 += psum[(TS + q) * P + X_lane];
+      }
+      if (!(t1 > 1e-30f) || !(t1 < 1e30f)) {
+        // loose bound: slice 0 redoes the whole pixel with the exact max
+        if (part == 0) {
+          float m = -CUDART_INF_F;
+          for (int n = 0; n < N; ++n) {
+            float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                      fmaf(wx[1], Vs[(c0 + 1) * NV + n], wx[0] * Vs[c0 * NV + n])));
+            orow[n] = x;
+            m = fmaxf(m, x);
+          }
+          float a1 = 0.f, a2 = 0.f;
+          for (int n = 0; n < N; ++n) {
+            float e = exp2f(orow[n] - m);
+            orow[n] = e;
+            a1 += e;
+            a2 = fmaf(e, __ldg(grow + (size_t)n * R * R), a2);
+          }
+          const float inv = 1.f / a1, dot = a2 * inv;
+          for (int n = 0; n < N; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+        }
+      } else {
+        const float inv = 1.f / t1, dot = t2 * inv;
+        for (int n = n_lo; n < n_hi; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- 3. transposed horizontal stencil as a gather: dVs[c][n] = sum_X wx[X][c - c0[X]] * dS[X][n]
+  for (int i = tid; i < (s + 4) * N; i += NT) {
+    const int c = i / N, n = i - c * N;
+    const int lo = xrange[2 * c], hi = xrange[2 * c + 1];
+    float a = 0.f;
+    for (int xi = lo; xi <= hi; ++xi) a = fmaf(wtab[4 * xi + (c - c0tab[xi])], stage[(size_t)xi * N + n], a);
+    dVs[c * NV + n] = a;
+  }
+  __syncthreads();
+  // ---- 4. fold the replicated halo columns, transposed vertical stencil: coalesced global atomics
+  float* dl = d_logits + (size_t)h * s * s * N;
+  for (int i = tid; i < s * N; i += NT) {
+    const int xs = i / N, n = i - xs * N;
+    float v = dVs[(xs + 2) * NV + n];
+    if (xs == 0) v += dVs[n] + dVs[NV + n];
+    if (xs == s - 1) v += dVs[(s + 2) * NV + n] + dVs[(s + 3) * NV + n];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(dl + ((size_t)rowj[j] * s + xs) * N + n, wy[j] * v);
+  }
+}
+
+// d_logits must be zero-initialised (accumulated over rows / x-blocks / taps).  *handled = false: shape not taken.
+int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
+                         cudaStream_t st, bool* handled) {
+  *handled = false;
+  int Np4 = (N + 3) & ~3;
+  int NV = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;
+  int XB = R;
+  if ((size_t)R * N * sizeof(float) > 100 * 1024) {
+    XB = (int)((96 * 1024) / ((size_t)N * sizeof(float)));
+    XB = XB >= 32 ? (XB / 32) * 32 : (XB / 4) * 4;
+    if (XB < 4) return SKP_OK;
+  }
+  int P = ((XB + 31) / 32) * 32;
+  if (P > 256) P = 256;
+  const int TS = (N >= 16) ? 2 : 1;
+  size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + 2 * (size_t)(s + 4) * NV + 32 + 2 * (size_t)TS * P + 5 * (size_t)XB +
+                  2 * (size_t)(s + 4);
+  size_t bytes = floats * sizeof(float);
+  if (bytes > 200 * 1024) return SKP_OK;
+  static size_t configured = 0;
+  if (bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(capture_mean_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("capture_mean_row_bwd: smem attr: %s", cudaGetErrorString(e));
+      return SKP_ERR_LAUNCH;
+    }
+    cudaFuncSetAttribute(capture_mean_row_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured = bytes;
+  }
+  dim3 grid(R, heads, (R + XB - 1) / XB);
+  capture_mean_row_bwd_kernel<<<grid, P * TS, bytes, st>>>(logits, d_maps, d_logits, s, N, R, NV, P, TS, XB, w);
+  SKP_CHECK_LAUNCH("capture_mean_row_bwd");
+  *handled = true;
+  return SKP_OK;
+}
+
 // Returns SKP_OK with *handled = true when the row kernel ran; *handled = false when the shape does not fit it.
 int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled) {
   *handled = false;
