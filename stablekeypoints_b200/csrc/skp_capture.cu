@@ -763,6 +763,7 @@ static int launch_quad(CapParams& p, cudaStream_t st, bool* fits, bool need_grid
 int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled);
 int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
                          cudaStream_t st, bool* handled);
+bool capture_mean_row_bwd_fits(int s, int N, int R);
 
 template <bool STORE, bool BWD>
 static int launch(CapParams& p, void* stream) {
@@ -858,8 +859,9 @@ extern "C" int skp_capture_mean_bwd(const float* const* logits, const int* s, in
     static const bool row_on = !(getenv("SKP_CAPTURE_BWD_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_BWD_ROW")) == 0);
     if (row_on && n_layers >= 1 && n_layers <= SKP_MAX_LAYERS && heads > 0 && N > 0 && R > 0) {
       bool all = true;
+      for (int l = 0; l < n_layers; ++l)   // every layer must fit before any is accumulated
+        if (logits[l] == nullptr || d_logits[l] == nullptr || s[l] <= 0 || !capture_mean_row_bwd_fits(s[l], N, R)) all = false;
       for (int l = 0; l < n_layers && all; ++l) {
-        if (logits[l] == nullptr || d_logits[l] == nullptr || s[l] <= 0) { all = false; break; }
         bool handled = false;
         int rr = capture_mean_row_bwd(logits[l], d_maps, d_logits[l], heads, s[l], N, R, 1.f / (float)(n_layers * heads),
                                       (cudaStream_t)stream, &handled);

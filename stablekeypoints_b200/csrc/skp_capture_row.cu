@@ -412,25 +412,43 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
   }
 }
 
-// d_logits must be zero-initialised (accumulated over rows / x-blocks / taps).  *handled = false: shape not taken.
-int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
-                         cudaStream_t st, bool* handled) {
-  *handled = false;
+// shared-memory plan of the backward row kernel: pixels per x-block (0 = does not fit) and bytes
+static int mean_row_bwd_plan(int s, int N, int R, int* NV_out, int* P_out, int* TS_out, size_t* bytes_out) {
   int Np4 = (N + 3) & ~3;
   int NV = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;
+  const int TS = (N >= 16) ? 2 : 1;
   int XB = R;
   if ((size_t)R * N * sizeof(float) > 100 * 1024) {
     XB = (int)((96 * 1024) / ((size_t)N * sizeof(float)));
     XB = XB >= 32 ? (XB / 32) * 32 : (XB / 4) * 4;
-    if (XB < 4) return SKP_OK;
   }
-  int P = ((XB + 31) / 32) * 32;
-  if (P > 256) P = 256;
-  const int TS = (N >= 16) ? 2 : 1;
-  size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + 2 * (size_t)(s + 4) * NV + 32 + 2 * (size_t)TS * P + 5 * (size_t)XB +
-                  2 * (size_t)(s + 4);
-  size_t bytes = floats * sizeof(float);
-  if (bytes > 200 * 1024) return SKP_OK;
+  for (; XB >= 4; XB = (XB > 32 ? 32 : XB / 2)) {
+    int P = ((XB + 31) / 32) * 32;
+    if (P > 256) P = 256;
+    size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + 2 * (size_t)(s + 4) * NV + 32 + 2 * (size_t)TS * P + 5 * (size_t)XB +
+                    2 * (size_t)(s + 4);
+    if (floats * sizeof(float) <= 200 * 1024) {
+      *NV_out = NV; *P_out = P; *TS_out = TS; *bytes_out = floats * sizeof(float);
+      return XB;
+    }
+  }
+  return 0;
+}
+
+bool capture_mean_row_bwd_fits(int s, int N, int R) {
+  int NV, P, TS;
+  size_t bytes;
+  return mean_row_bwd_plan(s, N, R, &NV, &P, &TS, &bytes) > 0;
+}
+
+// d_logits must be zero-initialised (accumulated over rows / x-blocks / taps).  *handled = false: shape not taken.
+int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
+                         cudaStream_t st, bool* handled) {
+  *handled = false;
+  int NV, P, TS;
+  size_t bytes;
+  const int XB = mean_row_bwd_plan(s, N, R, &NV, &P, &TS, &bytes);
+  if (XB == 0) return SKP_OK;
   static size_t configured = 0;
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(capture_mean_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
