@@ -43,6 +43,27 @@ def test_library_is_sm100a_with_tcgen05_and_tma(built):
         assert mnemonic in out.stdout, mnemonic
 
 
+def test_host_side_planners(built):
+    """Host-only entry points (no kernel launch): the GEMM tile planner honours the measured table, the attention
+    kernels report their operand padding / eligibility, and every row of the tuned table is a legal plan."""
+    import re
+    from stablekeypoints_b200 import _lib
+    L = _lib.lib()
+    assert [L.skp_self_attn_dp(d) for d in (8, 16, 24, 40, 48, 64, 80, 160, 161)] == [16, 16, 32, 48, 48, 80, 80, 160, 0]
+    # tcgen05 forward: S % 128 == 0 and even d <= 64 only; workspace = Q', K planes [2][h*S][64] + V^T planes [2][h*DV][S], bf16
+    assert L.skp_self_attn_tc_workspace(4096, 8, 40) == (4 * 8 * 4096 * 64 + 2 * 8 * 48 * 4096) * 2
+    for s, d in ((4000, 40), (4096, 80), (4096, 41), (0, 40)):
+        assert L.skp_self_attn_tc_workspace(s, 8, d) == 0
+    inc = open(os.path.join(ROOT, "stablekeypoints_b200", "csrc", "skp_gemm_tuned.inc")).read()
+    rows = re.findall(r"\{(\d+), (\d+), (\d+), (\d+), \{(\d+), (\d+)\}\}", inc)
+    assert len(rows) >= 20
+    for conv, m, n, k, bn, z in (tuple(int(x) for x in r) for r in rows):
+        assert bn in (64, 96, 128, 160, 256) and 1 <= z <= 32 and k % 64 == 0
+        assert z == 1 or (k // 64) // z >= 2                       # every K split keeps at least two 64-wide k-blocks
+        assert L.skp_gemm_nt_tc_plan(m, n, k) == z                 # the planner returns the measured split count
+    assert L.skp_gemm_nt_tc_plan(123, 457, 640) >= 1               # untuned shapes fall through to the cost model
+
+
 def test_no_cpu_fallback():
     from stablekeypoints_b200 import _lib, ops
     with pytest.raises(_lib.SkpError):
