@@ -107,6 +107,34 @@ def test_engine_param_table_matches_oracle_model(which):
         assert sum(torch.Size(s).numel() for s in want.values()) == 859520964  # SD1.x UNet
 
 
+def test_diffusers_format_weight_directory_loader(tmp_path):
+    """SURVEY 8 f4 (loader contract): a diffusers-format model directory (unet/ and vae/ safetensors or .bin with the
+    diffusers-0.8.0 key names) is read into exactly the tensors the engines' parameter tables ask for."""
+    from safetensors.torch import save_file
+    from oracle import sd15
+    from stablekeypoints_b200 import optimize_token
+    from stablekeypoints_b200.sd15_engine import UNetConfig, VAEConfig, unet_param_shapes, vae_encoder_param_shapes
+    ocfg, ovae = sd15.UNetConfig.tiny(), sd15.VAEConfig.tiny()
+    pipe = sd15.make_pipeline(ocfg, ovae, seed=3)
+    (tmp_path / "unet").mkdir()
+    (tmp_path / "vae").mkdir()
+    save_file({k: v.contiguous() for k, v in pipe.unet.state_dict().items()}, str(tmp_path / "unet" / "diffusion_pytorch_model.safetensors"))
+    torch.save(pipe.vae.state_dict(), str(tmp_path / "vae" / "diffusion_pytorch_model.bin"))
+    unet_sd = optimize_token._load_safetensors_dir(str(tmp_path), "unet")
+    vae_sd = optimize_token._load_safetensors_dir(str(tmp_path), "vae")
+    ucfg = UNetConfig(block_out_channels=ocfg.block_out_channels, cross_attention_dim=ocfg.cross_attention_dim,
+                      heads=ocfg.attention_head_dim, norm_num_groups=ocfg.norm_num_groups)
+    vcfg = VAEConfig(block_out_channels=ovae.block_out_channels, norm_num_groups=ovae.norm_num_groups)
+    for shapes, sd, ref in ((unet_param_shapes(ucfg), unet_sd, pipe.unet.state_dict()),
+                            (vae_encoder_param_shapes(vcfg), vae_sd, pipe.vae.state_dict())):
+        for k, shp in shapes.items():
+            assert k in sd, k
+            assert tuple(sd[k].shape) == tuple(shp), (k, tuple(sd[k].shape), shp)
+            assert torch.equal(sd[k], ref[k])
+    with pytest.raises(FileNotFoundError):
+        optimize_token._load_safetensors_dir(str(tmp_path), "text_encoder")
+
+
 def test_reference_surface_signatures():
     """Same parameter names (and order) as the reference functions they replace."""
     from stablekeypoints_b200 import eval as e, invertable_transform as it, optimize as o, optimize_token as ot, ptp_utils as p
