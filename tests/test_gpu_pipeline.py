@@ -308,3 +308,34 @@ def test_tiny_stage1_other_token_counts_vs_oracle(tiny, n_tokens, res):
     print(f"[tiny, N={n_tokens}, R={res}] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
     assert out["maps"].shape == (n_tokens, res, res)
     assert all(v < 1e-3 for v in errs.values()), errs
+
+
+def test_load_ldm_from_diffusers_directory(tiny, tmp_path):
+    """load_ldm(<local diffusers-format directory>) builds the same engines as explicit state dicts."""
+    from safetensors.torch import save_file
+    from stablekeypoints_b200 import optimize_token, ptp_utils
+    from stablekeypoints_b200.sd15_engine import UNetConfig, VAEConfig
+    g, pipe = tiny
+    (tmp_path / "unet").mkdir()
+    (tmp_path / "vae").mkdir()
+    save_file({k: v.contiguous() for k, v in pipe.unet.state_dict().items()}, str(tmp_path / "unet" / "diffusion_pytorch_model.safetensors"))
+    save_file({k: v.contiguous() for k, v in pipe.vae.state_dict().items()}, str(tmp_path / "vae" / "diffusion_pytorch_model.safetensors"))
+    oc, vc = pipe.unet.cfg, pipe.vae.cfg
+    ucfg = UNetConfig(block_out_channels=oc.block_out_channels, cross_attention_dim=oc.cross_attention_dim,
+                      heads=oc.attention_head_dim, norm_num_groups=oc.norm_num_groups)
+    vcfg = VAEConfig(block_out_channels=vc.block_out_channels, norm_num_groups=vc.norm_num_groups)
+    ldm_a, ctl_a, n_a = optimize_token.load_ldm("cuda", str(tmp_path), feature_upsample_res=TINY["res"], unet_config=ucfg,
+                                               vae_config=vcfg, precision="fp32")
+    ldm_b, ctl_b, _ = _product_ldm(pipe, TINY["res"])
+    assert n_a == 1 and len(ctl_a) == 1
+    image = torch.from_numpy(g["image"]).cuda()
+    ctx = torch.from_numpy(g["context"]).cuda()
+    noise = torch.from_numpy(g["noise_a"]).cuda()
+    with torch.no_grad():
+        maps_a = ptp_utils.run_and_find_attn(ldm_a, image, ctx, layers=[0, 1, 2, 3], upsample_res=-1, controllers=ctl_a, noise=noise)[0]
+        maps_b = ptp_utils.run_and_find_attn(ldm_b, image, ctx, layers=[0, 1, 2, 3], upsample_res=-1, controllers=ctl_b, noise=noise)[0]
+    assert maps_a.shape == (TINY["n_tokens"], TINY["res"], TINY["res"])
+    e_ab, e_gold = rel_err(maps_a.cpu(), maps_b.cpu()), rel_err(maps_a.cpu(), g["maps"])
+    print(f"[load_ldm from directory] vs state-dict engines {e_ab:.2e}, vs golden {e_gold:.2e}")
+    assert e_ab < 1e-4          # same weights; only the fp32 atomic order of the GroupNorm statistics differs
+    assert e_gold < 1e-3        # and both match the reference-minted golden
