@@ -18,7 +18,7 @@ def vote_top_k(indices_list: torch.Tensor, top_k: int) -> torch.Tensor:
 def find_best_indices(ldm, context, args, controllers, num_gpus, from_where=["down_cross", "mid_cross", "up_cross"]):
     """keypoint_regressor.py:16-108: `num_indices` no-grad captured forwards, per image the Gaussian-KL candidates and a
     furthest-point sample measured on the SAME maps (quirk: Stage 1 measures on the transformed maps), then a vote."""
-    dataset = _make_dataset(args)
+    dataset = _make_dataset(args, stage=2)
     loader = torch.utils.data.DataLoader(dataset, batch_size=num_gpus, shuffle=True, drop_last=True)
     it = iter(loader)
     picked = []

@@ -170,8 +170,13 @@ class EmbeddingOptimizer:
         # the kernel wrote through the raw pointer: tell autograd / the engine's K|V cache the tensor changed
         torch.autograd.graph.increment_version(self.context)
 
-    def zero_grad(self):
-        self.context.grad = None
+    def zero_grad(self, set_to_none: bool = True):
+        """set_to_none=False zeroes the gradient buffer in place: the buffer keeps its address, which is what lets separate
+        CUDA graphs (iterations / optimizer update) accumulate into and read from it (B//G > 1, optimize.py:420-425)."""
+        if set_to_none or self.context.grad is None:
+            self.context.grad = None
+        else:
+            self.context.grad.zero_()
 
 
 class Stage1Graph:
@@ -185,7 +190,15 @@ class Stage1Graph:
     def __init__(self, ldm, controllers, context, optimizer: "EmbeddingOptimizer", args, image_shape=(1, 3, 512, 512),
                  accum: int = 1, warmup: int = 3, from_where=None):
         assert optimizer.step_dev is not None, "Stage1Graph needs EmbeddingOptimizer(capturable=True)"
-        assert accum == 1, "gradient accumulation (B//G > 1) replays the eager step; the graph holds one full optimizer step"
+        if args.top_k_strategy in ("gaussian", "entropy", "consistent") and args.furthest_point_num_samples < args.top_k:
+            raise ValueError("Stage1Graph: furthest_point_num_samples < top_k makes the number of selected tokens data-dependent "
+                             "(ptp_utils.py:139-159); run the eager loop (cuda_graph=False)")
+        # accum == 1: ONE graph holds the whole optimizer step.  accum > 1 (the reference's B//G gradient accumulation,
+        # optimize.py:339,420-425): an ITERATION graph (two captured forwards + selection + losses + backward, the gradient
+        # added into a persistent buffer) replayed `accum` times, then an UPDATE graph (all-reduce + Adam + zeroing).
+        self.accum = int(accum)
+        self._iters_since_update = 0
+        self.update_graph = None
         dev = ldm.unet.device
         self.ldm, self.controllers, self.context, self.optimizer, self.args = ldm, controllers, context, optimizer, args
         self.image = torch.zeros(image_shape, device=dev)
@@ -233,10 +246,20 @@ class Stage1Graph:
             self._encode_next()
         return self
 
+    def _update(self):
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=self.accum == 1)
+        self.ldm.unet.invalidate_context_cache()
+
     def _step(self):
+        out = self._iteration()
+        self._update()
+        return out
+
+    def _iteration(self):
         if not self.prefetch:
             out = stage1_iteration(self.ldm, self.controllers, self.image, self.context, self.transform, self.args,
-                                   theta=self.theta, theta_inv=self.theta_inv, from_where=self.from_where,
+                                   accum=self.accum, theta=self.theta, theta_inv=self.theta_inv, from_where=self.from_where,
                                    side_stream=self.side)
         else:
             main = torch.cuda.current_stream()
@@ -248,11 +271,10 @@ class Stage1Graph:
             with torch.cuda.stream(self.vae_stream):
                 self._encode_next()
             out = stage1_iteration(self.ldm, self.controllers, None, self.context, self.transform, self.args,
-                                   theta=self.theta_cur, theta_inv=self.theta_inv_cur, from_where=self.from_where,
-                                   side_stream=self.side, latents=(self.lat_cur[0:1], self.lat_cur[1:2]))
+                                   accum=self.accum, theta=self.theta_cur, theta_inv=self.theta_inv_cur,
+                                   from_where=self.from_where, side_stream=self.side,
+                                   latents=(self.lat_cur[0:1], self.lat_cur[1:2]))
             main.wait_stream(self.vae_stream)
-        self.optimizer.step()
-        self.optimizer.zero_grad()
         return out
 
     def set_inputs(self, image: torch.Tensor, theta: torch.Tensor):
@@ -268,8 +290,10 @@ class Stage1Graph:
         saved_steps = opt.steps
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        if self.accum > 1:                     # persistent gradient buffer shared by the two graphs
+            self.context.grad = torch.zeros_like(self.context)
         with torch.cuda.stream(side):
-            for _ in range(self._warmup):      # cuDNN/cuBLAS autotuning, allocator warm-up, time-constant caches
+            for _ in range(self._warmup):      # allocator warm-up, time-constant caches
                 self._step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -280,13 +304,28 @@ class Stage1Graph:
         torch.autograd.graph.increment_version(self.context)
         self.ldm.unet.invalidate_context_cache()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self._step()
+        if self.accum == 1:
+            with torch.cuda.graph(self.graph):
+                self.out = self._step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.out = self._iteration()
+            self.update_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.update_graph, pool=self.graph.pool()):
+                self._update()
+        self._iters_since_update = 0
         return self
 
     def replay(self):
-        """Replays the step.  With the VAE prefetch the returned losses belong to the image of the previous set_inputs()."""
+        """Replays one iteration (accum == 1: the whole optimizer step; accum > 1: the update graph follows every
+        `accum`-th iteration).  With the VAE prefetch the returned losses belong to the image of the previous set_inputs()."""
         self.graph.replay()
+        if self.update_graph is not None:
+            self._iters_since_update += 1
+            if self._iters_since_update == self.accum:
+                self.update_graph.replay()
+                self._iters_since_update = 0
+                torch.autograd.graph.increment_version(self.context)
         return self.out
 
 
@@ -315,18 +354,21 @@ class SyntheticKeypointDataset(torch.utils.data.Dataset):
         return {"img": (0.7 * img + 0.3 * low).clamp(0, 1), "kpts": torch.zeros(1, 2), "visibility": torch.ones(1)}
 
 
-def _make_dataset(args):
-    """optimize.py:277-303.  The reference's dataset classes are host-side file readers that are out of scope here;
-    they are imported from the user's ``datasets`` package when present, `args.dataset` (an object) wins, and
-    "synthetic" builds the seeded synthetic set."""
+def _make_dataset(args, stage: int = 1):
+    """optimize.py:277-303 (stage 1) / keypoint_regressor.py:25-50 (stage 2: the same table without CelebA's max_len).
+    The reference's dataset classes are host-side file readers that are out of scope here; they are imported from the
+    user's ``datasets`` package when present, `args.dataset` (an object) wins, and "synthetic" builds the seeded
+    synthetic set."""
     if getattr(args, "dataset", None) is not None:
         return args.dataset
     name = args.dataset_name
     if name == "synthetic":
-        return SyntheticKeypointDataset(length=getattr(args, "max_len", 64) if getattr(args, "max_len", -1) > 0 else 64)
+        ml = getattr(args, "max_len", -1)
+        return SyntheticKeypointDataset(length=ml if ml is not None and ml > 0 else 64, size=getattr(args, "synthetic_size", 512))
     import importlib
-    table = {"celeba_aligned": ("datasets.celeba", "CelebA", dict(split="train", dataset_loc=args.dataset_loc, max_len=args.max_len)),
-             "celeba_wild": ("datasets.celeba", "CelebA", dict(split="train", dataset_loc=args.dataset_loc, align=False, max_len=args.max_len)),
+    ml = dict(max_len=args.max_len) if stage == 1 else {}
+    table = {"celeba_aligned": ("datasets.celeba", "CelebA", dict(split="train", dataset_loc=args.dataset_loc, **ml)),
+             "celeba_wild": ("datasets.celeba", "CelebA", dict(split="train", dataset_loc=args.dataset_loc, align=False, **ml)),
              "cub_aligned": ("datasets.cub", "TrainSet", dict(data_root=args.dataset_loc, image_size=512)),
              "cub_001": ("datasets.cub_parts", "CUBDataset", dict(dataset_root=args.dataset_loc, split="train", single_class=1)),
              "cub_002": ("datasets.cub_parts", "CUBDataset", dict(dataset_root=args.dataset_loc, split="train", single_class=2)),
@@ -363,9 +405,11 @@ def optimize_embedding(ldm, args, controllers, num_gpus, context=None,
     context = context.to(dev).detach().clone().contiguous()
     context.requires_grad = True
     accum = max(1, args.batch_size // (num_gpus * world))
-    # one image per optimizer step per rank (the reference's default batch_size == num_gpus): replay the whole step as
-    # ONE 3-stream CUDA graph (Stage1Graph); gradient accumulation (B//G > 1) keeps the eager loop
-    use_graph = accum == 1 and getattr(args, "cuda_graph", os.environ.get("SKP_LOOP_GRAPH", "1") != "0")
+    # every iteration replays a 3-stream CUDA graph (Stage1Graph); with gradient accumulation (B//G > 1, the reference CLI
+    # default batch_size=4) the Adam update is a second small graph replayed every `accum` iterations
+    use_graph = (getattr(args, "cuda_graph", os.environ.get("SKP_LOOP_GRAPH", "1") != "0")
+                 and args.furthest_point_num_samples >= args.top_k)
+    trace = getattr(args, "trace", None)       # optional list: per-iteration outputs are appended (tests / debugging)
     optimizer = EmbeddingOptimizer(context, lr=args.lr, capturable=bool(use_graph))
     start = it_start = time.time()
     running = {"equiv": 0.0, "sharp": 0.0, "total": 0.0}
@@ -376,12 +420,16 @@ def optimize_embedding(ldm, args, controllers, num_gpus, context=None,
     loader = torch.utils.data.DataLoader(dataset, batch_size=num_gpus, shuffle=sampler is None, sampler=sampler,
                                          drop_last=True, pin_memory=True)
     it = iter(loader)
+    epoch = 0
 
     def next_batch():
-        nonlocal it
+        nonlocal it, epoch
         try:
             return next(it)
         except StopIteration:
+            epoch += 1
+            if sampler is not None:            # DataLoader(shuffle=True) reshuffles every pass (optimize.py:341-345)
+                sampler.set_epoch(epoch)
             it = iter(loader)
             return next(it)
 
@@ -390,7 +438,7 @@ def optimize_embedding(ldm, args, controllers, num_gpus, context=None,
     if use_graph and n_iters > 0:
         first = next_batch()
         graph = Stage1Graph(ldm, controllers, context, optimizer, args, image_shape=tuple(first["img"].shape),
-                            from_where=from_where)
+                            accum=accum, from_where=from_where)
         graph.transform = transform
         graph.set_inputs(first["img"], transform.sample_theta(first["img"].shape[0]))
         graph.capture()            # warm-up steps are rolled back (optimizer state and embedding restored)
@@ -407,11 +455,14 @@ def optimize_embedding(ldm, args, controllers, num_gpus, context=None,
                 if iteration > 0:
                     graph.set_inputs(cur["img"], transform.sample_theta(cur["img"].shape[0]))
             out = graph.replay()
-            out = {k: v.clone() for k, v in out.items() if k in ("loss", "sharp", "equiv")}
+            out = {k: v.clone() for k, v in out.items() if k in (("loss", "sharp", "equiv", "indices") if trace is not None
+                                                                 else ("loss", "sharp", "equiv"))}
         else:
             batch = next_batch()
             out = stage1_iteration(ldm, controllers, batch["img"], context, transform, args, accum=accum,
                                    from_where=from_where)
+        if trace is not None:
+            trace.append({k: v.detach().clone() for k, v in out.items() if k in ("loss", "sharp", "equiv", "indices")})
         running["equiv"] += out["equiv"] / accum * args.equivariance_attn_loss_weight
         running["sharp"] += out["sharp"] / accum * args.sharpening_loss_weight
         running["total"] += out["loss"] / accum

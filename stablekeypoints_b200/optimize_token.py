@@ -41,13 +41,20 @@ def load_ldm(device, type="CompVis/stable-diffusion-v1-4", feature_upsample_res=
 
     One process drives ONE GPU (the multi-GPU layout is one process per GPU + NCCL, not nn.DataParallel), so
     ``controllers`` has exactly one AttentionStore keyed by this process's device and effective_num_gpus == 1.
-    ``type`` is a local diffusers-format directory (unet/, vae/ safetensors) or "synthetic[:seed]" for seeded
-    random weights of the SD1.x shapes (there is no hub access here); explicit state dicts override both."""
+    ``type`` is a local diffusers-format directory (unet/, vae/ safetensors), "synthetic[:seed]" for seeded random
+    weights of the SD1.x shapes (there is no hub access here) or "synthetic-small[:seed]" for a 1/10-width model of the
+    same topology; explicit state dicts override all of them."""
     if str(device) == "cpu":
         raise RuntimeError("stablekeypoints_b200 has no CPU path (the reference's CPU path is timed from oracle/)")
     dev = torch.device(device if str(device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
     if precision is not None:
         set_precision(precision)
+    if unet_state_dict is None and unet_config is None and type.startswith("synthetic-small"):
+        # same topology at 1/10 of the widths (768-wide context like SD1.x, so the reference's init_random_noise fits):
+        # lets the reference's own main.py run end to end in seconds where no checkpoint is available
+        unet_config = UNetConfig(block_out_channels=(32, 64, 128, 128), heads=4, norm_num_groups=8)
+        vae_config = vae_config or VAEConfig(block_out_channels=(8, 16, 32, 32), norm_num_groups=4)
+        attn_gain = 6.0 if attn_gain == 1.0 else attn_gain      # peaky (trained-looking) maps instead of near-uniform ones
     ucfg, vcfg = unet_config or UNetConfig(), vae_config or VAEConfig()
     if unet_state_dict is None:
         if type.startswith("synthetic"):

@@ -82,7 +82,12 @@ def furthest_point_sampling(attention_maps, top_k, top_initial_candidates):
     _, h, w = attention_maps.shape
     peaks = ops.argmax_flat(attention_maps)
     out, n_out = ops.furthest_point_sampling_flat(peaks, h, w, top_initial_candidates, top_k)
-    if top_initial_candidates.numel() < top_k:      # the reference returns fewer indices when candidates run out
+    if top_initial_candidates.numel() < top_k:
+        # the reference returns fewer indices when the candidates run out (ptp_utils.py:139-159).  That needs the count on
+        # the host, which a CUDA-graph capture cannot give: refuse instead of returning zero-padded indices.
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("furthest_point_sampling: fewer candidates (%d) than top_k (%d) cannot be captured in a CUDA graph"
+                               % (top_initial_candidates.numel(), top_k))
         return out[: int(n_out.item())]
     return out
 
@@ -132,7 +137,11 @@ def find_pred_noise(ldm, image, context, noise_level=-1, device="cuda", noise=No
         noise = noise.to(latent.device, latent.dtype)
     t = ldm.scheduler.timesteps[noise_level]
     noisy = ldm.scheduler.add_noise(latent, noise, t)
-    pred = ldm.unet(noisy, t.repeat(noisy.shape[0]), context.repeat(noisy.shape[0], 1, 1))["sample"]
+    b = noisy.shape[0]
+    # the reference passes context.repeat(B,1,1) (ptp_utils.py:229); at B == 1 (one image per rank) that is the tensor itself,
+    # and handing the leaf over keeps the engine's K|V projection cache valid for both forwards of an iteration
+    ctx = context if b == 1 else context.repeat(b, 1, 1)
+    pred = ldm.unet(noisy, t.repeat(b), ctx)["sample"]
     return noise, pred
 
 

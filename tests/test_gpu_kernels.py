@@ -280,6 +280,63 @@ def test_capture_store_fwd_bwd(ops, heads, s, n, res):
     assert rel_err(lc.grad.cpu(), lr.grad) < 5e-5
 
 
+def _skewed_logits(kind, heads, s, n, g):
+    """Logit distributions that trained weights produce and randn*3 never does: a large common offset,
+    a wide range, one hugely negative (masked-like) token, one dominant token.  The cheap softmax bound of the row kernel
+    (max |V| over the whole row) is useless on all of them."""
+    base = torch.randn(heads, s * s, n, generator=g) * 3
+    if kind == "offset":
+        return base - 60.0
+    if kind == "wide":
+        return (torch.rand(heads, s * s, n, generator=g) * 2 - 1) * 80.0
+    if kind == "neg_outlier":
+        base[:, :, n // 3] = -3.0e4
+        return base
+    if kind == "dominant":
+        base[:, :, 1] += 90.0
+        base[:, : (s * s) // 2, 0] -= 200.0
+        return base
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["offset", "wide", "neg_outlier", "dominant"])
+@pytest.mark.parametrize("heads,s,n,res", [(8, 16, 77, 128), (2, 32, 500, 128), (3, 16, 100, 64)])
+def test_capture_store_skewed_logits_fwd_bwd(ops, kind, heads, s, n, res):
+    g = torch.Generator().manual_seed(heads * 7 + n)
+    logits = _skewed_logits(kind, heads, s, n, g)
+    dp = torch.randn(heads, res * res, n, generator=g)
+    lr = logits.double().requires_grad_(True)
+    pref = _capture_ref(lr, res)
+    (pref * dp.double()).sum().backward()
+    lc = cu(logits).requires_grad_(True)
+    p = ops.capture_store(lc, res)
+    (p * cu(dp)).sum().backward()
+    assert bool(torch.isfinite(p).all()) and bool(torch.isfinite(lc.grad).all())
+    # wide-range logits lose absolute precision in the fp32 bicubic itself (|x| ~ 100 -> ulp 8e-6 before the exp)
+    assert rel_err(p.detach().cpu(), pref.detach()) < 2e-4, kind
+    assert torch.allclose(p.detach().sum(-1).cpu(), torch.ones(heads, res * res), atol=2e-5)
+    assert rel_err(lc.grad.cpu(), lr.grad) < 5e-4, kind
+
+
+@pytest.mark.parametrize("kind", ["offset", "wide", "neg_outlier", "dominant"])
+def test_capture_mean_skewed_logits_fwd_bwd(ops, kind):
+    heads, sides, n, res = 8, (16, 16, 16, 32), 77, 128
+    g = torch.Generator().manual_seed(11)
+    logits = [_skewed_logits(kind, heads, s, n, g) for s in sides]
+    dm = torch.randn(n, res, res, generator=g)
+    lr = [l.double().requires_grad_(True) for l in logits]
+    mref = torch.stack([_capture_ref(l, res) for l in lr]).mean(dim=(0, 1)).t().reshape(n, res, res)
+    (mref * dm.double()).sum().backward()
+    lc = [cu(l).requires_grad_(True) for l in logits]
+    m = ops.capture_mean(lc, res)
+    (m * cu(dm)).sum().backward()
+    assert bool(torch.isfinite(m).all())
+    assert rel_err(m.detach().cpu(), mref.detach()) < 2e-4, kind
+    for a, b in zip(lc, lr):
+        assert bool(torch.isfinite(a.grad).all())
+        assert rel_err(a.grad.cpu(), b.grad) < 5e-4, kind
+
+
 def test_capture_matches_literal_reference_formulation(ops):
     """The kernel's linearity form vs the reference's literal form (bicubic of x, second to_q) on one layer."""
     torch.manual_seed(3)
