@@ -210,7 +210,7 @@ def run_b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    graph = None
+    graph = g2 = ee_step = None
     launches_per_step = None
     if a.graph:
         # the whole optimizer step (2 captured forwards + selection + losses + backward + all-reduce + Adam) as ONE
@@ -312,12 +312,16 @@ def run_b200_arm(a):
             line["cpu_baseline"] = cpu_baseline(a)
         print(json.dumps(line), flush=True)
     if world > 1:
-        # the step's CUDA graph holds a captured NCCL all-reduce; tearing the communicator down underneath it can hang,
-        # so: make sure everyone is done, then leave without running destructors (exit code 0 for torchrun)
+        # the step graphs hold a captured NCCL all-reduce: release them BEFORE the communicator goes away (destroying the
+        # process group underneath a live graph is what used to hang), then tear down normally
         dist.barrier()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
+        graph = g2 = step = ee_step = None     # noqa: F841
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def timed_single(step, imgs, n):

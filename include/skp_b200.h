@@ -171,6 +171,9 @@ int skp_cross_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_
                           const float* d_logits_extra, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
                           int64_t lddv, int S, int N, int heads, int d, float scale, void* stream);
 
+/* Kernel selection switch for tests and A/B measurements: row formulation (1, default) or the tile kernels it falls back
+ * to (0) for the attn-store forward / the fused capture+collect backward; -1 leaves a setting unchanged. */
+void skp_capture_select(int row_fwd, int row_bwd);
 /* ------------------------------------------------------------------ attention-store ("capture")
  * ptp_utils.py:508-538: bicubic (align_corners=False, A=-0.75, clamped taps) upsample of the layer
  * input to R x R, to_q, q' k^T * scale, softmax over the TOKEN axis, stored as [heads, R*R, N].

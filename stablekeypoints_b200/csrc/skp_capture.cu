@@ -351,313 +351,6 @@ __global__ void __launch_bounds__(CAP_THREADS) capture_bwd_kernel(CapParams p) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------ forward, v2
-// Fast forward path for integer up-sampling factors R/s >= 4 (every real configuration: 16->128, 32->128, ...).
-// A thread owns a QUAD of 4 horizontally adjacent output pixels and a slice of the token groups (4 tokens each):
-//   * the 4 pixels touch at most 5 low-res columns and share their 4 rows, so the stencil is evaluated separably in
-//     registers: V[j] = sum_t wy[t] L[row_t][col_j]  (20 x LDS.128, 80 FMA), out[p] = sum_j W5[p][j] V[j] (80 FMA)
-//     -> 10 FMA and 1.25 shared loads per output element instead of 16 and 4;
-//   * lanes of a warp are 32 different quads (an 8x16-pixel tile), so no lane idles for any N; token slices live in
-//     different warps and meet through a small (max, sum) exchange in shared memory;
-//   * logits of up to QD_GPT groups stay in registers between the statistics sweep and the probability sweep;
-//   * results are staged token-major [n][pixel] with conflict-free 128-bit shared stores over the quad, then leave
-//     as coalesced 128 B global stores (STORE: [h, pix, n]; MEAN: [n, Y, X]).
-constexpr int QD_GPT_MAX = 3;
-
-struct QuadTaps {
-  float wy[4];
-  float w5[4][5];
-  int rowoff[4];
-  int coloff[5];
-};
-
-__device__ __forceinline__ void quad_logits(const float4* __restrict__ fp4, const QuadTaps& q, int n4, float4 o[4]) {
-  float4 V[5];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float4 v = fp4[q.rowoff[t] + q.coloff[j] + n4];
-      float w = q.wy[t];
-      a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
-    }
-    V[j] = a;
-  }
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      float w = q.w5[p][j];
-      a.x = fmaf(w, V[j].x, a.x); a.y = fmaf(w, V[j].y, a.y); a.z = fmaf(w, V[j].z, a.z); a.w = fmaf(w, V[j].w, a.w);
-    }
-    o[p] = a;
-  }
-}
-
-__device__ __forceinline__ float fast_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ void online_update(float v, float& m, float& s) {
-  if (v > m) { s *= __expf(m - v); m = v; }
-  s += __expf(v - m);
-}
-
-template <int TY, bool STORE, int QD_GPT>
-__global__ void __launch_bounds__(QD_GPT == 0 ? 320 : 512, QD_GPT == 0 ? 3 : 1) capture_fwd_quad_kernel(CapParams p) {
-  constexpr int NQD = TY * 4;    // quads per tile
-  constexpr int TP = TY * 16;    // pixels per tile
-  constexpr int PT = TP + 4;     // staging row pitch (floats): multiple of 4 for 128-bit accesses
-  extern __shared__ __align__(16) float smem[];
-  const int N = p.N, R = p.R, Nf = p.Nf, Nf4 = Nf >> 2;
-  const int NS = blockDim.x / NQD;
-  float* fp = smem;                                // [max_slots][Nf]
-  float* tile = fp + (size_t)p.max_slots * Nf;     // [N][PT]
-  float* st_m = tile + (size_t)N * PT;             // [NS][TP]
-  float* st_s = st_m + NS * TP;                    // [NS][TP]
-
-  const int quad = threadIdx.x % NQD, slice = threadIdx.x / NQD;
-  const int qy = quad >> 2, qx = quad & 3;
-  const int Y0 = blockIdx.y * TY, X0 = blockIdx.x * 16;
-  const int Y = Y0 + qy, X = X0 + 4 * qx;
-  const int pix0 = qy * 16 + 4 * qx;               // first pixel of the quad inside the tile
-  const int ngroups = (N + 3) >> 2;
-  const int gps = (ngroups + NS - 1) / NS;
-  const int g0 = slice * gps, g1 = min(ngroups, g0 + gps);
-  const bool cached = QD_GPT > 0 && gps <= QD_GPT;
-
-  if (!STORE)
-    for (int i = threadIdx.x; i < N * PT; i += blockDim.x) tile[i] = 0.f;
-
-  const int h_begin = STORE ? blockIdx.z : 0, h_end = STORE ? blockIdx.z + 1 : p.heads;
-  for (int l = 0; l < p.n_layers; ++l) {
-    const int s = p.s[l];
-    int wy0, wy1, wx0, wx1;
-    window(Y0, TY, R, s, &wy0, &wy1);
-    window(X0, 16, R, s, &wx0, &wx1);
-    const int wsy = wy1 - wy0 + 1, wsx = wx1 - wx0 + 1;
-    QuadTaps q;
-    {
-      const float scale = (float)s / (float)R;
-      float ry = scale * (Y + 0.5f) - 0.5f, fy = floorf(ry);
-      cubic_coeffs(ry - fy, q.wy);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) q.rowoff[t] = (clampi((int)fy - 1 + t, 0, s - 1) - wy0) * wsx * Nf4;
-      float rx0 = scale * (X + 0.5f) - 0.5f;
-      const int ix0 = (int)floorf(rx0);
-#pragma unroll
-      for (int j = 0; j < 5; ++j) q.coloff[j] = (clampi(ix0 - 1 + j, 0, s - 1) - wx0) * Nf4;
-#pragma unroll
-      for (int pp = 0; pp < 4; ++pp) {
-        float rx = scale * (X + pp + 0.5f) - 0.5f, fx = floorf(rx);
-        float cw[4];
-        cubic_coeffs(rx - fx, cw);
-        const bool d = ((int)fx - ix0) != 0;   // 0 or 1 for up-sampling factors >= 4
-        q.w5[pp][0] = d ? 0.f : cw[0];
-        q.w5[pp][1] = d ? cw[0] : cw[1];
-        q.w5[pp][2] = d ? cw[1] : cw[2];
-        q.w5[pp][3] = d ? cw[2] : cw[3];
-        q.w5[pp][4] = d ? cw[3] : 0.f;
-      }
-    }
-    for (int h = h_begin; h < h_end; ++h) {
-      __syncthreads();
-      {  // footprint of (l, h): rows of wsx*N contiguous floats
-        const float* lg = p.logits[l] + ((size_t)(h * s + wy0) * s + wx0) * N;
-        const int total = wsy * wsx * Nf;
-        constexpr int U = 8;  // issue U independent global loads before the first shared store (one latency, not U)
-        for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
-          float v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int i = base + u * blockDim.x;
-            v[u] = 0.f;
-            if (i < total) {
-              const int slot = i / Nf, n = i - slot * Nf;
-              const int sy = slot / wsx, sx = slot - sy * wsx;
-              if (n < N) v[u] = __ldg(lg + ((size_t)sy * s + sx) * N + n);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int i = base + u * blockDim.x;
-            if (i < total) fp[i] = v[u];
-          }
-        }
-      }
-      __syncthreads();
-      const float4* fp4 = reinterpret_cast<const float4*>(fp);
-      float4* tile4 = reinterpret_cast<float4*>(tile);
-      if (cached) {
-        // three light phases on register-resident logits: max -> exp2/sum -> scale+emit (no online rescaling)
-        constexpr float LOG2E = 1.4426950408889634f;
-        float4 cache[QD_GPT > 0 ? QD_GPT : 1][4];
-        float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-#pragma unroll
-        for (int gi = 0; gi < QD_GPT; ++gi) {
-          const int g = g0 + gi;
-          if (g < g1) {
-            quad_logits(fp4, q, g, cache[gi]);
-            const int rem = N - g * 4;   // < 4 only for the last, partial token group: mask the padding tokens
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-              float4& o = cache[gi][pp];
-              if (rem < 4) {
-                if (rem < 2) o.y = -CUDART_INF_F;
-                if (rem < 3) o.z = -CUDART_INF_F;
-                o.w = -CUDART_INF_F;
-              }
-              mx[pp] = fmaxf(fmaxf(mx[pp], fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
-            }
-          }
-        }
-        *reinterpret_cast<float4*>(st_m + slice * TP + pix0) = make_float4(mx[0], mx[1], mx[2], mx[3]);
-        __syncthreads();
-        float M[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-        for (int k = 0; k < NS; ++k) {
-          const float4 mk = *reinterpret_cast<const float4*>(st_m + k * TP + pix0);
-          M[0] = fmaxf(M[0], mk.x); M[1] = fmaxf(M[1], mk.y); M[2] = fmaxf(M[2], mk.z); M[3] = fmaxf(M[3], mk.w);
-        }
-        float sum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int gi = 0; gi < QD_GPT; ++gi) {
-          if (g0 + gi < g1) {
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-              float4& o = cache[gi][pp];
-              const float mb = -M[pp] * LOG2E;
-              o.x = fast_ex2(fmaf(o.x, LOG2E, mb)); o.y = fast_ex2(fmaf(o.y, LOG2E, mb));
-              o.z = fast_ex2(fmaf(o.z, LOG2E, mb)); o.w = fast_ex2(fmaf(o.w, LOG2E, mb));
-              sum[pp] += (o.x + o.y) + (o.z + o.w);
-            }
-          }
-        }
-        *reinterpret_cast<float4*>(st_s + slice * TP + pix0) = make_float4(sum[0], sum[1], sum[2], sum[3]);
-        __syncthreads();
-        float S[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < NS; ++k) {
-          const float4 sk = *reinterpret_cast<const float4*>(st_s + k * TP + pix0);
-          S[0] += sk.x; S[1] += sk.y; S[2] += sk.z; S[3] += sk.w;
-        }
-        float inv[4];
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) inv[pp] = (STORE ? 1.f : p.w) / S[pp];
-#pragma unroll
-        for (int gi = 0; gi < QD_GPT; ++gi) {
-          const int g = g0 + gi;
-          if (g < g1) {
-            const float4 a0 = cache[gi][0], a1 = cache[gi][1], a2 = cache[gi][2], a3 = cache[gi][3];
-            const float e[4][4] = {{a0.x, a1.x, a2.x, a3.x}, {a0.y, a1.y, a2.y, a3.y}, {a0.z, a1.z, a2.z, a3.z}, {a0.w, a1.w, a2.w, a3.w}};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int n = g * 4 + c;
-              if (n < N) {
-                float4 v = make_float4(e[c][0] * inv[0], e[c][1] * inv[1], e[c][2] * inv[2], e[c][3] * inv[3]);
-                float4* dst = tile4 + ((size_t)n * PT + pix0) / 4;
-                if (STORE) {
-                  *dst = v;
-                } else {
-                  float4 acc = *dst;
-                  acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                  *dst = acc;
-                }
-              }
-            }
-          }
-        }
-      } else {
-        // generic path (many tokens per thread): online statistics sweep, then a second sweep that recomputes
-        float m[4], sm[4];
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) { m[pp] = -CUDART_INF_F; sm[pp] = 0.f; }
-        for (int g = g0; g < g1; ++g) {
-          float4 o4[4];
-          quad_logits(fp4, q, g, o4);
-#pragma unroll
-          for (int pp = 0; pp < 4; ++pp) {
-            const float4 o = o4[pp];
-            const int n = g * 4;
-            online_update(o.x, m[pp], sm[pp]);
-            if (n + 1 < N) online_update(o.y, m[pp], sm[pp]);
-            if (n + 2 < N) online_update(o.z, m[pp], sm[pp]);
-            if (n + 3 < N) online_update(o.w, m[pp], sm[pp]);
-          }
-        }
-        *reinterpret_cast<float4*>(st_m + slice * TP + pix0) = make_float4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<float4*>(st_s + slice * TP + pix0) = make_float4(sm[0], sm[1], sm[2], sm[3]);
-        __syncthreads();
-        float M[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F}, S[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < NS; ++k) {
-          const float4 mk = *reinterpret_cast<const float4*>(st_m + k * TP + pix0);
-          M[0] = fmaxf(M[0], mk.x); M[1] = fmaxf(M[1], mk.y); M[2] = fmaxf(M[2], mk.z); M[3] = fmaxf(M[3], mk.w);
-        }
-        for (int k = 0; k < NS; ++k) {
-          const float4 mk = *reinterpret_cast<const float4*>(st_m + k * TP + pix0);
-          const float4 sk = *reinterpret_cast<const float4*>(st_s + k * TP + pix0);
-          S[0] += sk.x * __expf(mk.x - M[0]); S[1] += sk.y * __expf(mk.y - M[1]);
-          S[2] += sk.z * __expf(mk.z - M[2]); S[3] += sk.w * __expf(mk.w - M[3]);
-        }
-        float inv[4];
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) inv[pp] = (STORE ? 1.f : p.w) / S[pp];
-        for (int g = g0; g < g1; ++g) {
-          float4 o4[4];
-          quad_logits(fp4, q, g, o4);
-          float pr[4][4];
-#pragma unroll
-          for (int pp = 0; pp < 4; ++pp) {
-            pr[pp][0] = __expf(o4[pp].x - M[pp]) * inv[pp]; pr[pp][1] = __expf(o4[pp].y - M[pp]) * inv[pp];
-            pr[pp][2] = __expf(o4[pp].z - M[pp]) * inv[pp]; pr[pp][3] = __expf(o4[pp].w - M[pp]) * inv[pp];
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int n = g * 4 + c;
-            if (n < N) {
-              float4 v = make_float4(pr[0][c], pr[1][c], pr[2][c], pr[3][c]);
-              float4* dst = tile4 + ((size_t)n * PT + pix0) / 4;
-              if (STORE) {
-                *dst = v;
-              } else {
-                float4 acc = *dst;
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                *dst = acc;
-              }
-            }
-          }
-        }
-      }
-      if (STORE) {
-        __syncthreads();
-        {   // each tile row leaves as one contiguous run of 16*N floats; a warp copies whole pixels (no div/mod)
-          const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-          for (int pxl = wid; pxl < TP; pxl += nw) {
-            float* dst = p.out + ((size_t)h * R * R + (size_t)(Y0 + (pxl >> 4)) * R + X0 + (pxl & 15)) * N;
-            for (int n = lane; n < N; n += 32) __stcs(dst + n, tile[(size_t)n * PT + pxl]);
-          }
-        }
-      }
-    }
-  }
-  if (!STORE) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < N * TP; i += blockDim.x) {
-      const int n = i / TP, pp = i - n * TP;
-      p.out[((size_t)n * R + Y0 + (pp >> 4)) * R + X0 + (pp & 15)] = tile[(size_t)n * PT + pp];
-    }
-  }
-}
-
-static bool quad_eligible(const CapParams& p) {
-  if (p.R % 16 != 0 || p.N < 4) return false;
-  for (int l = 0; l < p.n_layers; ++l)
-    if (p.R % p.s[l] != 0 || p.R / p.s[l] < 4) return false;
-  return true;
-}
-
 // ------------------------------------------------------------------------------------------------ host
 static int footprint_slots(int R, int s, int TY, int* ok, int* mwy, int* mwx) {
   int best = 0;
@@ -717,60 +410,21 @@ static int launch_ty(CapParams& p, cudaStream_t st, bool* fits) {
   return SKP_OK;
 }
 
-template <int TY, bool STORE>
-static int launch_quad(CapParams& p, cudaStream_t st, bool* fits, bool need_grid) {
-  static const int gpt_env = getenv("SKP_CAPTURE_CACHE") ? atoi(getenv("SKP_CAPTURE_CACHE")) : 0;
-  const int QD_GPT = gpt_env > 0 ? QD_GPT_MAX : 0;
-  if (need_grid && (long)(p.R / 16) * (p.R / TY) * (STORE ? p.heads : 1) < 2 * 148) { *fits = false; return SKP_OK; }
-  constexpr int NQD = TY * 4, TP = TY * 16;
-  int slots = 0;
-  p.mwy = p.mwx = 1;
-  for (int l = 0; l < p.n_layers; ++l) {
-    int ok;
-    int v = footprint_slots(p.R, p.s[l], TY, &ok, &p.mwy, &p.mwx);
-    if (!ok) { *fits = false; return SKP_OK; }
-    if (v > slots) slots = v;
-  }
-  p.max_slots = slots;
-  // token slices: as many warps as keep every slice equally loaded (<= 512 threads), preferring register-cached sweeps
-  const int ngroups = (p.N + 3) / 4;
-  int best_ns = 4, best_cost = 1 << 30;
-  for (int ns = 4; ns <= 16 && ns * NQD <= (QD_GPT > 0 ? 512 : 320); ++ns) {
-    int gps = (ngroups + ns - 1) / ns;
-    int cost = gps * ns * 8 + (gps > QD_GPT ? gps * ns * 8 : 0) - ns;  // padded work (x2 when the sweep recomputes)
-    if (cost < best_cost) { best_cost = cost; best_ns = ns; }
-  }
-  size_t bytes = ((size_t)slots * p.Nf + (size_t)p.N * (TP + 4) + 2 * (size_t)best_ns * TP) * sizeof(float);
-  if (bytes > 200 * 1024) { *fits = false; return SKP_OK; }
-  *fits = true;
-  dim3 grid(p.R / 16, p.R / TY, STORE ? p.heads : 1);
-  cudaError_t e;
-  if (QD_GPT > 0) {
-    e = cudaFuncSetAttribute(capture_fwd_quad_kernel<TY, STORE, QD_GPT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    cudaFuncSetAttribute(capture_fwd_quad_kernel<TY, STORE, QD_GPT_MAX>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e == cudaSuccess) capture_fwd_quad_kernel<TY, STORE, QD_GPT_MAX><<<grid, NQD * best_ns, bytes, st>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(capture_fwd_quad_kernel<TY, STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    cudaFuncSetAttribute(capture_fwd_quad_kernel<TY, STORE, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e == cudaSuccess) capture_fwd_quad_kernel<TY, STORE, 0><<<grid, NQD * best_ns, bytes, st>>>(p);
-  }
-  if (e != cudaSuccess) { set_error("capture: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
-  SKP_CHECK_LAUNCH("capture_quad");
-  return SKP_OK;
-}
-
 // skp_capture_row.cu: the row-per-CTA attn-store kernel (any R, s; needs the row + footprint to fit shared memory)
 int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled);
 int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
                          cudaStream_t st, bool* handled);
 bool capture_mean_row_bwd_fits(int s, int N, int R);
 
+// kernel selection switches (tests / A-B measurements): initial value from the environment, skp_capture_select() at run time
+static int g_row_fwd = (getenv("SKP_CAPTURE_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_ROW")) == 0) ? 0 : 1;
+static int g_row_bwd = (getenv("SKP_CAPTURE_BWD_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_BWD_ROW")) == 0) ? 0 : 1;
+
 template <bool STORE, bool BWD>
 static int launch(CapParams& p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (STORE && !BWD) {
-    static const bool row_off = getenv("SKP_CAPTURE_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_ROW")) == 0;
-    if (!row_off) {
+    if (g_row_fwd) {
       bool handled = false;
       int rr = capture_store_row(p.logits[0], p.out, p.heads, p.s[0], p.N, p.R, st, &handled);
       if (rr != SKP_OK || handled) return rr;
@@ -780,19 +434,6 @@ static int launch(CapParams& p, void* stream) {
   p.Nf = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;
   p.Nb = p.N | 1;
   bool fits = false;
-  // measured on B200 (N=77, R=128): STORE v2 63-67 us vs v1 70 us; MEAN v2 377-550 us vs v1 297 us (the fused mean has
-  // only R*R/(16*TY) CTAs, each looping over all 32 (layer, head) slices) -> v2 serves STORE, v1 serves MEAN by default.
-  const char* force = getenv("SKP_CAPTURE_QUAD");
-  const bool use_quad = force ? atoi(force) != 0 : STORE;
-  if (!BWD && use_quad && quad_eligible(p) && getenv("SKP_CAPTURE_V1") == nullptr) {
-    // largest tile that still gives >= 2 CTAs per SM; the 2-row tile takes whatever is left
-    int rq = launch_quad<8, STORE>(p, st, &fits, true);
-    if (rq != SKP_OK || fits) return rq;
-    rq = launch_quad<4, STORE>(p, st, &fits, true);
-    if (rq != SKP_OK || fits) return rq;
-    rq = launch_quad<2, STORE>(p, st, &fits, false);
-    if (rq != SKP_OK || fits) return rq;
-  }
   int rc = launch_ty<4, STORE, BWD>(p, st, &fits);
   if (rc != SKP_OK || fits) return rc;
   rc = launch_ty<2, STORE, BWD>(p, st, &fits);
@@ -820,6 +461,11 @@ static int fill(CapParams& p, const float* const* logits, float* const* dlogits,
 }  // namespace skp
 
 using namespace skp;
+
+extern "C" void skp_capture_select(int row_fwd, int row_bwd) {
+  if (row_fwd >= 0) g_row_fwd = row_fwd != 0;
+  if (row_bwd >= 0) g_row_bwd = row_bwd != 0;
+}
 
 extern "C" int skp_capture_store_fwd(const float* logits, float* probs, int heads, int s, int N, int R, void* stream) {
   SKP_REQUIRE(probs != nullptr, "capture_store_fwd: null output");
@@ -856,8 +502,7 @@ extern "C" int skp_capture_mean_bwd(const float* const* logits, const int* s, in
   SKP_REQUIRE(logits != nullptr && s != nullptr && d_maps != nullptr && d_logits != nullptr,
               "capture_mean_bwd: null pointer");
   {   // row formulation (skp_capture_row.cu), one launch per layer; SKP_CAPTURE_BWD_ROW=0 keeps the tile kernel
-    static const bool row_on = !(getenv("SKP_CAPTURE_BWD_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_BWD_ROW")) == 0);
-    if (row_on && n_layers >= 1 && n_layers <= SKP_MAX_LAYERS && heads > 0 && N > 0 && R > 0) {
+    if (g_row_bwd && n_layers >= 1 && n_layers <= SKP_MAX_LAYERS && heads > 0 && N > 0 && R > 0) {
       bool all = true;
       for (int l = 0; l < n_layers; ++l)   // every layer must fit before any is accumulated
         if (logits[l] == nullptr || d_logits[l] == nullptr || s[l] <= 0 || !capture_mean_row_bwd_fits(s[l], N, R)) all = false;

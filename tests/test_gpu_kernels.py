@@ -373,17 +373,37 @@ def test_capture_mean_fwd_bwd(ops, heads, sides, n, res):
         assert rel_err(a.grad.cpu(), b.grad) < 5e-5
 
 
-@pytest.mark.parametrize("quad", ["0", "1"])
-def test_capture_kernel_variants_agree(ops, monkeypatch, quad):
-    """Both forward implementations (v1 pixel/token-slice, v2 quad/separable) for both modes, forced by env."""
-    monkeypatch.setenv("SKP_CAPTURE_QUAD", quad)
-    g = torch.Generator().manual_seed(int(quad) + 5)
-    logits = [torch.randn(8, s * s, 77, generator=g) * 3 for s in (16, 32)]
-    stack = torch.stack([_capture_ref(l, 128) for l in logits])
-    m = ops.capture_mean([cu(l) for l in logits], 128)
-    assert rel_err(m.cpu(), stack.mean(dim=(0, 1)).t().reshape(77, 128, 128)) < 2e-5
+@pytest.mark.parametrize("row", ["1", "0"])
+@pytest.mark.parametrize("n", [77, 500])
+def test_capture_kernel_variants_agree(ops, monkeypatch, row, n):
+    """The row attn-store / row backward kernels and the tile kernels they fall back to (skp_capture_select(0, 0); also
+    taken when R*N is not a multiple of 4) for both modes, forward and backward."""
+    from stablekeypoints_b200._lib import lib
+    lib().skp_capture_select(int(row), int(row))
+    monkeypatch.setattr(ops, "CAPTURE_MEAN_FWD", "store" if row == "1" else "fused")
+    try:
+        _variants_body(ops, row, n)
+    finally:
+        lib().skp_capture_select(1, 1)
+
+
+def _variants_body(ops, row, n):
+    g = torch.Generator().manual_seed(int(row) + 5)
+    logits = [torch.randn(8, s * s, n, generator=g) * 3 for s in (16, 32)]
+    dm = torch.randn(n, 128, 128, generator=g)
+    lr = [l.clone().requires_grad_(True) for l in logits]
+    stack = torch.stack([_capture_ref(l, 128) for l in lr])
+    mref = stack.mean(dim=(0, 1)).t().reshape(n, 128, 128)
+    (mref * dm).sum().backward()
+    lc = [cu(l).requires_grad_(True) for l in logits]
+    m = ops.capture_mean(lc, 128)
+    (m * cu(dm)).sum().backward()
+    assert rel_err(m.detach().cpu(), mref.detach()) < 2e-5
+    for a, b in zip(lc, lr):
+        assert rel_err(a.grad.cpu(), b.grad) < 5e-5
     p = ops.capture_store(cu(logits[1]), 128)
-    assert rel_err(p.cpu(), stack[1]) < 2e-5
+    assert bool(torch.isfinite(p).all())
+    assert rel_err(p.cpu(), stack[1].detach()) < 2e-5
 
 
 # ----------------------------------------------------------------------------- collect_maps
