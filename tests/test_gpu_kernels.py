@@ -280,6 +280,14 @@ def test_capture_store_fwd_bwd(ops, heads, s, n, res):
     assert rel_err(lc.grad.cpu(), lr.grad) < 5e-5
 
 
+def _grad_err(a, b, floor=1e-3):
+    """max|a-b| / max(max|b|, floor): saturated softmaxes have (numerically) zero gradients, where a relative error against
+    max|b| ~ 1e-36 would only measure fp32 cancellation noise of size 1e-8."""
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))
+
+
 def _skewed_logits(kind, heads, s, n, g):
     """Logit distributions that trained weights produce and randn*3 never does: a large common offset,
     a wide range, one hugely negative (masked-like) token, one dominant token.  The cheap softmax bound of the row kernel
@@ -315,7 +323,7 @@ def test_capture_store_skewed_logits_fwd_bwd(ops, kind, heads, s, n, res):
     # wide-range logits lose absolute precision in the fp32 bicubic itself (|x| ~ 100 -> ulp 8e-6 before the exp)
     assert rel_err(p.detach().cpu(), pref.detach()) < 2e-4, kind
     assert torch.allclose(p.detach().sum(-1).cpu(), torch.ones(heads, res * res), atol=2e-5)
-    assert rel_err(lc.grad.cpu(), lr.grad) < 5e-4, kind
+    assert _grad_err(lc.grad.cpu(), lr.grad) < 5e-4, kind
 
 
 @pytest.mark.parametrize("kind", ["offset", "wide", "neg_outlier", "dominant"])
@@ -334,7 +342,7 @@ def test_capture_mean_skewed_logits_fwd_bwd(ops, kind):
     assert rel_err(m.detach().cpu(), mref.detach()) < 2e-4, kind
     for a, b in zip(lc, lr):
         assert bool(torch.isfinite(a.grad).all())
-        assert rel_err(a.grad.cpu(), b.grad) < 5e-4, kind
+        assert _grad_err(a.grad.cpu(), b.grad) < 5e-4, kind
 
 
 def test_capture_matches_literal_reference_formulation(ops):
