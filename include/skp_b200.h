@@ -174,6 +174,23 @@ int skp_cross_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_
 /* Kernel selection switch for tests and A/B measurements: row formulation (1, default) or the tile kernels it falls back
  * to (0) for the attn-store forward / the fused capture+collect backward; -1 leaves a setting unchanged. */
 void skp_capture_select(int row_fwd, int row_bwd);
+/* The tcgen05 formulation of the attn-store / fused capture+collect forward (skp_capture_tc.cu: the horizontal bicubic pass
+ * is an M128 x N=tokens x K=s GEMM per output row, the softmax runs thread-per-pixel on the TMEM lanes, the row leaves
+ * through the copy engine) serves N <= 128 tokens and s <= 32.  on = 0: never; 1 (default): where it is the faster kernel
+ * (the fused capture+collect always, the attn-store for N > 96); 2: wherever the shape is eligible (tests, A/B runs). */
+void skp_capture_tc(int on);
+int skp_capture_tc_ok(const int* s, int n_layers, int N, int R, int store);
+/* Workspace bytes (row maxima of the low-res logits, written by a pre-pass) for the two entry points below. */
+int64_t skp_capture_tc_workspace(const int* s, int n_layers, int heads);
+/* skp_capture_store_fwd / skp_capture_mean_fwd on the tcgen05 kernel; shapes it does not take (N > 128, s > 32, s % 4 != 0,
+ * more than two distinct sides, a NULL workspace) run the SIMT kernels instead, so the result contract is the same. */
+int skp_capture_store_tc_fwd(const float* logits, float* probs, int heads, int s, int N, int R, float* workspace,
+                             void* stream);
+int skp_capture_mean_tc_fwd(const float* const* logits, const int* s, int n_layers, float* maps, int heads, int N,
+                            int R, float* workspace, void* stream);
+/* Debug: device buffer of 3*64*8 int64 that CTA 0 of the tcgen05 kernel fills with clock64() stamps per pipeline role
+ * (scripts/capture_tc_trace.py); NULL (default) switches the stamps off. */
+void skp_capture_tc_trace(void* buf);
 /* ------------------------------------------------------------------ attention-store ("capture")
  * ptp_utils.py:508-538: bicubic (align_corners=False, A=-0.75, clamped taps) upsample of the layer
  * input to R x R, to_q, q' k^T * scale, softmax over the TOKEN axis, stored as [heads, R*R, N].

@@ -55,6 +55,12 @@ _SIGNATURES: Dict[str, list] = {
     "skp_cross_attn_tc_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_cross_attn_tc_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P],
     "skp_capture_select": [_I, _I],
+    "skp_capture_tc": [_I],
+    "skp_capture_tc_trace": [_P],
+    "skp_capture_tc_ok": [_P, _I, _I, _I, _I],
+    "skp_capture_tc_workspace": [_P, _I, _I],
+    "skp_capture_store_tc_fwd": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "skp_capture_mean_tc_fwd": [_P, _P, _I, _P, _I, _I, _I, _P, _P],
     "skp_capture_store_fwd": [_P, _P, _I, _I, _I, _I, _P],
     "skp_capture_store_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "skp_capture_mean_fwd": [_P, _P, _I, _P, _I, _I, _I, _P],
@@ -78,8 +84,9 @@ _SIGNATURES: Dict[str, list] = {
     "skp_adam_step": [_P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _P],
     "skp_adam_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }
-_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None, "skp_capture_select": None,
-            "skp_self_attn_tc_workspace": C.c_int64}
+_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None, "skp_capture_select": None, "skp_capture_tc": None, "skp_capture_tc_trace": None,
+            "skp_self_attn_tc_workspace": C.c_int64,
+            "skp_capture_tc_workspace": C.c_int64}
 
 
 def declared_symbols() -> List[str]:

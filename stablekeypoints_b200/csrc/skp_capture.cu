@@ -415,6 +415,13 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
 int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
                          cudaStream_t st, bool* handled);
 bool capture_mean_row_bwd_fits(int s, int N, int R);
+// skp_capture_tc.cu: the tcgen05 formulation (horizontal bicubic pass as a GEMM, softmax thread-local on the TMEM lanes)
+int capture_tc(const float* const* logits, const int* s, int n_layers, float* out, int heads, int N, int R, bool store,
+               float* workspace, cudaStream_t st, bool* handled);
+bool capture_tc_eligible(const int* s, int n_layers, int N, int R, bool store);
+size_t capture_tc_workspace(const int* s, int n_layers, int heads);
+void capture_tc_enable(int on);
+void capture_tc_debug(long long* buf);
 
 // kernel selection switches (tests / A-B measurements): initial value from the environment, skp_capture_select() at run time
 static int g_row_fwd = (getenv("SKP_CAPTURE_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_ROW")) == 0) ? 0 : 1;
@@ -461,6 +468,41 @@ static int fill(CapParams& p, const float* const* logits, float* const* dlogits,
 }  // namespace skp
 
 using namespace skp;
+
+extern "C" int skp_capture_store_fwd(const float* logits, float* probs, int heads, int s, int N, int R, void* stream);
+extern "C" int skp_capture_mean_fwd(const float* const* logits, const int* s, int n_layers, float* maps, int heads, int N,
+                                    int R, void* stream);
+
+extern "C" void skp_capture_tc(int on) { capture_tc_enable(on); }
+extern "C" void skp_capture_tc_trace(void* buf) { capture_tc_debug(reinterpret_cast<long long*>(buf)); }
+
+/* 1 when skp_capture_store_fwd (store != 0) / skp_capture_mean_fwd (store == 0) would run the tcgen05 kernel for this shape */
+extern "C" int skp_capture_tc_ok(const int* s, int n_layers, int N, int R, int store) {
+  return s != nullptr && capture_tc_eligible(s, n_layers, N, R, store != 0) ? 1 : 0;
+}
+
+extern "C" int64_t skp_capture_tc_workspace(const int* s, int n_layers, int heads) {
+  if (s == nullptr || n_layers < 1 || n_layers > SKP_MAX_LAYERS || heads < 1) return 0;
+  return (int64_t)capture_tc_workspace(s, n_layers, heads);
+}
+
+extern "C" int skp_capture_store_tc_fwd(const float* logits, float* probs, int heads, int s, int N, int R, float* workspace,
+                                        void* stream) {
+  SKP_REQUIRE(logits != nullptr && probs != nullptr, "capture_store_tc_fwd: null pointer");
+  bool handled = false;
+  int rc = capture_tc(&logits, &s, 1, probs, heads, N, R, true, workspace, (cudaStream_t)stream, &handled);
+  if (rc != SKP_OK || handled) return rc;
+  return skp_capture_store_fwd(logits, probs, heads, s, N, R, stream);   // shapes the tensor-core kernel does not take
+}
+
+extern "C" int skp_capture_mean_tc_fwd(const float* const* logits, const int* s, int n_layers, float* maps, int heads, int N,
+                                       int R, float* workspace, void* stream) {
+  SKP_REQUIRE(logits != nullptr && s != nullptr && maps != nullptr, "capture_mean_tc_fwd: null pointer");
+  bool handled = false;
+  int rc = capture_tc(logits, s, n_layers, maps, heads, N, R, false, workspace, (cudaStream_t)stream, &handled);
+  if (rc != SKP_OK || handled) return rc;
+  return skp_capture_mean_fwd(logits, s, n_layers, maps, heads, N, R, stream);
+}
 
 extern "C" void skp_capture_select(int row_fwd, int row_bwd) {
   if (row_fwd >= 0) g_row_fwd = row_fwd != 0;

@@ -640,7 +640,11 @@ class _CaptureStore(torch.autograd.Function):
         h, _, n = logits.shape
         s = _side(logits)
         probs = torch.empty(h, res * res, n, dtype=torch.float32, device=logits.device)
-        check(lib().skp_capture_store_fwd(ptr(logits), ptr(probs), h, s, n, res, stream()), "skp_capture_store_fwd")
+        if lib().skp_capture_tc_ok(int_array([s]), 1, n, res, 1):      # tcgen05 attn-store kernel (N <= 128)
+            ws = torch.empty(int(lib().skp_capture_tc_workspace(int_array([s]), 1, h)), dtype=torch.uint8, device=logits.device)
+            check(lib().skp_capture_store_tc_fwd(ptr(logits), ptr(probs), h, s, n, res, ptr(ws), stream()), "skp_capture_store_tc_fwd")
+        else:
+            check(lib().skp_capture_store_fwd(ptr(logits), ptr(probs), h, s, n, res, stream()), "skp_capture_store_fwd")
         ctx.save_for_backward(logits)
         ctx.res = res
         return probs
@@ -673,7 +677,12 @@ class _CaptureMean(torch.autograd.Function):
         h, _, n = logits[0].shape
         sides = [_side(l) for l in logits]
         maps = torch.empty(n, res, res, dtype=torch.float32, device=logits[0].device)
-        if CAPTURE_MEAN_FWD == "store" and h * res * res * n * 4 * len(logits) <= (1 << 30):
+        if lib().skp_capture_tc_ok(int_array(sides), len(logits), n, res, 0):
+            # tcgen05 kernel: one launch, CTA = output row, the (layer, head) mean accumulated in registers
+            ws = torch.empty(int(lib().skp_capture_tc_workspace(int_array(sides), len(logits), h)), dtype=torch.uint8, device=maps.device)
+            check(lib().skp_capture_mean_tc_fwd(ptr_array(logits), int_array(sides), len(logits), ptr(maps), h, n, res, ptr(ws), stream()),
+                  "skp_capture_mean_tc_fwd")
+        elif CAPTURE_MEAN_FWD == "store" and h * res * res * n * 4 * len(logits) <= (1 << 30):
             # forward through the row attn-store kernel + the collect mean: the per-layer probabilities make a round trip
             # through L2 (161 MB at N=77) but both kernels run near their memory roofline, which beats the fused tile kernel
             stored = [torch.empty(h, res * res, n, dtype=torch.float32, device=maps.device) for _ in logits]

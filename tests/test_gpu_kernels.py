@@ -264,7 +264,7 @@ def _capture_ref(logits, res):
 @pytest.mark.parametrize("heads,s,n,res", [(8, 16, 77, 128), (8, 32, 77, 128), (4, 4, 12, 16), (8, 16, 500, 128),
                                             (8, 8, 100, 64), (2, 16, 20, 24), (8, 32, 16, 16), (8, 16, 100, 128),
                                             (3, 32, 77, 256), (2, 16, 13, 40)])
-def test_capture_store_fwd_bwd(ops, heads, s, n, res):
+def test_capture_store_fwd_bwd(ops, capture_policy, heads, s, n, res):
     g = torch.Generator().manual_seed(heads + s + n)
     logits = torch.randn(heads, s * s, n, generator=g) * 3
     dp = torch.randn(heads, res * res, n, generator=g)
@@ -275,7 +275,8 @@ def test_capture_store_fwd_bwd(ops, heads, s, n, res):
     p = ops.capture_store(lc, res)
     (p * cu(dp)).sum().backward()
     assert p.shape == (heads, res * res, n)
-    assert rel_err(p.detach().cpu(), pref.detach()) < 2e-5
+    # the tcgen05 kernel does the horizontal bicubic pass as a split-bf16 GEMM (~2e-5); the SIMT kernels are fp32 (~1e-6)
+    assert rel_err(p.detach().cpu(), pref.detach()) < 5e-5
     assert torch.allclose(p.detach().sum(-1).cpu(), torch.ones(heads, res * res), atol=1e-5)
     assert rel_err(lc.grad.cpu(), lr.grad) < 5e-5
 
@@ -307,9 +308,18 @@ def _skewed_logits(kind, heads, s, n, g):
     raise ValueError(kind)
 
 
+@pytest.fixture(params=["auto", "tc"])
+def capture_policy(request):
+    """auto: the library's choice per shape; tc: the tcgen05 kernel wherever the shape is eligible."""
+    from stablekeypoints_b200._lib import lib
+    lib().skp_capture_tc(2 if request.param == "tc" else 1)
+    yield request.param
+    lib().skp_capture_tc(1)
+
+
 @pytest.mark.parametrize("kind", ["offset", "wide", "neg_outlier", "dominant"])
 @pytest.mark.parametrize("heads,s,n,res", [(8, 16, 77, 128), (2, 32, 500, 128), (3, 16, 100, 64)])
-def test_capture_store_skewed_logits_fwd_bwd(ops, kind, heads, s, n, res):
+def test_capture_store_skewed_logits_fwd_bwd(ops, capture_policy, kind, heads, s, n, res):
     g = torch.Generator().manual_seed(heads * 7 + n)
     logits = _skewed_logits(kind, heads, s, n, g)
     dp = torch.randn(heads, res * res, n, generator=g)
@@ -360,7 +370,7 @@ def test_capture_matches_literal_reference_formulation(ops):
     k = mod.to_k(ctx)[0]
     logits = torch.einsum("shd,nhd->hsn", q.reshape(s * s, heads, d), k.reshape(n, heads, d)) * mod.scale
     got = ops.capture_store(cu(logits.detach().contiguous()), res)
-    assert rel_err(got.cpu(), want.detach()) < 2e-5
+    assert rel_err(got.cpu(), want.detach()) < 5e-5
 
 
 @pytest.mark.parametrize("heads,sides,n,res", [(8, (16, 16, 16, 32), 77, 128), (4, (4, 4, 4, 8), 12, 16),
@@ -376,27 +386,30 @@ def test_capture_mean_fwd_bwd(ops, heads, sides, n, res):
     lc = [cu(l).requires_grad_(True) for l in logits]
     m = ops.capture_mean(lc, res)
     (m * cu(dm)).sum().backward()
-    assert rel_err(m.detach().cpu(), mref.detach()) < 2e-5
+    assert rel_err(m.detach().cpu(), mref.detach()) < 5e-5
     for a, b in zip(lc, lr):
         assert rel_err(a.grad.cpu(), b.grad) < 5e-5
 
 
-@pytest.mark.parametrize("row", ["1", "0"])
+@pytest.mark.parametrize("row", ["tc", "1", "0"])
 @pytest.mark.parametrize("n", [77, 500])
 def test_capture_kernel_variants_agree(ops, monkeypatch, row, n):
-    """The row attn-store / row backward kernels and the tile kernels they fall back to (skp_capture_select(0, 0); also
-    taken when R*N is not a multiple of 4) for both modes, forward and backward."""
+    """The tcgen05 forward, the SIMT row attn-store / row backward kernels and the tile kernels they fall back to
+    (skp_capture_select(0, 0); also taken when R*N is not a multiple of 4) for both modes, forward and backward."""
     from stablekeypoints_b200._lib import lib
-    lib().skp_capture_select(int(row), int(row))
-    monkeypatch.setattr(ops, "CAPTURE_MEAN_FWD", "store" if row == "1" else "fused")
+    lib().skp_capture_tc(2 if row == "tc" else 0)          # tcgen05 forward (N <= 128) vs the SIMT kernels
+    if row != "tc":
+        lib().skp_capture_select(int(row), int(row))
+    monkeypatch.setattr(ops, "CAPTURE_MEAN_FWD", "fused" if row == "0" else "store")
     try:
         _variants_body(ops, row, n)
     finally:
         lib().skp_capture_select(1, 1)
+        lib().skp_capture_tc(1)
 
 
 def _variants_body(ops, row, n):
-    g = torch.Generator().manual_seed(int(row) + 5)
+    g = torch.Generator().manual_seed({"tc": 2, "1": 1, "0": 0}[row] + 5)
     logits = [torch.randn(8, s * s, n, generator=g) * 3 for s in (16, 32)]
     dm = torch.randn(n, 128, 128, generator=g)
     lr = [l.clone().requires_grad_(True) for l in logits]
@@ -406,12 +419,12 @@ def _variants_body(ops, row, n):
     lc = [cu(l).requires_grad_(True) for l in logits]
     m = ops.capture_mean(lc, 128)
     (m * cu(dm)).sum().backward()
-    assert rel_err(m.detach().cpu(), mref.detach()) < 2e-5
+    assert rel_err(m.detach().cpu(), mref.detach()) < 5e-5
     for a, b in zip(lc, lr):
         assert rel_err(a.grad.cpu(), b.grad) < 5e-5
     p = ops.capture_store(cu(logits[1]), 128)
     assert bool(torch.isfinite(p).all())
-    assert rel_err(p.cpu(), stack[1].detach()) < 2e-5
+    assert rel_err(p.cpu(), stack[1].detach()) < 5e-5
 
 
 # ----------------------------------------------------------------------------- collect_maps
