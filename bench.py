@@ -50,6 +50,8 @@ def parse():
                     help="tc: trunk convs/linears on the tcgen05 split-bf16 GEMM (fp32-grade accuracy); torch: cuDNN/cuBLAS")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="drive the step from Python instead of one CUDA graph")
     ap.add_argument("--no-vae", action="store_true", help="feed latents directly (VAE encoder is a 'next' row)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the 1-GPU context lines (full forward, N=100/500, batch_size=4 accumulation, torch eager)")
     return ap.parse_args()
 
 
@@ -141,37 +143,91 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(a, cpu=True),
+        "impl_detail": {"precision": "fp32", "trunk": "cpu oracle port (oracle/sd15.py + oracle/hotpath.py)", "cuda_graph": False},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def workload_config(a, cpu=False):
+    """The WORKLOAD only (identical for both arms; implementation descriptors live in `impl_detail`)."""
     return {"workload": "cfg2: CelebA-wild-like synthetic 512x512 embedding optimisation, K=10 of N tokens, batch=1 per GPU",
             "tokens": a.tokens, "feature_upsample_res": a.res, "top_k": 10, "candidates": 25,
-            "precision": "fp32" if cpu else a.precision, "trunk": "cpu" if cpu else a.trunk, "early_exit": bool(a.early_exit) and not cpu,
-            "cuda_graph": (not cpu) and bool(getattr(a, "graph", False)),
-            "streams": "cpu" if cpu else ("3 inside the step graph: the two captured forwards (+ their backwards) overlap, and the VAE "
-                                           "encodes of the NEXT image are prefetched during this step (one-step software pipeline; every "
-                                           "timed step still runs 2 VAE encodes + 2 UNet forwards + backward + Adam)"
-                                           if os.environ.get("SKP_VAE_PREFETCH", "1") != "0" and not getattr(a, "no_vae", False) else
-                                           "2 inside the step graph (the two captured forwards overlap)"),
             "vae_encode": "included" if (cpu or not a.no_vae) else "skipped (latents fed directly)",
             "l2": "no flush needed: 3.4 GB of fp32 UNet weights are streamed every forward (>> 126 MB L2)",
             "weights": "random-init SD1.5-shaped (no checkpoints offline)"}
 
 
+def impl_detail(a):
+    from stablekeypoints_b200 import ptp_utils
+    return {"precision": a.precision, "trunk": a.trunk, "cuda_graph": bool(a.graph),
+            "early_exit": bool(ptp_utils.EARLY_EXIT or a.early_exit),
+            "early_exit_note": "run_and_find_attn stops the UNet after the 4th captured layer: the reference discards pred_noise "
+                               "(ptp_utils.py:246), outputs are identical (tests/test_gpu_pipeline.py::test_tiny_early_exit_same_maps); "
+                               "the full-forward rate is reported as full_forward_images_per_s_1gpu",
+            "streams": ("3 inside the step graph: the two captured forwards (+ their backwards) overlap, and the VAE encodes of the NEXT "
+                        "image are prefetched during this step (one-step software pipeline; every timed step still runs 2 VAE encodes + "
+                        "2 UNet forwards + backward + Adam)" if os.environ.get("SKP_VAE_PREFETCH", "1") != "0" and not a.no_vae else
+                        "2 inside the step graph (the two captured forwards overlap)")}
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
-ALGO = {
-    # entry point -> (bound, function(meta) -> algorithmic bytes or flops per launch) for the roofline of the top kernel
-}
+class Stage1Runner:
+    """One rank's Stage-1 loop for the bench: graph (default) or eager steps over device / pinned-host images."""
+
+    def __init__(self, ldm, controllers, tokens, dev, rank, graph=True, accum=1, no_vae=False):
+        from stablekeypoints_b200 import optimize, ptp_utils
+        from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+        from stablekeypoints_b200.optimize import SyntheticKeypointDataset
+        self.ldm, self.controllers, self.accum = ldm, controllers, accum
+        self.args = stage1_args(tokens)
+        g = torch.Generator().manual_seed(2)
+        self.context = torch.randn(1, tokens, 768, generator=g).to(dev).requires_grad_(True)
+        self.opt = optimize.EmbeddingOptimizer(self.context, lr=self.args.lr, capturable=True)
+        self.tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
+        ds = SyntheticKeypointDataset(length=8, seed=1 + rank)
+        self.host_imgs = [ds[i]["img"][None].contiguous().pin_memory() for i in range(4)]
+        self.dev_imgs = [h.to(dev) for h in self.host_imgs]
+        if no_vae:
+            self.dev_imgs = [ptp_utils.image2latent(ldm, x, "cuda") for x in self.dev_imgs]
+        self.optimize = optimize
+        self.graph = None
+        self.launches_per_iter = None
+        if graph:
+            from stablekeypoints_b200 import _lib
+            self.graph = optimize.Stage1Graph(ldm, controllers, self.context, self.opt, self.args, image_shape=tuple(self.dev_imgs[0].shape),
+                                              accum=accum)
+            self.graph.set_inputs(self.dev_imgs[0], self.tr.sample_theta(1))
+            l0 = _lib.launch_count()
+            self.graph.capture()
+            self.launches_per_iter = (_lib.launch_count() - l0) // (self.graph._warmup + 1)
+            self.graph.set_inputs(self.dev_imgs[0], self.tr.sample_theta(1))
+            self.graph.prime()                              # VAE prefetch pipeline: encode the first image ahead of step 0
+        self._it = 0
+
+    def eager_iteration(self, img):
+        out = self.optimize.stage1_iteration(self.ldm, self.controllers, img, self.context, self.tr, self.args, accum=self.accum)
+        self._it += 1
+        if self._it % self.accum == 0:
+            self.opt.step()
+            self.opt.zero_grad()
+            self.ldm.unet.invalidate_context_cache()
+        return out
+
+    def iteration(self, img):
+        """One image: set_inputs (pinned host -> static device buffer is an async H2D copy) + graph replay, or the eager step."""
+        if self.graph is None:
+            return self.eager_iteration(img)
+        self.graph.set_inputs(img, self.tr.sample_theta(1))
+        return self.graph.replay()
+
+    def close(self):
+        self.graph = None
 
 
 def run_b200_arm(a):
     import torch.distributed as dist
-    from stablekeypoints_b200 import _lib, optimize, optimize_token
-    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
-    from stablekeypoints_b200.optimize import SyntheticKeypointDataset
+    from stablekeypoints_b200 import _lib, optimize_token, ptp_utils
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,26 +239,8 @@ def run_b200_arm(a):
     ldm, controllers, _ = optimize_token.load_ldm(f"cuda:{local}", "synthetic:0", feature_upsample_res=a.res, attn_gain=4.0,
                                                   precision=a.precision, trunk=a.trunk)
     ldm.unet.early_exit = a.early_exit
-    args = stage1_args(a.tokens)
-    g = torch.Generator().manual_seed(2)
-    context = torch.randn(1, a.tokens, 768, generator=g).to(dev).requires_grad_(True)
-    opt = optimize.EmbeddingOptimizer(context, lr=args.lr, capturable=True)
-    tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
-    ds = SyntheticKeypointDataset(length=8, seed=1 + rank)
-    host_imgs = [ds[i]["img"][None].contiguous().pin_memory() for i in range(4)]
-    dev_imgs = [h.to(dev) for h in host_imgs]
-    if a.no_vae:
-        from stablekeypoints_b200 import ptp_utils
-        dev_imgs = [ptp_utils.image2latent(ldm, x, "cuda") for x in dev_imgs]
     torch.manual_seed(1000 + rank)
-
-    def eager_step(img):
-        out = optimize.stage1_iteration(ldm, controllers, img, context, tr, args, accum=1)
-        opt.step()
-        opt.zero_grad()
-        return out
-
-    step = eager_step
+    run = Stage1Runner(ldm, controllers, a.tokens, dev, rank, graph=a.graph, no_vae=a.no_vae)
 
     def barrier():
         torch.cuda.synchronize()
@@ -210,60 +248,44 @@ def run_b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    graph = g2 = ee_step = None
-    launches_per_step = None
-    if a.graph:
-        # the whole optimizer step (2 captured forwards + selection + losses + backward + all-reduce + Adam) as ONE
-        # CUDA graph; per-step inputs (image, theta) go through static buffers
-        graph = optimize.Stage1Graph(ldm, controllers, context, opt, args, image_shape=tuple(dev_imgs[0].shape))
-        graph.set_inputs(dev_imgs[0], tr.sample_theta(1))
-        l0 = _lib.launch_count()
-        graph.capture()
-        launches_per_step = (_lib.launch_count() - l0) // (graph._warmup + 1)
-        graph.set_inputs(dev_imgs[0], tr.sample_theta(1))
-        graph.prime()                                   # VAE prefetch pipeline: encode the first image ahead of step 0
-
-        def step(img):  # noqa: F811
-            graph.set_inputs(img, tr.sample_theta(1))   # pinned host -> static device buffer (async H2D) or D2D
-            return graph.replay()
-
-    def timed(n, feed_host):
-        barrier()
+    def timed(r, n, feed_host, sync_ranks=True):
+        """n images through r (device-resident or pinned-host fed with the loss read back); CUDA events, max over ranks."""
+        barrier() if sync_ranks else torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         s.record()
         for i in range(n):
             if feed_host:
-                out = step(host_imgs[i % len(host_imgs)])      # H2D of the pinned image inside the step
-                float(out["loss"])                             # D2H read of the step's result
+                out = r.iteration(r.host_imgs[i % len(r.host_imgs)])   # H2D of the pinned image inside the step
+                float(out["loss"])                                     # D2H read of the step's result
             else:
-                step(dev_imgs[i % len(dev_imgs)])
+                r.iteration(r.dev_imgs[i % len(r.dev_imgs)])
         e.record()
-        barrier()
+        barrier() if sync_ranks else torch.cuda.synchronize()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
-        if world > 1:
+        if world > 1 and sync_ranks:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        nl = launches_per_step * n if launches_per_step is not None else _lib.launch_count() - l0
+        nl = r.launches_per_iter * n if r.launches_per_iter is not None else _lib.launch_count() - l0
         return float(ms.item()), nl
 
     for i in range(a.warmup):
-        step(dev_imgs[i % len(dev_imgs)])
+        run.iteration(run.dev_imgs[i % len(run.dev_imgs)])
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms, launches = timed(a.steps, feed_host=False)
+    ms, launches = timed(run, a.steps, feed_host=False)
     clk = clocks.stop() if rank == 0 else None
     value = world * a.steps / (ms / 1e3)
-    ms_e2e, _ = timed(a.steps, feed_host=not a.no_vae)
+    ms_e2e, _ = timed(run, a.steps, feed_host=not a.no_vae)
     e2e = world * a.steps / (ms_e2e / 1e3)
 
-    # ---- per-kernel shares of one step (our C-ABI launches bracketed by CUDA events) + attn-store kernel roofline
+    # ---- per-kernel shares of one step (our C-ABI launches bracketed by CUDA events) + rooflines + context lines
     extra = {}
     # the profiled step contains the gradient all-reduce: EVERY rank must run it (only rank 0 reports)
     _lib.start_profile()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    eager_step(dev_imgs[0])
+    run.eager_iteration(run.dev_imgs[0])
     e.record()
     prof = _lib.stop_profile()
     step_ms = s.elapsed_time(e)
@@ -271,30 +293,40 @@ def run_b200_arm(a):
         shares = {k: {"calls": len(v), "ms": round(sum(v), 4)} for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1]))}
         extra["skp_kernel_ms_in_one_profiled_step"] = shares
         extra["profiled_eager_step_ms"] = round(step_ms, 3)
-        host_only = ("skp_gemm_nt_tc_plan", "skp_self_attn_dp", "skp_gemm_tc_force_bn")
+        host_only = ("skp_gemm_nt_tc_plan", "skp_self_attn_dp", "skp_gemm_tc_force_bn", "skp_capture_tc_ok", "skp_capture_tc_workspace")
         extra["skp_kernel_ms_total_eager"] = round(sum(sum(v) for k, v in prof.items() if k not in host_only), 3)
         extra["profile_note"] = ("per-entry-point CUDA-event brackets of ONE eager (un-graphed, CPU-launch-bound) step: use the "
                                  "shares, not the absolute ms; the timed region above replays the whole step as one CUDA graph")
-        extra["roofline"] = attn_store_roofline(a, dev)
+        extra["roofline"], extra["roofline_l2_resident"] = attn_store_rooflines(a, dev)
         extra["roofline_gemm"] = gemm_roofline(dev)
-        if a.early_exit is False and world == 1:
-            ldm.unet.early_exit = True
-            ee_step = eager_step
-            if a.graph:
-                g2 = optimize.Stage1Graph(ldm, controllers, context, opt, args, image_shape=tuple(dev_imgs[0].shape))
-                g2.set_inputs(dev_imgs[0], tr.sample_theta(1))
-                g2.capture()
-                g2.set_inputs(dev_imgs[0], tr.sample_theta(1))
-                g2.prime()
+    if world == 1 and a.extras:
+        # context lines (1 GPU only, never the headline): same loop at other settings; each builds its own step graph
+        def rate(tokens=a.tokens, accum=1, graph=a.graph, n=a.steps, env=None, ldm_=None, ctl_=None):
+            r = Stage1Runner(ldm_ or ldm, ctl_ or controllers, tokens, dev, rank, graph=graph, accum=accum, no_vae=a.no_vae)
+            for i in range(2 * accum):
+                r.iteration(r.dev_imgs[i % len(r.dev_imgs)])
+            ms_, _ = timed(r, n * accum, feed_host=False, sync_ranks=False)
+            r.close()
+            del r
+            torch.cuda.empty_cache()
+            return round(n * accum / (ms_ / 1e3), 3)
 
-                def ee_step(img):
-                    g2.set_inputs(img, tr.sample_theta(1))
-                    return g2.replay()
-            for i in range(2):
-                ee_step(dev_imgs[i % len(dev_imgs)])
-            ms_ee, _ = timed_single(ee_step, dev_imgs, a.steps)
-            extra["early_exit_images_per_s_1gpu"] = round(a.steps / (ms_ee / 1e3), 3)
-            ldm.unet.early_exit = False
+        if not a.early_exit and ptp_utils.EARLY_EXIT:
+            ptp_utils.EARLY_EXIT = False
+            extra["full_forward_images_per_s_1gpu"] = rate()
+            ptp_utils.EARLY_EXIT = True
+        if a.tokens == 77:
+            extra["tokens_100_images_per_s_1gpu"] = rate(tokens=100)
+            extra["tokens_500_images_per_s_1gpu"] = rate(tokens=500, n=max(3, a.steps // 2))
+        extra["batch4_accum_images_per_s_1gpu"] = rate(accum=4, n=max(2, a.steps // 2))
+        extra["batch4_accum_note"] = ("reference CLI default batch_size=4 on one GPU: B//G = 4 accumulated iterations per optimizer step "
+                                      "(optimize.py:339,420-425) through the iteration / update CUDA graphs; images/s, to compare with `value`")
+        # the honest same-box library bar: the SAME loop with the trunk on cuDNN / cuBLAS (torch eager, no graph), TF32 as the
+        # reference's torch defaults allow and strict fp32, each with its parity error against this build's maps
+        try:
+            extra["torch_eager_b200"] = torch_eager_context(a, dev, rank, ldm, controllers, rate)
+        except Exception as ex:       # context only: never fail the bench line on it
+            extra["torch_eager_b200"] = {"error": repr(ex)[:300]}
     if world > 1:
         dist.barrier()
 
@@ -302,7 +334,7 @@ def run_b200_arm(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(a), "clocks": clk,
+            "data": "synthetic", "config": workload_config(a), "impl_detail": impl_detail(a), "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0 if a.no_vae else 3 * 512 * 512 * 4 * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches,
@@ -316,7 +348,7 @@ def run_b200_arm(a):
         # process group underneath a live graph is what used to hang), then tear down normally
         dist.barrier()
         torch.cuda.synchronize()
-        graph = g2 = step = ee_step = None     # noqa: F841
+        run.close()
         import gc
         gc.collect()
         torch.cuda.synchronize()
@@ -324,70 +356,104 @@ def run_b200_arm(a):
         dist.destroy_process_group()
 
 
-def timed_single(step, imgs, n):
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for i in range(n):
-        step(imgs[i % len(imgs)])
-    e.record()
-    torch.cuda.synchronize()
-    return s.elapsed_time(e), 0
+def torch_eager_context(a, dev, rank, ldm, controllers, rate):
+    """torch-eager-on-B200 context: library trunk (cuDNN convs, cuBLAS linears, SDPA attention) under the same surface."""
+    from stablekeypoints_b200 import optimize_token, ptp_utils
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(1, 3, 512, 512, generator=g).to(dev)
+    ctx = torch.randn(1, a.tokens, 768, generator=g).to(dev)
+    noise = torch.randn(1, 4, 64, 64, generator=g).to(dev)
+    with torch.no_grad():
+        ref_maps = ptp_utils.run_and_find_attn(ldm, img, ctx, layers=[0, 1, 2, 3], upsample_res=-1, controllers=controllers, noise=noise)[0]
+    for prec in ("reference", "fp32"):
+        ldm_t, ctl_t, _ = optimize_token.load_ldm(str(dev), "synthetic:0", feature_upsample_res=a.res, attn_gain=4.0, precision=prec,
+                                                  trunk="torch")
+        with torch.no_grad():
+            m = ptp_utils.run_and_find_attn(ldm_t, img, ctx, layers=[0, 1, 2, 3], upsample_res=-1, controllers=ctl_t, noise=noise)[0]
+        err = float((m - ref_maps).abs().max() / ref_maps.abs().max())
+        out[prec] = {"images_per_s": rate(graph=False, n=3, ldm_=ldm_t, ctl_=ctl_t), "maps_rel_diff_vs_this_build": err,
+                     "what": "cuDNN TF32 convolutions + fp32 cuBLAS (the reference's torch defaults)" if prec == "reference"
+                             else "strict fp32 cuDNN / cuBLAS"}
+        del ldm_t, ctl_t
+        torch.cuda.empty_cache()
+    optimize_token.set_precision(a.precision)
+    out["note"] = "torch eager (no CUDA graph), same surface and loop; context only -- the tolerance of the path is 1e-3"
+    return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE capture_store_row_kernel launch (N=77, R=128, s=16) from the
-# `ncu --set full` capture summarised in profiles/r01_attn_store_row.md
-ATTN_STORE_DRAM_TRAFFIC = 1372928
-ATTN_STORE_TRAFFIC_NOTE = ("inside the kernel the 40.4 MB store is absorbed by the 126 MB L2 (write-back happens after the kernel): "
-                           "DRAM traffic during the launch is 0.66 MB read + 0.71 MB written")
-
-
-def attn_store_roofline(a, dev):
-    """The attn-store kernel (skp_capture_store_fwd) on the C=1280 captured layer shape: HBM-bound, algorithmic bytes =
-    the probability store heads*R^2*N*4 (+ the low-res logits read), timed live with CUDA events, L2 flushed between."""
-    from stablekeypoints_b200 import ops
-    peaks = {}
+def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        peaks = json.load(open(p))
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def _ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summaries
+    (profiles/r02_attn_store_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep of the same command)."""
+    p = os.path.join(ROOT, "profiles", "r02_attn_store_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(key)
+    return (d["dram_bytes"], d["source"]) if d else (None, None)
+
+
+def _time_capture_store(ops, lib, logits, res, flush, tc, reps=5, warm=3):
+    lib().skp_capture_tc(2 if tc else 0)
+    ts = []
+    for i in range(reps + warm):
+        flush.fill_(float(i))
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        ops.capture_store(logits, res)
+        en.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ts.append(st.elapsed_time(en))
+    lib().skp_capture_tc(1)
+    return sum(ts) / len(ts)
+
+
+def attn_store_rooflines(a, dev):
+    """The attn-store kernel (the kernel BASELINE.json's metric names), HBM-bound: algorithmic bytes = the probability store
+    heads*R^2*N*4 + the low-res logits read, timed live with CUDA events on the launching stream, L2 flushed (512 MiB fill)
+    between launches.  Both implementations are timed (tcgen05 formulation skp_capture_tc.cu, SIMT row kernel
+    skp_capture_row.cu); the line reports the one the library's policy picks for the shape.
+      roofline             : BASELINE cfg5's SDXL-shaped layer (20 heads, 32x32 -> R=256): a 404 MB store that does NOT fit
+                             the 126 MB L2, i.e. a real HBM stream;
+      roofline_l2_resident : the SD1.5 C=1280 captured layer (8 heads, 16x16 -> R=128, N tokens): the 40 MB store is absorbed
+                             by L2 inside the launch, the kernel is instruction / latency bound -- GB/s there is an L2 write
+                             rate, reported for continuity with round 1, not an HBM fraction."""
+    from stablekeypoints_b200 import ops
+    from stablekeypoints_b200._lib import lib
+    peaks = _peaks()
     peak, src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
-    heads, s, n, r = 8, 16, a.tokens, a.res
-    logits = torch.randn(heads, s * s, n, device=dev) * 3
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
-    times = []
-    for i in range(8):
-        flush.fill_(float(i))
-        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        st.record()
-        ops.capture_store(logits, r)
-        en.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            times.append(st.elapsed_time(en))
-    ms = sum(times) / len(times)
-    algo = heads * r * r * n * 4 + heads * s * s * n * 4
-    ach = algo / (ms * 1e-3) / 1e9
-    # BASELINE cfg5 (SDXL-shaped capture: 20 heads, 32x32 layer, R=256): a 404 MB store that does not fit the 126 MB L2
-    lg5 = torch.randn(20, 32 * 32, n, device=dev) * 3
-    t5 = []
-    for i in range(6):
-        flush.fill_(float(i))
-        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        st.record()
-        ops.capture_store(lg5, 256)
-        en.record()
-        torch.cuda.synchronize()
-        if i >= 2:
-            t5.append(st.elapsed_time(en))
-    ms5 = sum(t5) / len(t5)
-    algo5 = 20 * 256 * 256 * n * 4 + lg5.numel() * 4
-    cfg5 = {"shape": "h=20, s=32 -> R=256, N=%d (BASELINE cfg5, SDXL-shaped)" % n, "achieved": round(algo5 / (ms5 * 1e-3) / 1e9, 1),
-            "frac": round(algo5 / (ms5 * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": algo5, "ms_per_launch": round(ms5, 5)}
-    del lg5
-    return {"kernel": "skp_capture_store_fwd (attn-store, C=1280 layer: h=8, s=16 -> R=%d, N=%d)" % (r, n), "bound": "hbm", "cfg5": cfg5,
-            "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(ach / peak, 4),
-            "traffic": ATTN_STORE_DRAM_TRAFFIC if (n, r) == (77, 128) else None, "traffic_note": ATTN_STORE_TRAFFIC_NOTE,
-            "algorithmic_bytes": algo, "ms_per_launch": round(ms, 5), "l2": "flushed (512 MiB fill) between launches"}
+    n = a.tokens
+
+    def one(heads, s, r, key, label, note):
+        logits = torch.randn(heads, s * s, n, device=dev) * 3
+        algo = heads * r * r * n * 4 + logits.numel() * 4
+        ms_tc = _time_capture_store(ops, lib, logits, r, flush, True) if n <= 128 else None
+        ms_simt = _time_capture_store(ops, lib, logits, r, flush, False)
+        picked_tc = bool(lib().skp_capture_tc_ok((__import__("ctypes").c_int * 1)(s), 1, n, r, 1))
+        ms = ms_tc if (picked_tc and ms_tc is not None) else ms_simt
+        ach = algo / (ms * 1e-3) / 1e9
+        traffic, tsrc = _ncu_traffic(key + ("_tc" if picked_tc else "_simt")) if n == 77 else (None, None)
+        out = {"kernel": "skp_capture_store%s_fwd (attn-store, %s)" % ("_tc" if picked_tc else "", label), "bound": "hbm",
+               "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(ach / peak, 4),
+               "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes": algo, "ms_per_launch": round(ms, 5),
+               "implementation": "tcgen05 (skp_capture_tc.cu)" if picked_tc else "SIMT row kernel (skp_capture_row.cu)",
+               "ms_tcgen05": None if ms_tc is None else round(ms_tc, 5), "ms_simt_row": round(ms_simt, 5),
+               "l2": "flushed (512 MiB fill) between launches", "note": note}
+        del logits
+        return out
+
+    big = one(20, 32, 256, "cfg5", "h=20, s=32 -> R=256, N=%d: BASELINE cfg5, SDXL-shaped" % n,
+              "404 MB store > 126 MB L2: an HBM stream")
+    small = one(8, 16, a.res, "sd15", "SD1.5 C=1280 layer: h=8, s=16 -> R=%d, N=%d" % (a.res, n),
+                "L2-resident: the store is absorbed by L2 during the launch; the kernel is instruction/latency bound, so this "
+                "figure is an L2 write rate, not an HBM fraction")
+    return big, small
 
 
 def gemm_roofline(dev):
@@ -395,10 +461,7 @@ def gemm_roofline(dev):
     Tensor-bound; algorithmic FLOPs = 2*M*N*K (each is ISSUED three times -- hi.hi, hi.lo, lo.hi -- for fp32-grade accuracy,
     so the algorithmic ceiling is peak/3).  Shape: the 128^2 x 512 -> 512 VAE 3x3 convolution as an implicit GEMM."""
     from stablekeypoints_b200 import ops
-    peaks = {}
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        peaks = json.load(open(p))
+    peaks = _peaks()
     peak, src = (peaks.get("bf16_tflops"), "measured burst (MEASURED_PEAKS.json)") if peaks.get("bf16_tflops") else (1590.0, "fallback (B200_PROFILING.md)")
     h = w = 128
     cin = cout = 512

@@ -1,3 +1,3 @@
-python scripts/capture_tc_trace.py 16 77 128 8 store 2>&1 | head -40
-timeout 300 python scripts/capture_bench.py --json gpurun_out/r2f_capture_bench.json 2>&1 | cut -c1-420
-timeout 400 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "capture" 2>&1 | tail -8
+for v in 0 1; do echo "SKP_CTX_REPEAT=$v"; SKP_CTX_REPEAT=$v timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['gpu_launches'])"; done

@@ -103,6 +103,22 @@ def gemm_nt_presplit(a_hi, a_lo, m: int, b_split, n: int, bias=None, residual=No
     return out
 
 
+class _StreamAlias(torch.autograd.Function):
+    """Identity whose backward node belongs to the stream it was created on (autograd replays a node on its forward stream)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def stream_alias(x: torch.Tensor) -> torch.Tensor:
+    return _StreamAlias.apply(x) if x.requires_grad else x
+
+
 # ----------------------------------------------------------------------------- frozen 3x3 convolution (channels-last)
 def im2col3x3_split(x2d: torch.Tensor, h: int, w: int, ho: int, wo: int, stride: int, pad: int):
     """x2d [h*w, C] fp32 channels-last -> split-bf16 im2col operand ([ho*wo, pad64(9C)] hi, lo)."""

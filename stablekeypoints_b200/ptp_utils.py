@@ -140,9 +140,15 @@ def find_pred_noise(ldm, image, context, noise_level=-1, device="cuda", noise=No
     b = noisy.shape[0]
     # the reference passes context.repeat(B,1,1) (ptp_utils.py:229); at B == 1 (one image per rank) that is the tensor itself,
     # and handing the leaf over keeps the engine's K|V projection cache valid for both forwards of an iteration
-    ctx = context if b == 1 else context.repeat(b, 1, 1)
+    ctx = context if (b == 1 and os.environ.get("SKP_CTX_REPEAT", "0") != "1") else context.repeat(b, 1, 1)
     pred = ldm.unet(noisy, t.repeat(b), ctx)["sample"]
     return noise, pred
+
+
+# run_and_find_attn drops pred_noise (ptp_utils.py:246), so nothing observable depends on the ~40 % of the UNet forward
+# that follows the 4th captured layer: the engine stops there.  find_pred_noise itself always runs the full forward.
+# SKP_EARLY_EXIT=0 keeps the full forward inside run_and_find_attn too (A/B measurements).
+EARLY_EXIT = os.environ.get("SKP_EARLY_EXIT", "1") != "0"
 
 
 def _fused_ok(ldm, controllers, upsample_res, indices) -> bool:
@@ -165,12 +171,13 @@ def run_and_find_attn(ldm, image, context, noise_level=-1, device="cuda",
     from .optimize import collect_maps
     unet = ldm.unet
     fused = _fused_ok(ldm, controllers, upsample_res, indices)
-    prev_mode = unet.capture_mode
+    prev_mode, prev_exit = unet.capture_mode, unet.early_exit
     unet.capture_mode = "fused" if fused else "store"
+    unet.early_exit = prev_exit or (EARLY_EXIT and len(controllers) == 1)
     try:
         find_pred_noise(ldm, image, context, noise_level=noise_level, device=device, noise=noise)
     finally:
-        unet.capture_mode = prev_mode
+        unet.capture_mode, unet.early_exit = prev_mode, prev_exit
     attention_maps = []
     for key in controllers:
         ctl = controllers[key]

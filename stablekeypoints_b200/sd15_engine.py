@@ -532,7 +532,9 @@ class UNetEngine:
         cfg, w = self.cfg, self.w
         t = int(torch.as_tensor(timestep).reshape(-1)[0].item()) if not isinstance(timestep, int) else timestep
         tb = self._time_constants(t)
-        kv_all = self.project_context(context)
+        # one alias node per forward: the 32 K / V slice gradients of THIS forward accumulate on this forward's stream and
+        # cross over to the shared projection once (otherwise every slice of the side-stream forward syncs the two streams)
+        kv_all = ops.stream_alias(self.project_context(context))
         state = {"captured": len(self.controller.step_store["attn"]) if (self.controller is not None and self.capture_mode == "store") else 0,
                  "logits": []}
         self.last_logits = state["logits"]

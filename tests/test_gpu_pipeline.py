@@ -144,18 +144,25 @@ def test_tiny_cuda_graph_step_equals_eager_step(tiny, monkeypatch):
     assert rel_err(torch.tensor(le[0]), g["loss"]) < 1e-3      # first step still matches the reference golden
 
 
-def test_tiny_early_exit_same_maps(tiny):
+def test_tiny_early_exit_same_maps(tiny, monkeypatch):
+    """run_and_find_attn stops the UNet after the 4th captured layer by default (the reference drops pred_noise,
+    ptp_utils.py:246); the maps equal those of the full forward, and find_pred_noise itself still returns pred_noise."""
     from stablekeypoints_b200 import ptp_utils
     g, pipe = tiny
     ldm, controllers, _ = _product_ldm(pipe, TINY["res"])
     ctx = torch.from_numpy(g["context"]).cuda()
     kw = dict(layers=[0, 1, 2, 3], upsample_res=-1, controllers=controllers, noise=torch.from_numpy(g["noise_a"]))
     with torch.no_grad():
-        full = ptp_utils.run_and_find_attn(ldm, torch.from_numpy(g["image"]), ctx, **kw)[0]
-        ldm.unet.early_exit = True
+        assert ptp_utils.EARLY_EXIT
         early = ptp_utils.run_and_find_attn(ldm, torch.from_numpy(g["image"]), ctx, **kw)[0]
+        monkeypatch.setattr(ptp_utils, "EARLY_EXIT", False)
+        full = ptp_utils.run_and_find_attn(ldm, torch.from_numpy(g["image"]), ctx, **kw)[0]
+        _, pred = ptp_utils.find_pred_noise(ldm, torch.from_numpy(g["image"]), ctx, noise=torch.from_numpy(g["noise_a"]))
     # same kernels on the same data; only the fp32 atomic order of the GroupNorm statistics differs run to run
     assert rel_err(early.cpu(), full.cpu()) < 1e-4
+    assert rel_err(early.cpu(), g["maps"]) < 1e-3
+    assert pred is not None and rel_err(pred.cpu(), g["pred_noise"]) < 1e-3
+    assert ldm.unet.early_exit is False          # the switch is scoped to the call
 
 
 def test_engine_rejects_cpu_and_bad_batch(tiny):
