@@ -24,8 +24,9 @@
 //   warps 8..8+PW  producers : vertical pass out of shared memory (the four source rows of a group of output rows arrive
 //                              as cp.async.bulk copies, double buffered); unit = (pair of low-res columns, 32 tokens), lanes
 //                              run over tokens: conflict-free shared loads, split, one swizzled 32-bit store per plane
-//   (STORE) the last producer warp instead drives the copy engine: it waits for a staged row, issues its cp.async.bulk and
-//                              frees the staging buffer once the engine has read it -- the epilogue never waits for a store
+//   DMA warp (the last of the PW): one lane polls two cursors -- the next group of source rows to fetch (cp.async.bulk into a
+//                              free row slot) and, in STORE mode, the next staged row to hand to the copy engine -- so that
+//                              neither the producers nor the epilogue ever wait for an issue slot of the engine
 //   last warp      MMA issuer: one lane; tcgen05.commit releases the B stage and publishes the accumulator
 // Pipelines: B stages in shared memory (full / empty mbarriers) and TMEM accumulators (acc_full / acc_empty), so the
 // vertical pass of row i+2, the MMA of row i+1 and the softmax of row i overlap.
@@ -102,6 +103,17 @@ __device__ __forceinline__ void ct_mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("nanosleep.u32 32;" ::: "memory");
   }
 }
+__device__ __forceinline__ bool ct_mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void ct_named_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -133,16 +145,26 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int col) {
          ((uint32_t)col & 7u) * 2u;
 }
 
-// max over tokens of every low-res logit row (one warp per row); non-finite maxima are reported as 0 (no shift)
-__global__ void capture_rowmax_kernel(const float* __restrict__ logits, float* __restrict__ out, int rows, int N) {
+// max over tokens of every low-res logit row of every layer of the launch (one warp per row, one launch); non-finite
+// maxima are reported as 0 (no shift)
+struct CapRowmaxParams {
+  const float* logits[SKP_MAX_LAYERS];
+  float* out[SKP_MAX_LAYERS];
+  int row_end[SKP_MAX_LAYERS];   // prefix sums of heads * s * s
+  int n_layers, N;
+};
+__global__ void capture_rowmax_kernel(const CapRowmaxParams rp) {
   const int lane = threadIdx.x & 31;
-  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if (row >= rows) return;
-  const float* src = logits + (size_t)row * N;
+  int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= rp.row_end[rp.n_layers - 1]) return;
+  int l = 0;
+  while (row >= rp.row_end[l]) ++l;
+  if (l > 0) row -= rp.row_end[l - 1];
+  const float* src = rp.logits[l] + (size_t)row * rp.N;
   float m = -CUDART_INF_F;
-  for (int n = lane; n < N; n += 32) m = fmaxf(m, __ldg(src + n));
+  for (int n = lane; n < rp.N; n += 32) m = fmaxf(m, __ldg(src + n));
   m = warp_max(m);
-  if (lane == 0) out[row] = fabsf(m) < 3.0e38f ? m : 0.f;
+  if (lane == 0) rp.out[l][row] = fabsf(m) < 3.0e38f ? m : 0.f;
 }
 
 template <int NPT>
@@ -175,7 +197,7 @@ __global__ void __launch_bounds__((9 + PW) * 32, 1) capture_tc_kernel(const CapT
   const uint32_t bars = sRows + 2 * row_slot_bytes;
   const uint32_t FULL = bars, EMPTY = bars + 8 * CT_MAX_STAGES, AFULL = bars + 16 * CT_MAX_STAGES, AEMPTY = AFULL + 8 * Cfg::NACC;
   const uint32_t RFULL = AEMPTY + 8 * Cfg::NACC, REMPTY = RFULL + 16, SFULL = REMPTY + 16, SFREE = SFULL + 16;
-  constexpr int NPROD = MODE == 0 ? PW - 1 : PW;          // STORE: the last producer warp drives the copy engine instead
+  constexpr int NPROD = PW - 1;                            // the last of the PW warps is the DMA warp
   uint8_t* after_bars = gen + (bars - base) + 8 * Cfg::NBARS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(after_bars);
   float2* xch = reinterpret_cast<float2*>(after_bars + 16);                       // [2 parities][2 halves][128 pixels]
@@ -303,114 +325,143 @@ __global__ void __launch_bounds__((9 + PW) * 32, 1) capture_tc_kernel(const CapT
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (MODE == 0 && warp == 8 + PW - 1) {
-    // =========================================================== store warp: staged rows -> copy engine
+  // first item of the group after the one `it` belongs to (n_items: none)
+  auto next_group_start = [&](int it) {
+    if (MODE == 1) return it + 1;
+    int l0, h0, Y0, iy0;
+    decode(it, l0, h0, Y0, iy0);
+    int j = it + 1;
+    for (; j < n_items; ++j) {
+      int l, h, Y, iy;
+      decode(j, l, h, Y, iy);
+      if (h != h0 || iy != iy0) break;
+    }
+    return j;
+  };
+
+  if (warp == 8 + PW - 1) {
+    // =========================================================== DMA warp: source rows in, staged rows out
     if (lane == 0) {
-      for (int it = 0; it < n_items; ++it) {
-        int l, h, Y, iy;
-        decode(it, l, h, Y, iy);
-        const uint32_t b = (uint32_t)it & 1u;
-        mbar_wait(SFULL + 8 * b, ((uint32_t)it >> 1) & 1u);
-        const float* stg = staging + (size_t)(p.nstg == 2 ? b : 0) * stage_floats;
-        float* dst = p.out + (((size_t)h * R + Y) * R + x0) * N;
-        const size_t bytes = (size_t)cnt * N * sizeof(float);
-        const bool al16 = ((bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        if (al16 && p.store_path == 0) {                 // otherwise the epilogue warps stored the row themselves
-          const uint32_t src = smem_u32(stg);
-          const char* d8 = reinterpret_cast<const char*>(dst);
-          for (size_t off = 0; off < bytes; off += 32768) {
-            const uint32_t nb = (uint32_t)(bytes - off < 32768 ? bytes - off : 32768);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d8 + off), "r"(src + (uint32_t)off), "r"(nb)
-                         : "memory");
+      const int max_rowfl = (p.slot_floats - 128) >> 2;      // floats of one source row inside a slot
+      int lg = 0, lit = 0;                                   // next group to fetch and its first item
+      int sit = 0;                                           // next item to store (STORE)
+      const int n_store = MODE == 0 ? n_items : 0;
+      while (lit < n_items || sit < n_store) {
+        bool progressed = false;
+        if (lit < n_items && ct_mbar_test(REMPTY + 8 * (lg & 1), (((uint32_t)lg >> 1) & 1u) ^ 1u)) {
+          // the 4 source rows of the group and their row maxima -> row slot lg & 1
+          int l, h, Y, iy;
+          decode(lit, l, h, Y, iy);
+          const int s = p.s[l];
+          const uint32_t slot = (uint32_t)lg & 1u, bytes = (uint32_t)(s * N) * 4u, mbytes = (uint32_t)s * 4u;
+          mbar_expect_tx(RFULL + 8 * slot, 4u * (bytes + mbytes));
+          const uint32_t dst = sRows + slot * row_slot_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            int r = iy - 1 + j;
+            r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
+            ct_bulk_load(dst + (uint32_t)(j * max_rowfl) * 4u, p.logits[l] + ((size_t)h * s + r) * s * N, bytes, RFULL + 8 * slot);
+            ct_bulk_load(dst + (uint32_t)(4 * max_rowfl + 32 * j) * 4u, p.rowmax[l] + ((size_t)h * s + r) * s, mbytes, RFULL + 8 * slot);
           }
+          lit = next_group_start(lit);
+          ++lg;
+          progressed = true;
         }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (p.nstg == 2) {
-          if (it > 0) {
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            ct_mbar_arrive(SFREE + 8 * (b ^ 1u));       // the row of the previous item has left its buffer
+        if (sit < n_store && ct_mbar_test(SFULL + 8 * (sit & 1), ((uint32_t)sit >> 1) & 1u)) {
+          int l, h, Y, iy;
+          decode(sit, l, h, Y, iy);
+          const uint32_t b = (uint32_t)sit & 1u;
+          const float* stg = staging + (size_t)(p.nstg == 2 ? b : 0) * stage_floats;
+          float* dst = p.out + (((size_t)h * R + Y) * R + x0) * N;
+          const size_t bytes = (size_t)cnt * N * sizeof(float);
+          const bool al16 = ((bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (al16 && p.store_path == 0) {                 // otherwise the epilogue warps stored the row themselves
+            const uint32_t src = smem_u32(stg);
+            const char* d8 = reinterpret_cast<const char*>(dst);
+            for (size_t off = 0; off < bytes; off += 32768) {
+              const uint32_t nb = (uint32_t)(bytes - off < 32768 ? bytes - off : 32768);
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d8 + off), "r"(src + (uint32_t)off), "r"(nb)
+                           : "memory");
+            }
           }
-        } else {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          ct_mbar_arrive(SFREE + 8 * b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (p.nstg == 2) {
+            if (sit > 0) {
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              ct_mbar_arrive(SFREE + 8 * (b ^ 1u));       // the row of the previous item has left its buffer
+            }
+          } else {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            ct_mbar_arrive(SFREE + 8 * b);
+          }
+          ++sit;
+          progressed = true;
         }
+        if (!progressed) asm volatile("nanosleep.u32 20;" ::: "memory");
       }
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the engine's reads
     }
     __syncwarp();
   } else if (warp >= 8 && warp < 8 + NPROD) {
-    // =========================================================== producers: source rows (copy engine) -> vertical pass -> B stage
+    // =========================================================== producers: vertical pass (shared memory -> B stage)
     const int pw = warp - 8;
-    const int max_rowfl = (p.slot_floats - 128) >> 2;      // floats of one source row slot
-    // loader (lane 0 of the first producer warp): the 4 source rows of group g and their row maxima go to row slot g & 1
-    auto load_group = [&](int g, int it_first) {
-      int l, h, Y, iy;
-      decode(it_first, l, h, Y, iy);
-      const int s = p.s[l];
-      const uint32_t slot = (uint32_t)g & 1u, bytes = (uint32_t)(s * N) * 4u, mbytes = (uint32_t)s * 4u;
-      ct_mbar_wait(REMPTY + 8 * slot, (((uint32_t)g >> 1) & 1u) ^ 1u);
-      mbar_expect_tx(RFULL + 8 * slot, 4u * (bytes + mbytes));
-      const uint32_t dst = sRows + slot * row_slot_bytes;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int r = iy - 1 + j;
-        r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
-        ct_bulk_load(dst + (uint32_t)(j * max_rowfl) * 4u, p.logits[l] + ((size_t)h * s + r) * s * N, bytes, RFULL + 8 * slot);
-        ct_bulk_load(dst + (uint32_t)(4 * max_rowfl + 32 * j) * 4u, p.rowmax[l] + ((size_t)h * s + r) * s, mbytes, RFULL + 8 * slot);
-      }
-    };
-    // first item of the group after the one `it` belongs to (n_items: none)
-    auto next_group_start = [&](int it) {
-      if (MODE == 1) return it + 1;
-      int l0, h0, Y0, iy0;
-      decode(it, l0, h0, Y0, iy0);
-      int j = it + 1;
-      for (; j < n_items; ++j) {
-        int l, h, Y, iy;
-        decode(j, l, h, Y, iy);
-        if (h != h0 || iy != iy0) break;
-      }
-      return j;
-    };
-    int g = 0, g_next_start = n_items > 0 ? next_group_start(0) : 0;
-    if (pw == 0 && lane == 0 && n_items > 0) {
-      load_group(0, 0);
-      if (g_next_start < n_items) load_group(1, g_next_start);
-    }
-    bool fresh = true;                   // the current group's rows have not been waited for yet
-    // swizzled byte offset of this lane's token rows (one per 32-token chunk): fixed for the whole kernel
+    const int max_rowfl = (p.slot_floats - 128) >> 2;      // floats of one source row inside a slot
     constexpr int NC = NPT / 32;
-    uint32_t tokoff[NC];
-    uint32_t toksw[NC];
+    // unit = (pair of low-res columns, chunk of 32 tokens); the units of a side are dealt round-robin to the producer warps
+    // and a warp's share is at most MAXU (s <= 32).  Their source / destination offsets depend only on the side s: they are
+    // tabulated in registers when s changes (once per launch for STORE, once per layer-side for MEAN), so that the loop over
+    // the items is loads, FMAs, converts and stores with immediate offsets -- no index arithmetic.
+    constexpr int MAXU = (16 * NC + NPROD - 1) / NPROD;
+    int u_src[MAXU];                       // float offset of (xs, n) inside a source row ((xs + 1, n) is N floats further)
+    uint32_t u_dst[MAXU];                  // swizzled byte offset of (n, xs) inside a B plane
+    int u_xs[MAXU];                        // xs, or -1: no unit / token beyond N (nothing is stored)
+    int tab_s = -1, nunits_w = 0;
+    auto tabulate = [&](int s) {
+      tab_s = s;
+      const int npairs = (s + 1) >> 1, nunits = npairs * NC;
+      nunits_w = 0;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int n = c * 32 + lane;
-      tokoff[c] = (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u;
-      toksw[c] = (uint32_t)(n & 7);
+      for (int q = 0; q < MAXU; ++q) {
+        const int u = pw + q * NPROD;
+        const int uu = min(u, nunits - 1);
+        const int pi = uu / NC, c = uu - pi * NC;
+        const int xs = 2 * pi;
+        const int n = c * 32 + lane, nn = min(n, N - 1);
+        u_src[q] = xs * N + nn;
+        u_dst[q] = sw128_off(nn, xs);
+        u_xs[q] = (u < nunits && n < N) ? xs : -1;
+        if (u < nunits) nunits_w = q + 1;
+      }
+    };
+    // item iterator (no divisions in the loop)
+    int l = 0, h = 0, Y = 0;
+    if (MODE == 0) {
+      h = row0 / R;
+      Y = row0 - h * R;
+    } else {
+      Y = blockIdx.x;
     }
+    int g = 0, prev_h = h, prev_iy = 0x7fffffff, prev_l = l;
     for (int it = 0; it < n_items; ++it) {
-      int l, h, Y, iy;
-      decode(it, l, h, Y, iy);
-      if (it == g_next_start) {          // entering the next group: release the old slot, request the group after the next
+      const int s = p.s[l];
+      const float scale = (float)s / (float)R;
+      const float ry = scale * (Y + 0.5f) - 0.5f, fy = floorf(ry);
+      const int iy = (int)fy;
+      bool fresh = it == 0;
+      if (it > 0 && (MODE == 1 || h != prev_h || iy != prev_iy || l != prev_l)) {   // next group: release the old row slot
         __syncwarp();
         if (lane == 0) ct_mbar_arrive(REMPTY + 8 * (g & 1));
         ++g;
-        g_next_start = next_group_start(it);
         fresh = true;
-        if (pw == 0 && lane == 0 && g_next_start < n_items) load_group(g + 1, g_next_start);
       }
-      const int s = p.s[l];
+      prev_h = h; prev_iy = iy; prev_l = l;
+      if (s != tab_s) tabulate(s);
       const int st = it % nst;
       const uint32_t ph = (uint32_t)(it / nst) & 1u;
-      const float scale = (float)s / (float)R;
-      const float ry = scale * (Y + 0.5f) - 0.5f;
       float wy[4];
-      cubic_coeffs(ry - floorf(ry), wy);
+      cubic_coeffs(ry - fy, wy);
       if (pw == 0 && lane == 0) CT_STAMP(0, it, 0);
-      if (fresh) {
-        ct_mbar_wait(RFULL + 8 * (g & 1), ((uint32_t)g >> 1) & 1u);
-        fresh = false;
-      }
+      if (fresh) ct_mbar_wait(RFULL + 8 * (g & 1), ((uint32_t)g >> 1) & 1u);
       const float* src = rows_smem + (size_t)(g & 1) * p.slot_floats;
       // shift of column xs = lane: the vertically interpolated row maximum (lanes >= s hold garbage that is never used)
       const float* mxs = src + 4 * max_rowfl + lane;
@@ -419,55 +470,48 @@ __global__ void __launch_bounds__((9 + PW) * 32, 1) capture_tc_kernel(const CapT
       if (pw == 0 && lane == 0) CT_STAMP(0, it, 1);
       uint8_t* Bh = gen + (sB - base) + st * Cfg::B_STAGE;
       uint8_t* Bl = Bh + Cfg::B_PLANE;
-      // unit = (pair of low-res columns, chunk of 32 tokens); units are dealt round-robin to the producer warps
-      const int npairs = (s + 1) >> 1, nunits = npairs * NC;
-      // UB units per trip: all their shared loads are issued before the first use (a single producer warp per scheduler
-      // cannot hide the load -> FMA -> convert -> store latency of one unit at a time)
-      constexpr int UB = 4;
-      for (int u0 = pw; u0 < nunits; u0 += NPROD * UB) {
-        float raw[UB][2][4];
-        int uxs[UB], uc[UB];
+      // trips of TRIP units: all their shared loads are issued before the first use
+      constexpr int TRIP = 4;
+      const bool odd_s = (s & 1) != 0;
 #pragma unroll
-        for (int q = 0; q < UB; ++q) {
-          const int u = min(u0 + q * NPROD, nunits - 1);       // clamped: a surplus slot repeats the last unit (no store)
-          const int pi = u / NC, c = u - pi * NC;
-          uxs[q] = 2 * pi;
-          uc[q] = c;
-          const int xs1 = min(2 * pi + 1, s - 1);
-          const int nn = min(c * 32 + lane, N - 1);
-          const float* a0 = src + 2 * pi * N + nn;
-          const float* b0 = src + xs1 * N + nn;
+      for (int q0 = 0; q0 < MAXU; q0 += TRIP) {
+        if (q0 < nunits_w) {
+          float raw[TRIP][2][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            raw[q][0][j] = a0[j * max_rowfl];
-            raw[q][1][j] = b0[j * max_rowfl];
-          }
-        }
+          for (int q = 0; q < TRIP; ++q)
+            if (q0 + q < MAXU) {
+              const bool two = !(odd_s && u_xs[q0 + q] == s - 1);
+              const float* a0 = src + u_src[q0 + q];
+              const float* b0 = a0 + (two ? N : 0);
 #pragma unroll
-        for (int q = 0; q < UB; ++q) {
-          const int xs = uxs[q], c = uc[q];
-          const float sh0 = __shfl_sync(0xffffffffu, shift, xs), sh1 = __shfl_sync(0xffffffffu, shift, min(xs + 1, s - 1));
-          float a = fmaf(wy[0], raw[q][0][0], -sh0), b = fmaf(wy[0], raw[q][1][0], -sh1);
+              for (int j = 0; j < 4; ++j) {
+                raw[q][0][j] = a0[j * max_rowfl];
+                raw[q][1][j] = b0[j * max_rowfl];
+              }
+            }
+          if (pw == 0 && lane == 0 && q0 == 0) CT_STAMP(0, it, 4);
 #pragma unroll
-          for (int j = 1; j < 4; ++j) {
-            a = fmaf(wy[j], raw[q][0][j], a);
-            b = fmaf(wy[j], raw[q][1][j], b);
-          }
-          if (xs + 1 >= s) b = 0.f;
-          const int n = c * 32 + lane;
-          if (u0 + q * NPROD < nunits && n < N) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
-            const float2 f = __bfloat1622float2(hh);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(a - f.x, b - f.y);
-            // tokoff / toksw are indexed by the (runtime) chunk: select without local memory
-            uint32_t to = tokoff[0], ts = toksw[0];
+          for (int q = 0; q < TRIP; ++q)
+            if (q0 + q < MAXU) {
+              const int xq = u_xs[q0 + q];
+              const int xs = xq < 0 ? 0 : xq;
+              const bool two = !(odd_s && xq == s - 1);
+              const float sh0 = __shfl_sync(0xffffffffu, shift, xs), sh1 = __shfl_sync(0xffffffffu, shift, min(xs + 1, 31));
+              float a = fmaf(wy[0], raw[q][0][0], -sh0), b = fmaf(wy[0], raw[q][1][0], -sh1);
 #pragma unroll
-            for (int k = 1; k < NC; ++k)
-              if (c == k) { to = tokoff[k]; ts = toksw[k]; }
-            const uint32_t off = to + ((((uint32_t)xs >> 3) ^ ts) << 4) + ((uint32_t)xs & 7u) * 2u;
-            *reinterpret_cast<__nv_bfloat162*>(Bh + off) = hh;
-            *reinterpret_cast<__nv_bfloat162*>(Bl + off) = ll;
-          }
+              for (int j = 1; j < 4; ++j) {
+                a = fmaf(wy[j], raw[q][0][j], a);
+                b = fmaf(wy[j], raw[q][1][j], b);
+              }
+              if (!two) b = 0.f;
+              if (xq >= 0) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+                const float2 f = __bfloat1622float2(hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(a - f.x, b - f.y);
+                *reinterpret_cast<__nv_bfloat162*>(Bh + u_dst[q0 + q]) = hh;
+                *reinterpret_cast<__nv_bfloat162*>(Bl + u_dst[q0 + q]) = ll;
+              }
+            }
         }
       }
       if (pw == 0 && lane == 0) CT_STAMP(0, it, 2);
@@ -475,6 +519,12 @@ __global__ void __launch_bounds__((9 + PW) * 32, 1) capture_tc_kernel(const CapT
       __syncwarp();
       if (lane == 0) ct_mbar_arrive(FULL + 8 * st);
       if (pw == 0 && lane == 0) CT_STAMP(0, it, 3);
+      // next item
+      if (MODE == 0) {
+        if (++Y == R) { Y = 0; ++h; }
+      } else {
+        if (++h == p.heads) { h = 0; ++l; }
+      }
     }
   } else if (warp == MMA_WARP) {
     // =========================================================== MMA issuer
@@ -548,9 +598,13 @@ __global__ void __launch_bounds__((9 + PW) * 32, 1) capture_tc_kernel(const CapT
       const float2 negm = make_float2(-m, -m);
 #pragma unroll
       for (int i = 0; i < HALF / 2; ++i) {
-        const float2 t = ct_add2(make_float2(x[2 * i], x[2 * i + 1]), negm);
-        e[i] = make_float2(ct_ex2(t.x), ct_ex2(t.y));
-        s2[i & 1] = ct_add2(s2[i & 1], e[i]);
+        if (2 * i < nv) {          // uniform: tokens beyond N (padding, exp2 == 0) take no SFU slot
+          const float2 t = ct_add2(make_float2(x[2 * i], x[2 * i + 1]), negm);
+          e[i] = make_float2(ct_ex2(t.x), ct_ex2(t.y));
+          s2[i & 1] = ct_add2(s2[i & 1], e[i]);
+        } else {
+          e[i] = make_float2(0.f, 0.f);
+        }
       }
       const float sum = (s2[0].x + s2[0].y) + (s2[1].x + s2[1].y);
       // the two halves of the pixel exchange (max, sum); the barrier also orders the staging buffer hand-over below
@@ -735,13 +789,18 @@ int capture_tc(const float* const* logits, const int* s, int n_layers, float* ou
   p.n_slots = 0;
   int kcols = 0, max_s = 0;
   float* ws = workspace;
+  CapRowmaxParams rp{};
+  rp.n_layers = n_layers; rp.N = N;
+  int rows_total = 0;
   for (int l = 0; l < n_layers; ++l) {
     p.logits[l] = logits[l];
     p.s[l] = s[l];
     p.rowmax[l] = ws;
     const int rows = heads * s[l] * s[l];
-    capture_rowmax_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(logits[l], ws, rows, N);
-    SKP_CHECK_LAUNCH("capture_rowmax");
+    rp.logits[l] = logits[l];
+    rp.out[l] = ws;
+    rows_total += rows;
+    rp.row_end[l] = rows_total;
     ws += (rows + 3) & ~3;
     if (s[l] > max_s) max_s = s[l];
     int k = 0;
@@ -756,9 +815,11 @@ int capture_tc(const float* const* logits, const int* s, int n_layers, float* ou
     p.kofs[l] = p.slot_kofs[k];
   }
   p.slot_floats = 4 * max_s * N + 128;
+  capture_rowmax_kernel<<<(int)(((size_t)rows_total * 32 + 255) / 256), 256, 0, st>>>(rp);
+  SKP_CHECK_LAUNCH("capture_rowmax");
   const int npt = npt_of(N);
   int rc;
-  // 7 producer warps (16 warps, 128 registers per thread) unless the MEAN accumulators of 128 tokens need the wider budget
+  // 16 warps: 8 epilogue, 6 producers, the DMA warp, the MMA warp (128 registers per thread)
   if (store) {
     switch (npt) {
       case 32: rc = capture_tc_launch<32, 0, 7>(p, st); break;
@@ -771,7 +832,7 @@ int capture_tc(const float* const* logits, const int* s, int n_layers, float* ou
       case 32: rc = capture_tc_launch<32, 1, 7>(p, st); break;
       case 64: rc = capture_tc_launch<64, 1, 7>(p, st); break;
       case 96: rc = capture_tc_launch<96, 1, 7>(p, st); break;
-      default: rc = capture_tc_launch<128, 1, 3>(p, st); break;
+      default: rc = capture_tc_launch<128, 1, 7>(p, st); break;
     }
   }
   if (rc == SKP_ERR_UNSUPPORTED) return SKP_OK;
