@@ -158,6 +158,17 @@ int skp_self_attn_tc_fwd(const float* q, int64_t ldq, const float* k, int64_t ld
 int skp_self_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         void* planes, int S, int heads, int d, float scale, void* stream);
 
+/* Cross-attention (attn2, ptp_utils.py:480-506) and short-sequence self-attention forward on tcgen05 / TMEM / TMA
+ * (skp_xattn_tc.cu): any Sq / Skv, even head dims up to 160 (64-column K chunks), keys in tiles of 64 with the accumulator
+ * resident in tensor memory.  logits != NULL (captured layers, ptp_utils.py:508-538): the scaled logits [heads, Sq, Skv] are
+ * written by the same kernel.  lse is in base 2 (scores pre-multiplied by log2 e), like skp_cross_attn_tc_fwd.
+ * skp_cross_attn_split makes the operand planes skp_cross_attn_tc_bwd needs from q / k / v. */
+int64_t skp_xattn_tc_workspace(int Sq, int Skv, int heads, int d);
+int skp_xattn_tc_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, float* o,
+                     int64_t ldo, float* lse, float* logits, void* workspace, int Sq, int Skv, int heads, int d,
+                     float scale, void* stream);
+int skp_cross_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                         void* q_planes, void* kv_planes, int S, int N, int heads, int d, float scale, void* stream);
 /* Cross-attention core on the same split-bf16 tensor-core kernels (S queries, N << S keys): the tensor-core
  * replacement of skp_cross_attn_fwd/bwd.  logits (nullable) receives the scaled scores [heads, S, N] of a captured
  * layer; lse[heads, S]; q_planes: 2*heads*S*DP bf16, kv_planes: 4*heads*N*DP bf16 (kept for the backward).

@@ -52,6 +52,9 @@ _SIGNATURES: Dict[str, list] = {
     "skp_self_attn_split": [_P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _F, _P],
     "skp_self_attn_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _F, _P],
     "skp_self_attn_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P],
+    "skp_xattn_tc_workspace": [_I, _I, _I, _I],
+    "skp_xattn_tc_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "skp_cross_attn_split": [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_cross_attn_tc_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "skp_cross_attn_tc_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _F, _P],
     "skp_capture_select": [_I, _I],
@@ -86,7 +89,7 @@ _SIGNATURES: Dict[str, list] = {
 }
 _RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None, "skp_capture_select": None, "skp_capture_tc": None, "skp_capture_tc_trace": None,
             "skp_self_attn_tc_workspace": C.c_int64,
-            "skp_capture_tc_workspace": C.c_int64}
+            "skp_capture_tc_workspace": C.c_int64, "skp_xattn_tc_workspace": C.c_int64}
 
 
 def declared_symbols() -> List[str]:

@@ -904,6 +904,23 @@ extern "C" int skp_cross_attn_tc_bwd(const float* d_o, int64_t lddo, const float
                      d_logits_extra, dq, lddq, dk, lddk, dv, lddv, S, N, heads, d, scale, true, (cudaStream_t)stream);
 }
 
+/* Operand split only for the cross-attention backward (the planes skp_cross_attn_tc_bwd needs) -- used when the forward
+ * ran on the tcgen05 kernel (skp_xattn_tc.cu), which keeps its own operand layout. */
+extern "C" int skp_cross_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                    void* q_planes, void* kv_planes, int S, int N, int heads, int d, float scale, void* stream) {
+  SKP_REQUIRE(q && k && v && q_planes && kv_planes, "skp_cross_attn_split: null pointer");
+  int DP;
+  int rc = sa_check("cross_attn_split", S, N, heads, d, &DP);
+  if (rc) return rc;
+  int64_t total = (int64_t)heads * (S + 2 * (int64_t)N) * (DP / 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sa_split_qkv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, (bf16*)q_planes, (bf16*)kv_planes, S, N, heads, d,
+                                                                 DP, scale * 1.4426950408889634f);
+  SKP_CHECK_LAUNCH("sa_split_qkv_kernel");
+  return SKP_OK;
+}
+
 /* Operand split only (the planes skp_self_attn_bwd needs) -- used when the forward ran on the tcgen05 kernel
  * (skp_attn_tc.cu), which keeps its own operand layout. */
 extern "C" int skp_self_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,

@@ -525,11 +525,21 @@ class _CrossAttnTC(torch.autograd.Function):
         o = torch.empty_like(q)
         lse = torch.empty(heads, s, dtype=torch.float32, device=dev)
         logits = torch.empty(heads, s, n, dtype=torch.float32, device=dev) if want_logits else None
-        qp = torch.empty(2 * heads * s * dp, dtype=torch.bfloat16, device=dev)
-        kvp = torch.empty(4 * heads * n * dp, dtype=torch.bfloat16, device=dev)
-        check(lib().skp_cross_attn_tc_fwd(ptr(q), c, ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), c, ptr(lse), ptr(logits),
-                                          ptr(qp), ptr(kvp), s, n, heads, d, scale, stream()), "skp_cross_attn_tc_fwd")
-        ctx.save_for_backward(o, lse, qp, kvp)
+        ws_bytes = int(lib().skp_xattn_tc_workspace(s, n, heads, d)) if XATTN_TC else 0
+        if ws_bytes > 0:
+            # tcgen05 / TMEM / TMA forward (skp_xattn_tc.cu); the captured layers get their scaled logits from the same kernel
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib().skp_xattn_tc_fwd(ptr(q), c, ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), c, ptr(lse), ptr(logits),
+                                         ptr(ws), s, n, heads, d, scale, stream()), "skp_xattn_tc_fwd")
+            ctx.save_for_backward(o, lse, q, k, v)
+            ctx.tc = True
+        else:
+            qp = torch.empty(2 * heads * s * dp, dtype=torch.bfloat16, device=dev)
+            kvp = torch.empty(4 * heads * n * dp, dtype=torch.bfloat16, device=dev)
+            check(lib().skp_cross_attn_tc_fwd(ptr(q), c, ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), c, ptr(lse), ptr(logits),
+                                              ptr(qp), ptr(kvp), s, n, heads, d, scale, stream()), "skp_cross_attn_tc_fwd")
+            ctx.save_for_backward(o, lse, qp, kvp)
+            ctx.tc = False
         ctx.meta = (s, n, c, heads, d, dp, scale)
         if logits is None:
             logits = torch.empty(0, dtype=torch.float32, device=dev)
@@ -538,8 +548,15 @@ class _CrossAttnTC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_o, d_logits):
-        o, lse, qp, kvp = ctx.saved_tensors
         s, n, c, heads, d, dp, scale = ctx.meta
+        if ctx.tc:       # the tcgen05 forward keeps its own operand layout: make the mma.sync planes from q / k / v now
+            o, lse, q, k, v = ctx.saved_tensors
+            qp = torch.empty(2 * heads * s * dp, dtype=torch.bfloat16, device=o.device)
+            kvp = torch.empty(4 * heads * n * dp, dtype=torch.bfloat16, device=o.device)
+            check(lib().skp_cross_attn_split(ptr(q), c, ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(qp), ptr(kvp), s, n, heads, d,
+                                             scale, stream()), "skp_cross_attn_split")
+        else:
+            o, lse, qp, kvp = ctx.saved_tensors
         dev = o.device
         if d_o is None:
             d_o = torch.zeros_like(o)
@@ -557,6 +574,11 @@ class _CrossAttnTC(torch.autograd.Function):
 
 # "tc": split-bf16 tensor-core kernels (default); "simt": the exact-fp32 FMA kernels of skp_attn.cu
 CROSS_ATTN_IMPL = os.environ.get("SKP_CROSS_ATTN", "tc")
+# cross-attention forward on the tcgen05 kernel of skp_xattn_tc.cu.  Measured on B200 (scripts/xattn_bench.py,
+# profiles/r02_xattn_tc.md): with N = 77 .. 500 keys the op is a latency chain of 2 - 8 key tiles on 16 - 256 CTAs, and the
+# register-resident mma.sync flash kernel of skp_selfattn.cu finishes it sooner (12 - 19 us vs 17 - 26 us per call) -- the
+# tensor-core issue rate is not what bounds it.  So the tcgen05 kernel is opt-in (SKP_XATTN_TC=1; parity-tested either way).
+XATTN_TC = os.environ.get("SKP_XATTN_TC", "0") == "1"
 
 
 def cross_attn_core(q, k, v, heads: int, scale: float, want_logits: bool = False, impl: Optional[str] = None):

@@ -180,8 +180,11 @@ def _attn_ref(q, k, v, heads, scale, extra_w=None):
 
 @pytest.mark.parametrize("s,n,heads,d", [(256, 77, 8, 160), (1024, 77, 8, 80), (64, 500, 8, 40), (16, 12, 4, 8),
                                          (4096, 100, 8, 40), (100, 33, 2, 24)])
-@pytest.mark.parametrize("impl,tol", [("simt", 2e-5), ("tc", 1e-4)])
-def test_cross_attn_fwd_bwd(ops, s, n, heads, d, impl, tol):
+@pytest.mark.parametrize("impl,tol", [("simt", 2e-5), ("tc", 1e-4), ("tcgen05", 1e-4)])
+def test_cross_attn_fwd_bwd(ops, monkeypatch, s, n, heads, d, impl, tol):
+    # "tc": mma.sync flash kernels (the default); "tcgen05": forward on skp_xattn_tc.cu (TMEM / TMA), backward on mma.sync
+    monkeypatch.setattr(ops, "XATTN_TC", impl == "tcgen05")
+    impl = "tc" if impl == "tcgen05" else impl
     g = torch.Generator().manual_seed(s + n)
     c = heads * d
     q = torch.randn(s, c, generator=g, dtype=torch.float64)
