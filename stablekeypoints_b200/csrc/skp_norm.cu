@@ -11,6 +11,7 @@
 // Replaces diffusers ResnetBlock2D / Transformer2DModel GroupNorm + SiLU inside the UNet / VAE the
 // path runs through (ptp_utils.py:227-229, 299-302).
 #include "skp_common.cuh"
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -393,10 +394,32 @@ __global__ void __launch_bounds__(GN_THREADS) gn_im2col3x3_split_kernel(const fl
   }
 }
 
-// ------------------------------------------------------------------------------------------------ one CTA per group
-// Small activations (the UNet at one image per rank: 64..4096 rows): statistics AND normalisation in ONE launch, one CTA per
-// group -- no atomics, no memset, no second kernel.  The CTA sweeps its [rows x cg] slab twice (the second sweep hits L1/L2).
-// Thread = (channel pair, row lane).  The (sum, sumsq) pair is still published (replica 0; the others zeroed) for the backward.
+// ------------------------------------------------------------------------------------------------ one cluster per group
+// Small and medium activations (the UNet at one image per rank: 64..4096 rows): statistics AND normalisation in ONE launch,
+// one thread-block CLUSTER of 1..8 CTAs per group -- no atomics, no memset, no second kernel, bit-reproducible.  Each CTA
+// sweeps its share of the rows of the [rows x cg] slab twice (the second sweep hits L1/L2); the per-CTA partial sums meet
+// through distributed shared memory (every CTA reads the partials of all ranks in rank order, so all of them hold the same
+// totals).  Thread = (channel pair, row lane).  The (sum, sumsq) pair is still published (replica 0; the others zeroed) for
+// the backward.
+namespace cgx = cooperative_groups;
+
+// sum over the cluster of one (a, b) pair of block totals, in rank order; the two cluster syncs bracket the remote reads
+__device__ __forceinline__ void cluster_sum2(double& a, double& b, double* part) {
+  cgx::cluster_group cl = cgx::this_cluster();
+  const unsigned n = cl.num_blocks();
+  if (n == 1) return;
+  if (threadIdx.x == 0) { part[0] = a; part[1] = b; }
+  cl.sync();
+  double sa = 0.0, sb = 0.0;
+  for (unsigned r = 0; r < n; ++r) {
+    const double* rp = cl.map_shared_rank(part, r);
+    sa += rp[0];
+    sb += rp[1];
+  }
+  cl.sync();          // nobody leaves (or overwrites part) while a peer still reads it
+  a = sa;
+  b = sb;
+}
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
@@ -415,31 +438,35 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_fwd_kernel(const float* _
                                                                   int64_t ldy, __nv_bfloat16* __restrict__ hi,
                                                                   __nv_bfloat16* __restrict__ lo, int Kpad, double* __restrict__ sums) {
   __shared__ double red[GN_THREADS / 32];
+  __shared__ double part[2];
   const int g = blockIdx.x, G = gridDim.x, c0 = g * cg;
+  const int rank = blockIdx.y, CL = gridDim.y;                       // cluster = the CL CTAs of this group
+  const int rbeg = (int)((long)rows * rank / CL), rend = (int)((long)rows * (rank + 1) / CL);
   const int PP = cg >> 1, RL = GN_THREADS / PP;
   const int p = threadIdx.x % PP, ry = threadIdx.x / PP;
   const bool active = ry < RL;
   const float* xc = x + c0 + 2 * p;
   float s = 0.f, ss = 0.f;
   if (active)
-    for (int r = ry; r < rows; r += 4 * RL) {   // 4 independent loads in flight per thread
+    for (int r = rbeg + ry; r < rend; r += 4 * RL) {   // 4 independent loads in flight per thread
       float2 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        v[u] = (r + u * RL < rows) ? __ldg(reinterpret_cast<const float2*>(xc + (size_t)(r + u * RL) * ldx)) : make_float2(0.f, 0.f);
+        v[u] = (r + u * RL < rend) ? __ldg(reinterpret_cast<const float2*>(xc + (size_t)(r + u * RL) * ldx)) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         s += v[u].x + v[u].y;
         ss = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, ss));
       }
     }
-  const double S = block_sum_d((double)s, red), SS = block_sum_d((double)ss, red);
+  double S = block_sum_d((double)s, red), SS = block_sum_d((double)ss, red);
+  cluster_sum2(S, SS, part);
   const double count = (double)rows * cg;
   const double md = S / count;
   double var = SS / count - md * md;
   if (var < 0.0) var = 0.0;
   const float mean = (float)md, rstd = (float)(1.0 / sqrt(var + (double)eps));
-  if (threadIdx.x < 2 * GN_REPL) {   // replica 0 carries the sums, the rest must read as zero
+  if (rank == 0 && threadIdx.x < 2 * GN_REPL) {   // replica 0 carries the sums, the rest must read as zero
     const int r = threadIdx.x >> 1, w = threadIdx.x & 1;
     sums[(size_t)r * 2 * G + 2 * g + w] = r == 0 ? (w == 0 ? S : SS) : 0.0;
   }
@@ -447,15 +474,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_fwd_kernel(const float* _
     const float g0 = __ldg(gamma + c0 + 2 * p), g1 = __ldg(gamma + c0 + 2 * p + 1);
     const float sc0 = rstd * g0, sc1 = rstd * g1;
     const float sh0 = fmaf(-mean, sc0, __ldg(beta + c0 + 2 * p)), sh1 = fmaf(-mean, sc1, __ldg(beta + c0 + 2 * p + 1));
-    for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+    for (int r0 = rbeg + ry; r0 < rend; r0 += 4 * RL) {
       float2 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        v[u] = (r0 + u * RL < rows) ? __ldg(reinterpret_cast<const float2*>(xc + (size_t)(r0 + u * RL) * ldx)) : make_float2(0.f, 0.f);
+        v[u] = (r0 + u * RL < rend) ? __ldg(reinterpret_cast<const float2*>(xc + (size_t)(r0 + u * RL) * ldx)) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int r = r0 + u * RL;
-        if (r >= rows) break;
+        if (r >= rend) break;
         float z0 = fmaf(v[u].x, sc0, sh0), z1 = fmaf(v[u].y, sc1, sh1);
         if (silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
         if (y) *reinterpret_cast<float2*>(y + (size_t)r * ldy + c0 + 2 * p) = make_float2(z0, z1);
@@ -469,10 +496,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_fwd_kernel(const float* _
       }
     }
   }
-  if (hi && Kpad > C && g == G - 1) {   // zero the K padding of the operand
+  if (hi && Kpad > C && g == G - 1) {   // zero the K padding of the operand (this CTA's rows)
     const int padp = (Kpad - C) >> 1;
-    for (int i = threadIdx.x; i < rows * padp; i += GN_THREADS) {
-      const int r = i / padp, c = C + 2 * (i - r * padp);
+    for (int i = threadIdx.x; i < (rend - rbeg) * padp; i += GN_THREADS) {
+      const int r = rbeg + i / padp, c = C + 2 * (i % padp);
       *reinterpret_cast<uint32_t*>(hi + (size_t)r * Kpad + c) = 0u;
       *reinterpret_cast<uint32_t*>(lo + (size_t)r * Kpad + c) = 0u;
     }
@@ -485,8 +512,11 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_bwd_kernel(const float* _
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   int silu, float* __restrict__ dx, int64_t ldd) {
   __shared__ double red[GN_THREADS / 32];
+  __shared__ double part[2];
   __shared__ float st[2];
   const int g = blockIdx.x, G = gridDim.x, c0 = g * cg;
+  const int rank = blockIdx.y, CL = gridDim.y;
+  const int rbeg = (int)((long)rows * rank / CL), rend = (int)((long)rows * (rank + 1) / CL);
   const double count = (double)rows * cg;
   if (threadIdx.x == 0) {
     double s1 = 0.0, s2 = 0.0;
@@ -511,11 +541,11 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_bwd_kernel(const float* _
   const float sc = rstd, sh = -mean * rstd;
   float a1 = 0.f, a2 = 0.f;
   if (active)
-    for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+    for (int r0 = rbeg + ry; r0 < rend; r0 += 4 * RL) {
       float2 v[4], gv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const bool ok = r0 + u * RL < rows;
+        const bool ok = r0 + u * RL < rend;
         v[u] = ok ? __ldg(reinterpret_cast<const float2*>(x + (size_t)(r0 + u * RL) * ldx + c)) : make_float2(0.f, 0.f);
         gv[u] = ok ? __ldg(reinterpret_cast<const float2*>(gr + (size_t)(r0 + u * RL) * ldg + c)) : make_float2(0.f, 0.f);
       }
@@ -529,21 +559,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_bwd_kernel(const float* _
         a2 = fmaf(d0, xh0, fmaf(d1, xh1, a2));
       }
     }
-  const double A1 = block_sum_d((double)a1, red), A2 = block_sum_d((double)a2, red);
+  double A1 = block_sum_d((double)a1, red), A2 = block_sum_d((double)a2, red);
+  cluster_sum2(A1, A2, part);
   const float m1 = (float)(A1 / count), m2 = (float)(A2 / count);
   if (active)
-    for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+    for (int r0 = rbeg + ry; r0 < rend; r0 += 4 * RL) {
       float2 v[4], gv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const bool ok = r0 + u * RL < rows;
+        const bool ok = r0 + u * RL < rend;
         v[u] = ok ? __ldg(reinterpret_cast<const float2*>(x + (size_t)(r0 + u * RL) * ldx + c)) : make_float2(0.f, 0.f);
         gv[u] = ok ? __ldg(reinterpret_cast<const float2*>(gr + (size_t)(r0 + u * RL) * ldg + c)) : make_float2(0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int r = r0 + u * RL;
-        if (r >= rows) break;
+        if (r >= rend) break;
         const float xh0 = fmaf(v[u].x, sc, sh), xh1 = fmaf(v[u].y, sc, sh);
         float dz0 = gv[u].x, dz1 = gv[u].y;
         if (silu) { dz0 *= silu_grad(fmaf(g0, xh0, b0)); dz1 *= silu_grad(fmaf(g1, xh1, b1)); }
@@ -553,11 +584,37 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_bwd_kernel(const float* _
     }
 }
 
-// the one-CTA-per-group kernels take even group widths up to 512 channels and slabs of at most 20K elements (beyond
-// that 32 CTAs are too few: measured 29 us per GroupNorm against 15 us for the two-kernel path)
+// the one-cluster-per-group kernels take even group widths up to 512 channels and slabs of at most 20K elements per CTA
+// of the cluster (1, 2, 4 or 8 CTAs: 32 .. 256 CTAs in flight); beyond that the two-kernel path streams better
+constexpr int GN_SLAB_PER_CTA = 20480;
+static int g_gn_cluster_max = getenv("SKP_GN_CLUSTER") ? atoi(getenv("SKP_GN_CLUSTER")) : 8;
+static inline int gn_cluster_size(int rows, int cg) {
+  const size_t slab = (size_t)rows * cg;
+  int cl = 1;
+  while (cl < g_gn_cluster_max && slab > (size_t)4096 * cl) cl *= 2;     // ~4K elements per CTA: the sweep is latency-bound
+  while (cl > 1 && rows / cl < 1) cl /= 2;
+  return cl;
+}
 static inline bool gn_group_ok(int rows, int C, int groups, const float* x, int64_t ldx) {
   const int cg = C / groups;
-  return (cg % 2 == 0) && cg <= 2 * GN_THREADS && (size_t)rows * cg <= 20480 && (ldx % 2 == 0) && ((((uintptr_t)x) & 7) == 0);
+  return (cg % 2 == 0) && cg <= 2 * GN_THREADS && (size_t)rows * cg <= (size_t)GN_SLAB_PER_CTA * g_gn_cluster_max && (ldx % 2 == 0) &&
+         ((((uintptr_t)x) & 7) == 0);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t gn_launch_cluster(void (*kernel)(KArgs...), int groups, int cl, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups, cl);
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = cl;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // Rows per CTA.  Large activations (VAE): ~6 CTAs per SM so enough loads are in flight.  Small ones (the UNet at one image
@@ -637,8 +694,9 @@ extern "C" int skp_gn_fwd(const float* x, int64_t ldx, int rows, int C, int grou
   static const bool group_off = getenv("SKP_GN_GROUP") != nullptr && atoi(getenv("SKP_GN_GROUP")) == 0;
   if (!group_off && gn_group_ok(rows, C, groups, x, ldx) && (!y || (ldy % 2 == 0 && ((((uintptr_t)y) & 7) == 0))) &&
       (!hi || (((((uintptr_t)hi) | ((uintptr_t)lo)) & 3) == 0))) {
-    gn_group_fwd_kernel<<<groups, GN_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, C / groups, eps, gamma, beta, silu, y, ldy,
-                                                                        (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad, sums);
+    cudaError_t le = gn_launch_cluster(gn_group_fwd_kernel, groups, gn_cluster_size(rows, C / groups), (cudaStream_t)stream, x, ldx, rows, C,
+                                       C / groups, eps, gamma, beta, silu, y, ldy, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kpad, sums);
+    if (le != cudaSuccess) { set_error("gn_group_fwd: cluster launch: %s", cudaGetErrorString(le)); return SKP_ERR_LAUNCH; }
     SKP_CHECK_LAUNCH("gn_group_fwd");
     return SKP_OK;
   }
@@ -673,7 +731,9 @@ extern "C" int skp_gn_bwd(const float* x, int64_t ldx, const float* g, int64_t l
   static const bool group_off = getenv("SKP_GN_GROUP") != nullptr && atoi(getenv("SKP_GN_GROUP")) == 0;
   if (!group_off && gn_group_ok(rows, C, groups, x, ldx) && (ldg % 2 == 0) && (ldd % 2 == 0) &&
       (((((uintptr_t)g) | ((uintptr_t)dx)) & 7) == 0)) {
-    gn_group_bwd_kernel<<<groups, GN_THREADS, 0, st>>>(x, ldx, g, ldg, rows, C, C / groups, sums, eps, gamma, beta, silu, dx, ldd);
+    cudaError_t le = gn_launch_cluster(gn_group_bwd_kernel, groups, gn_cluster_size(rows, C / groups), st, x, ldx, g, ldg, rows, C, C / groups,
+                                       sums, eps, gamma, beta, silu, dx, ldd);
+    if (le != cudaSuccess) { set_error("gn_group_bwd: cluster launch: %s", cudaGetErrorString(le)); return SKP_ERR_LAUNCH; }
     SKP_CHECK_LAUNCH("gn_group_bwd");
     return SKP_OK;
   }
