@@ -228,6 +228,7 @@ class CrossLayer:
     channels: int
     kv_offset: int       # column offset of K in the batched K|V projection; V follows at +channels
     in_up: bool
+    index: int = 0       # position in execution order (K, V are views 2*index, 2*index + 1 of the split projection)
 
 
 class _EarlyExit(Exception):
@@ -293,7 +294,7 @@ class UNetEngine:
         for tp, c, in_up in self._attention_prefixes():
             b = f"{tp}.transformer_blocks.0"
             a2 = f"{b}.attn2"
-            self.cross_layers.append(CrossLayer(a2, c, off, in_up))
+            self.cross_layers.append(CrossLayer(a2, c, off, in_up, len(self.cross_layers)))
             kv_rows += [w[f"{a2}.to_k.weight"], w[f"{a2}.to_v.weight"]]
             off += 2 * c
             self._fw[f"{a2}.to_q"] = ops.FrozenWeight(w[f"{a2}.to_q.weight"])
@@ -373,8 +374,9 @@ class UNetEngine:
         layer = self._layer_by_prefix[p]
         c, heads = layer.channels, self.cfg.heads
         d = c // heads
-        k = kv_all[:, layer.kv_offset: layer.kv_offset + c]
-        v = kv_all[:, layer.kv_offset + c: layer.kv_offset + 2 * c]
+        # kv_all arrives as the tuple of per-layer (K, V) column views made by ONE split: its backward is a single
+        # concatenation of the 32 slice gradients instead of 32 zero-filled full-width tensors added one by one
+        k, v = kv_all[2 * layer.index], kv_all[2 * layer.index + 1]
         s = y.shape[0]
         ctl = self.controller
         capture = (ctl is not None and layer.in_up and s <= self.max_capture_tokens
@@ -535,6 +537,7 @@ class UNetEngine:
         # one alias node per forward: the 32 K / V slice gradients of THIS forward accumulate on this forward's stream and
         # cross over to the shared projection once (otherwise every slice of the side-stream forward syncs the two streams)
         kv_all = ops.stream_alias(self.project_context(context))
+        kv_all = kv_all.split([l.channels for l in self.cross_layers for _ in (0, 1)], dim=1)
         state = {"captured": len(self.controller.step_store["attn"]) if (self.controller is not None and self.capture_mode == "store") else 0,
                  "logits": []}
         self.last_logits = state["logits"]
