@@ -217,8 +217,11 @@ int skp_capture_store_bwd(const float* logits, const float* d_probs, float* d_lo
  * never materialising them.  _bwd recomputes and accumulates into d_logits[l] (zero-initialised). */
 int skp_capture_mean_fwd(const float* const* logits, const int* s, int n_layers, float* maps, int heads,
                          int N, int R, void* stream);
+/* workspace: skp_capture_mean_bwd_workspace bytes (per-row partial gradients [heads, R, s, N] of the largest layer; the
+ * transposed bicubic is then two gathers -- no atomics, bit-reproducible); NULL runs the tile kernel (shared atomics). */
+int64_t skp_capture_mean_bwd_workspace(const int* s, int n_layers, int heads, int N, int R);
 int skp_capture_mean_bwd(const float* const* logits, const int* s, int n_layers, const float* d_maps,
-                         float* const* d_logits, int heads, int N, int R, void* stream);
+                         float* const* d_logits, int heads, int N, int R, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------ collect_maps (optimize.py:27-79)
  * stored[l] : [BH, R*R, N].  out[T, R2, R2] = bilinear_{R->R2}( mean_{l,bh} stored[l][bh, :, idx[t]] ),

@@ -67,7 +67,8 @@ _SIGNATURES: Dict[str, list] = {
     "skp_capture_store_fwd": [_P, _P, _I, _I, _I, _I, _P],
     "skp_capture_store_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "skp_capture_mean_fwd": [_P, _P, _I, _P, _I, _I, _I, _P],
-    "skp_capture_mean_bwd": [_P, _P, _I, _P, _P, _I, _I, _I, _P],
+    "skp_capture_mean_bwd_workspace": [_P, _I, _I, _I, _I],
+    "skp_capture_mean_bwd": [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P],
     "skp_collect_maps_fwd": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P],
     "skp_collect_maps_bwd": [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P],
     "skp_argmax_rows": [_P, _I, _I, _P, _P],
@@ -89,7 +90,8 @@ _SIGNATURES: Dict[str, list] = {
 }
 _RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None, "skp_capture_select": None, "skp_capture_tc": None, "skp_capture_tc_trace": None,
             "skp_self_attn_tc_workspace": C.c_int64,
-            "skp_capture_tc_workspace": C.c_int64, "skp_xattn_tc_workspace": C.c_int64}
+            "skp_capture_tc_workspace": C.c_int64, "skp_xattn_tc_workspace": C.c_int64,
+            "skp_capture_mean_bwd_workspace": C.c_int64}
 
 
 def declared_symbols() -> List[str]:

@@ -412,9 +412,10 @@ static int launch_ty(CapParams& p, cudaStream_t st, bool* fits) {
 
 // skp_capture_row.cu: the row-per-CTA attn-store kernel (any R, s; needs the row + footprint to fit shared memory)
 int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled);
-int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
-                         cudaStream_t st, bool* handled);
+int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, float* workspace, int heads, int s, int N, int R,
+                         float w, cudaStream_t st, bool* handled);
 bool capture_mean_row_bwd_fits(int s, int N, int R);
+size_t capture_mean_row_bwd_workspace(int heads, int s, int N, int R);
 // skp_capture_tc.cu: the tcgen05 formulation (horizontal bicubic pass as a GEMM, softmax thread-local on the TMEM lanes)
 int capture_tc(const float* const* logits, const int* s, int n_layers, float* out, int heads, int N, int R, bool store,
                float* workspace, cudaStream_t st, bool* handled);
@@ -539,18 +540,29 @@ extern "C" int skp_capture_mean_fwd(const float* const* logits, const int* s, in
   return launch<false, false>(p, stream);
 }
 
+extern "C" int64_t skp_capture_mean_bwd_workspace(const int* s, int n_layers, int heads, int N, int R) {
+  if (s == nullptr || n_layers < 1 || n_layers > SKP_MAX_LAYERS || heads < 1 || N < 1 || R < 1) return 0;
+  size_t fl = 0;                       // the layers run one after the other on the stream: they share the buffer
+  for (int l = 0; l < n_layers; ++l) {
+    const size_t f = capture_mean_row_bwd_workspace(heads, s[l], N, R);
+    if (f > fl) fl = f;
+  }
+  return (int64_t)(fl * sizeof(float));
+}
+
 extern "C" int skp_capture_mean_bwd(const float* const* logits, const int* s, int n_layers, const float* d_maps,
-                                    float* const* d_logits, int heads, int N, int R, void* stream) {
+                                    float* const* d_logits, int heads, int N, int R, float* workspace, void* stream) {
   SKP_REQUIRE(logits != nullptr && s != nullptr && d_maps != nullptr && d_logits != nullptr,
               "capture_mean_bwd: null pointer");
-  {   // row formulation (skp_capture_row.cu), one launch per layer; SKP_CAPTURE_BWD_ROW=0 keeps the tile kernel
-    if (g_row_bwd && n_layers >= 1 && n_layers <= SKP_MAX_LAYERS && heads > 0 && N > 0 && R > 0) {
+  {   // row formulation (skp_capture_row.cu): two launches per layer, no atomics; needs the workspace.  Without one (or with
+      // skp_capture_select(., 0)) the tile kernel runs
+    if (g_row_bwd && workspace != nullptr && n_layers >= 1 && n_layers <= SKP_MAX_LAYERS && heads > 0 && N > 0 && R > 0) {
       bool all = true;
       for (int l = 0; l < n_layers; ++l)   // every layer must fit before any is accumulated
         if (logits[l] == nullptr || d_logits[l] == nullptr || s[l] <= 0 || !capture_mean_row_bwd_fits(s[l], N, R)) all = false;
       for (int l = 0; l < n_layers && all; ++l) {
         bool handled = false;
-        int rr = capture_mean_row_bwd(logits[l], d_maps, d_logits[l], heads, s[l], N, R, 1.f / (float)(n_layers * heads),
+        int rr = capture_mean_row_bwd(logits[l], d_maps, d_logits[l], workspace, heads, s[l], N, R, 1.f / (float)(n_layers * heads),
                                       (cudaStream_t)stream, &handled);
         if (rr != SKP_OK) return rr;
         if (!handled) {

@@ -30,13 +30,28 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 constexpr int ROW_MAX_THREADS = 512;
+
+// token slices per pixel: 2 for the whole-row blocks of N = 77 / 100 (128 pixel lanes); wide token axes (N = 500: x-blocks
+// of 32 pixels) get as many slices as fill the CTA -- 64 threads per SM cannot hide anything
+static inline int row_token_slices(int N, int P) {
+  if (N < 16) return 1;
+  int ts = 2;
+  if (P <= 64) {
+    ts = ROW_MAX_THREADS / P;
+    if (ts > 16) ts = 16;
+    while (ts > 2 && (N >> 2) / ts < 4) ts >>= 1;       // keep >= 4 float4 token groups per slice
+  }
+  return ts;
+}
 constexpr int ROWS_PER_CTA = 2;   // consecutive output rows per CTA: the per-pixel horizontal setup is shared
 
+template <bool ONE_BLOCK>
 __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(const float* __restrict__ logits,
                                                                             float* __restrict__ probs, int s, int N, int R,
-                                                                            int NV, int P, int TS, int XB) {
+                                                                            int NV, int P, int TS, int XB_) {
+  const int XB = ONE_BLOCK ? R : XB_;
   extern __shared__ __align__(16) unsigned char row_smem[];
-  float* stage = reinterpret_cast<float*>(row_smem);                 // [XB][N]  (this CTA's pixels of the output row, global layout)
+  float* stage = reinterpret_cast<float*>(row_smem);                 // [XB][N]  (an x-block of the output row, global layout)
   float* Vs = stage + (((size_t)XB * N + 3) & ~(size_t)3);           // [s+4][NV]
   float* red = Vs + (size_t)(s + 4) * NV;                            // [32] per-warp max |V|
   float* psum = red + 32;                                            // [TS][P] partial softmax sums
@@ -47,15 +62,16 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
   // P pixel lanes x TS token slices: thread = (pixel X, slice of the token axis); slices meet through psum[].
   const int N4 = N >> 2;
   const int X_lane = tid % P, part = tid / P;
-  // pixels [xb0, xb1) of the row belong to this CTA (blockIdx.z): wide token axes (N = 500) do not fit a whole row
-  const int xb0 = blockIdx.z * XB, xb1 = min(R, xb0 + XB);
   const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;      // float4 token groups of this slice
   const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;     // the last slice also takes the N % 4 tail
-  // horizontal taps of this thread's pixel in the first pixel block: the same for every row this CTA produces
+  const bool vec4 = (N & 3) == 0;
+  // wide token axes (N = 500) do not fit a whole row: the row leaves in x-blocks of XB pixels, one after the other, out of
+  // the SAME vertical pass.  With a single x-block the taps of this thread's pixel are the same for every row of the CTA.
+  constexpr bool one_block = ONE_BLOCK;
   float pwx[4] = {0.f, 0.f, 0.f, 0.f}, psabs = 0.f;
   int pc0 = 1;
-  if (xb0 + X_lane < xb1) {
-    float rx = scale * (xb0 + X_lane + 0.5f) - 0.5f, fx = floorf(rx);
+  if (one_block && X_lane < R) {
+    float rx = scale * (X_lane + 0.5f) - 0.5f, fx = floorf(rx);
     cubic_coeffs(rx - fx, pwx);
     pc0 = (int)fx + 1;   // column of tap 0 in the halo'd array (ix - 1 + 2)
 #pragma unroll
@@ -64,6 +80,7 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
       psabs += fabsf(pwx[i]);
     }
   }
+  bool store_pending = false;                                        // tid 0: a bulk copy may still be reading the staging tile
 
   for (int rr = 0; rr < ROWS_PER_CTA; ++rr) {
   const int Y = blockIdx.x * ROWS_PER_CTA + rr;
@@ -116,12 +133,19 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
     amax = warp_max(amax);
     if ((tid & 31) == 0) red[tid >> 5] = amax;
   }
-  if (rr > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging is free again
+  // single x-block: the wait for the previous row's copy rides on the barrier that publishes the vertical pass
+  if (one_block && tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncthreads();
   // M = max |V| over the row's footprint: x_n = sum_i wx[i] V_i[n] <= (sum_i |wx[i]|) * M for every token
   float M = 0.f;
   for (int w = 0; w < (NT >> 5); ++w) M = fmaxf(M, red[w]);
 
+  for (int xb0 = 0; xb0 < R; xb0 += XB) {
+  const int xb1 = min(R, xb0 + XB);
+  if (!one_block) {
+    if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging is free again
+    __syncthreads();
+  }
   // ---- 2. + 3. horizontal pass, softmax over tokens, in-place normalisation.
   for (int X0 = xb0; X0 < xb1; X0 += P) {
     const int X = X0 + X_lane;
@@ -131,7 +155,7 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
     float U = 0.f, sum = 0.f;
     float* orow = stage + (size_t)(live ? X - xb0 : 0) * N;
     if (live) {
-      if (X0 == xb0) {
+      if (one_block && X0 == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) wx[i] = pwx[i];
         c0 = pc0;
@@ -158,10 +182,14 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
         float e1 = ex2_approx(fmaf(wx[3], d.y, fmaf(wx[2], c.y, fmaf(wx[1], b.y, fmaf(wx[0], a.y, -U)))));
         float e2 = ex2_approx(fmaf(wx[3], d.z, fmaf(wx[2], c.z, fmaf(wx[1], b.z, fmaf(wx[0], a.z, -U)))));
         float e3 = ex2_approx(fmaf(wx[3], d.w, fmaf(wx[2], c.w, fmaf(wx[1], b.w, fmaf(wx[0], a.w, -U)))));
-        orow[4 * g] = e0;
-        orow[4 * g + 1] = e1;
-        orow[4 * g + 2] = e2;
-        orow[4 * g + 3] = e3;
+        if (vec4) {                       // N % 4 == 0: the pixel rows of the staging tile are 16-byte aligned (conflict-free
+          *reinterpret_cast<float4*>(orow + 4 * g) = make_float4(e0, e1, e2, e3);   // 128-bit stores; scalar ones collide 4-way
+        } else {                          // when the row pitch N is a multiple of 4 floats)
+          orow[4 * g] = e0;
+          orow[4 * g + 1] = e1;
+          orow[4 * g + 2] = e2;
+          orow[4 * g + 3] = e3;
+        }
         sum += (e0 + e1) + (e2 + e3);
       }
       if (part == TS - 1)
@@ -199,13 +227,23 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
         }
       } else {
         const float inv = 1.f / total;
+        if (vec4) {
+          float4* o4 = reinterpret_cast<float4*>(orow);
+#pragma unroll 4
+          for (int g = g0; g < g1; ++g) {
+            float4 v = o4[g];
+            v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+            o4[g] = v;
+          }
+        } else {
 #pragma unroll 8
-        for (int n = n_lo; n < n_hi; ++n) orow[n] *= inv;
+          for (int n = n_lo; n < n_hi; ++n) orow[n] *= inv;
+        }
       }
     }
     __syncthreads();   // psum is reused by the next pixel block
   }
-  // ---- bulk store of the row: generic-proxy writes -> async proxy, then one thread drives the copy engine
+  // ---- bulk store of the x-block: generic-proxy writes -> async proxy, then one thread drives the copy engine
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
@@ -218,7 +256,9 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
                    : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    store_pending = true;
   }
+  }   // x-blocks of the row
   }   // rows of this CTA
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the engine's reads
 }
@@ -226,18 +266,24 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
 // ------------------------------------------------------------------------------------------------ backward (fused mean)
 // d_logits[l][h, ys, xs, n] += bicubic^T( p o (g - <p, g>) ),  g[n] = w * d_maps[n, Y, X],  p = softmax_tokens(bicubic(logits)):
 // the input gradient of  maps = mean_{l,h} softmax_tokens(bicubic(logits[l][h]))  (ptp_utils.py:508-538 + optimize.py:50-75).
-// Same row formulation as the forward: CTA = (output row Y, head h, x-block); the probabilities are recomputed, the
-// gradient of the scores replaces them in the staging tile, and the TRANSPOSED bicubic is applied as a gather
-// (thread = (low-res column, token) sums the <= 4*F pixels whose taps touch that column: no shared atomics), then the
-// four vertical taps are scattered with coalesced global atomics (4*s*N per CTA, lanes = consecutive tokens).
+// Two kernels, no atomics, bit-reproducible:
+//  (1) capture_mean_row_bwd_kernel, CTA = (output row Y, head h): the same row formulation as the forward.  The vertical
+//      pass runs once; then, x-block by x-block (the whole row when it fits, 32 pixels at N = 500), the probabilities are
+//      recomputed, the gradient of the scores replaces them in the staging tile, and the TRANSPOSED horizontal stencil is
+//      applied as a gather (thread = (low-res column, token) sums the <= 4*F pixels whose taps touch that column) into a
+//      shared accumulator that lives across the x-blocks.  Result: dV[h, Y, xs, n], the gradient with respect to the
+//      vertically interpolated logits of row Y, written once, coalesced.
+//  (2) capture_mean_vgather_kernel: the transposed VERTICAL stencil as a gather too -- thread = (h, ys, xs, 4 tokens) sums
+//      wy_j(Y) * dV[h, Y, xs, n] over the <= 4*F+ rows Y that have ys among their four (clamped) taps.
+// (The one-kernel version scattered 4*s*N global atomics per (row, x-block, head): 131 M per layer at N = 500, 3.8 ms.)
 __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kernel(const float* __restrict__ logits,
                                                                                const float* __restrict__ d_maps,
-                                                                               float* __restrict__ d_logits, int s, int N, int R,
+                                                                               float* __restrict__ dvrow, int s, int N, int R,
                                                                                int NV, int P, int TS, int XB, float w) {
   extern __shared__ __align__(16) unsigned char row_smem[];
   float* stage = reinterpret_cast<float*>(row_smem);                 // [XB][N]  e_n, then dS_n
   float* Vs = stage + (((size_t)XB * N + 3) & ~(size_t)3);           // [s+4][NV] vertically interpolated logits
-  float* dVs = Vs + (size_t)(s + 4) * NV;                            // [s+4][NV] gradient wrt Vs
+  float* dVs = Vs + (size_t)(s + 4) * NV;                            // [s+4][NV] gradient wrt Vs (accumulated over the x-blocks)
   float* red = dVs + (size_t)(s + 4) * NV;                           // [32]
   float* psum = red + 32;                                            // [2][TS][P]  partial (sum e, sum e*g)
   float* wtab = psum + 2 * TS * P;                                   // [XB][4] raw horizontal weights
@@ -249,18 +295,10 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
   const float LOG2E = 1.4426950408889634f;
   const int N4 = N >> 2;
   const int X_lane = tid % P, part = tid / P;
-  const int xb0 = blockIdx.z * XB, xb1 = min(R, xb0 + XB), nx = xb1 - xb0;
   const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;
   const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;
+  (void)g1;
 
-  // per-pixel tap tables (raw weights: the transposed stencil needs them un-scaled)
-  for (int i = tid; i < nx; i += NT) {
-    float rx = scale * (xb0 + i + 0.5f) - 0.5f, fx = floorf(rx);
-    float cw[4];
-    cubic_coeffs(rx - fx, cw);
-    wtab[4 * i] = cw[0]; wtab[4 * i + 1] = cw[1]; wtab[4 * i + 2] = cw[2]; wtab[4 * i + 3] = cw[3];
-    c0tab[i] = (int)fx + 1;
-  }
   // vertical weights / rows of this output row
   float wy[4];
   int rowj[4];
@@ -274,7 +312,7 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
       rowj[j] = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
     }
   }
-  // ---- 1. vertical pass (as the forward)
+  // ---- 1. vertical pass (as the forward), once per row; the dVs accumulator starts at zero
   float amax = 0.f;
   {
     const float* rows[4];
@@ -311,104 +349,158 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
         *reinterpret_cast<float4*>(Vs + (s + 3) * NV + n0) = q;
       }
     }
+    for (int i = tid; i < (s + 4) * NV; i += NT) dVs[i] = 0.f;
     amax = warp_max(amax);
     if ((tid & 31) == 0) red[tid >> 5] = amax;
   }
   __syncthreads();
-  // pixel range of every halo'd column (c0tab is non-decreasing in X): pixels with c0 <= c <= c0 + 3
-  for (int c = tid; c < s + 4; c += NT) {
-    int lo = nx, hi = -1;
-    for (int i = 0; i < nx; ++i) {
-      const int d = c - c0tab[i];
-      if (d >= 0 && d <= 3) { lo = min(lo, i); hi = i; }
-    }
-    xrange[2 * c] = lo;
-    xrange[2 * c + 1] = hi;
-  }
   float M = 0.f;
   for (int q = 0; q < (NT >> 5); ++q) M = fmaxf(M, red[q]);
 
-  // ---- 2. horizontal pass: e_n staged, partial (sum e, sum e*g) per token slice; g read coalesced over X from d_maps
-  for (int X0 = 0; X0 < nx; X0 += P) {
-    const int xi = X0 + X_lane;           // local pixel
-    const bool live = xi < nx;
-    const int X = xb0 + xi;
-    float wx[4] = {0.f, 0.f, 0.f, 0.f};
-    int c0 = 1;
-    float U = 0.f, s1 = 0.f, s2 = 0.f;
-    float* orow = stage + (size_t)(live ? xi : 0) * N;
-    const float* grow = d_maps + (size_t)Y * R + (live ? X : 0);     // + n*R*R per token
-    if (live) {
-      c0 = c0tab[xi];
+  for (int xb0 = 0; xb0 < R; xb0 += XB) {
+    const int xb1 = min(R, xb0 + XB), nx = xb1 - xb0;
+    // per-pixel tap tables of this x-block (raw weights: the transposed stencil needs them un-scaled)
+    for (int i = tid; i < nx; i += NT) {
+      float rx = scale * (xb0 + i + 0.5f) - 0.5f, fx = floorf(rx);
+      float cw[4];
+      cubic_coeffs(rx - fx, cw);
+      wtab[4 * i] = cw[0]; wtab[4 * i + 1] = cw[1]; wtab[4 * i + 2] = cw[2]; wtab[4 * i + 3] = cw[3];
+      c0tab[i] = (int)fx + 1;
+    }
+    __syncthreads();
+    // pixel range of every halo'd column (c0tab is non-decreasing in X): pixels with c0 <= c <= c0 + 3
+    for (int c = tid; c < s + 4; c += NT) {
+      int lo = nx, hi = -1;
+      for (int i = 0; i < nx; ++i) {
+        const int d = c - c0tab[i];
+        if (d >= 0 && d <= 3) { lo = min(lo, i); hi = i; }
+      }
+      xrange[2 * c] = lo;
+      xrange[2 * c + 1] = hi;
+    }
+    // ---- 2. horizontal pass: e_n staged, partial (sum e, sum e*g) per token slice; g read coalesced over X from d_maps
+    for (int X0 = 0; X0 < nx; X0 += P) {
+      const int xi = X0 + X_lane;           // local pixel
+      const bool live = xi < nx;
+      const int X = xb0 + xi;
+      float wx[4] = {0.f, 0.f, 0.f, 0.f};
+      int c0 = 1;
+      float U = 0.f, s1 = 0.f, s2 = 0.f;
+      float* orow = stage + (size_t)(live ? xi : 0) * N;
+      const float* grow = d_maps + (size_t)Y * R + (live ? X : 0);     // + n*R*R per token
+      if (live) {
+        c0 = c0tab[xi];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        wx[i] = wtab[4 * xi + i] * LOG2E;
-        U += fabsf(wx[i]);
-      }
-      U *= M;
-      for (int n = n_lo; n < n_hi; ++n) {
-        float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
-                  fmaf(wx[1], Vs[(c0 + 1) * NV + n], fmaf(wx[0], Vs[c0 * NV + n], -U))));
-        float e = ex2_approx(x);
-        orow[n] = e;
-        s1 += e;
-        s2 = fmaf(e, __ldg(grow + (size_t)n * R * R), s2);
-      }
-      psum[part * P + X_lane] = s1;
-      psum[(TS + part) * P + X_lane] = s2;
-    }
-    __syncthreads();
-    if (live) {
-      float t1 = 0.f, t2 = 0.f;
-      for (int q = 0; q < TS; ++q) {
-        t1 += psum[q * P + X_lane];
-        t2 += psum[(TS + q) * P + X_lane];
-      }
-      if (!(t1 > 1e-30f) || !(t1 < 1e30f)) {
-        // loose bound: slice 0 redoes the whole pixel with the exact max
-        if (part == 0) {
-          float m = -CUDART_INF_F;
-          for (int n = 0; n < N; ++n) {
-            float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
-                      fmaf(wx[1], Vs[(c0 + 1) * NV + n], wx[0] * Vs[c0 * NV + n])));
-            orow[n] = x;
-            m = fmaxf(m, x);
-          }
-          float a1 = 0.f, a2 = 0.f;
-          for (int n = 0; n < N; ++n) {
-            float e = exp2f(orow[n] - m);
-            orow[n] = e;
-            a1 += e;
-            a2 = fmaf(e, __ldg(grow + (size_t)n * R * R), a2);
-          }
-          const float inv = 1.f / a1, dot = a2 * inv;
-          for (int n = 0; n < N; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+        for (int i = 0; i < 4; ++i) {
+          wx[i] = wtab[4 * xi + i] * LOG2E;
+          U += fabsf(wx[i]);
         }
-      } else {
-        const float inv = 1.f / t1, dot = t2 * inv;
-        for (int n = n_lo; n < n_hi; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+        U *= M;
+        for (int n = n_lo; n < n_hi; ++n) {
+          float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                    fmaf(wx[1], Vs[(c0 + 1) * NV + n], fmaf(wx[0], Vs[c0 * NV + n], -U))));
+          float e = ex2_approx(x);
+          orow[n] = e;
+          s1 += e;
+          s2 = fmaf(e, __ldg(grow + (size_t)n * R * R), s2);
+        }
+        psum[part * P + X_lane] = s1;
+        psum[(TS + part) * P + X_lane] = s2;
       }
+      __syncthreads();
+      if (live) {
+        float t1 = 0.f, t2 = 0.f;
+        for (int q = 0; q < TS; ++q) {
+          t1 += psum[q * P + X_lane];
+          t2 += psum[(TS + q) * P + X_lane];
+        }
+        if (!(t1 > 1e-30f) || !(t1 < 1e30f)) {
+          // loose bound: slice 0 redoes the whole pixel with the exact max
+          if (part == 0) {
+            float m = -CUDART_INF_F;
+            for (int n = 0; n < N; ++n) {
+              float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
+                        fmaf(wx[1], Vs[(c0 + 1) * NV + n], wx[0] * Vs[c0 * NV + n])));
+              orow[n] = x;
+              m = fmaxf(m, x);
+            }
+            float a1 = 0.f, a2 = 0.f;
+            for (int n = 0; n < N; ++n) {
+              float e = exp2f(orow[n] - m);
+              orow[n] = e;
+              a1 += e;
+              a2 = fmaf(e, __ldg(grow + (size_t)n * R * R), a2);
+            }
+            const float inv = 1.f / a1, dot = a2 * inv;
+            for (int n = 0; n < N; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+          }
+        } else {
+          const float inv = 1.f / t1, dot = t2 * inv;
+          for (int n = n_lo; n < n_hi; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- 3. transposed horizontal stencil as a gather, accumulated over the x-blocks:
+    //         dVs[c][n] += sum_X wx[X][c - c0[X]] * dS[X][n]   (thread <-> (c, n) is the same in every x-block: no race)
+    for (int i = tid; i < (s + 4) * N; i += NT) {
+      const int c = i / N, n = i - c * N;
+      const int lo = xrange[2 * c], hi = xrange[2 * c + 1];
+      float a = 0.f;
+      for (int xi = lo; xi <= hi; ++xi) a = fmaf(wtab[4 * xi + (c - c0tab[xi])], stage[(size_t)xi * N + n], a);
+      dVs[c * NV + n] += a;
     }
     __syncthreads();
   }
-  // ---- 3. transposed horizontal stencil as a gather: dVs[c][n] = sum_X wx[X][c - c0[X]] * dS[X][n]
-  for (int i = tid; i < (s + 4) * N; i += NT) {
-    const int c = i / N, n = i - c * N;
-    const int lo = xrange[2 * c], hi = xrange[2 * c + 1];
-    float a = 0.f;
-    for (int xi = lo; xi <= hi; ++xi) a = fmaf(wtab[4 * xi + (c - c0tab[xi])], stage[(size_t)xi * N + n], a);
-    dVs[c * NV + n] = a;
-  }
-  __syncthreads();
-  // ---- 4. fold the replicated halo columns, transposed vertical stencil: coalesced global atomics
-  float* dl = d_logits + (size_t)h * s * s * N;
+  // ---- 4. fold the replicated halo columns; the row's dV leaves once, coalesced
+  float* dv = dvrow + (((size_t)h * R + Y) * s) * N;
   for (int i = tid; i < s * N; i += NT) {
     const int xs = i / N, n = i - xs * N;
     float v = dVs[(xs + 2) * NV + n];
     if (xs == 0) v += dVs[n] + dVs[NV + n];
     if (xs == s - 1) v += dVs[(s + 2) * NV + n] + dVs[(s + 3) * NV + n];
+    dv[i] = v;
+  }
+}
+
+// d_logits[h, ys, xs, n] += sum over the output rows Y whose (clamped) vertical taps include ys of wy_j(Y) * dV[h, Y, xs, n]
+__global__ void capture_mean_vgather_kernel(const float* __restrict__ dvrow, float* __restrict__ d_logits, int heads, int s, int N,
+                                            int R) {
+  const long total = (long)heads * s * s * N;
+  const float scale = (float)s / (float)R;
+  const int F = (R + s - 1) / s;                       // output rows per low-res row (rounded up)
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    long t = i / N;
+    const int xs = (int)(t % s);
+    t /= s;
+    const int ys = (int)(t % s), h = (int)(t / s);
+    // rows Y with iy = floor(scale*(Y+0.5)-0.5) in [ys-2, ys+1] touch ys un-clamped; at the borders clamping adds more:
+    // scan a conservative window and test the taps exactly as the forward computes them
+    int ylo = (int)floorf(((float)(ys - 2) + 0.5f) / scale - 0.5f) - 1, yhi = (int)ceilf(((float)(ys + 2) + 0.5f) / scale - 0.5f) + 1;
+    if (ys == 0) ylo = 0;
+    if (ys == s - 1) yhi = R - 1;
+    ylo = max(ylo, 0);
+    yhi = min(yhi, R - 1);
+    (void)F;
+    float acc = 0.f;
+    const float* src = dvrow + (((size_t)h * R) * s + xs) * N + n;
+    for (int Y = ylo; Y <= yhi; ++Y) {
+      const float ry = scale * (Y + 0.5f) - 0.5f, fy = floorf(ry);
+      const int iy = (int)fy;
+      if (ys < min(max(iy - 1, 0), s - 1) || ys > min(max(iy + 2, 0), s - 1)) continue;
+      float wyv[4];
+      cubic_coeffs(ry - fy, wyv);
+      float wsum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(dl + ((size_t)rowj[j] * s + xs) * N + n, wy[j] * v);
+      for (int j = 0; j < 4; ++j) {
+        int r = iy - 1 + j;
+        r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
+        if (r == ys) wsum += wyv[j];
+      }
+      acc = fmaf(wsum, __ldg(src + (size_t)Y * s * N), acc);
+    }
+    d_logits[i] += acc;
   }
 }
 
@@ -416,7 +508,6 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
 static int mean_row_bwd_plan(int s, int N, int R, int* NV_out, int* P_out, int* TS_out, size_t* bytes_out) {
   int Np4 = (N + 3) & ~3;
   int NV = ((Np4 >> 2) & 1) ? Np4 : Np4 + 4;
-  const int TS = (N >= 16) ? 2 : 1;
   int XB = R;
   if ((size_t)R * N * sizeof(float) > 100 * 1024) {
     XB = (int)((96 * 1024) / ((size_t)N * sizeof(float)));
@@ -425,6 +516,7 @@ static int mean_row_bwd_plan(int s, int N, int R, int* NV_out, int* P_out, int* 
   for (; XB >= 4; XB = (XB > 32 ? 32 : XB / 2)) {
     int P = ((XB + 31) / 32) * 32;
     if (P > 256) P = 256;
+    const int TS = row_token_slices(N, P);
     size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + 2 * (size_t)(s + 4) * NV + 32 + 2 * (size_t)TS * P + 5 * (size_t)XB +
                     2 * (size_t)(s + 4);
     if (floats * sizeof(float) <= 200 * 1024) {
@@ -441,14 +533,18 @@ bool capture_mean_row_bwd_fits(int s, int N, int R) {
   return mean_row_bwd_plan(s, N, R, &NV, &P, &TS, &bytes) > 0;
 }
 
-// d_logits must be zero-initialised (accumulated over rows / x-blocks / taps).  *handled = false: shape not taken.
-int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, int heads, int s, int N, int R, float w,
-                         cudaStream_t st, bool* handled) {
+// floats of the dV workspace of one layer: [heads, R, s, N]
+size_t capture_mean_row_bwd_workspace(int heads, int s, int N, int R) { return (size_t)heads * R * s * N; }
+
+// d_logits is accumulated into (single writer per element).  workspace: capture_mean_row_bwd_workspace floats.
+// *handled = false: shape not taken.
+int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, float* workspace, int heads, int s, int N, int R,
+                         float w, cudaStream_t st, bool* handled) {
   *handled = false;
   int NV, P, TS;
   size_t bytes;
   const int XB = mean_row_bwd_plan(s, N, R, &NV, &P, &TS, &bytes);
-  if (XB == 0) return SKP_OK;
+  if (XB == 0 || workspace == nullptr) return SKP_OK;
   static size_t configured = 0;
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(capture_mean_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -459,9 +555,14 @@ int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logi
     cudaFuncSetAttribute(capture_mean_row_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = bytes;
   }
-  dim3 grid(R, heads, (R + XB - 1) / XB);
-  capture_mean_row_bwd_kernel<<<grid, P * TS, bytes, st>>>(logits, d_maps, d_logits, s, N, R, NV, P, TS, XB, w);
+  dim3 grid(R, heads);
+  capture_mean_row_bwd_kernel<<<grid, P * TS, bytes, st>>>(logits, d_maps, workspace, s, N, R, NV, P, TS, XB, w);
   SKP_CHECK_LAUNCH("capture_mean_row_bwd");
+  const long total = (long)heads * s * s * N;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  capture_mean_vgather_kernel<<<(int)blocks, 256, 0, st>>>(workspace, d_logits, heads, s, N, R);
+  SKP_CHECK_LAUNCH("capture_mean_vgather");
   *handled = true;
   return SKP_OK;
 }
@@ -483,24 +584,26 @@ int capture_store_row(const float* logits, float* probs, int heads, int s, int N
   if (((size_t)XB * N) % 4 != 0) return SKP_OK;
   int P = ((XB + 31) / 32) * 32;               // pixel lanes (whole warps)
   if (P > 256) P = 256;
-  int TS = (N >= 16) ? 2 : 1;                  // token slices per pixel: 2 x the warps to hide the LDS->FMA->EX2->STS chain
+  int TS = row_token_slices(N, P);             // token slices per pixel: more warps to hide the LDS->FMA->EX2->STS chain
   static const int ts_env = getenv("SKP_ROW_TS") ? atoi(getenv("SKP_ROW_TS")) : 0;   // tuning knob (1, 2 or 4)
   if (ts_env > 0 && N >= 8 * ts_env && P * ts_env <= ROW_MAX_THREADS) TS = ts_env;
   size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + (size_t)(s + 4) * NV + 32 + (size_t)TS * P;
   size_t bytes = floats * sizeof(float);
   if (bytes > 200 * 1024) return SKP_OK;
-  static size_t configured = 0;
-  if (bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(capture_store_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  static size_t configured[2] = {0, 0};
+  const bool one = XB >= R;
+  auto kern = one ? capture_store_row_kernel<true> : capture_store_row_kernel<false>;
+  if (bytes > configured[one]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
       set_error("capture_store_row: smem attr: %s", cudaGetErrorString(e));
       return SKP_ERR_LAUNCH;
     }
-    cudaFuncSetAttribute(capture_store_row_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    configured = bytes;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured[one] = bytes;
   }
-  dim3 grid((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA, heads, (R + XB - 1) / XB);
-  capture_store_row_kernel<<<grid, P * TS, bytes, st>>>(logits, probs, s, N, R, NV, P, TS, XB);
+  dim3 grid((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA, heads);
+  kern<<<grid, P * TS, bytes, st>>>(logits, probs, s, N, R, NV, P, TS, XB);
   SKP_CHECK_LAUNCH("capture_store_row");
   *handled = true;
   return SKP_OK;

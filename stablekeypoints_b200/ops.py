@@ -740,8 +740,10 @@ class _CaptureMean(torch.autograd.Function):
         logits = list(ctx.saved_tensors)
         h, _, n = logits[0].shape
         d_logits = [torch.zeros_like(l) for l in logits]
+        ws = torch.empty(int(lib().skp_capture_mean_bwd_workspace(int_array(ctx.sides), len(logits), h, n, ctx.res)), dtype=torch.uint8,
+                         device=d_maps.device)
         check(lib().skp_capture_mean_bwd(ptr_array(logits), int_array(ctx.sides), len(logits), ptr(_f32c(d_maps)),
-                                         ptr_array(d_logits), h, n, ctx.res, stream()), "skp_capture_mean_bwd")
+                                         ptr_array(d_logits), h, n, ctx.res, ptr(ws), stream()), "skp_capture_mean_bwd")
         return (None, *d_logits)
 
 
