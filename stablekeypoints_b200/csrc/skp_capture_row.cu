@@ -463,18 +463,18 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
   }
 }
 
-// d_logits[h, ys, xs, n] += sum over the output rows Y whose (clamped) vertical taps include ys of wy_j(Y) * dV[h, Y, xs, n]
-__global__ void capture_mean_vgather_kernel(const float* __restrict__ dvrow, float* __restrict__ d_logits, int heads, int s, int N,
-                                            int R) {
-  const long total = (long)heads * s * s * N;
+// d_logits[h, ys, xs, n] += sum over the output rows Y whose (clamped) vertical taps include ys of wy_j(Y) * dV[h, Y, xs, n].
+// CTA = (head, low-res row ys): the (<= VG_MAXW) contributing rows and their summed tap weights are tabulated once in shared
+// memory, then every thread streams its (xs, n) elements: one coalesced load + FMA per contributing row.
+constexpr int VG_MAXW = 96;
+__global__ void __launch_bounds__(256) capture_mean_vgather_kernel(const float* __restrict__ dvrow, float* __restrict__ d_logits,
+                                                                   int s, int N, int R) {
+  __shared__ float wtab[VG_MAXW];
+  __shared__ int ytab[VG_MAXW];
+  __shared__ int cnt;
+  const int ys = blockIdx.x, h = blockIdx.y;
   const float scale = (float)s / (float)R;
-  const int F = (R + s - 1) / s;                       // output rows per low-res row (rounded up)
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int n = (int)(i % N);
-    long t = i / N;
-    const int xs = (int)(t % s);
-    t /= s;
-    const int ys = (int)(t % s), h = (int)(t / s);
+  if (threadIdx.x == 0) {
     // rows Y with iy = floor(scale*(Y+0.5)-0.5) in [ys-2, ys+1] touch ys un-clamped; at the borders clamping adds more:
     // scan a conservative window and test the taps exactly as the forward computes them
     int ylo = (int)floorf(((float)(ys - 2) + 0.5f) / scale - 0.5f) - 1, yhi = (int)ceilf(((float)(ys + 2) + 0.5f) / scale - 0.5f) + 1;
@@ -482,25 +482,34 @@ __global__ void capture_mean_vgather_kernel(const float* __restrict__ dvrow, flo
     if (ys == s - 1) yhi = R - 1;
     ylo = max(ylo, 0);
     yhi = min(yhi, R - 1);
-    (void)F;
-    float acc = 0.f;
-    const float* src = dvrow + (((size_t)h * R) * s + xs) * N + n;
+    int c = 0;
     for (int Y = ylo; Y <= yhi; ++Y) {
       const float ry = scale * (Y + 0.5f) - 0.5f, fy = floorf(ry);
       const int iy = (int)fy;
-      if (ys < min(max(iy - 1, 0), s - 1) || ys > min(max(iy + 2, 0), s - 1)) continue;
       float wyv[4];
       cubic_coeffs(ry - fy, wyv);
       float wsum = 0.f;
+      bool hit = false;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int r = iy - 1 + j;
         r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
-        if (r == ys) wsum += wyv[j];
+        if (r == ys) { wsum += wyv[j]; hit = true; }
       }
-      acc = fmaf(wsum, __ldg(src + (size_t)Y * s * N), acc);
+      if (hit && c < VG_MAXW) { wtab[c] = wsum; ytab[c] = Y; ++c; }
     }
-    d_logits[i] += acc;
+    cnt = c;
+  }
+  __syncthreads();
+  const int nrows = cnt;
+  const size_t row_stride = (size_t)s * N;                      // floats between consecutive output rows of dV
+  const float* src = dvrow + (size_t)h * R * row_stride;
+  float* dst = d_logits + ((size_t)h * s + ys) * row_stride;
+  const int total = s * N;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    float acc = 0.f;
+    for (int k = 0; k < nrows; ++k) acc = fmaf(wtab[k], __ldg(src + (size_t)ytab[k] * row_stride + i), acc);
+    dst[i] += acc;
   }
 }
 
@@ -530,7 +539,7 @@ static int mean_row_bwd_plan(int s, int N, int R, int* NV_out, int* P_out, int* 
 bool capture_mean_row_bwd_fits(int s, int N, int R) {
   int NV, P, TS;
   size_t bytes;
-  return mean_row_bwd_plan(s, N, R, &NV, &P, &TS, &bytes) > 0;
+  return mean_row_bwd_plan(s, N, R, &NV, &P, &TS, &bytes) > 0 && 4 * ((R + s - 1) / s) + 8 <= 96;
 }
 
 // floats of the dV workspace of one layer: [heads, R, s, N]
@@ -544,7 +553,8 @@ int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logi
   int NV, P, TS;
   size_t bytes;
   const int XB = mean_row_bwd_plan(s, N, R, &NV, &P, &TS, &bytes);
-  if (XB == 0 || workspace == nullptr) return SKP_OK;
+  // every low-res row is touched by <= 4 * ceil(R / s) + a few output rows (more only when down-sampling, R < s)
+  if (XB == 0 || workspace == nullptr || 4 * ((R + s - 1) / s) + 8 > VG_MAXW) return SKP_OK;
   static size_t configured = 0;
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(capture_mean_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -558,10 +568,7 @@ int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logi
   dim3 grid(R, heads);
   capture_mean_row_bwd_kernel<<<grid, P * TS, bytes, st>>>(logits, d_maps, workspace, s, N, R, NV, P, TS, XB, w);
   SKP_CHECK_LAUNCH("capture_mean_row_bwd");
-  const long total = (long)heads * s * s * N;
-  long blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  capture_mean_vgather_kernel<<<(int)blocks, 256, 0, st>>>(workspace, d_logits, heads, s, N, R);
+  capture_mean_vgather_kernel<<<dim3(s, heads), 256, 0, st>>>(workspace, d_logits, s, N, R);
   SKP_CHECK_LAUNCH("capture_mean_vgather");
   *handled = true;
   return SKP_OK;
