@@ -245,6 +245,8 @@ int skp_k_argmax(const float* maps, int T, int H, int W, int num, float* work, i
  * peaks[num, T] are flat arg-max indices (num_subjects of them; the target is their mean). */
 int skp_gaussian_kl_scores(const float* maps, int T, int H, int W, const int64_t* peaks, int num,
                            float sigma, float eps, float* kl, void* stream);
+/* ptp_utils.py:165-187 entropy_sort (--top_k_strategy entropy): entropy of softmax-over-pixels of each [P] map. */
+int skp_entropy_scores(const float* maps, int T, int P, float* ent, void* stream);
 /* ptp_utils.py:110-112: ascending arg-sort of T scores (stable), first top_k indices. */
 int skp_argsort_topk(const float* scores, int T, int top_k, int64_t* out_idx, void* stream);
 /* ptp_utils.py:115-159 furthest_point_sampling on arg-max locations (flat indices of the maps it is

@@ -187,6 +187,14 @@ def find_top_k_gaussian(maps: torch.Tensor, top_k: int, sigma: float = 3, epsilo
     return torch.argsort(gaussian_kl_scores(maps, sigma, epsilon, num_subjects), dim=-1, descending=False)[:top_k]
 
 
+def entropy_sort(maps: torch.Tensor, top_k: int) -> torch.Tensor:
+    """ptp_utils.py:165-187 -- ascending entropy of softmax-over-pixels (Categorical(probs).entropy()), first top_k."""
+    t = maps.shape[0]
+    p = torch.softmax(maps.reshape(t, -1), dim=-1)
+    ent = torch.distributions.Categorical(probs=p).entropy()
+    return torch.argsort(ent, dim=-1, descending=False)[:top_k]
+
+
 def furthest_point_sampling(maps: torch.Tensor, top_k: int, candidates: torch.Tensor) -> torch.Tensor:
     """ptp_utils.py:115-159 -- furthest pair among candidates (strict '>' so the first maximum in
     (i<j) lexicographic order wins, :135), then greedy max-min-distance (strict '>', :152)."""

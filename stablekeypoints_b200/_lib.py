@@ -74,6 +74,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_argmax_rows": [_P, _I, _I, _P, _P],
     "skp_k_argmax": [_P, _I, _I, _I, _I, _P, _P, _P],
     "skp_gaussian_kl_scores": [_P, _I, _I, _I, _P, _I, _F, _F, _P, _P],
+    "skp_entropy_scores": [_P, _I, _I, _P, _P],
     "skp_argsort_topk": [_P, _I, _I, _P, _P],
     "skp_furthest_point_sampling": [_P, _I, _I, _P, _I, _I, _P, _P, _P],
     "skp_sharpen_loss_fwd": [_P, _I, _I, _P, _I, _P, _I, _F, _P, _P],

@@ -247,6 +247,43 @@ extern "C" int skp_k_argmax(const float* maps, int T, int H, int W, int num, flo
   return SKP_OK;
 }
 
+// ptp_utils.py:165-187 entropy_sort: entropy of softmax-over-pixels of every token map,
+//   H = lse - sum_i softmax_i * m_i   (== -sum p log p), one CTA per token, three block reductions.
+__global__ void __launch_bounds__(512) entropy_kernel(const float* __restrict__ maps, int P, float* __restrict__ ent) {
+  __shared__ float red[32];
+  const float* m = maps + (size_t)blockIdx.x * P;
+  float mx = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) mx = fmaxf(mx, m[i]);
+  mx = warp_max(mx);
+  {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = mx;
+    __syncthreads();
+    float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -CUDART_INF_F;
+    r = warp_max(r);
+    __syncthreads();
+    if (threadIdx.x == 0) red[0] = r;
+    __syncthreads();
+    mx = red[0];
+  }
+  float se = 0.f, sm = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float e = expf(m[i] - mx);
+    se += e;
+    sm = fmaf(e, m[i], sm);
+  }
+  se = block_sum(se, red);
+  sm = block_sum(sm, red);
+  if (threadIdx.x == 0) ent[blockIdx.x] = (mx + logf(se)) - sm / se;
+}
+
+extern "C" int skp_entropy_scores(const float* maps, int T, int P, float* ent, void* stream) {
+  SKP_REQUIRE(maps && ent && T > 0 && P > 0, "entropy_scores: bad arguments");
+  entropy_kernel<<<T, 512, 0, (cudaStream_t)stream>>>(maps, P, ent);
+  SKP_CHECK_LAUNCH("entropy");
+  return SKP_OK;
+}
+
 extern "C" int skp_gaussian_kl_scores(const float* maps, int T, int H, int W, const int64_t* peaks, int num,
                                       float sigma, float eps, float* kl, void* stream) {
   SKP_REQUIRE(maps && peaks && kl && T > 0 && H > 0 && W > 0 && num > 0 && sigma > 0.f, "gaussian_kl_scores: bad arguments");

@@ -822,6 +822,16 @@ def gaussian_kl_scores(maps: torch.Tensor, peaks: torch.Tensor, sigma: float, ep
     return kl
 
 
+def entropy_scores(maps: torch.Tensor) -> torch.Tensor:
+    """Entropy of softmax-over-pixels of every token map (ptp_utils.py:178-181) -> fp32 [T]."""
+    require_cuda(maps)
+    maps = _f32c(maps.detach())
+    t = maps.shape[0]
+    ent = torch.empty(t, dtype=torch.float32, device=maps.device)
+    check(lib().skp_entropy_scores(ptr(maps), t, maps[0].numel(), ptr(ent), stream()), "skp_entropy_scores")
+    return ent
+
+
 def argsort_topk(scores: torch.Tensor, top_k: int) -> torch.Tensor:
     require_cuda(scores)
     scores = _f32c(scores)

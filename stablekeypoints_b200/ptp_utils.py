@@ -94,10 +94,7 @@ def furthest_point_sampling(attention_maps, top_k, top_initial_candidates):
 
 def entropy_sort(attention_maps, top_k, min_dist=0.05):
     """ptp_utils.py:165-187 (non-default --top_k_strategy entropy): ascending entropy of softmax-over-pixels."""
-    t = attention_maps.shape[0]
-    p = torch.softmax(attention_maps.detach().reshape(t, -1).float(), dim=-1)
-    ent = -(p * torch.log(p.clamp_min(torch.finfo(p.dtype).tiny))).sum(-1)
-    return ops.argsort_topk(ent, top_k)
+    return ops.argsort_topk(ops.entropy_scores(attention_maps), top_k)
 
 
 # ----------------------------------------------------------------------------- capture registration

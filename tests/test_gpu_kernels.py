@@ -494,6 +494,19 @@ def test_selection_golden(ops):
     assert np.array_equal(allc.cpu().numpy(), post["fps_all_candidates"])
 
 
+def test_entropy_sort_vs_oracle(ops):
+    """--top_k_strategy entropy (ptp_utils.py:165-187): entropies to 1e-5, the ascending order bit-exact on separated maps."""
+    from stablekeypoints_b200 import ptp_utils
+    g = torch.Generator().manual_seed(4)
+    maps = torch.rand(77, 128, 128, generator=g) * torch.linspace(0.5, 12.0, 77).reshape(77, 1, 1)
+    maps = maps[torch.randperm(77, generator=g)]
+    p = torch.softmax(maps.reshape(77, -1).double(), -1)
+    want = -(p * p.log()).sum(-1)
+    got = ops.entropy_scores(cu(maps))
+    assert rel_err(got.cpu(), want) < 1e-5
+    assert np.array_equal(ptp_utils.entropy_sort(cu(maps), 25).cpu().numpy(), hp.entropy_sort(maps, 25).numpy())
+
+
 @pytest.mark.parametrize("t,h,seed", [(77, 128, 0), (500, 128, 1), (10, 512, 2), (25, 33, 3)])
 def test_selection_vs_oracle_full_size(ops, t, h, seed):
     from stablekeypoints_b200 import ptp_utils
