@@ -49,8 +49,11 @@ int skp_gemm_nt_simt(const float* A, int64_t lda, const float* B, int64_t ldb, f
  * cols_pad >= cols is a multiple of 64 and the pad is zero-filled. */
 int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, int cols_pad, void* hi, void* lo,
                    void* stream);
-/* splits > 1 runs split-K over blockIdx.z (partial sums in splitk_ws[splits*M*N], then one reduce+epilogue
- * kernel); skp_gemm_nt_tc_plan returns the split count that fills the 148 SMs for a given problem. */
+/* Split-K for the small-M layers that cannot fill 148 SMs.  splits == 0 (the product's setting): the library plans the
+ * K-splits; the splits of one output tile are the CTAs of one thread-block cluster (<= 8) that reduce their partial tiles
+ * through distributed shared memory in rank order inside the same kernel -- no workspace (splitk_ws may be NULL), no second
+ * launch, bit-reproducible.  splits == 1: no split.  splits > 1: the older path for A/B measurements, partial sums in
+ * splitk_ws[splits*M*N] then one reduce+epilogue kernel; skp_gemm_nt_tc_plan returns the planner's split count. */
 int skp_gemm_nt_tc_plan(int M, int N, int Kpad);
 /* Tuning hook: force the N tile (64/96/128/160/256; 0 = planner) of skp_gemm_nt_tc / skp_conv3x3_tc (scripts/gemm_sweep.py). */
 void skp_gemm_tc_force_bn(int bn);
@@ -182,8 +185,9 @@ int skp_cross_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_
                           const float* d_logits_extra, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
                           int64_t lddv, int S, int N, int heads, int d, float scale, void* stream);
 
-/* Kernel selection switch for tests and A/B measurements: row formulation (1, default) or the tile kernels it falls back
- * to (0) for the attn-store forward / the fused capture+collect backward; -1 leaves a setting unchanged. */
+/* Kernel selection switch for tests and A/B measurements.  row_fwd (attn-store forward): 2 (default) register formulation
+ * (skp_capture_store.cu), 1 row formulation (skp_capture_row.cu), 0 the tile kernel they fall back to.  row_bwd (fused
+ * capture+collect backward): 1 (default) row formulation, 0 tile kernel.  -1 leaves a setting unchanged. */
 void skp_capture_select(int row_fwd, int row_bwd);
 /* The tcgen05 formulation of the attn-store / fused capture+collect forward (skp_capture_tc.cu: the horizontal bicubic pass
  * is an M128 x N=tokens x K=s GEMM per output row, the softmax runs thread-per-pixel on the TMEM lanes, the row leaves

@@ -35,9 +35,9 @@ def main():
     heads = int(os.environ.get("SAN_HEADS", "2"))
     res = int(os.environ.get("SAN_RES", "64"))
     worst = 0.0
-    for row in (2, 1, 0):                 # 2: tcgen05 kernels forced where eligible; 1: SIMT row kernels; 0: SIMT tile kernels
-        lib().skp_capture_tc(2 if row == 2 else 0)
-        lib().skp_capture_select(1 if row else 0, 1 if row else 0)
+    for row in (3, 2, 1, 0):   # 3: tcgen05 kernels forced where eligible; 2: register store kernel + row backward; 1: SIMT row kernels; 0: tile kernels
+        lib().skp_capture_tc(2 if row == 3 else 0)
+        lib().skp_capture_select(min(row, 2), 1 if row else 0)
         ops.CAPTURE_MEAN_FWD = "store" if row else "fused"
         for n in (77, 100, 500):
             for scale, shift in ((3.0, 0.0), (3.0, -60.0), (40.0, 0.0)):
@@ -60,7 +60,7 @@ def main():
                 worst = max(worst, max(errs))
                 print(f"row={row} N={n} scale={scale} shift={shift}: finite={finite} errs=" + " ".join(f"{e:.1e}" for e in errs), flush=True)
                 assert finite and max(errs) < 1e-3, errs
-    lib().skp_capture_select(1, 1)
+    lib().skp_capture_select(2, 1)
     lib().skp_capture_tc(1)
     print(f"SANITIZE_CASES_OK worst_rel_err={worst:.2e}")
 

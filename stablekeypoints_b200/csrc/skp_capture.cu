@@ -412,6 +412,8 @@ static int launch_ty(CapParams& p, cudaStream_t st, bool* fits) {
 
 // skp_capture_row.cu: the row-per-CTA attn-store kernel (any R, s; needs the row + footprint to fit shared memory)
 int capture_store_row(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled);
+// skp_capture_store.cu: the register formulation of the same kernel (exponentials never re-read from shared memory)
+int capture_store_reg(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled);
 int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logits, float* workspace, int heads, int s, int N, int R,
                          float w, cudaStream_t st, bool* handled);
 bool capture_mean_row_bwd_fits(int s, int N, int R);
@@ -425,13 +427,19 @@ void capture_tc_enable(int on);
 void capture_tc_debug(long long* buf);
 
 // kernel selection switches (tests / A-B measurements): initial value from the environment, skp_capture_select() at run time
-static int g_row_fwd = (getenv("SKP_CAPTURE_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_ROW")) == 0) ? 0 : 1;
+// forward store: 2 = register kernel (skp_capture_store.cu), 1 = row kernel (skp_capture_row.cu), 0 = tile kernel
+static int g_row_fwd = getenv("SKP_CAPTURE_ROW") != nullptr ? atoi(getenv("SKP_CAPTURE_ROW")) : 2;
 static int g_row_bwd = (getenv("SKP_CAPTURE_BWD_ROW") != nullptr && atoi(getenv("SKP_CAPTURE_BWD_ROW")) == 0) ? 0 : 1;
 
 template <bool STORE, bool BWD>
 static int launch(CapParams& p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (STORE && !BWD) {
+    if (g_row_fwd >= 2) {
+      bool handled = false;
+      int rr = capture_store_reg(p.logits[0], p.out, p.heads, p.s[0], p.N, p.R, st, &handled);
+      if (rr != SKP_OK || handled) return rr;
+    }
     if (g_row_fwd) {
       bool handled = false;
       int rr = capture_store_row(p.logits[0], p.out, p.heads, p.s[0], p.N, p.R, st, &handled);
@@ -506,7 +514,7 @@ extern "C" int skp_capture_mean_tc_fwd(const float* const* logits, const int* s,
 }
 
 extern "C" void skp_capture_select(int row_fwd, int row_bwd) {
-  if (row_fwd >= 0) g_row_fwd = row_fwd != 0;
+  if (row_fwd >= 0) g_row_fwd = row_fwd;
   if (row_bwd >= 0) g_row_bwd = row_bwd != 0;
 }
 

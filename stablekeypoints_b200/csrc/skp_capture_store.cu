@@ -1,0 +1,415 @@
+// Attention-store kernel, register formulation (forward, STORE): ptp_utils.py:508-538 by linearity (see skp_capture.cu):
+//   probs[h, Y*R + X, :] = softmax_tokens( bicubic(logits[h])(Y, X, :) )
+// Same data flow as the row kernel of skp_capture_row.cu (vertical pass into shared memory, horizontal pass + softmax per
+// pixel, finished pixels leave shared memory through bulk asynchronous copies), rebuilt after two ncu passes on BASELINE
+// cfg5's shape (20 heads, 32x32 -> 256x256, 77 tokens, a 404 MB store): the row kernel issued 0.92 warp instructions per
+// output element (29 per lane) and, once those were gone, spent 40 % of its stall samples in the vertical pass (L2 latency
+// of the source rows + everybody waiting at the barrier behind it).  Here
+//   * the four low-res source rows of a CTA's output rows arrive in shared memory through the copy engine (cp.async.bulk +
+//     mbarrier) while the CTA builds its per-pixel tap table; the vertical pass of BOTH output rows of the CTA (they share
+//     their source rows when R/s is a multiple of 4) then runs out of shared memory, once;
+//   * a thread = (pixel X, slice of the token axis) keeps its PER float4 groups of exponentials in REGISTERS between the
+//     exponential and the normalisation (fully unrolled, immediate-offset addressing, no predicates: token padding of the
+//     vertical tile is a large negative number whose exponential is exactly 0): per element one 128-bit shared load per 4
+//     tokens and column (broadcast across the lanes that share a source column), 4 FMA, 1 EX2, 1 add, 1 multiply and one
+//     conflict-free shared store -- the staged row is written once, already normalised;
+//   * the 32 pixels of a warp-column (TS warps, one per token slice) form a GROUP with its own named barrier and its own
+//     bulk store of 32*N*4 contiguous bytes: groups never wait for each other inside the x-block loop, and the wait for a
+//     group's previous copy sits right before its staging segment is overwritten;
+//   * two CTAs of 512 threads share an SM.
+// Pixels whose cheap exponent bound under-flows the sum (pathological logits) are redone with the exact maximum, as in the
+// row kernel.  Shapes this kernel does not take (rows that are not 16-byte multiples, token axes beyond 8*16 float4 groups)
+// fall through to skp_capture_row.cu.
+#include "skp_common.cuh"
+#include <math_constants.h>
+
+namespace skp {
+
+namespace {
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void group_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+constexpr int FS_THREADS = 512;
+constexpr int FS_ROWS = 2;           // consecutive output rows per unit (one vertical pass when they share their source rows)
+static_assert(FS_ROWS == 2, "the vertical pass selects between two rows");
+constexpr float FS_PAD = -1.0e4f;    // token padding of the vertical tile: exp2(pad * log2(e) - U) == 0 exactly
+
+struct FsPlan {
+  int NV, P, TS, per, threads, rows, raw;
+  size_t stage_floats, bytes;
+};
+
+// PER = float4 token groups per slice (every slice computes PER groups; groups past the token axis read the padding and
+// contribute exact zeros), VEC4 = the token axis is a multiple of 4 (128-bit staging stores), RAW = the source rows are
+// staged in shared memory by the copy engine (else read through L1 with 128-bit loads).
+template <int PER, bool VEC4, bool RAW>
+__global__ void __launch_bounds__(FS_THREADS, 2)
+capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ probs, int s, int N, int R, int NV, int P, int TS,
+                         int rows_per_cta, int stage_floats, int pad_shift) {
+  extern __shared__ __align__(16) unsigned char fs_smem[];
+  const int vs_floats = (s + 4) * NV;
+  const int row_floats = s * N;                                      // one low-res source row [s][N], contiguous
+  float* stage = reinterpret_cast<float*>(fs_smem);                  // [P][N]: an x-block of the output row, global layout
+  float* raw = stage + stage_floats;                                 // RAW: [4][s*N] source rows (iy-1 .. iy+2, clamped)
+  float* Vs = raw + (RAW ? 4 * row_floats : 0);                      // [rows_per_cta][s+4][NV] vertically interpolated logits (+ halos)
+  float4* wtab = reinterpret_cast<float4*>(Vs + (size_t)rows_per_cta * vs_floats);   // [R] horizontal taps * log2(e)
+  float* utab = reinterpret_cast<float*>(wtab + R);                  // [R] sum |taps| * log2(e)
+  int* ctab = reinterpret_cast<int*>(utab + R);                      // [R] first (halo'd) source column
+  float* red = reinterpret_cast<float*>(ctab + R);                   // [FS_ROWS][32]
+  float* psum = red + FS_ROWS * 32;                                  // [TS][P]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(psum + TS * P);       // RAW: arrival of the source rows
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const float scale = (float)s / (float)R;
+  const int X_lane = tid % P, part = tid / P;
+  const int pg = X_lane >> 5;                                        // pixel group (32 lanes x TS slices) and its named barrier
+  const int Gfull = N >> 2;                                          // whole float4 token groups
+  const int tail_valid = N & 3;                                      // tokens of the partial group Gfull (0: none)
+  const int g0 = part * PER;
+  const int NV4 = NV >> 2;
+  const int nwarps = NT >> 5;
+  const int gcount = TS * 32;                                         // threads of a pixel group
+  const bool issuer = part == 0 && lane == 0;                         // drives the group's bulk copies
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+  const uint32_t row_bytes = (uint32_t)row_floats * 4u;
+  auto issue_raw = [&](int h, int iy) {                               // one thread: four bulk loads completing on the barrier
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * row_bytes) : "memory");
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = iy - 1 + j;
+      r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
+      const char* src = reinterpret_cast<const char*>(logits + ((size_t)h * s + r) * row_floats);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw + (size_t)j * row_floats);
+      for (uint32_t off = 0; off < row_bytes; off += 16384u) {
+        const uint32_t nb = row_bytes - off < 16384u ? row_bytes - off : 16384u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                     "l"(src + off), "r"(nb), "r"(bar)
+                     : "memory");
+      }
+    }
+  };
+  // one unit = (head, rows_per_cta consecutive output rows sharing their four source rows iy-1 .. iy+2, clamped)
+  const int h = blockIdx.y;
+  const int Y0 = blockIdx.x * rows_per_cta;
+  const int iy = (int)floorf(scale * (Y0 + 0.5f) - 0.5f);
+  const int nrows = min(rows_per_cta, R - Y0);
+  if (RAW && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue_raw(h, iy);
+  }
+  // ---- once per CTA: per-pixel horizontal taps; token padding of the vertical tiles
+  for (int X = tid; X < R; X += NT) {
+    float rx = scale * (X + 0.5f) - 0.5f, fx = floorf(rx);
+    float w[4];
+    cubic_coeffs(rx - fx, w);
+    const float L2E = 1.4426950408889634f;
+    wtab[X] = make_float4(w[0] * L2E, w[1] * L2E, w[2] * L2E, w[3] * L2E);
+    utab[X] = (fabsf(w[0]) + fabsf(w[1]) + fabsf(w[2]) + fabsf(w[3])) * L2E;
+    ctab[X] = (int)fx + 1;                                           // column of tap 0 in the halo'd array (ix - 1 + 2)
+  }
+  for (int i = tid; i < (rows_per_cta * (s + 4)) << pad_shift; i += NT) {   // (column, padding token) without a division
+    const int c = i >> pad_shift, k = i & ((1 << pad_shift) - 1);
+    if (N + k < NV) Vs[c * NV + N + k] = FS_PAD;
+  }
+  __syncthreads();                                                    // barrier object, tables and padding are published
+  bool store_pending = false;
+  if (RAW) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "FS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra FS_DONE;\n\t"
+        "bra FS_WAIT;\n\t"
+        "FS_DONE:\n\t"
+        "}" ::"r"(bar), "r"(0u)
+        : "memory");
+  }
+  // ---- 1. vertical pass of all rows of the CTA: 128-bit reads of the four source rows, scattered into the padded tiles
+  {
+    float wy[FS_ROWS][4];
+    float amax[FS_ROWS];
+#pragma unroll
+    for (int rr = 0; rr < FS_ROWS; ++rr) {
+      const float ry = scale * (Y0 + rr + 0.5f) - 0.5f;
+      cubic_coeffs(ry - (float)iy, wy[rr]);                           // rows of a CTA share floor(ry) (host-checked)
+      amax[rr] = 0.f;
+    }
+    const float invN = 1.f / (float)N;
+    const int items = row_floats >> 2;
+    const float4* src[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (RAW) {
+        src[j] = reinterpret_cast<const float4*>(raw + j * row_floats);
+      } else {
+        int r = iy - 1 + j;
+        r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
+        src[j] = reinterpret_cast<const float4*>(logits + ((size_t)h * s + r) * row_floats);
+      }
+    }
+    const float4 *src0 = src[0], *src1 = src[1], *src2 = src[2], *src3 = src[3];
+    for (int i = tid; i < items; i += NT) {
+      float4 a, b, c, d;
+      if (RAW) { a = src0[i]; b = src1[i]; c = src2[i]; d = src3[i]; }
+      else { a = __ldg(src0 + i); b = __ldg(src1 + i); c = __ldg(src2 + i); d = __ldg(src3 + i); }
+      const int f = i << 2;
+      const int xs = (int)((f + 0.5f) * invN);                        // f / N (the quotient is never within 0.5/N of an integer)
+      const int n = f - xs * N;
+      const int kw = N - n;                                           // elements k >= kw belong to the next column (one wrap at most)
+      const bool edge = xs == 0 || xs >= s - 2;
+#pragma unroll
+      for (int rr = 0; rr < FS_ROWS; ++rr) {
+        if (rr < nrows) {
+          const float* w = wy[rr];
+          float v[4];
+          v[0] = fmaf(w[3], d.x, fmaf(w[2], c.x, fmaf(w[1], b.x, w[0] * a.x)));
+          v[1] = fmaf(w[3], d.y, fmaf(w[2], c.y, fmaf(w[1], b.y, w[0] * a.y)));
+          v[2] = fmaf(w[3], d.z, fmaf(w[2], c.z, fmaf(w[1], b.z, w[0] * a.z)));
+          v[3] = fmaf(w[3], d.w, fmaf(w[2], c.w, fmaf(w[1], b.w, w[0] * a.w)));
+          amax[rr] = fmaxf(fmaxf(amax[rr], fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
+          float* V = Vs + rr * vs_floats;
+          float* d0 = V + (xs + 2) * NV + n;
+          float* d1 = d0 + (NV - N);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) (k < kw ? d0 : d1)[k] = v[k];
+          if (edge) {                                                 // replicated halo columns: the horizontal taps never clamp
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int col = xs + (k >= kw ? 1 : 0), nn = n + k - (k >= kw ? N : 0);
+              if (col == 0) {
+                V[nn] = v[k];
+                V[NV + nn] = v[k];
+              } else if (col == s - 1) {
+                V[(s + 2) * NV + nn] = v[k];
+                V[(s + 3) * NV + nn] = v[k];
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < FS_ROWS; ++rr) {
+      const float m = warp_max(amax[rr]);
+      if (lane == 0) red[rr * 32 + (tid >> 5)] = m;
+    }
+  }
+  __syncthreads();                                                    // vertical tiles are published
+
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int Y = Y0 + rr;
+    const float M = warp_max(lane < nwarps ? red[rr * 32 + lane] : 0.f);   // max |V| of the row: x_n <= (sum_i |wx_i|) * M
+    const float4* V4 = reinterpret_cast<const float4*>(Vs + rr * vs_floats);
+    for (int xb0 = 0; xb0 < R; xb0 += P) {
+      if (xb0 + 32 * pg >= R) break;                                  // this group has no pixels in the (last, partial) x-block
+      const int X = xb0 + X_lane;
+      const bool live = X < R;
+      // ---- 2. horizontal pass + exponentials, kept in registers
+      float4 e[PER];
+      float4 wx = make_float4(0.f, 0.f, 0.f, 0.f);
+      int c0 = 1;
+      if (live) {
+        wx = wtab[X];
+        c0 = ctab[X];
+        const float U = utab[X] * M;
+        const float4* v0 = V4 + (size_t)c0 * NV4 + g0;
+        const float4* v1 = v0 + NV4;
+        const float4* v2 = v1 + NV4;
+        const float4* v3 = v2 + NV4;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const float4 a = v0[i], b = v1[i], c = v2[i], d = v3[i];
+          float4 q;
+          q.x = ex2f(fmaf(wx.w, d.x, fmaf(wx.z, c.x, fmaf(wx.y, b.x, fmaf(wx.x, a.x, -U)))));
+          q.y = ex2f(fmaf(wx.w, d.y, fmaf(wx.z, c.y, fmaf(wx.y, b.y, fmaf(wx.x, a.y, -U)))));
+          q.z = ex2f(fmaf(wx.w, d.z, fmaf(wx.z, c.z, fmaf(wx.y, b.z, fmaf(wx.x, a.z, -U)))));
+          q.w = ex2f(fmaf(wx.w, d.w, fmaf(wx.z, c.w, fmaf(wx.y, b.w, fmaf(wx.x, a.w, -U)))));
+          e[i] = q;
+          sum += (q.x + q.y) + (q.z + q.w);
+        }
+        psum[part * P + X_lane] = sum;
+      }
+      if (issuer && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the group's segment is free
+      group_bar(1 + pg, gcount);
+      // ---- 3. normalise out of the registers into the staging tile (global layout of the x-block)
+      if (live) {
+        float total = 0.f;
+        for (int q = 0; q < TS; ++q) total += psum[q * P + X_lane];
+        float* orow = stage + (size_t)X_lane * N;
+        if (!(total > 1e-30f) || !(total < 1e30f)) {
+          // the bound was too loose (or not finite): slice 0 redoes the whole pixel with the exact max, the others stand by
+          if (part == 0) {
+            const float* vs0 = Vs + rr * vs_floats + (size_t)c0 * NV;
+            float m = -CUDART_INF_F;
+            for (int n = 0; n < N; ++n) {
+              float x = fmaf(wx.w, vs0[3 * NV + n], fmaf(wx.z, vs0[2 * NV + n], fmaf(wx.y, vs0[NV + n], wx.x * vs0[n])));
+              orow[n] = x;
+              m = fmaxf(m, x);
+            }
+            float t = 0.f;
+            for (int n = 0; n < N; ++n) {
+              float ee = exp2f(orow[n] - m);
+              orow[n] = ee;
+              t += ee;
+            }
+            const float inv = 1.f / t;
+            for (int n = 0; n < N; ++n) orow[n] *= inv;
+          }
+        } else {
+          const float inv = 1.f / total;
+          float* o = orow + 4 * g0;
+          if (g0 + PER <= Gfull) {                                    // every group of this slice is whole (warp-uniform)
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+              const float4 q = e[i];
+              if (VEC4) {
+                *reinterpret_cast<float4*>(o + 4 * i) = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+              } else {
+                o[4 * i] = q.x * inv;
+                o[4 * i + 1] = q.y * inv;
+                o[4 * i + 2] = q.z * inv;
+                o[4 * i + 3] = q.w * inv;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+              const float4 q = e[i];
+              const int g = g0 + i;
+              if (g < Gfull) {
+                if (VEC4) {
+                  *reinterpret_cast<float4*>(o + 4 * i) = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+                } else {
+                  o[4 * i] = q.x * inv;
+                  o[4 * i + 1] = q.y * inv;
+                  o[4 * i + 2] = q.z * inv;
+                  o[4 * i + 3] = q.w * inv;
+                }
+              } else if (!VEC4 && g == Gfull) {                       // the partial group: only its tail_valid tokens exist
+                if (tail_valid > 0) o[4 * i] = q.x * inv;
+                if (tail_valid > 1) o[4 * i + 1] = q.y * inv;
+                if (tail_valid > 2) o[4 * i + 2] = q.z * inv;
+              }
+            }
+          }
+        }
+      }
+      // ---- bulk store of the group's 32 pixels: generic-proxy writes -> async proxy, then one thread drives the copy engine
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      group_bar(1 + pg, gcount);
+      if (issuer) {
+        const int x0 = xb0 + 32 * pg;
+        const int npx = min(32, R - x0);
+        const uint32_t bytes = (uint32_t)((size_t)npx * N * sizeof(float));
+        char* dst = reinterpret_cast<char*>(probs + (((size_t)h * R + Y) * R + x0) * N);
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage + (size_t)(32 * pg) * N);
+        for (uint32_t off = 0; off < bytes; off += 16384u) {
+          const uint32_t nb = bytes - off < 16384u ? bytes - off : 16384u;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src + off), "r"(nb)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        store_pending = true;
+      }
+    }   // x-blocks of the row
+  }     // rows of this CTA
+  if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the engine's reads
+}
+
+bool fs_plan(int s, int N, int R, FsPlan* pl) {
+  if (N < 4 || s < 2 || R < 1) return false;
+  if (((size_t)s * N) % 4 != 0) return false;                        // flat 128-bit source rows
+  const int G = (N + 3) / 4;
+  int TS = 1;
+  while (TS < 16 && (G + TS - 1) / TS > 8) TS <<= 1;
+  if ((G + TS - 1) / TS > 8) return false;
+  if (TS < 4 && G >= 16) TS = 4;                                      // N = 77: 5 groups per slice, two x-blocks per 256-pixel row
+  int P = FS_THREADS / TS;
+  const int Rp = ((R + 31) / 32) * 32;
+  if (P > Rp) P = Rp;
+  if (P > 256) P = 256;
+  if (P / 32 > 15) return false;                                      // one named barrier per pixel group (ids 1..15)
+  if (((size_t)R * N) % 4 != 0) return false;                         // every group segment (32 pixels, or the row's tail) is a 16-byte multiple
+  pl->per = (G + TS - 1) / TS;
+  pl->TS = TS;
+  pl->P = P;
+  pl->threads = P * TS;
+  int NV = 4 * TS * pl->per;                                          // every slice reads PER whole groups (padding beyond N)
+  if (((NV >> 2) & 1) == 0) NV += 4;                                  // NV/4 odd: distinct columns land in distinct bank groups
+  pl->NV = NV;
+  pl->stage_floats = ((size_t)P * N + 3) & ~(size_t)3;
+  // rows of a CTA must share their four source rows: floor(scale*(Y+0.5)-0.5) equal within every aligned pair
+  pl->rows = FS_ROWS;
+  const float scale = (float)s / (float)R;
+  for (int Y = 0; Y + 1 < R && pl->rows > 1; Y += FS_ROWS)
+    for (int k = 1; k < FS_ROWS && Y + k < R; ++k)
+      if (floorf(scale * (Y + k + 0.5f) - 0.5f) != floorf(scale * (Y + 0.5f) - 0.5f)) pl->rows = 1;
+  for (;; pl->rows = 1) {                                             // two rows per CTA when both vertical tiles fit, else one
+    const size_t base = pl->stage_floats + (size_t)pl->rows * (s + 4) * pl->NV + 4 * (size_t)R + 2 * (size_t)R + FS_ROWS * 32 +
+                        (size_t)TS * P + 4;
+    const size_t with_raw = base + 4 * (size_t)s * N;
+    pl->raw = with_raw * sizeof(float) <= 112 * 1024;                 // two CTAs per SM
+    pl->bytes = (pl->raw ? with_raw : base) * sizeof(float);
+    if (pl->bytes <= 112 * 1024 || pl->rows == 1) break;
+  }
+  return pl->bytes <= 112 * 1024;
+}
+
+template <int PER, bool VEC4, bool RAW>
+int fs_launch(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st) {
+  static size_t configured = 0;
+  auto kern = capture_store_reg_kernel<PER, VEC4, RAW>;
+  if (pl.bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.bytes);
+    if (e != cudaSuccess) {
+      set_error("capture_store_reg: smem attr: %s", cudaGetErrorString(e));
+      return SKP_ERR_LAUNCH;
+    }
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured = pl.bytes;
+  }
+  int pad_shift = 0;
+  while ((1 << pad_shift) < pl.NV - N) ++pad_shift;
+  dim3 grid((R + pl.rows - 1) / pl.rows, heads);
+  kern<<<grid, pl.threads, pl.bytes, st>>>(logits, probs, s, N, R, pl.NV, pl.P, pl.TS, pl.rows, (int)pl.stage_floats, pad_shift);
+  SKP_CHECK_LAUNCH("capture_store_reg");
+  return SKP_OK;
+}
+
+template <bool VEC4, bool RAW>
+int fs_dispatch(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st) {
+  switch (pl.per) {
+    case 1: return fs_launch<1, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    case 2: return fs_launch<2, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    case 3: return fs_launch<3, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    case 4: return fs_launch<4, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    case 5: return fs_launch<5, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    case 6: return fs_launch<6, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    case 7: return fs_launch<7, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    default: return fs_launch<8, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+  }
+}
+
+}  // namespace
+
+// Returns SKP_OK with *handled = true when the register kernel ran; *handled = false when the shape does not fit it.
+int capture_store_reg(const float* logits, float* probs, int heads, int s, int N, int R, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if ((reinterpret_cast<uintptr_t>(probs) & 15) != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) != 0) return SKP_OK;
+  FsPlan pl;
+  if (!fs_plan(s, N, R, &pl)) return SKP_OK;
+  int rc;
+  if ((N & 3) == 0) rc = pl.raw ? fs_dispatch<true, true>(logits, probs, heads, s, N, R, pl, st) : fs_dispatch<true, false>(logits, probs, heads, s, N, R, pl, st);
+  else rc = pl.raw ? fs_dispatch<false, true>(logits, probs, heads, s, N, R, pl, st) : fs_dispatch<false, false>(logits, probs, heads, s, N, R, pl, st);
+  if (rc == SKP_OK) *handled = true;
+  return rc;
+}
+
+}  // namespace skp

@@ -752,7 +752,7 @@ static int capture_tc_launch(CapTcParams& p, cudaStream_t st) {
 bool capture_tc_eligible(const int* s, int n_layers, int N, int R, bool store) {
   if (!g_capture_tc || npt_of(N) == 0 || n_layers < 1 || n_layers > SKP_MAX_LAYERS || R < 1) return false;
   if (store && n_layers != 1) return false;
-  if (store && g_capture_tc == 1 && N <= 96) return false;   // the SIMT row kernel is faster there (22.6 vs 27.6 us at N = 77)
+  if (store && g_capture_tc == 1) return false;   // store mode: the register kernel (skp_capture_store.cu) is faster at every N (cfg5: 116 vs 168 us)
   int slots[CT_MAX_SLOTS], ns = 0, kcols = 0;
   for (int l = 0; l < n_layers; ++l) {
     if (s[l] < 4 || s[l] > 32 || (s[l] & 3)) return false;   // source rows and their maxima travel as 16-byte multiples

@@ -11,9 +11,16 @@
 //   warp 1      MMA issuer   : allocates TMEM, one lane issues tcgen05.mma.cta_group::1.kind::f16
 //                              (M=128, N=BN, K=16) x 4 K-steps x 3 split terms per stage, tcgen05.commit
 //                              releases the stage and finally signals the epilogue
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 (one accumulator row per thread), alpha/bias/residual,
-//                              vectorised global stores
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 (one accumulator row per thread) into a padded fp32 tile in the (now
+//                              idle) stage ring, then row-contiguous 128-bit global stores with alpha/bias/residual --
+//                              whole 128 B lines instead of 32 row-strided 16 B pieces per instruction
+// Split-K (small-M layers that cannot fill 148 SMs): the K-splits of one output tile are the CTAs of ONE thread-block
+// cluster (<= 8); every CTA parks its partial tile in its own shared memory, and after a cluster barrier CTA z reduces
+// rows [z*128/Z, (z+1)*128/Z) over all Z partial tiles through distributed shared memory in rank order (deterministic)
+// and runs the epilogue on them.  No workspace, no second launch.  (splits > 0 with a workspace keeps the older
+// partial-sums + reduce-kernel path for A/B measurements.)
 #include "skp_tc.cuh"
+#include <stdlib.h>
 
 namespace skp {
 
@@ -45,13 +52,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                   float* C, int64_t ldc, int M, int N, int num_kb_total, int kb_per_split, float alpha,
-                  const float* bias, const float* residual, int64_t ldr, float* __restrict__ splitk_ws, ConvGeom cg) {
+                  const float* bias, const float* residual, int64_t ldr, float* __restrict__ splitk_ws, ConvGeom cg, int mode) {
   using Cfg = TcCfg<BN, STAGES>;
   pdl_launch_dependents();
-  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb); partial sums go to splitk_ws[z][M][N] (reduced afterwards)
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb).  mode 0: direct epilogue from registers (legacy; with
+  // gridDim.z > 1 partial sums go to splitk_ws[z][M][N] and a second kernel reduces them); mode 1: epilogue staged through
+  // shared memory; mode 2: the gridDim.z CTAs of the tile form one cluster and reduce through distributed shared memory.
   const int kb0 = blockIdx.z * kb_per_split;
   const int num_kb = min(kb_per_split, num_kb_total - kb0);
-  const bool partial = gridDim.z > 1;
+  const bool partial = gridDim.z > 1 && mode != 2;
+  const bool staged = mode != 0;
+  const bool clustered = mode == 2 && gridDim.z > 1;
+  constexpr int PITCH = BN + 4;                  // fp32 staging tile [128][PITCH]: rows 16 B-staggered across the banks
+  static_assert(TC_BM * PITCH * 4 <= STAGES * Cfg::STAGE_BYTES, "epilogue staging tile must fit the stage ring");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -105,6 +118,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tm_b_lo, full, kc, n0);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
@@ -129,6 +143,21 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       umma_commit(bars + 8 * (2 * STAGES));    // accumulator complete
     }
     __syncwarp();
+  } else if (staged) {
+    // ---- epilogue, phase A: accumulator -> padded fp32 tile in the stage ring (every load of the ring has landed and every
+    // MMA reading it has retired once the accumulator barrier fires)
+    mbar_wait(bars + 8 * (2 * STAGES), 0);
+    tc_fence_after();
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    float* tile = reinterpret_cast<float*>(gen) + (size_t)(quarter * 32 + lane) * PITCH;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(tile + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    tc_fence_before();
   } else {
     mbar_wait(bars + 8 * (2 * STAGES), 0);
     tc_fence_after();
@@ -183,6 +212,104 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       }
     }
     tc_fence_before();
+  }
+  if (staged) {
+    // ---- phase B: the partial tiles of the cluster (or this CTA's tile) are published
+    if (clustered) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else if (warp >= 2) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // ---- phase C: rows [r0, r1) of the tile: sum over the cluster ranks in order, alpha / bias / residual, coalesced stores
+    if (warp >= 2) {
+      const int Z = clustered ? (int)gridDim.z : 1;
+      uint32_t my_rank = 0;
+      if (clustered) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(my_rank));
+      const int r0 = clustered ? (int)(my_rank * TC_BM) / Z : 0;
+      const int r1 = clustered ? (int)((my_rank + 1) * TC_BM) / Z : TC_BM;
+      float* Cout = C;
+      int64_t ldo = ldc;
+      float al = alpha;
+      const float* bi = bias;
+      const float* re = residual;
+      if (partial) { Cout = splitk_ws + (size_t)blockIdx.z * M * N; ldo = N; al = 1.f; bi = nullptr; re = nullptr; }
+      const bool vec = ((ldo & 3) == 0) && ((((uintptr_t)Cout) & 15) == 0) && ((N & 3) == 0) &&
+                       (!re || (((ldr & 3) == 0) && ((((uintptr_t)re) & 15) == 0))) && (!bi || ((((uintptr_t)bi) & 15) == 0));
+      constexpr int Q = BN / 4;
+      const int te = threadIdx.x - 64;
+      const uint32_t tile_s = base;                       // shared-window address of this CTA's tile (same offset in every rank)
+      // four independent items per thread and pass: every load (tile / peer tiles, bias, residual) is issued before the
+      // first use, so a pass costs one memory latency instead of four
+      constexpr int UN = 4;
+      const int total = (r1 - r0) * Q;
+      for (int it0 = te; it0 < total; it0 += 128 * UN) {
+        float4 acc[UN], rv[UN], bv[UN];
+        float* dstp[UN];
+        int ncol[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int it = it0 + 128 * u;
+          dstp[u] = nullptr;
+          ncol[u] = 0;
+          acc[u] = rv[u] = bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (it >= total) continue;
+          const int rq = it / Q;
+          const int r = r0 + rq, c4 = it - rq * Q;
+          int row = m0 + r;
+          if (CONV) {
+            const int py = cy0 + r / cg.BW, px = cx0 + r % cg.BW;
+            row = (py < cg.H && px < cg.W) ? py * cg.W + px : M;
+          }
+          const int n = n0 + 4 * c4;
+          if (row >= M || n >= N) continue;
+          dstp[u] = Cout + (size_t)row * ldo + n;
+          ncol[u] = n;
+          if (clustered) {
+            const uint32_t local = tile_s + (uint32_t)(r * PITCH + 4 * c4) * 4u;
+            for (int z = 0; z < Z; ++z) {
+              uint32_t remote;
+              asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(z));
+              float4 t;
+              asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(remote));
+              acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
+            }
+          } else {
+            acc[u] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gen) + (size_t)r * PITCH + 4 * c4);
+          }
+          if (vec) {
+            if (bi) bv[u] = __ldg(reinterpret_cast<const float4*>(bi + n));
+            if (re) rv[u] = __ldg(reinterpret_cast<const float4*>(re + (size_t)row * ldr + n));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          if (dstp[u] == nullptr) continue;
+          float4 a = acc[u];
+          a.x *= al; a.y *= al; a.z *= al; a.w *= al;
+          if (vec) {
+            a.x += bv[u].x + rv[u].x; a.y += bv[u].y + rv[u].y; a.z += bv[u].z + rv[u].z; a.w += bv[u].w + rv[u].w;
+            *reinterpret_cast<float4*>(dstp[u]) = a;
+          } else {
+            const float o[4] = {a.x, a.y, a.z, a.w};
+            const int n = ncol[u];
+            const size_t roff = (size_t)(dstp[u] - Cout) / (size_t)ldo;   // global row of this item
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < N) {
+                float v = o[j];
+                if (bi) v += bi[n + j];
+                if (re) v += re[roff * ldr + n + j];
+                dstp[u][j] = v;
+              }
+          }
+        }
+      }
+    }
+    if (clustered) {   // no CTA may leave (and free its shared memory) while a peer still reads its partial tile
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -390,10 +517,43 @@ static void launch_splitk_reduce(const float* ws, int zs, int M, int N, float* C
   else launch_pdl(splitk_reduce_kernel<false>, dim3(blocks), dim3(256), 0, st, ws, zs, M, N, C, ldc, alpha, bias, residual, ldr);
 }
 
+// one launch of the GEMM kernel: optional cluster along z (the K-splits of a tile), optional PDL
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_gemm(void (*kernel)(KArgs...), dim3 grid, size_t smem, cudaStream_t st, int cluster_z, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster_z > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 1;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = (unsigned)cluster_z;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+constexpr int TC_MAX_CLUSTER = 8;   // portable cluster size: K-splits reduced through distributed shared memory
+// epilogue of the un-split / workspace paths: 0 (default) = straight from registers, 1 = staged through shared memory
+// (coalesced stores).  Measured on B200 inside the Stage-1 step graph: the direct epilogue keeps 8 residual loads in flight per
+// thread and wins (44.4 vs 41.9 images/s); the staged form is what the cluster reduce needs and stays selectable for A/B.
+static int g_epilogue_staged = (getenv("SKP_GEMM_EPILOGUE") != nullptr && atoi(getenv("SKP_GEMM_EPILOGUE")) == 1) ? 1 : 0;
+
 template <int BN, int STAGES>
 static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin, const void* B_hi, const void* B_lo, float* C,
                        int64_t ldc, int N, float alpha, const float* bias, const float* residual, int64_t ldr, int splits, float* ws,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool cluster) {
   using Cfg = TcCfg<BN, STAGES>;
   ConvGeom cg;
   cg.H = H; cg.W = W;
@@ -415,10 +575,12 @@ static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin
   const int per = (num_kb + splits - 1) / splits;
   const int zs = (num_kb + per - 1) / per;
   dim3 grid((N + BN - 1) / BN, tiles_y * cg.tiles_x, zs);
-  launch_pdl(gemm_nt_tc_kernel<BN, STAGES, true>, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N,
-             num_kb, per, alpha, bias, residual, ldr, ws, cg);
+  const int mode = (cluster && zs > 1) ? 2 : g_epilogue_staged;
+  cudaError_t le = launch_gemm(gemm_nt_tc_kernel<BN, STAGES, true>, grid, (size_t)Cfg::SMEM, st, mode == 2 ? zs : 1, ta_hi, ta_lo, tb_hi,
+                               tb_lo, C, ldc, M, N, num_kb, per, alpha, bias, residual, ldr, ws, cg, mode);
+  if (le != cudaSuccess) { set_error("conv3x3_tc: launch: %s", cudaGetErrorString(le)); return SKP_ERR_LAUNCH; }
   SKP_CHECK_LAUNCH("conv3x3_tc");
-  if (zs > 1) {
+  if (zs > 1 && mode != 2) {
     launch_splitk_reduce(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr, st);
     SKP_CHECK_LAUNCH("splitk_reduce");
   }
@@ -428,7 +590,7 @@ static int launch_conv(const void* X_hi, const void* X_lo, int H, int W, int Cin
 template <int BN, int STAGES>
 static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C, int64_t ldc,
                      int M, int N, float alpha, const float* bias, const float* residual, int64_t ldr, int splits, float* ws,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool cluster) {
   using Cfg = TcCfg<BN, STAGES>;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
@@ -442,10 +604,12 @@ static int launch_tc(const void* A_hi, const void* A_lo, const void* B_hi, const
   const int per = (num_kb + splits - 1) / splits;
   const int zs = (num_kb + per - 1) / per;  // every z gets >= 1 k-block
   dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM, zs);
-  launch_pdl(gemm_nt_tc_kernel<BN, STAGES, false>, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, C, ldc, M, N,
-             num_kb, per, alpha, bias, residual, ldr, ws, ConvGeom{});
+  const int mode = (cluster && zs > 1) ? 2 : g_epilogue_staged;
+  cudaError_t le = launch_gemm(gemm_nt_tc_kernel<BN, STAGES, false>, grid, (size_t)Cfg::SMEM, st, mode == 2 ? zs : 1, ta_hi, ta_lo, tb_hi,
+                               tb_lo, C, ldc, M, N, num_kb, per, alpha, bias, residual, ldr, ws, ConvGeom{}, mode);
+  if (le != cudaSuccess) { set_error("gemm_nt_tc: launch: %s", cudaGetErrorString(le)); return SKP_ERR_LAUNCH; }
   SKP_CHECK_LAUNCH("gemm_nt_tc");
-  if (zs > 1) {
+  if (zs > 1 && mode != 2) {
     launch_splitk_reduce(ws, zs, M, N, C, ldc, alpha, bias, residual, ldr, st);
     SKP_CHECK_LAUNCH("splitk_reduce");
   }
@@ -571,10 +735,11 @@ extern "C" int skp_conv3x3_tc(const void* X_hi, const void* X_lo, int H, int W, 
   SKP_REQUIRE(((((uintptr_t)X_hi) | ((uintptr_t)X_lo) | ((uintptr_t)B_hi) | ((uintptr_t)B_lo)) & 15) == 0,
               "conv3x3_tc: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (splits < 1) splits = 1;
-  SKP_REQUIRE(splits == 1 || splitk_ws != nullptr, "conv3x3_tc: split-K needs a workspace of splits*H*W*Cout floats");
-  const TcPlan pl = plan_tiles(H * W, Cout, 9 * Cin, splits, true);
-  SKP_TC_DISPATCH(launch_conv, pl.bn, X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st)
+  const bool cluster = splits <= 0;      // 0: the library plans the K-splits and reduces them inside one cluster (no workspace)
+  SKP_REQUIRE(splits <= 1 || splitk_ws != nullptr, "conv3x3_tc: explicit split-K needs a workspace of splits*H*W*Cout floats");
+  const TcPlan pl = plan_tiles(H * W, Cout, 9 * Cin, cluster ? 0 : splits, true);
+  if (cluster) splits = pl.splits > TC_MAX_CLUSTER ? TC_MAX_CLUSTER : pl.splits;
+  SKP_TC_DISPATCH(launch_conv, pl.bn, X_hi, X_lo, H, W, Cin, B_hi, B_lo, C, ldc, Cout, alpha, bias, residual, ldr, splits, splitk_ws, st, cluster)
 }
 
 extern "C" int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad, float* C,
@@ -585,8 +750,9 @@ extern "C" int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_
   SKP_REQUIRE(((((uintptr_t)A_hi) | ((uintptr_t)A_lo) | ((uintptr_t)B_hi) | ((uintptr_t)B_lo)) & 15) == 0,
               "gemm_nt_tc: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (splits < 1) splits = 1;
-  SKP_REQUIRE(splits == 1 || splitk_ws != nullptr, "gemm_nt_tc: split-K needs a workspace of splits*M*N floats");
-  const TcPlan pl = plan_tiles(M, N, Kpad, splits);
-  SKP_TC_DISPATCH(launch_tc, pl.bn, A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, splits, splitk_ws, st)
+  const bool cluster = splits <= 0;      // 0: the library plans the K-splits and reduces them inside one cluster (no workspace)
+  SKP_REQUIRE(splits <= 1 || splitk_ws != nullptr, "gemm_nt_tc: explicit split-K needs a workspace of splits*M*N floats");
+  const TcPlan pl = plan_tiles(M, N, Kpad, cluster ? 0 : splits);
+  if (cluster) splits = pl.splits > TC_MAX_CLUSTER ? TC_MAX_CLUSTER : pl.splits;
+  SKP_TC_DISPATCH(launch_tc, pl.bn, A_hi, A_lo, B_hi, B_lo, Kpad, C, ldc, M, N, alpha, bias, residual, ldr, splits, splitk_ws, st, cluster)
 }

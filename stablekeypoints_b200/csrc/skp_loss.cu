@@ -1,7 +1,8 @@
 // Loss-side kernels: sharpening (optimize.py:166-206, optimize_token.py:203-241), equivariance
 // (optimize.py:157-163, invertable_transform.py:38-92), soft-arg-max (eval.py:113-155), Adam (optimize.py:320,424).
-// All are small ([K,R,R] with K=10, R=128 -> 0.66 MB): launch-latency bound, so each loss is ONE kernel with a
-// deterministic in-block reduction (no atomics on the scalar), and the backward kernels fuse the loss weight.
+// All are small ([K,R,R] with K=10, R=128 -> 0.66 MB): launch-latency bound, so each loss is ONE multi-CTA kernel: a
+// deterministic in-block reduction, then one atomicAdd of the CTA's share into the zeroed scalar (the logged loss value
+// can differ in its last bits from run to run; no gradient depends on it).  The backward kernels fuse the loss weight.
 #include "skp_common.cuh"
 
 namespace skp {

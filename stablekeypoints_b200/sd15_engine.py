@@ -3,17 +3,24 @@
 Replaces what the reference gets from ``diffusers==0.8.0`` (optimize_token.py:16-39; call sites
 ptp_utils.py:221-229, 297-303).  Design (B200-first, not a module tree):
 
-  * weights live in one flat dict keyed by the diffusers state-dict names, fp32 in HBM (3.4 GB + 0.14 GB of 180 GB);
+  * weights live in one flat dict keyed by the diffusers state-dict names, fp32 in HBM (3.4 GB + 0.14 GB of 180 GB),
+    plus their split-bf16 K-major GEMM operands (forward and transposed / tap-flipped for the input gradients);
+  * activations are channels-last matrices [H*W, C]; every convolution / linear of the frozen trunk -- UNet and VAE --
+    runs on libskp_b200's tcgen05 split-bf16 GEMM (3x3 convolutions as implicit GEMMs through shifted TMA boxes),
+    GroupNorm / LayerNorm / GEGLU are fused into the operand split of the GEMM that follows, self- and cross-attention
+    are the library's flash-style split-bf16 kernels (tcgen05 for the long sequences); everything takes part in
+    autograd through ops.py's Functions, so d(context) is exact through the frozen trunk;
   * the timestep is a run constant (noise_level=-1, main.py:144-149), so the whole time-embedding branch and
     every resnet's time_emb_proj are folded into the conv1 biases once per timestep;
   * the K|V projections of all 16 cross-attention layers are ONE [N,768] x [768, 2*sum(C)] GEMM per context version,
-    shared by both forwards of a Stage-1 iteration (tcgen05 split-bf16 kernel);
-  * each cross-attention layer runs the hand-written kernels of libskp_b200 (projection GEMMs on tcgen05, the
-    fp32 attention core, and -- for the first four eligible up-block layers -- the capture of its low-res logits);
-  * everything the path does not name (resnet convs, GroupNorm/LayerNorm, self-attention, GEGLU) is plain torch
-    (cuDNN / SDPA) and takes part in autograd, so d(context) is exact through the frozen trunk;
+    shared by both forwards of a Stage-1 iteration;
+  * for the first four eligible up-block cross-attention layers the low-res logits are kept for the capture
+    (ptp_utils.py:508-538 by linearity: skp_capture_*);
   * optional early exit right after the 4th captured layer: the reference discards pred_noise
     (ptp_utils.py:246), so nothing observable depends on the remaining ~40 % of the forward.
+
+``trunk="torch"`` keeps the un-named part of the trunk on cuDNN / cuBLAS / SDPA: an A/B and context-line path only
+(bench.py's torch_eager_b200 lines); the product default is ``trunk="tc"``.
 """
 from __future__ import annotations
 

@@ -26,7 +26,8 @@ def _product_ldm(pipe, res, precision="fp32"):
     from stablekeypoints_b200.sd15_engine import UNetConfig, VAEConfig
     oc, vc = pipe.unet.cfg, pipe.vae.cfg
     ucfg = UNetConfig(block_out_channels=oc.block_out_channels, cross_attention_dim=oc.cross_attention_dim,
-                      heads=oc.attention_head_dim, norm_num_groups=oc.norm_num_groups)
+                      heads=oc.attention_head_dim, norm_num_groups=oc.norm_num_groups, layers_per_block=oc.layers_per_block,
+                      down_has_attn=oc.down_has_attn)
     vcfg = VAEConfig(block_out_channels=vc.block_out_channels, norm_num_groups=vc.norm_num_groups)
     return optimize_token.load_ldm("cuda", feature_upsample_res=res, unet_state_dict=pipe.unet.state_dict(),
                                    vae_state_dict=pipe.vae.state_dict(), unet_config=ucfg, vae_config=vcfg,
@@ -250,6 +251,57 @@ def test_full_sd15_stage1_iteration_vs_oracle(full, n_tokens, precision):
     torch.cuda.empty_cache()
 
 
+def test_cfg5_sdxl_shaped_stage1_vs_oracle():
+    """BASELINE cfg5: the cross-attention capture path at SDXL-base shapes -- 1024^2 image -> 128^2 latent, a
+    2048-wide context, every captured layer at 32x32 with C = 1280 = 20 heads x 64, R = 256 (a 404 MB store per layer in the
+    reference), K = 16 of N = 77 tokens -- through the same surface (load_ldm / run_and_find_attn / stage1_iteration) against
+    the fp32 CPU oracle: two captured forwards, selection, both losses and d(context).  The trunk around the captured
+    layers is a 3-level UNet of the SDXL widths (320, 640, 1280; no attention at 128^2) with one transformer block per
+    attention module, so the hook finds three eligible layers (S <= 32^2), all of the SDXL shape; the VAE is a narrow
+    encoder (the encoder is not part of cfg5).  Tolerance: 1e-3 norm-wise, token indices forced, candidates asserted."""
+    from oracle import sd15
+    from stablekeypoints_b200 import optimize
+    from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
+    ucfg = sd15.UNetConfig(block_out_channels=(320, 640, 1280), cross_attention_dim=2048, attention_head_dim=20,
+                           down_has_attn=(False, True, True))
+    pipe = sd15.make_pipeline(ucfg, sd15.VAEConfig.tiny(), seed=5, attn_gain=4.0)
+    image = hp.synthetic_image(seed=11, size=1024, blobs=16)
+    g = torch.Generator().manual_seed(55)
+    context = torch.randn(1, 77, 2048, generator=g)
+    noise_a, noise_b = torch.randn(1, 4, 128, 128, generator=g), torch.randn(1, 4, 128, 128, generator=g)
+    theta = hp.affine_theta(-6.0, 0.92, -0.08, 0.05)
+    ldm_o, ctl_o, _ = hp.load_oracle_ldm(pipe, 256)
+    ctx_o = context.clone().requires_grad_(True)
+    ref = hp.stage1_iteration(ldm_o, ctl_o, image, ctx_o, theta, noise_a, noise_b, top_k=16, num_candidates=32, sigma=2.0)
+    ldm, controllers, _ = _product_ldm(pipe, 256)
+    assert sum(1 for l in ldm.unet.cross_layers if l.in_up and l.channels == 1280) == 3 and ldm.unet.cfg.heads == 20
+    ctx = context.clone().cuda().requires_grad_(True)
+    tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
+    out = optimize.stage1_iteration(ldm, controllers, image, ctx, tr, _args(top_k=16, furthest_point_num_samples=32), theta=theta,
+                                    noise_a=noise_a, noise_b=noise_b, forced_indices=ref["indices"])
+    errs = {"maps": rel_err(out["maps"].cpu(), ref["maps"]), "maps_t": rel_err(out["maps_t"].cpu(), ref["maps_t"]),
+            "sharp": rel_err(out["sharp"].cpu(), ref["sharp"]), "equiv": rel_err(out["equiv"].cpu(), ref["equiv"]),
+            "dcontext": rel_err(ctx.grad.cpu(), ctx_o.grad)}
+    same = _assert_candidates_agree(out["maps"], ref["maps"], 32, 2.0)
+    print("[cfg5 SDXL-shaped parity, N=77, R=256, K=16] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items())
+          + f" candidates {same}/32")
+    assert out["maps"].shape == (77, 256, 256) and len(ref["indices"]) == 16
+    for k, v in errs.items():
+        assert v < 1e-3, (k, v)
+    # the same forward through the controller (store mode, what AttentionStore holds in the reference): [20, 256*256, 77] x 3
+    from stablekeypoints_b200 import ptp_utils
+    with torch.no_grad():
+        ldm.unet.capture_mode, ldm.unet.early_exit = "store", True
+        ptp_utils.find_pred_noise(ldm, image, ctx.detach(), noise=noise_a)
+        stored = controllers[next(iter(controllers))].step_store["attn"]
+        assert len(stored) == 3 and all(tuple(t.shape) == (20, 256 * 256, 77) for t in stored)
+        mean = torch.stack([t.mean(0) for t in stored]).mean(0).t().reshape(77, 256, 256)
+        assert rel_err(mean.cpu(), ref["maps"]) < 1e-3
+        controllers[next(iter(controllers))].reset()
+    del ldm, controllers, stored
+    torch.cuda.empty_cache()
+
+
 def test_tiny_eval_ensemble_matches_reference_golden(tiny):
     """SURVEY 'next' row f2: eval.run_image_with_context_augmented (augment -> captured forward with K tokens at 64^2 ->
     fused un-warp + accumulate -> sum/num) against the reference's own output; f3: the Stage-2 vote."""
@@ -353,7 +405,8 @@ def test_load_ldm_from_diffusers_directory(tiny, tmp_path):
     save_file({k: v.contiguous() for k, v in pipe.vae.state_dict().items()}, str(tmp_path / "vae" / "diffusion_pytorch_model.safetensors"))
     oc, vc = pipe.unet.cfg, pipe.vae.cfg
     ucfg = UNetConfig(block_out_channels=oc.block_out_channels, cross_attention_dim=oc.cross_attention_dim,
-                      heads=oc.attention_head_dim, norm_num_groups=oc.norm_num_groups)
+                      heads=oc.attention_head_dim, norm_num_groups=oc.norm_num_groups, layers_per_block=oc.layers_per_block,
+                      down_has_attn=oc.down_has_attn)
     vcfg = VAEConfig(block_out_channels=vc.block_out_channels, norm_num_groups=vc.norm_num_groups)
     ldm_a, ctl_a, n_a = optimize_token.load_ldm("cuda", str(tmp_path), feature_upsample_res=TINY["res"], unet_config=ucfg,
                                                vae_config=vcfg, precision="fp32")
