@@ -55,8 +55,8 @@ def parse():
     return ap.parse_args()
 
 
-def stage1_args(tokens):
-    return argparse.Namespace(layers=[0, 1, 2, 3], noise_level=-1, device="cuda", top_k=10, furthest_point_num_samples=25,
+def stage1_args(tokens, top_k=10, candidates=25):
+    return argparse.Namespace(layers=[0, 1, 2, 3], noise_level=-1, device="cuda", top_k=top_k, furthest_point_num_samples=candidates,
                               sigma=2.0, num_subjects=1, top_k_strategy="gaussian", equivariance_attn_loss_weight=1000.0,
                               sharpening_loss_weight=100.0, num_tokens=tokens, lr=5e-3)
 
@@ -175,17 +175,18 @@ def impl_detail(a):
 class Stage1Runner:
     """One rank's Stage-1 loop for the bench: graph (default) or eager steps over device / pinned-host images."""
 
-    def __init__(self, ldm, controllers, tokens, dev, rank, graph=True, accum=1, no_vae=False):
+    def __init__(self, ldm, controllers, tokens, dev, rank, graph=True, accum=1, no_vae=False, image_size=512, top_k=10,
+                 candidates=25):
         from stablekeypoints_b200 import optimize, ptp_utils
         from stablekeypoints_b200.invertable_transform import RandomAffineWithInverse
         from stablekeypoints_b200.optimize import SyntheticKeypointDataset
         self.ldm, self.controllers, self.accum = ldm, controllers, accum
-        self.args = stage1_args(tokens)
+        self.args = stage1_args(tokens, top_k, candidates)
         g = torch.Generator().manual_seed(2)
-        self.context = torch.randn(1, tokens, 768, generator=g).to(dev).requires_grad_(True)
+        self.context = torch.randn(1, tokens, ldm.unet.cfg.cross_attention_dim, generator=g).to(dev).requires_grad_(True)
         self.opt = optimize.EmbeddingOptimizer(self.context, lr=self.args.lr, capturable=True)
         self.tr = RandomAffineWithInverse(degrees=15, scale=(0.8, 1.0), translate=(0.25, 0.25))
-        ds = SyntheticKeypointDataset(length=8, seed=1 + rank)
+        ds = SyntheticKeypointDataset(length=8, size=image_size, seed=1 + rank)
         self.host_imgs = [ds[i]["img"][None].contiguous().pin_memory() for i in range(4)]
         self.dev_imgs = [h.to(dev) for h in self.host_imgs]
         if no_vae:
@@ -321,6 +322,12 @@ def run_b200_arm(a):
         extra["batch4_accum_images_per_s_1gpu"] = rate(accum=4, n=max(2, a.steps // 2))
         extra["batch4_accum_note"] = ("reference CLI default batch_size=4 on one GPU: B//G = 4 accumulated iterations per optimizer step "
                                       "(optimize.py:339,420-425) through the iteration / update CUDA graphs; images/s, to compare with `value`")
+        # BASELINE cfg5: the same loop at SDXL-base shapes (1024^2 image, 2048-wide context, captured layers 32x32 / 20 heads x 64,
+        # R = 256, K = 16); parity at this shape: tests/test_gpu_pipeline.py::test_cfg5_sdxl_shaped_stage1_vs_oracle
+        try:
+            extra["cfg5_sdxl_shaped_1gpu"] = cfg5_context(a, dev, rank, timed)
+        except Exception as ex:       # context only: never fail the bench line on it
+            extra["cfg5_sdxl_shaped_1gpu"] = {"error": repr(ex)[:300]}
         # the honest same-box library bar: the SAME loop with the trunk on cuDNN / cuBLAS (torch eager, no graph), TF32 as the
         # reference's torch defaults allow and strict fp32, each with its parity error against this build's maps
         try:
@@ -354,6 +361,33 @@ def run_b200_arm(a):
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cfg5_context(a, dev, rank, timed):
+    """Stage-1 images/s on BASELINE cfg5's shapes: a 3-level UNet of the SDXL-base widths (320, 640, 1280; attention at
+    64^2 and 32^2 only; one transformer block per attention module) with a 2048-wide context and 20 heads (head dim 64 at the
+    captured 32x32 / C=1280 layers), 1024^2 synthetic images through the SD VAE encoder, R = 256, K = 16 of 77 tokens."""
+    from stablekeypoints_b200 import optimize_token
+    from stablekeypoints_b200.sd15_engine import UNetConfig, VAEConfig
+    ucfg = UNetConfig(block_out_channels=(320, 640, 1280), cross_attention_dim=2048, heads=20, down_has_attn=(False, True, True))
+    ldm5, ctl5, _ = optimize_token.load_ldm(str(dev), "synthetic:5", feature_upsample_res=256, attn_gain=4.0, precision=a.precision,
+                                            trunk=a.trunk, unet_config=ucfg, vae_config=VAEConfig())
+    r = Stage1Runner(ldm5, ctl5, 77, dev, rank, graph=a.graph, image_size=1024, top_k=16, candidates=32)
+    for i in range(2):
+        r.iteration(r.dev_imgs[i % len(r.dev_imgs)])
+    n = max(3, a.steps // 2)
+    ms_, _ = timed(r, n, feed_host=False, sync_ranks=False)
+    ms_e, _ = timed(r, n, feed_host=True, sync_ranks=False)
+    out = {"images_per_s": round(n / (ms_ / 1e3), 3), "ms_per_step": round(ms_ / n, 3), "e2e_images_per_s": round(n / (ms_e / 1e3), 3),
+           "config": {"workload": "cfg5: SDXL-shaped 1024x1024 cross-attention capture path, K=16 of 77 tokens, batch=1", "tokens": 77,
+                      "context_dim": 2048, "feature_upsample_res": 256, "top_k": 16, "candidates": 32, "captured_layers": "3 x (32x32, C=1280, 20 heads x 64)",
+                      "unet": "3 levels (320, 640, 1280), one transformer block per attention module", "vae_encode": "included (1024^2)"},
+           "launches_per_step": r.launches_per_iter}
+    r.close()
+    del r, ldm5, ctl5
+    torch.cuda.empty_cache()
+    optimize_token.set_precision(a.precision)
+    return out
 
 
 def torch_eager_context(a, dev, rank, ldm, controllers, rate):
@@ -416,8 +450,8 @@ def _time_capture_store(ops, lib, logits, res, flush, tc, reps=5, warm=3):
 def attn_store_rooflines(a, dev):
     """The attn-store kernel (the kernel BASELINE.json's metric names), HBM-bound: algorithmic bytes = the probability store
     heads*R^2*N*4 + the low-res logits read, timed live with CUDA events on the launching stream, L2 flushed (512 MiB fill)
-    between launches.  Both implementations are timed (tcgen05 formulation skp_capture_tc.cu, SIMT row kernel
-    skp_capture_row.cu); the line reports the one the library's policy picks for the shape.
+    between launches.  Both implementations are timed (tcgen05 formulation skp_capture_tc.cu, SIMT register kernel
+    skp_capture_store.cu); the line reports the one the library's policy picks for the shape.
       roofline             : BASELINE cfg5's SDXL-shaped layer (20 heads, 32x32 -> R=256): a 404 MB store that does NOT fit
                              the 126 MB L2, i.e. a real HBM stream;
       roofline_l2_resident : the SD1.5 C=1280 captured layer (8 heads, 16x16 -> R=128, N tokens): the 40 MB store is absorbed
@@ -438,12 +472,12 @@ def attn_store_rooflines(a, dev):
         picked_tc = bool(lib().skp_capture_tc_ok((__import__("ctypes").c_int * 1)(s), 1, n, r, 1))
         ms = ms_tc if (picked_tc and ms_tc is not None) else ms_simt
         ach = algo / (ms * 1e-3) / 1e9
-        traffic, tsrc = _ncu_traffic(key + ("_tc" if picked_tc else "_simt")) if n == 77 else (None, None)
+        traffic, tsrc = _ncu_traffic(key + ("_tc" if picked_tc else "_reg")) if n == 77 else (None, None)
         out = {"kernel": "skp_capture_store%s_fwd (attn-store, %s)" % ("_tc" if picked_tc else "", label), "bound": "hbm",
                "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(ach / peak, 4),
                "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes": algo, "ms_per_launch": round(ms, 5),
-               "implementation": "tcgen05 (skp_capture_tc.cu)" if picked_tc else "SIMT row kernel (skp_capture_row.cu)",
-               "ms_tcgen05": None if ms_tc is None else round(ms_tc, 5), "ms_simt_row": round(ms_simt, 5),
+               "implementation": "tcgen05 (skp_capture_tc.cu)" if picked_tc else "SIMT register kernel (skp_capture_store.cu)",
+               "ms_tcgen05": None if ms_tc is None else round(ms_tc, 5), "ms_simt": round(ms_simt, 5),
                "l2": "flushed (512 MiB fill) between launches", "note": note}
         del logits
         return out

@@ -32,6 +32,14 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Blackwell packed fp32: one issue slot for two FMAs / adds / multiplies on a 64-bit register pair (SASS FFMA2 / FADD2 / FMUL2).
+// The kernel is issue-bound, so the horizontal taps, the softmax sums and the normalisation run on pairs of tokens.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ void group_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 constexpr int FS_THREADS = 512;
@@ -142,22 +150,29 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
     }
     const float invN = 1.f / (float)N;
     const int items = row_floats >> 2;
-    const float4* src[4];
+    const ulonglong2* src[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (RAW) {
-        src[j] = reinterpret_cast<const float4*>(raw + j * row_floats);
+        src[j] = reinterpret_cast<const ulonglong2*>(raw + j * row_floats);
       } else {
         int r = iy - 1 + j;
         r = r < 0 ? 0 : (r > s - 1 ? s - 1 : r);
-        src[j] = reinterpret_cast<const float4*>(logits + ((size_t)h * s + r) * row_floats);
+        src[j] = reinterpret_cast<const ulonglong2*>(logits + ((size_t)h * s + r) * row_floats);
       }
     }
-    const float4 *src0 = src[0], *src1 = src[1], *src2 = src[2], *src3 = src[3];
+    const ulonglong2 *src0 = src[0], *src1 = src[1], *src2 = src[2], *src3 = src[3];
     for (int i = tid; i < items; i += NT) {
-      float4 a, b, c, d;
+      ulonglong2 a, b, c, d;
       if (RAW) { a = src0[i]; b = src1[i]; c = src2[i]; d = src3[i]; }
-      else { a = __ldg(src0 + i); b = __ldg(src1 + i); c = __ldg(src2 + i); d = __ldg(src3 + i); }
+      else {
+        const float4 fa = __ldg(reinterpret_cast<const float4*>(src0) + i), fb = __ldg(reinterpret_cast<const float4*>(src1) + i);
+        const float4 fc = __ldg(reinterpret_cast<const float4*>(src2) + i), fd = __ldg(reinterpret_cast<const float4*>(src3) + i);
+        a = make_ulonglong2(pk2(fa.x, fa.y), pk2(fa.z, fa.w));
+        b = make_ulonglong2(pk2(fb.x, fb.y), pk2(fb.z, fb.w));
+        c = make_ulonglong2(pk2(fc.x, fc.y), pk2(fc.z, fc.w));
+        d = make_ulonglong2(pk2(fd.x, fd.y), pk2(fd.z, fd.w));
+      }
       const int f = i << 2;
       const int xs = (int)((f + 0.5f) * invN);                        // f / N (the quotient is never within 0.5/N of an integer)
       const int n = f - xs * N;
@@ -167,11 +182,10 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
       for (int rr = 0; rr < FS_ROWS; ++rr) {
         if (rr < nrows) {
           const float* w = wy[rr];
+          const u64 w0 = pk2(w[0], w[0]), w1 = pk2(w[1], w[1]), w2 = pk2(w[2], w[2]), w3 = pk2(w[3], w[3]);
           float v[4];
-          v[0] = fmaf(w[3], d.x, fmaf(w[2], c.x, fmaf(w[1], b.x, w[0] * a.x)));
-          v[1] = fmaf(w[3], d.y, fmaf(w[2], c.y, fmaf(w[1], b.y, w[0] * a.y)));
-          v[2] = fmaf(w[3], d.z, fmaf(w[2], c.z, fmaf(w[1], b.z, w[0] * a.z)));
-          v[3] = fmaf(w[3], d.w, fmaf(w[2], c.w, fmaf(w[1], b.w, w[0] * a.w)));
+          upk2(fma2(w3, d.x, fma2(w2, c.x, fma2(w1, b.x, mul2(w0, a.x)))), v[0], v[1]);
+          upk2(fma2(w3, d.y, fma2(w2, c.y, fma2(w1, b.y, mul2(w0, a.y)))), v[2], v[3]);
           amax[rr] = fmaxf(fmaxf(amax[rr], fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
           float* V = Vs + rr * vs_floats;
           float* d0 = V + (xs + 2) * NV + n;
@@ -211,30 +225,34 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
       const int X = xb0 + X_lane;
       const bool live = X < R;
       // ---- 2. horizontal pass + exponentials, kept in registers
-      float4 e[PER];
+      u64 e[2 * PER];                                                // pairs of exponentials (tokens 4i, 4i+1 | 4i+2, 4i+3)
       float4 wx = make_float4(0.f, 0.f, 0.f, 0.f);
       int c0 = 1;
       if (live) {
         wx = wtab[X];
         c0 = ctab[X];
         const float U = utab[X] * M;
-        const float4* v0 = V4 + (size_t)c0 * NV4 + g0;
-        const float4* v1 = v0 + NV4;
-        const float4* v2 = v1 + NV4;
-        const float4* v3 = v2 + NV4;
-        float sum = 0.f;
+        const u64 w0 = pk2(wx.x, wx.x), w1 = pk2(wx.y, wx.y), w2 = pk2(wx.z, wx.z), w3 = pk2(wx.w, wx.w), nu = pk2(-U, -U);
+        const ulonglong2* v0 = reinterpret_cast<const ulonglong2*>(V4 + (size_t)c0 * NV4 + g0);
+        const ulonglong2* v1 = v0 + NV4;
+        const ulonglong2* v2 = v1 + NV4;
+        const ulonglong2* v3 = v2 + NV4;
+        u64 sum2 = pk2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-          const float4 a = v0[i], b = v1[i], c = v2[i], d = v3[i];
-          float4 q;
-          q.x = ex2f(fmaf(wx.w, d.x, fmaf(wx.z, c.x, fmaf(wx.y, b.x, fmaf(wx.x, a.x, -U)))));
-          q.y = ex2f(fmaf(wx.w, d.y, fmaf(wx.z, c.y, fmaf(wx.y, b.y, fmaf(wx.x, a.y, -U)))));
-          q.z = ex2f(fmaf(wx.w, d.z, fmaf(wx.z, c.z, fmaf(wx.y, b.z, fmaf(wx.x, a.z, -U)))));
-          q.w = ex2f(fmaf(wx.w, d.w, fmaf(wx.z, c.w, fmaf(wx.y, b.w, fmaf(wx.x, a.w, -U)))));
-          e[i] = q;
-          sum += (q.x + q.y) + (q.z + q.w);
+          const ulonglong2 a = v0[i], b = v1[i], c = v2[i], d = v3[i];
+          const u64 t0 = fma2(w3, d.x, fma2(w2, c.x, fma2(w1, b.x, fma2(w0, a.x, nu))));
+          const u64 t1 = fma2(w3, d.y, fma2(w2, c.y, fma2(w1, b.y, fma2(w0, a.y, nu))));
+          float x0, x1, x2, x3;
+          upk2(t0, x0, x1);
+          upk2(t1, x2, x3);
+          e[2 * i] = pk2(ex2f(x0), ex2f(x1));
+          e[2 * i + 1] = pk2(ex2f(x2), ex2f(x3));
+          sum2 = add2(sum2, add2(e[2 * i], e[2 * i + 1]));
         }
-        psum[part * P + X_lane] = sum;
+        float sa, sb;
+        upk2(sum2, sa, sb);
+        psum[part * P + X_lane] = sa + sb;
       }
       if (issuer && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the group's segment is free
       group_bar(1 + pg, gcount);
@@ -264,38 +282,43 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
           }
         } else {
           const float inv = 1.f / total;
+          const u64 inv2 = pk2(inv, inv);
           float* o = orow + 4 * g0;
           if (g0 + PER <= Gfull) {                                    // every group of this slice is whole (warp-uniform)
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
-              const float4 q = e[i];
+              float q0, q1, q2, q3;
+              upk2(mul2(e[2 * i], inv2), q0, q1);
+              upk2(mul2(e[2 * i + 1], inv2), q2, q3);
               if (VEC4) {
-                *reinterpret_cast<float4*>(o + 4 * i) = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+                *reinterpret_cast<float4*>(o + 4 * i) = make_float4(q0, q1, q2, q3);
               } else {
-                o[4 * i] = q.x * inv;
-                o[4 * i + 1] = q.y * inv;
-                o[4 * i + 2] = q.z * inv;
-                o[4 * i + 3] = q.w * inv;
+                o[4 * i] = q0;
+                o[4 * i + 1] = q1;
+                o[4 * i + 2] = q2;
+                o[4 * i + 3] = q3;
               }
             }
           } else {
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
-              const float4 q = e[i];
+              float q0, q1, q2, q3;
+              upk2(mul2(e[2 * i], inv2), q0, q1);
+              upk2(mul2(e[2 * i + 1], inv2), q2, q3);
               const int g = g0 + i;
               if (g < Gfull) {
                 if (VEC4) {
-                  *reinterpret_cast<float4*>(o + 4 * i) = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+                  *reinterpret_cast<float4*>(o + 4 * i) = make_float4(q0, q1, q2, q3);
                 } else {
-                  o[4 * i] = q.x * inv;
-                  o[4 * i + 1] = q.y * inv;
-                  o[4 * i + 2] = q.z * inv;
-                  o[4 * i + 3] = q.w * inv;
+                  o[4 * i] = q0;
+                  o[4 * i + 1] = q1;
+                  o[4 * i + 2] = q2;
+                  o[4 * i + 3] = q3;
                 }
               } else if (!VEC4 && g == Gfull) {                       // the partial group: only its tail_valid tokens exist
-                if (tail_valid > 0) o[4 * i] = q.x * inv;
-                if (tail_valid > 1) o[4 * i + 1] = q.y * inv;
-                if (tail_valid > 2) o[4 * i + 2] = q.z * inv;
+                if (tail_valid > 0) o[4 * i] = q0;
+                if (tail_valid > 1) o[4 * i + 1] = q1;
+                if (tail_valid > 2) o[4 * i + 2] = q2;
               }
             }
           }
