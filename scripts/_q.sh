@@ -1,8 +1,4 @@
-timeout 1500 python -m pytest tests/ -x -q -m gpu --timeout 900 -s 2>&1 | grep -E "parity|passed|failed|error" | cut -c1-400 | tail -20
-( time timeout 1500 python bench.py > gpurun_out/r3c_bench.json 2> gpurun_out/r3c_bench.err ) 2>&1 | tail -3
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r3c_bench.json').read().strip().splitlines()[-1])
-for k in ('value','ms_per_step','e2e','gpu_launches','roofline','cfg5_sdxl_shaped_1gpu','tokens_100_images_per_s_1gpu','tokens_500_images_per_s_1gpu','batch4_accum_images_per_s_1gpu','full_forward_images_per_s_1gpu','clocks'):
-    print(k, json.dumps(d.get(k))[:400])
-PY
+timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "capture or attn_store" 2>&1 | tail -3 | cut -c1-300
+python scripts/attn_store_probe.py --impl 0 --cases cfg5,n500,n500s32,sd15,n100 2>&1 | tee gpurun_out/r4a_probe_fixed.jsonl
+SKP_ATTN_STORE_DYNAMIC=1 SKP_ATTN_STORE_BIG=0 python scripts/attn_store_probe.py --impl 0 --cases cfg5,n500,n500s32 2>&1 | tee gpurun_out/r4a_probe_dyn.jsonl
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:capture_store_reg -s 2 -c 1 -o gpurun_out/r4a_store_reg_cfg5 python scripts/attn_store_probe.py --impl 0 --cases cfg5 --reps 1 > gpurun_out/r4a_ncu.log 2>&1

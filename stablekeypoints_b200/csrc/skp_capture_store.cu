@@ -52,13 +52,32 @@ struct FsPlan {
   size_t stage_floats, bytes;
 };
 
+// Compile-time shape of the hot configurations (0 everywhere = the run-time arguments are used).  With the shape known the
+// index arithmetic of the x-block loop and of the vertical pass folds into immediates (ncu on cfg5: 140 of the 260 warp
+// instructions per x-block iteration and most of the 690-instruction prologue were address / parameter arithmetic).
+template <int S_, int N_, int R_, int NV_, int P_, int TS_, int ROWS_>
+struct FsShape {
+  static constexpr int S = S_, N = N_, R = R_, NV = NV_, P = P_, TS = TS_, ROWS = ROWS_;
+  static constexpr bool FIXED = S_ != 0;
+  static constexpr int pad_shift() {
+    int sh = 0;
+    while ((1 << sh) < NV_ - N_) ++sh;
+    return sh;
+  }
+};
+using FsDynamic = FsShape<0, 0, 0, 0, 0, 0, 0>;
+
 // PER = float4 token groups per slice (every slice computes PER groups; groups past the token axis read the padding and
 // contribute exact zeros), VEC4 = the token axis is a multiple of 4 (128-bit staging stores), RAW = the source rows are
-// staged in shared memory by the copy engine (else read through L1 with 128-bit loads).
-template <int PER, bool VEC4, bool RAW>
+// staged in shared memory by the copy engine (else read through L1 with 128-bit loads), SH = compile-time shape or FsDynamic.
+template <int PER, bool VEC4, bool RAW, class SH>
 __global__ void __launch_bounds__(FS_THREADS, 2)
-capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ probs, int s, int N, int R, int NV, int P, int TS,
-                         int rows_per_cta, int stage_floats, int pad_shift) {
+capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ probs, int s_, int N_, int R_, int NV_, int P_, int TS_,
+                         int rows_per_cta_, int stage_floats_, int pad_shift_) {
+  const int s = SH::FIXED ? SH::S : s_, N = SH::FIXED ? SH::N : N_, R = SH::FIXED ? SH::R : R_, NV = SH::FIXED ? SH::NV : NV_;
+  const int P = SH::FIXED ? SH::P : P_, TS = SH::FIXED ? SH::TS : TS_, rows_per_cta = SH::FIXED ? SH::ROWS : rows_per_cta_;
+  const int stage_floats = SH::FIXED ? ((SH::P * SH::N + 3) & ~3) : stage_floats_;
+  const int pad_shift = SH::FIXED ? SH::pad_shift() : pad_shift_;
   extern __shared__ __align__(16) unsigned char fs_smem[];
   const int vs_floats = (s + 4) * NV;
   const int row_floats = s * N;                                      // one low-res source row [s][N], contiguous
@@ -71,7 +90,7 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
   float* red = reinterpret_cast<float*>(ctab + R);                   // [FS_ROWS][32]
   float* psum = red + FS_ROWS * 32;                                  // [TS][P]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(psum + TS * P);       // RAW: arrival of the source rows
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int tid = threadIdx.x, NT = SH::FIXED ? SH::P * SH::TS : (int)blockDim.x, lane = tid & 31;
   const float scale = (float)s / (float)R;
   const int X_lane = tid % P, part = tid / P;
   const int pg = X_lane >> 5;                                        // pixel group (32 lanes x TS slices) and its named barrier
@@ -382,13 +401,17 @@ bool fs_plan(int s, int N, int R, FsPlan* pl) {
     pl->bytes = (pl->raw ? with_raw : base) * sizeof(float);
     if (pl->bytes <= 112 * 1024 || pl->rows == 1) break;
   }
-  return pl->bytes <= 112 * 1024;
+  if (pl->bytes <= 112 * 1024) return true;
+  // one CTA per SM for the shapes whose single-row footprint exceeds half an SM (N = 500 at s = 32: 144 KB): still ahead of
+  // the row kernel's 32-pixel x-blocks.  SKP_ATTN_STORE_BIG=0 sends them to the row kernel (A/B).
+  static const bool big = !(getenv("SKP_ATTN_STORE_BIG") && getenv("SKP_ATTN_STORE_BIG")[0] == '0');
+  return big && pl->bytes <= 200 * 1024;
 }
 
-template <int PER, bool VEC4, bool RAW>
+template <int PER, bool VEC4, bool RAW, class SH>
 int fs_launch(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st) {
   static size_t configured = 0;
-  auto kern = capture_store_reg_kernel<PER, VEC4, RAW>;
+  auto kern = capture_store_reg_kernel<PER, VEC4, RAW, SH>;
   if (pl.bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.bytes);
     if (e != cudaSuccess) {
@@ -409,15 +432,38 @@ int fs_launch(const float* logits, float* probs, int heads, int s, int N, int R,
 template <bool VEC4, bool RAW>
 int fs_dispatch(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st) {
   switch (pl.per) {
-    case 1: return fs_launch<1, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
-    case 2: return fs_launch<2, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
-    case 3: return fs_launch<3, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
-    case 4: return fs_launch<4, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
-    case 5: return fs_launch<5, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
-    case 6: return fs_launch<6, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
-    case 7: return fs_launch<7, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
-    default: return fs_launch<8, VEC4, RAW>(logits, probs, heads, s, N, R, pl, st);
+    case 1: return fs_launch<1, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
+    case 2: return fs_launch<2, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
+    case 3: return fs_launch<3, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
+    case 4: return fs_launch<4, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
+    case 5: return fs_launch<5, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
+    case 6: return fs_launch<6, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
+    case 7: return fs_launch<7, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
+    default: return fs_launch<8, VEC4, RAW, FsDynamic>(logits, probs, heads, s, N, R, pl, st);
   }
+}
+
+// The shapes the reference actually runs (SD1.5 captures 16x16 and 32x32 layers at R = 128 with 77 / 100 / 500 tokens; BASELINE
+// cfg5 is 32x32 -> 256 with 77) as compile-time specialisations.  A specialisation is used only when the run-time plan equals
+// its constants, so the planner stays the single source of truth.
+template <int PER, bool VEC4, bool RAW, class SH>
+bool fs_try_fixed(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st, int* rc) {
+  if (s != SH::S || N != SH::N || R != SH::R || pl.NV != SH::NV || pl.P != SH::P || pl.TS != SH::TS || pl.rows != SH::ROWS ||
+      pl.per != PER || (bool)pl.raw != RAW || ((N & 3) == 0) != VEC4)
+    return false;
+  *rc = fs_launch<PER, VEC4, RAW, SH>(logits, probs, heads, s, N, R, pl, st);
+  return true;
+}
+
+bool fs_fixed_dispatch(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st, int* rc) {
+  //                                          S   N    R    NV   P   TS  ROWS
+  if (fs_try_fixed<5, false, true, FsShape<32, 77, 256, 84, 128, 4, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+  if (fs_try_fixed<5, false, true, FsShape<16, 77, 128, 84, 128, 4, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+  if (fs_try_fixed<5, false, true, FsShape<32, 77, 128, 84, 128, 4, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+  if (fs_try_fixed<7, true, true, FsShape<16, 100, 128, 116, 128, 4, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+  if (fs_try_fixed<7, true, false, FsShape<32, 100, 128, 116, 128, 4, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+  if (fs_try_fixed<8, true, false, FsShape<16, 500, 128, 516, 32, 16, 1>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+  return false;
 }
 
 }  // namespace
@@ -429,6 +475,11 @@ int capture_store_reg(const float* logits, float* probs, int heads, int s, int N
   FsPlan pl;
   if (!fs_plan(s, N, R, &pl)) return SKP_OK;
   int rc;
+  static const bool no_fixed = getenv("SKP_ATTN_STORE_DYNAMIC") != nullptr;   // A/B: run-time shape arithmetic only
+  if (!no_fixed && fs_fixed_dispatch(logits, probs, heads, s, N, R, pl, st, &rc)) {
+    if (rc == SKP_OK) *handled = true;
+    return rc;
+  }
   if ((N & 3) == 0) rc = pl.raw ? fs_dispatch<true, true>(logits, probs, heads, s, N, R, pl, st) : fs_dispatch<true, false>(logits, probs, heads, s, N, R, pl, st);
   else rc = pl.raw ? fs_dispatch<false, true>(logits, probs, heads, s, N, R, pl, st) : fs_dispatch<false, false>(logits, probs, heads, s, N, R, pl, st);
   if (rc == SKP_OK) *handled = true;
