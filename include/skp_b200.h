@@ -161,6 +161,18 @@ int skp_self_attn_tc_fwd(const float* q, int64_t ldq, const float* k, int64_t ld
 int skp_self_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         void* planes, int S, int heads, int d, float scale, void* stream);
 
+/* Long-sequence self-attention BACKWARD on tcgen05 (skp_attn_tc_bwd.cu; the autograd pass through ptp_utils.py:493-506):
+ * one launch whose CTAs own either 128 keys (dK, dV accumulated in TMEM over all query tiles) or 128 queries (dQ); scores
+ * and dP recomputed per tile as tcgen05.mma, P / dS handed back to the tensor core through 128B-swizzled shared memory;
+ * split-bf16 products, no atomics.  Same eligibility as skp_self_attn_tc_fwd (S % 128 == 0, even d <= 64), whose o and
+ * base-2 lse it takes together with the fp32 q / k / v it re-splits; workspace = skp_self_attn_tc_bwd_workspace bytes,
+ * 128-byte aligned (0 = shape not eligible). */
+int64_t skp_self_attn_tc_bwd_workspace(int S, int heads, int d);
+int skp_self_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse, const float* q,
+                         int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, void* workspace, float* dq,
+                         int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale,
+                         void* stream);
+
 /* Cross-attention (attn2, ptp_utils.py:480-506) and short-sequence self-attention forward on tcgen05 / TMEM / TMA
  * (skp_xattn_tc.cu): any Sq / Skv, even head dims up to 160 (64-column K chunks), keys in tiles of 64 with the accumulator
  * resident in tensor memory.  logits != NULL (captured layers, ptp_utils.py:508-538): the scaled logits [heads, Sq, Skv] are

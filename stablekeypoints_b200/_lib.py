@@ -50,6 +50,8 @@ _SIGNATURES: Dict[str, list] = {
     "skp_self_attn_tc_workspace": [_I, _I, _I],
     "skp_self_attn_tc_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _F, _P],
     "skp_self_attn_split": [_P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _F, _P],
+    "skp_self_attn_tc_bwd_workspace": [_I, _I, _I],
+    "skp_self_attn_tc_bwd": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P],
     "skp_self_attn_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _F, _P],
     "skp_self_attn_bwd": [_P, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P],
     "skp_xattn_tc_workspace": [_I, _I, _I, _I],
@@ -90,7 +92,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_adam_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }
 _RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None, "skp_capture_select": None, "skp_capture_tc": None, "skp_capture_tc_trace": None,
-            "skp_self_attn_tc_workspace": C.c_int64,
+            "skp_self_attn_tc_workspace": C.c_int64, "skp_self_attn_tc_bwd_workspace": C.c_int64,
             "skp_capture_tc_workspace": C.c_int64, "skp_xattn_tc_workspace": C.c_int64,
             "skp_capture_mean_bwd_workspace": C.c_int64}
 

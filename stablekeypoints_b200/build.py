@@ -14,7 +14,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libskp_b200.so")
-SOURCES = ["skp_api.cu", "skp_capture.cu", "skp_capture_row.cu", "skp_capture_store.cu", "skp_capture_tc.cu", "skp_collect.cu", "skp_select.cu", "skp_loss.cu", "skp_attn.cu", "skp_selfattn.cu", "skp_attn_tc.cu", "skp_xattn_tc.cu", "skp_gemm_tc.cu", "skp_norm.cu", "skp_rowops.cu"]
+SOURCES = ["skp_api.cu", "skp_capture.cu", "skp_capture_row.cu", "skp_capture_store.cu", "skp_capture_tc.cu", "skp_collect.cu", "skp_select.cu", "skp_loss.cu", "skp_attn.cu", "skp_selfattn.cu", "skp_attn_tc.cu", "skp_attn_tc_bwd.cu", "skp_xattn_tc.cu", "skp_gemm_tc.cu", "skp_norm.cu", "skp_rowops.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-cudart", "static"]
 

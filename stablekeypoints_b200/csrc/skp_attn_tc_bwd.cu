@@ -1,0 +1,426 @@
+// Self-attention BACKWARD on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) for the long-sequence layers of the
+// frozen UNet (attn1 of the 64x64 blocks: S = 4096 tokens, 8 heads x d = 40; the autograd pass through ptp_utils.py:493-506
+// that carries d loss / d context back to the earlier cross-attention layers).  Numerics contract of skp_selfattn.cu and
+// skp_attn_tc.cu: every contraction is a split-bf16 product (hi.hi + hi.lo + lo.hi, fp32 accumulate), the probabilities
+// are recomputed from the forward's base-2 log-sum-exp, nothing [S, S]-sized touches HBM, no atomics (bit-reproducible).
+//
+// One launch, two kinds of CTA (blockIdx.z), both built from the same loop "resident 128-row block x streamed 64-row tiles":
+//   z = 0  dK / dV of 128 keys:  S^T = K Q'^T and dP^T = V dO^T (M128 x N64, accumulators in TMEM columns 0..127);
+//          P^T = exp2(S^T - lse[q]), dS^T = P^T (dP^T - delta[q]) by the element-wise warps (thread = key = TMEM lane),
+//          written split-bf16 into 128B-swizzled K-major shared memory; dV += P^T dO and dK += dS^T Q' as
+//          tcgen05.mma with the two [128 x DV] accumulators RESIDENT in TMEM (columns 128.., 192..) for the whole loop.
+//   z = 1  dQ of 128 queries:    S = Q' K^T, dP = dO V^T, dS = P (dP - delta[row]); dQ += dS K in TMEM.
+// Warp roles: 0 = TMA of the streamed row tiles, 1 = MMA issuer (software-pipelined: the score MMAs of tile j+1 are issued
+// before the accumulation MMAs of tile j, so they run while the element-wise warps work on tile j), 2 = TMA of the streamed
+// transposed tiles, 3..10 = element-wise (two warps per TMEM lane quarter, 32 score columns each).
+// Operands come pre-split from sa_tc_bwd_split_kernel: Q' (scaled by scale*log2 e), K, V, dO as [heads*S][64] planes and
+// Q'^T, K^T, dO^T as [heads*DV][S] planes (the B operands of the accumulation products), delta = rowsum(dO * O).
+// Eligibility (host): S % 128 == 0, d even and <= 64 -- the shapes the tcgen05 forward takes.
+#include "skp_tc.cuh"
+#include <math_constants.h>
+
+namespace skp {
+
+namespace {
+
+constexpr int BT_BM = 128;                       // resident rows per CTA
+constexpr int BT_BN = 64;                        // streamed rows per step
+constexpr int BT_EW_WARPS = 8;
+constexpr int BT_THREADS = 96 + 32 * BT_EW_WARPS;   // 352
+constexpr int BT_A_BYTES = BT_BM * 128;          // one bf16 plane of a 128-row tile (64 columns = 128 B per row)
+constexpr int BT_B_BYTES = BT_BN * 128;
+constexpr int BT_T_BYTES = 64 * 128;             // one plane of a transposed tile: up to 64 channel rows x 64 streamed rows
+constexpr int BT_SMEM = 8 * BT_A_BYTES + 4 * BT_B_BYTES + 4 * BT_T_BYTES + 256 + 1024;
+constexpr int BT_TMEM_COLS = 256;                // scores 0..63, dP 64..127, accumulators 128.. and 192..
+
+struct BtMaps {
+  CUtensorMap a1h, a1l, a2h, a2l;                // resident tiles (128 rows): K, V (z = 0) / Q', dO (z = 1)
+  CUtensorMap b1h, b1l, b2h, b2l;                // streamed tiles (64 rows):  Q', dO (z = 0) / K, V (z = 1)
+  CUtensorMap t1h, t1l, t2h, t2l;                // streamed transposed tiles [DV][64]: dO^T, Q'^T (z = 0) / -, K^T (z = 1)
+};
+
+__device__ __forceinline__ void bt_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float bt_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 8 consecutive fp32 -> one 16-byte chunk of the hi plane and one of the lo plane
+__device__ __forceinline__ void bt_split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+    float2 f = __bfloat1622float2(hh);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * e] - f.x, x[2 * e + 1] - f.y);
+    hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+    lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  hi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// q,k,v [S, heads*d] and d_o, o [S, heads*d] fp32 (leading dims) ->
+//   row planes   RP[t][2][heads*S][64]  t = Q' (scaled), K, V, dO          (hi, lo; zero padded to 64 columns)
+//   transposed   TP[t][2][heads*DV][S]  t = Q'^T, K^T, dO^T
+//   delta[heads][S] = sum_c dO * O
+__global__ void sa_tc_bwd_split_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
+                                       const float* __restrict__ v, int64_t ldv, const float* __restrict__ d_o, int64_t lddo,
+                                       const float* __restrict__ o, int64_t ldo, __nv_bfloat16* __restrict__ RP,
+                                       __nv_bfloat16* __restrict__ TP, float* __restrict__ delta, int S, int heads, int d, int DV,
+                                       float qscale) {
+  const long nrow = (long)heads * S * 32;           // bf16 pairs of one row plane
+  const long ntr = (long)heads * DV * (S / 2);      // bf16 pairs of one transposed plane
+  const long nd = (long)heads * S;
+  const long total = 4 * nrow + 3 * ntr + nd;
+  const size_t rp = (size_t)heads * S * 64, tp = (size_t)heads * DV * S;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float x, y;
+    __nv_bfloat16 *hi, *lo;
+    if (i < 4 * nrow) {
+      const int t = (int)(i / nrow);
+      const long r = i - (long)t * nrow;
+      const int c = (int)(r & 31) << 1;
+      const long hr = r >> 5;                        // h * S + row
+      const int h = (int)(hr / S), row = (int)(hr - (long)h * S);
+      const float* src = (t == 0 ? q + (size_t)row * ldq : t == 1 ? k + (size_t)row * ldk : t == 2 ? v + (size_t)row * ldv
+                                                                                                  : d_o + (size_t)row * lddo) + h * d;
+      x = c < d ? __ldg(src + c) : 0.f;
+      y = c + 1 < d ? __ldg(src + c + 1) : 0.f;
+      if (t == 0) { x *= qscale; y *= qscale; }
+      hi = RP + (size_t)t * 2 * rp + (size_t)hr * 64 + c;
+      lo = hi + rp;
+    } else if (i < 4 * nrow + 3 * ntr) {
+      // channel fastest: the row reads are coalesced, the transposed 4-byte writes scatter (absorbed by L2)
+      const long r0 = i - 4 * nrow;
+      const int t = (int)(r0 / ntr);
+      const long r = r0 - (long)t * ntr;
+      const int half = S >> 1;
+      const int c = (int)(r % DV);
+      const long hs = r / DV;                        // h * half + row pair
+      const int h = (int)(hs / half), s2 = (int)(hs - (long)h * half) << 1;
+      const float* src = t == 0 ? q : t == 1 ? k : d_o;
+      const int64_t ld = t == 0 ? ldq : t == 1 ? ldk : lddo;
+      x = c < d ? __ldg(src + (size_t)s2 * ld + h * d + c) : 0.f;
+      y = c < d ? __ldg(src + (size_t)(s2 + 1) * ld + h * d + c) : 0.f;
+      if (t == 0) { x *= qscale; y *= qscale; }
+      hi = TP + (size_t)t * 2 * tp + ((size_t)h * DV + c) * S + s2;
+      lo = hi + tp;
+    } else {
+      const long r = i - 4 * nrow - 3 * ntr;         // row * heads + h
+      const int row = (int)(r / heads), h = (int)(r - (long)row * heads);
+      const float* a = d_o + (size_t)row * lddo + h * d;
+      const float* b = o + (size_t)row * ldo + h * d;
+      float acc = 0.f;
+      for (int c = 0; c < d; ++c) acc = fmaf(__ldg(a + c), __ldg(b + c), acc);
+      delta[(size_t)h * S + row] = acc;
+      continue;
+    }
+    __nv_bfloat162 hh = __floats2bfloat162_rn(x, y);
+    float2 f = __bfloat1622float2(hh);
+    *reinterpret_cast<__nv_bfloat162*>(hi) = hh;
+    *reinterpret_cast<__nv_bfloat162*>(lo) = __floats2bfloat162_rn(x - f.x, y - f.y);
+  }
+}
+
+// DKV = true: resident rows are keys, out1 = dV, out2 = dK; false: resident rows are queries, out2 = dQ.
+template <int DV, bool DKV>
+__device__ __forceinline__ void bt_body(const BtMaps& mp, const float* __restrict__ lse, const float* __restrict__ delta,
+                                        float* __restrict__ out1, int64_t ld1, float* __restrict__ out2, int64_t ld2, int S, int d,
+                                        int ksteps, float scale2, uint8_t* smem_raw) {
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t sA1h = base, sA1l = sA1h + BT_A_BYTES, sA2h = sA1l + BT_A_BYTES, sA2l = sA2h + BT_A_BYTES;
+  const uint32_t sB1h = sA2l + BT_A_BYTES, sB1l = sB1h + BT_B_BYTES, sB2h = sB1l + BT_B_BYTES, sB2l = sB2h + BT_B_BYTES;
+  const uint32_t sT1h = sB2l + BT_B_BYTES, sT1l = sT1h + BT_T_BYTES, sT2h = sT1l + BT_T_BYTES, sT2l = sT2h + BT_T_BYTES;
+  const uint32_t sPh = sT2l + BT_T_BYTES, sPl = sPh + BT_A_BYTES, sDh = sPl + BT_A_BYTES, sDl = sDh + BT_A_BYTES;
+  const uint32_t bars = sDl + BT_A_BYTES;
+  enum { A_FULL = 0, B_FULL, B_EMPTY, T_FULL, T_EMPTY, S_FULL, S_EMPTY, E_FULL, E_EMPTY, DONE, NBARS };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * NBARS);
+  uint8_t* gPh = gen + (sPh - base);
+  uint8_t* gPl = gen + (sPl - base);
+  uint8_t* gDh = gen + (sDh - base);
+  uint8_t* gDl = gen + (sDl - base);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, r0 = blockIdx.x * BT_BM;
+  const int ntiles = S / BT_BN;
+  constexpr uint32_t EW = 32u * BT_EW_WARPS;
+
+  if (warp == 0 && lane == 0) {
+    for (int b = 0; b < NBARS; ++b) mbar_init(bars + 8 * b, (b == S_EMPTY || b == E_FULL) ? EW : 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BT_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bars + 8 * A_FULL, 4 * BT_A_BYTES);
+      tma_load_2d(sA1h, &mp.a1h, bars + 8 * A_FULL, 0, h * S + r0);
+      tma_load_2d(sA1l, &mp.a1l, bars + 8 * A_FULL, 0, h * S + r0);
+      tma_load_2d(sA2h, &mp.a2h, bars + 8 * A_FULL, 0, h * S + r0);
+      tma_load_2d(sA2l, &mp.a2l, bars + 8 * A_FULL, 0, h * S + r0);
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(bars + 8 * B_EMPTY, ((uint32_t)j & 1u) ^ 1u);
+        mbar_expect_tx(bars + 8 * B_FULL, 4 * BT_B_BYTES);
+        tma_load_2d(sB1h, &mp.b1h, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
+        tma_load_2d(sB1l, &mp.b1l, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
+        tma_load_2d(sB2h, &mp.b2h, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
+        tma_load_2d(sB2l, &mp.b2l, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(bars + 8 * T_EMPTY, ((uint32_t)j & 1u) ^ 1u);
+        mbar_expect_tx(bars + 8 * T_FULL, (DKV ? 4 : 2) * DV * 128);
+        if (DKV) {
+          tma_load_2d(sT1h, &mp.t1h, bars + 8 * T_FULL, j * BT_BN, h * DV);
+          tma_load_2d(sT1l, &mp.t1l, bars + 8 * T_FULL, j * BT_BN, h * DV);
+        }
+        tma_load_2d(sT2h, &mp.t2h, bars + 8 * T_FULL, j * BT_BN, h * DV);
+        tma_load_2d(sT2l, &mp.t2l, bars + 8 * T_FULL, j * BT_BN, h * DV);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptors: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (scores) / DV (accumulators)
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT_BN >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
+      const uint64_t dA1h = make_smem_desc(sA1h), dA1l = make_smem_desc(sA1l), dA2h = make_smem_desc(sA2h), dA2l = make_smem_desc(sA2l);
+      const uint64_t dB1h = make_smem_desc(sB1h), dB1l = make_smem_desc(sB1l), dB2h = make_smem_desc(sB2h), dB2l = make_smem_desc(sB2l);
+      const uint64_t dT1h = make_smem_desc(sT1h), dT1l = make_smem_desc(sT1l), dT2h = make_smem_desc(sT2h), dT2l = make_smem_desc(sT2l);
+      const uint64_t dPh = make_smem_desc(sPh), dPl = make_smem_desc(sPl), dDh = make_smem_desc(sDh), dDl = make_smem_desc(sDl);
+      auto issue_scores = [&](int j) {
+        mbar_wait(bars + 8 * B_FULL, (uint32_t)j & 1u);
+        if (j > 0) mbar_wait(bars + 8 * S_EMPTY, (uint32_t)(j - 1) & 1u);   // the previous scores have left TMEM
+        tc_fence_after();
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          umma_bf16(tmem, dA1l + adv, dB1h + adv, idesc_s, k != 0);
+          umma_bf16(tmem, dA1h + adv, dB1l + adv, idesc_s, 1u);
+          umma_bf16(tmem, dA1h + adv, dB1h + adv, idesc_s, 1u);
+        }
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          umma_bf16(tmem + 64, dA2l + adv, dB2h + adv, idesc_s, k != 0);
+          umma_bf16(tmem + 64, dA2h + adv, dB2l + adv, idesc_s, 1u);
+          umma_bf16(tmem + 64, dA2h + adv, dB2h + adv, idesc_s, 1u);
+        }
+        umma_commit(bars + 8 * B_EMPTY);   // streamed row tiles free once these MMAs retire
+        umma_commit(bars + 8 * S_FULL);    // ... and both score tiles are complete
+      };
+      mbar_wait(bars + 8 * A_FULL, 0);
+      issue_scores(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_scores(j + 1);
+        mbar_wait(bars + 8 * E_FULL, (uint32_t)j & 1u);    // P^T / dS of tile j are in shared memory
+        mbar_wait(bars + 8 * T_FULL, (uint32_t)j & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BT_BN / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          const uint32_t acc = (j != 0 || k != 0) ? 1u : 0u;
+          if (DKV) {
+            umma_bf16(tmem + 128, dPl + adv, dT1h + adv, idesc_o, acc);
+            umma_bf16(tmem + 128, dPh + adv, dT1l + adv, idesc_o, 1u);
+            umma_bf16(tmem + 128, dPh + adv, dT1h + adv, idesc_o, 1u);
+          }
+          umma_bf16(tmem + 192, dDl + adv, dT2h + adv, idesc_o, acc);
+          umma_bf16(tmem + 192, dDh + adv, dT2l + adv, idesc_o, 1u);
+          umma_bf16(tmem + 192, dDh + adv, dT2h + adv, idesc_o, 1u);
+        }
+        umma_commit(bars + 8 * T_EMPTY);
+        umma_commit(bars + 8 * E_EMPTY);
+      }
+      umma_commit(bars + 8 * DONE);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 3) >> 2;             // which 32 of the 64 score columns
+    const int r = quarter * 32 + lane;            // resident row inside the block
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t prow = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;   // K-major 128B-swizzled row
+    const uint32_t sw = (uint32_t)(r & 7);
+    float lse_r = 0.f, delta_r = 0.f;
+    if (!DKV) {
+      lse_r = __ldg(lse + (size_t)h * S + r0 + r);
+      delta_r = __ldg(delta + (size_t)h * S + r0 + r);
+    }
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      float lv[32], dl[32];
+      if (DKV) {                                  // per-column statistics of the streamed queries (warp-uniform addresses)
+        const float4* lp = reinterpret_cast<const float4*>(lse + (size_t)h * S + j * BT_BN + 32 * half);
+        const float4* dp = reinterpret_cast<const float4*>(delta + (size_t)h * S + j * BT_BN + 32 * half);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = __ldg(lp + i), b = __ldg(dp + i);
+          lv[4 * i] = a.x; lv[4 * i + 1] = a.y; lv[4 * i + 2] = a.z; lv[4 * i + 3] = a.w;
+          dl[4 * i] = b.x; dl[4 * i + 1] = b.y; dl[4 * i + 2] = b.z; dl[4 * i + 3] = b.w;
+        }
+      }
+      mbar_wait(bars + 8 * S_FULL, ph);
+      tc_fence_after();
+      float s[32], g[32];
+      tmem_ld32(trow + 32 * half, s);
+      tmem_ld32(trow + 64 + 32 * half, g);
+      tc_fence_before();
+      bt_arrive(bars + 8 * S_EMPTY);              // the score columns may be overwritten by tile j + 1
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p = bt_ex2(s[i] - (DKV ? lv[i] : lse_r));
+        s[i] = p;
+        g[i] = p * (g[i] - (DKV ? dl[i] : delta_r));
+      }
+      mbar_wait(bars + 8 * E_EMPTY, ph ^ 1u);     // the accumulation MMAs of tile j - 1 have read the staging tiles
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off = prow + ((((uint32_t)(4 * half + c)) ^ sw) << 4);
+        uint4 hi, lo;
+        if (DKV) {
+          bt_split8(s + 8 * c, hi, lo);
+          *reinterpret_cast<uint4*>(gPh + off) = hi;
+          *reinterpret_cast<uint4*>(gPl + off) = lo;
+        }
+        bt_split8(g + 8 * c, hi, lo);
+        *reinterpret_cast<uint4*>(gDh + off) = hi;
+        *reinterpret_cast<uint4*>(gDl + off) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      tc_fence_before();
+      bt_arrive(bars + 8 * E_FULL);
+    }
+    // ---- epilogue: the accumulators leave TMEM; this thread owns row r, columns [half*DV/2, (half+1)*DV/2)
+    mbar_wait(bars + 8 * DONE, 0);
+    tc_fence_after();
+    const int row = r0 + r;
+    constexpr int HC = DV / 2;
+#pragma unroll
+    for (int which = DKV ? 0 : 1; which < 2; ++which) {
+      float* orow = (which == 0 ? out1 + (size_t)row * ld1 : out2 + (size_t)row * ld2) + h * d;
+      const float sc = which == 0 ? 1.f : scale2;
+#pragma unroll
+      for (int c8 = 0; c8 < HC / 8; ++c8) {
+        float a[8];
+        const int c0 = half * HC + 8 * c8;
+        tmem_ld8(trow + (which == 0 ? 128 : 192) + c0, a);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2)
+          if (c0 + i < d) *reinterpret_cast<float2*>(orow + c0 + i) = make_float2(a[i] * sc, a[i + 1] * sc);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BT_TMEM_COLS));
+  }
+}
+
+template <int DV>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+sa_tc_bwd_kernel(const __grid_constant__ BtMaps kv, const __grid_constant__ BtMaps qm, const float* __restrict__ lse,
+                 const float* __restrict__ delta, float* __restrict__ dq, int64_t lddq, float* __restrict__ dk, int64_t lddk,
+                 float* __restrict__ dv, int64_t lddv, int S, int d, int ksteps, float scale) {
+  extern __shared__ uint8_t bt_smem_raw[];
+  if (blockIdx.z == 0)        // dK = ln 2 * dS^T Q'  (Q' carries scale * log2 e),  dV = P^T dO
+    bt_body<DV, true>(kv, lse, delta, dv, lddv, dk, lddk, S, d, ksteps, 0.6931471805599453f, bt_smem_raw);
+  else                        // dQ = scale * dS K
+    bt_body<DV, false>(qm, lse, delta, nullptr, 0, dq, lddq, S, d, ksteps, scale, bt_smem_raw);
+}
+
+int bt_dv(int d) { return d <= 16 ? 16 : d <= 32 ? 32 : d <= 48 ? 48 : 64; }
+
+template <int DV>
+int bt_launch(const __nv_bfloat16* RP, const __nv_bfloat16* TP, const float* lse, const float* delta, float* dq, int64_t lddq,
+              float* dk, int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale, cudaStream_t st) {
+  const size_t rp = (size_t)heads * S * 64, tp = (size_t)heads * DV * S;
+  const __nv_bfloat16 *Qh = RP, *Ql = RP + rp, *Kh = RP + 2 * rp, *Kl = RP + 3 * rp, *Vh = RP + 4 * rp, *Vl = RP + 5 * rp;
+  const __nv_bfloat16 *Dh = RP + 6 * rp, *Dl = RP + 7 * rp;
+  const __nv_bfloat16 *QTh = TP, *QTl = TP + tp, *KTh = TP + 2 * tp, *KTl = TP + 3 * tp, *DTh = TP + 4 * tp, *DTl = TP + 5 * tp;
+  BtMaps kv, qm;
+  int rc;
+  const int rows = heads * S, trows = heads * DV;
+#define BT_MAP(dst, ptr, R, KP, BOX) if ((rc = tc_make_map(&(dst), (ptr), (R), (KP), (BOX)))) return rc
+  BT_MAP(kv.a1h, Kh, rows, 64, BT_BM); BT_MAP(kv.a1l, Kl, rows, 64, BT_BM); BT_MAP(kv.a2h, Vh, rows, 64, BT_BM); BT_MAP(kv.a2l, Vl, rows, 64, BT_BM);
+  BT_MAP(kv.b1h, Qh, rows, 64, BT_BN); BT_MAP(kv.b1l, Ql, rows, 64, BT_BN); BT_MAP(kv.b2h, Dh, rows, 64, BT_BN); BT_MAP(kv.b2l, Dl, rows, 64, BT_BN);
+  BT_MAP(kv.t1h, DTh, trows, S, DV); BT_MAP(kv.t1l, DTl, trows, S, DV); BT_MAP(kv.t2h, QTh, trows, S, DV); BT_MAP(kv.t2l, QTl, trows, S, DV);
+  BT_MAP(qm.a1h, Qh, rows, 64, BT_BM); BT_MAP(qm.a1l, Ql, rows, 64, BT_BM); BT_MAP(qm.a2h, Dh, rows, 64, BT_BM); BT_MAP(qm.a2l, Dl, rows, 64, BT_BM);
+  BT_MAP(qm.b1h, Kh, rows, 64, BT_BN); BT_MAP(qm.b1l, Kl, rows, 64, BT_BN); BT_MAP(qm.b2h, Vh, rows, 64, BT_BN); BT_MAP(qm.b2l, Vl, rows, 64, BT_BN);
+  BT_MAP(qm.t2h, KTh, trows, S, DV); BT_MAP(qm.t2l, KTl, trows, S, DV);
+#undef BT_MAP
+  qm.t1h = qm.t2h;
+  qm.t1l = qm.t2l;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sa_tc_bwd_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
+    if (e != cudaSuccess) { set_error("self_attn_tc_bwd: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
+    configured = true;
+  }
+  dim3 grid(S / BT_BM, heads, 2);
+  sa_tc_bwd_kernel<DV><<<grid, BT_THREADS, BT_SMEM, st>>>(kv, qm, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, d, (d + 15) / 16, scale);
+  SKP_CHECK_LAUNCH("sa_tc_bwd_kernel");
+  return SKP_OK;
+}
+
+}  // namespace
+
+}  // namespace skp
+
+using namespace skp;
+
+// workspace bytes: 4 row-plane pairs [heads*S][64] + 3 transposed pairs [heads*DV][S] (bf16) + delta [heads][S] (fp32)
+extern "C" int64_t skp_self_attn_tc_bwd_workspace(int S, int heads, int d) {
+  if (S <= 0 || heads <= 0 || d <= 0 || d > 64 || (d & 1) || S % BT_BM != 0) return 0;
+  return ((int64_t)8 * heads * S * 64 + (int64_t)6 * heads * bt_dv(d) * S) * 2 + (int64_t)heads * S * 4;
+}
+
+extern "C" int skp_self_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse, const float* q,
+                                    int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, void* workspace,
+                                    float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, int S, int heads,
+                                    int d, float scale, void* stream) {
+  SKP_REQUIRE(d_o && o && lse && q && k && v && workspace && dq && dk && dv, "skp_self_attn_tc_bwd: null pointer");
+  SKP_REQUIRE(skp_self_attn_tc_bwd_workspace(S, heads, d) > 0, "skp_self_attn_tc_bwd: needs S %% 128 == 0 and even d <= 64 (S=%d d=%d)", S, d);
+  SKP_REQUIRE((lddq | lddk | lddv) % 2 == 0 && ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(workspace) & 127) == 0 && (reinterpret_cast<uintptr_t>(lse) & 15) == 0,
+              "skp_self_attn_tc_bwd: gradients must be 8-byte aligned with even ld, lse 16-byte and the workspace 128-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int DV = bt_dv(d);
+  __nv_bfloat16* RP = (__nv_bfloat16*)workspace;
+  __nv_bfloat16* TP = RP + (size_t)8 * heads * S * 64;
+  float* delta = reinterpret_cast<float*>(TP + (size_t)6 * heads * DV * S);
+  const long total = (long)4 * heads * S * 32 + (long)3 * heads * DV * (S / 2) + (long)heads * S;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sa_tc_bwd_split_kernel<<<(int)blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, d_o, lddo, o, ldo, RP, TP, delta, S, heads, d, DV,
+                                                      scale * 1.4426950408889634f);
+  SKP_CHECK_LAUNCH("sa_tc_bwd_split_kernel");
+  switch (DV) {
+    case 16: return bt_launch<16>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
+    case 32: return bt_launch<32>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
+    case 48: return bt_launch<48>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
+    default: return bt_launch<64>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
+  }
+}

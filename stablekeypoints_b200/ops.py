@@ -610,6 +610,8 @@ SELF_ATTN_MAX_D = 160
 # long sequences (S % 128 == 0, d <= 64): forward on the tcgen05/TMEM kernel of skp_attn_tc.cu ("0" = mma.sync kernels only)
 SELF_ATTN_TC = os.environ.get("SKP_SELF_ATTN_TC", "1") != "0"
 SELF_ATTN_TC_MIN_S = 1024
+# ... and their backward on the tcgen05 kernel of skp_attn_tc_bwd.cu ("0" = mma.sync backward on re-split planes)
+SELF_ATTN_TC_BWD = os.environ.get("SKP_SELF_ATTN_TC_BWD", "1") != "0"
 
 
 class _SelfAttnCore(torch.autograd.Function):
@@ -653,6 +655,15 @@ class _SelfAttnCore(torch.autograd.Function):
         o, lse, third = ctx.saved_tensors
         s, c, heads, d, dp, scale = ctx.meta
         d_o = _f32c(d_o)
+        if ctx.tc and SELF_ATTN_TC_BWD:   # tcgen05 backward (skp_attn_tc_bwd.cu): re-splits q / k / v / dO into its own operand planes
+            qkv, e, c3 = third, third.element_size(), 3 * c
+            ws = torch.empty(int(lib().skp_self_attn_tc_bwd_workspace(s, heads, d)), dtype=torch.uint8, device=o.device)
+            dqkv = torch.empty(s, 3 * c, dtype=torch.float32, device=o.device)
+            base = dqkv.data_ptr()
+            check(lib().skp_self_attn_tc_bwd(ptr(d_o), c, ptr(o), c, ptr(lse), qkv.data_ptr(), c3, qkv.data_ptr() + c * e, c3,
+                                             qkv.data_ptr() + 2 * c * e, c3, ptr(ws), base, 3 * c, base + 4 * c, 3 * c,
+                                             base + 8 * c, 3 * c, s, heads, d, scale, stream()), "skp_self_attn_tc_bwd")
+            return dqkv, None, None
         if ctx.tc:        # the tcgen05 forward keeps its own operand layout: make the mma.sync planes from qkv now
             qkv, e, c3 = third, third.element_size(), 3 * c
             planes = torch.empty(6 * heads * s * dp, dtype=torch.bfloat16, device=o.device)

@@ -218,9 +218,11 @@ def test_cross_attn_fwd_bwd(ops, monkeypatch, s, n, heads, d, impl, tol):
 @pytest.mark.parametrize("s,heads,d", [(4096, 8, 40), (1024, 8, 80), (256, 8, 160), (64, 8, 160), (16, 4, 8), (100, 2, 16),
                                        (4, 4, 32), (1100, 3, 24), (77, 2, 48), (128, 2, 16), (256, 3, 64), (1024, 4, 32),
                                        (384, 2, 48)])
-@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("tc", ["tcgen05", "tcgen05_fwd", "mma"])
 def test_self_attn_fwd_bwd(ops, s, heads, d, tc, monkeypatch):
-    monkeypatch.setattr(ops, "SELF_ATTN_TC", tc)            # tcgen05 forward (eligible shapes only) vs mma.sync forward
+    # tcgen05 forward + backward (eligible shapes only) / tcgen05 forward + mma.sync backward / mma.sync both
+    monkeypatch.setattr(ops, "SELF_ATTN_TC", tc != "mma")
+    monkeypatch.setattr(ops, "SELF_ATTN_TC_BWD", tc == "tcgen05")
     monkeypatch.setattr(ops, "SELF_ATTN_TC_MIN_S", 128)
     """Flash-style split-bf16 kernels vs float64 attention of the same packed [S, 3C] projection (fp32-grade: the
     softmax sits upstream of every captured map).  Ragged S, padded d and every tile shape are covered."""
@@ -239,7 +241,7 @@ def test_self_attn_fwd_bwd(ops, s, heads, d, tc, monkeypatch):
     (o * cu(do.float())).sum().backward()
     errs = [rel_err(o.detach().cpu(), o_ref.detach())]
     errs += [rel_err(x.grad[:, i * c:(i + 1) * c].cpu(), ref_in.grad[:, i * c:(i + 1) * c]) for i in range(3)]   # dq, dk, dv
-    print(f"self-attn S={s} h={heads} d={d}: rel err o/dq/dk/dv = {errs}")
+    print(f"self-attn[{tc}] S={s} h={heads} d={d}: rel err o/dq/dk/dv = {errs}")
     assert errs[0] < 5e-5 and max(errs[1:]) < 1e-4, errs
 
 
