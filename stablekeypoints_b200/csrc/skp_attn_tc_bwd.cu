@@ -5,14 +5,16 @@
 // are recomputed from the forward's base-2 log-sum-exp, nothing [S, S]-sized touches HBM, no atomics (bit-reproducible).
 //
 // One launch, two kinds of CTA (blockIdx.z), both built from the same loop "resident 128-row block x streamed 64-row tiles":
-//   z = 0  dK / dV of 128 keys:  S^T = K Q'^T and dP^T = V dO^T (M128 x N64, accumulators in TMEM columns 0..127);
+//   z = 0  dK / dV of 128 keys:  S^T = K Q'^T and dP^T = V dO^T (M128 x N64 into a TMEM score buffer);
 //          P^T = exp2(S^T - lse[q]), dS^T = P^T (dP^T - delta[q]) by the element-wise warps (thread = key = TMEM lane),
-//          written split-bf16 into 128B-swizzled K-major shared memory; dV += P^T dO and dK += dS^T Q' as
-//          tcgen05.mma with the two [128 x DV] accumulators RESIDENT in TMEM (columns 128.., 192..) for the whole loop.
+//          written back split-bf16 IN PLACE (tcgen05.st) as the A operands of dV += P^T dO and dK += dS^T Q', whose two
+//          [128 x DV] accumulators stay resident in TMEM for the whole loop.
 //   z = 1  dQ of 128 queries:    S = Q' K^T, dP = dO V^T, dS = P (dP - delta[row]); dQ += dS K in TMEM.
-// Warp roles: 0 = TMA of the streamed row tiles, 1 = MMA issuer (software-pipelined: the score MMAs of tile j+1 are issued
-// before the accumulation MMAs of tile j, so they run while the element-wise warps work on tile j), 2 = TMA of the streamed
-// transposed tiles, 3..10 = element-wise (two warps per TMEM lane quarter, 32 score columns each).
+// Every MMA takes its A operand from tensor memory (the resident block is copied there once per CTA) and only B through
+// shared memory; score buffers, streamed row tiles and streamed transposed tiles are double-buffered.
+// Warp roles: 0 = TMA of the streamed row tiles, 1 = MMA issuer (software-pipelined: the score MMAs of tile j+2 are issued
+// right behind the accumulation MMAs of tile j, so they run while the element-wise warps work on tile j+1), 2 = TMA of the
+// streamed transposed tiles, 3..10 = element-wise (two warps per TMEM lane quarter, 32 score columns each).
 // Operands come pre-split from sa_tc_bwd_split_kernel: Q' (scaled by scale*log2 e), K, V, dO as [heads*S][64] planes and
 // Q'^T, K^T, dO^T as [heads*DV][S] planes (the B operands of the accumulation products), delta = rowsum(dO * O).
 // Eligibility (host): S % 128 == 0, d even and <= 64 -- the shapes the tcgen05 forward takes.
@@ -27,20 +29,32 @@ constexpr int BT_BM = 128;                       // resident rows per CTA
 constexpr int BT_BN = 64;                        // streamed rows per step
 constexpr int BT_EW_WARPS = 8;
 constexpr int BT_THREADS = 96 + 32 * BT_EW_WARPS;   // 352
-constexpr int BT_A_BYTES = BT_BM * 128;          // one bf16 plane of a 128-row tile (64 columns = 128 B per row)
 constexpr int BT_B_BYTES = BT_BN * 128;
-constexpr int BT_T_BYTES = 64 * 128;             // one plane of a transposed tile: up to 64 channel rows x 64 streamed rows
-constexpr int BT_SMEM = 8 * BT_A_BYTES + 4 * BT_B_BYTES + 4 * BT_T_BYTES + 256 + 1024;
-constexpr int BT_TMEM_COLS = 256;                // scores 0..63, dP 64..127, accumulators 128.. and 192..
+constexpr int BT_TMEM_COLS = 512;                // the whole tensor memory of the SM: map in front of bt_body
+// double-buffered streamed row tiles [64][64] and transposed tiles [DV][64], four bf16 planes each (the resident block and
+// the P / dS staging live in tensor memory)
+constexpr int bt_smem(int DV) { return 8 * BT_B_BYTES + 8 * DV * 128 + 256 + 1024; }
 
 struct BtMaps {
-  CUtensorMap a1h, a1l, a2h, a2l;                // resident tiles (128 rows): K, V (z = 0) / Q', dO (z = 1)
   CUtensorMap b1h, b1l, b2h, b2l;                // streamed tiles (64 rows):  Q', dO (z = 0) / K, V (z = 1)
   CUtensorMap t1h, t1l, t2h, t2l;                // streamed transposed tiles [DV][64]: dO^T, Q'^T (z = 0) / -, K^T (z = 1)
 };
 
 __device__ __forceinline__ void bt_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// one elected lane of a converged warp: unlike `lane == 0` the compiler knows exactly one thread runs the region, so the
+// uniform-register operands of tcgen05.mma need no per-lane serialisation loop (ELECT / BRA.U.ANY around every UTCHMMA)
+__device__ __forceinline__ bool bt_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ float bt_ex2(float x) {
   float y;
@@ -56,19 +70,73 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-// 8 consecutive fp32 -> one 16-byte chunk of the hi plane and one of the lo plane
-__device__ __forceinline__ void bt_split8(const float* x, uint4& hi, uint4& lo) {
-  uint32_t hw[4], lw[4];
+// two 32-column loads of this warp's TMEM lanes, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, float a[32], float b[32]) {
+  uint32_t r[32], q[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+        "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+        "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int i = 0; i < 32; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(q[i]);
+  }
+}
+// 32 consecutive fp32 -> 16 bf16 pairs of the hi plane and 16 of the lo plane (element 2c in the low half of word c)
+__device__ __forceinline__ void bt_split32(const float* x, uint32_t hi[16], uint32_t lo[16]) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
     __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
     float2 f = __bfloat1622float2(hh);
     __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * e] - f.x, x[2 * e + 1] - f.y);
-    hw[e] = *reinterpret_cast<uint32_t*>(&hh);
-    lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+    hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+    lo[e] = *reinterpret_cast<uint32_t*>(&ll);
   }
-  hi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-  lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+// tcgen05.st: this thread's TMEM lane, 32 / 16 consecutive columns (completion: tcgen05.wait::st by the caller)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// tcgen05.mma with the A operand in tensor memory (lane = row, 16 bf16 of K = 8 columns), B through a shared-memory descriptor
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
 }
 
 // q,k,v [S, heads*d] and d_o, o [S, heads*d] fp32 (leading dims) ->
@@ -135,32 +203,38 @@ __global__ void sa_tc_bwd_split_kernel(const float* __restrict__ q, int64_t ldq,
 }
 
 // DKV = true: resident rows are keys, out1 = dV, out2 = dK; false: resident rows are queries, out2 = dQ.
+// TMEM map (512 columns x 128 lanes, lane = resident row):
+//   [0,128) and [128,256)  score buffers: S | dP (fp32) from the tensor core, overwritten IN PLACE by the element-wise warps
+//                          with P hi | P lo | dS hi | dS lo (bf16 pairs, 32 columns each) -- the A operands of the accumulation MMAs
+//   [256,320) [320,384)    accumulators (dV, dK  /  -, dQ), resident for the whole loop
+//   [384,512)              the resident block itself, split-bf16: A1 hi | A1 lo | A2 hi | A2 lo (A operands of the score MMAs)
+// Every MMA takes A from tensor memory and only B through shared memory: with three MMAs per product the shared-memory
+// re-reads of A were what bound the first version of this kernel (ncu: 33 % tensor pipe, ~2 us per 64-row step).
 template <int DV, bool DKV>
-__device__ __forceinline__ void bt_body(const BtMaps& mp, const float* __restrict__ lse, const float* __restrict__ delta,
+__device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* __restrict__ a1_planes,
+                                        const __nv_bfloat16* __restrict__ a2_planes, size_t plane_stride,
+                                        const float* __restrict__ lse, const float* __restrict__ delta,
                                         float* __restrict__ out1, int64_t ld1, float* __restrict__ out2, int64_t ld2, int S, int d,
                                         int ksteps, float scale2, uint8_t* smem_raw) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t sA1h = base, sA1l = sA1h + BT_A_BYTES, sA2h = sA1l + BT_A_BYTES, sA2l = sA2h + BT_A_BYTES;
-  const uint32_t sB1h = sA2l + BT_A_BYTES, sB1l = sB1h + BT_B_BYTES, sB2h = sB1l + BT_B_BYTES, sB2l = sB2h + BT_B_BYTES;
-  const uint32_t sT1h = sB2l + BT_B_BYTES, sT1l = sT1h + BT_T_BYTES, sT2h = sT1l + BT_T_BYTES, sT2l = sT2h + BT_T_BYTES;
-  const uint32_t sPh = sT2l + BT_T_BYTES, sPl = sPh + BT_A_BYTES, sDh = sPl + BT_A_BYTES, sDl = sDh + BT_A_BYTES;
-  const uint32_t bars = sDl + BT_A_BYTES;
-  enum { A_FULL = 0, B_FULL, B_EMPTY, T_FULL, T_EMPTY, S_FULL, S_EMPTY, E_FULL, E_EMPTY, DONE, NBARS };
+  constexpr int BT_T_BYTES = DV * 128;
+  const uint32_t sB = base;                        // [2 buffers][B1h, B1l, B2h, B2l]
+  const uint32_t sT = sB + 8 * BT_B_BYTES;         // [2 buffers][T1h, T1l, T2h, T2l]
+  const uint32_t bars = sT + 8 * BT_T_BYTES;
+  // B_*, T_*, S_FULL, E_FULL exist per buffer (index + (j & 1), phase (j >> 1) & 1)
+  enum { A_FULL = 0, B_FULL, B_FULL1, B_EMPTY, B_EMPTY1, T_FULL, T_FULL1, T_EMPTY, T_EMPTY1, S_FULL, S_FULL1, E_FULL, E_FULL1, DONE, NBARS };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * NBARS);
-  uint8_t* gPh = gen + (sPh - base);
-  uint8_t* gPl = gen + (sPl - base);
-  uint8_t* gDh = gen + (sDh - base);
-  uint8_t* gDl = gen + (sDl - base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, r0 = blockIdx.x * BT_BM;
   const int ntiles = S / BT_BN;
   constexpr uint32_t EW = 32u * BT_EW_WARPS;
+  constexpr uint32_t TM_ACC1 = 256, TM_ACC2 = 320, TM_A = 384;
 
   if (warp == 0 && lane == 0) {
-    for (int b = 0; b < NBARS; ++b) mbar_init(bars + 8 * b, (b == S_EMPTY || b == E_FULL) ? EW : 1u);
+    for (int b = 0; b < NBARS; ++b) mbar_init(bars + 8 * b, (b == A_FULL || b == E_FULL || b == E_FULL1) ? EW : 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -174,83 +248,93 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const float* __restric
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bars + 8 * A_FULL, 4 * BT_A_BYTES);
-      tma_load_2d(sA1h, &mp.a1h, bars + 8 * A_FULL, 0, h * S + r0);
-      tma_load_2d(sA1l, &mp.a1l, bars + 8 * A_FULL, 0, h * S + r0);
-      tma_load_2d(sA2h, &mp.a2h, bars + 8 * A_FULL, 0, h * S + r0);
-      tma_load_2d(sA2l, &mp.a2l, bars + 8 * A_FULL, 0, h * S + r0);
       for (int j = 0; j < ntiles; ++j) {
-        mbar_wait(bars + 8 * B_EMPTY, ((uint32_t)j & 1u) ^ 1u);
-        mbar_expect_tx(bars + 8 * B_FULL, 4 * BT_B_BYTES);
-        tma_load_2d(sB1h, &mp.b1h, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
-        tma_load_2d(sB1l, &mp.b1l, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
-        tma_load_2d(sB2h, &mp.b2h, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
-        tma_load_2d(sB2l, &mp.b2l, bars + 8 * B_FULL, 0, h * S + j * BT_BN);
+        const int b = j & 1;
+        const uint32_t full = bars + 8 * (B_FULL + b), dst = sB + (uint32_t)b * 4u * BT_B_BYTES;
+        mbar_wait(bars + 8 * (B_EMPTY + b), (((uint32_t)j >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(full, 4 * BT_B_BYTES);
+        tma_load_2d(dst, &mp.b1h, full, 0, h * S + j * BT_BN);
+        tma_load_2d(dst + BT_B_BYTES, &mp.b1l, full, 0, h * S + j * BT_BN);
+        tma_load_2d(dst + 2 * BT_B_BYTES, &mp.b2h, full, 0, h * S + j * BT_BN);
+        tma_load_2d(dst + 3 * BT_B_BYTES, &mp.b2l, full, 0, h * S + j * BT_BN);
       }
     }
   } else if (warp == 2) {
     if (lane == 0) {
       for (int j = 0; j < ntiles; ++j) {
-        mbar_wait(bars + 8 * T_EMPTY, ((uint32_t)j & 1u) ^ 1u);
-        mbar_expect_tx(bars + 8 * T_FULL, (DKV ? 4 : 2) * DV * 128);
+        const int b = j & 1;
+        const uint32_t full = bars + 8 * (T_FULL + b), dst = sT + (uint32_t)b * 4u * BT_T_BYTES;
+        mbar_wait(bars + 8 * (T_EMPTY + b), (((uint32_t)j >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(full, (DKV ? 4 : 2) * BT_T_BYTES);
         if (DKV) {
-          tma_load_2d(sT1h, &mp.t1h, bars + 8 * T_FULL, j * BT_BN, h * DV);
-          tma_load_2d(sT1l, &mp.t1l, bars + 8 * T_FULL, j * BT_BN, h * DV);
+          tma_load_2d(dst, &mp.t1h, full, j * BT_BN, h * DV);
+          tma_load_2d(dst + BT_T_BYTES, &mp.t1l, full, j * BT_BN, h * DV);
         }
-        tma_load_2d(sT2h, &mp.t2h, bars + 8 * T_FULL, j * BT_BN, h * DV);
-        tma_load_2d(sT2l, &mp.t2l, bars + 8 * T_FULL, j * BT_BN, h * DV);
+        tma_load_2d(dst + 2 * BT_T_BYTES, &mp.t2h, full, j * BT_BN, h * DV);
+        tma_load_2d(dst + 3 * BT_T_BYTES, &mp.t2l, full, j * BT_BN, h * DV);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (bt_elect_one()) {
       // instruction descriptors: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (scores) / DV (accumulators)
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT_BN >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
-      const uint64_t dA1h = make_smem_desc(sA1h), dA1l = make_smem_desc(sA1l), dA2h = make_smem_desc(sA2h), dA2l = make_smem_desc(sA2l);
-      const uint64_t dB1h = make_smem_desc(sB1h), dB1l = make_smem_desc(sB1l), dB2h = make_smem_desc(sB2h), dB2l = make_smem_desc(sB2l);
-      const uint64_t dT1h = make_smem_desc(sT1h), dT1l = make_smem_desc(sT1l), dT2h = make_smem_desc(sT2h), dT2l = make_smem_desc(sT2l);
-      const uint64_t dPh = make_smem_desc(sPh), dPl = make_smem_desc(sPl), dDh = make_smem_desc(sDh), dDl = make_smem_desc(sDl);
+      const uint32_t tA1h = tmem + TM_A, tA1l = tA1h + 32, tA2h = tA1h + 64, tA2l = tA1h + 96;
       auto issue_scores = [&](int j) {
-        mbar_wait(bars + 8 * B_FULL, (uint32_t)j & 1u);
-        if (j > 0) mbar_wait(bars + 8 * S_EMPTY, (uint32_t)(j - 1) & 1u);   // the previous scores have left TMEM
+        const int b = j & 1;
+        const uint32_t ts = tmem + (uint32_t)b * 128u;
+        const uint32_t sb = sB + (uint32_t)b * 4u * BT_B_BYTES;
+        const uint64_t dB1h = make_smem_desc(sb), dB1l = make_smem_desc(sb + BT_B_BYTES);
+        const uint64_t dB2h = make_smem_desc(sb + 2 * BT_B_BYTES), dB2l = make_smem_desc(sb + 3 * BT_B_BYTES);
+        mbar_wait(bars + 8 * (B_FULL + b), ((uint32_t)j >> 1) & 1u);
         tc_fence_after();
+        // (the buffer's previous tenant, tile j - 2, was consumed by accumulation MMAs issued before these: in-order pipe)
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          umma_bf16(tmem, dA1l + adv, dB1h + adv, idesc_s, k != 0);
-          umma_bf16(tmem, dA1h + adv, dB1l + adv, idesc_s, 1u);
-          umma_bf16(tmem, dA1h + adv, dB1h + adv, idesc_s, 1u);
+          const uint32_t ka = 8u * (uint32_t)k;             // 16 bf16 of K = 8 TMEM columns
+          umma_bf16_ts(ts, tA1l + ka, dB1h + adv, idesc_s, k != 0);
+          umma_bf16_ts(ts, tA1h + ka, dB1l + adv, idesc_s, 1u);
+          umma_bf16_ts(ts, tA1h + ka, dB1h + adv, idesc_s, 1u);
         }
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          umma_bf16(tmem + 64, dA2l + adv, dB2h + adv, idesc_s, k != 0);
-          umma_bf16(tmem + 64, dA2h + adv, dB2l + adv, idesc_s, 1u);
-          umma_bf16(tmem + 64, dA2h + adv, dB2h + adv, idesc_s, 1u);
+          const uint32_t ka = 8u * (uint32_t)k;
+          umma_bf16_ts(ts + 64, tA2l + ka, dB2h + adv, idesc_s, k != 0);
+          umma_bf16_ts(ts + 64, tA2h + ka, dB2l + adv, idesc_s, 1u);
+          umma_bf16_ts(ts + 64, tA2h + ka, dB2h + adv, idesc_s, 1u);
         }
-        umma_commit(bars + 8 * B_EMPTY);   // streamed row tiles free once these MMAs retire
-        umma_commit(bars + 8 * S_FULL);    // ... and both score tiles are complete
+        umma_commit(bars + 8 * (B_EMPTY + b));   // this buffer of streamed row tiles is free once these MMAs retire
+        umma_commit(bars + 8 * (S_FULL + b));    // ... and both score tiles are complete
       };
-      mbar_wait(bars + 8 * A_FULL, 0);
+      mbar_wait(bars + 8 * A_FULL, 0);            // the resident block is in tensor memory
+      tc_fence_after();
       issue_scores(0);
+      if (ntiles > 1) issue_scores(1);
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_scores(j + 1);
-        mbar_wait(bars + 8 * E_FULL, (uint32_t)j & 1u);    // P^T / dS of tile j are in shared memory
-        mbar_wait(bars + 8 * T_FULL, (uint32_t)j & 1u);
+        const int b = j & 1;
+        const uint32_t par = ((uint32_t)j >> 1) & 1u, ts = tmem + (uint32_t)b * 128u;
+        const uint32_t st = sT + (uint32_t)b * 4u * BT_T_BYTES;
+        const uint64_t dT1h = make_smem_desc(st), dT1l = make_smem_desc(st + BT_T_BYTES);
+        const uint64_t dT2h = make_smem_desc(st + 2 * BT_T_BYTES), dT2l = make_smem_desc(st + 3 * BT_T_BYTES);
+        mbar_wait(bars + 8 * (E_FULL + b), par);    // P^T / dS of tile j sit in the score buffer
+        mbar_wait(bars + 8 * (T_FULL + b), par);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BT_BN / 16; ++k) {
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          const uint32_t ka = 8u * (uint32_t)k;
           const uint32_t acc = (j != 0 || k != 0) ? 1u : 0u;
           if (DKV) {
-            umma_bf16(tmem + 128, dPl + adv, dT1h + adv, idesc_o, acc);
-            umma_bf16(tmem + 128, dPh + adv, dT1l + adv, idesc_o, 1u);
-            umma_bf16(tmem + 128, dPh + adv, dT1h + adv, idesc_o, 1u);
+            umma_bf16_ts(tmem + TM_ACC1, ts + 32 + ka, dT1h + adv, idesc_o, acc);
+            umma_bf16_ts(tmem + TM_ACC1, ts + ka, dT1l + adv, idesc_o, 1u);
+            umma_bf16_ts(tmem + TM_ACC1, ts + ka, dT1h + adv, idesc_o, 1u);
           }
-          umma_bf16(tmem + 192, dDl + adv, dT2h + adv, idesc_o, acc);
-          umma_bf16(tmem + 192, dDh + adv, dT2l + adv, idesc_o, 1u);
-          umma_bf16(tmem + 192, dDh + adv, dT2h + adv, idesc_o, 1u);
+          umma_bf16_ts(tmem + TM_ACC2, ts + 96 + ka, dT2h + adv, idesc_o, acc);
+          umma_bf16_ts(tmem + TM_ACC2, ts + 64 + ka, dT2l + adv, idesc_o, 1u);
+          umma_bf16_ts(tmem + TM_ACC2, ts + 64 + ka, dT2h + adv, idesc_o, 1u);
         }
-        umma_commit(bars + 8 * T_EMPTY);
-        umma_commit(bars + 8 * E_EMPTY);
+        umma_commit(bars + 8 * (T_EMPTY + b));
+        if (j + 2 < ntiles) issue_scores(j + 2);   // runs while the element-wise warps work on tile j + 1
       }
       umma_commit(bars + 8 * DONE);
     }
@@ -260,56 +344,69 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const float* __restric
     const int half = (warp - 3) >> 2;             // which 32 of the 64 score columns
     const int r = quarter * 32 + lane;            // resident row inside the block
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t prow = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;   // K-major 128B-swizzled row
-    const uint32_t sw = (uint32_t)(r & 7);
+    // ---- the resident block goes to tensor memory: this thread's row of A1 (half 0) or A2 (half 1), hi and lo planes
+    {
+      const __nv_bfloat16* src = (half == 0 ? a1_planes : a2_planes) + ((size_t)h * S + r0 + r) * 64;
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(src + (size_t)pl * plane_stride);
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(p4 + i);
+          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        tmem_st32(trow + TM_A + 64 * half + 32 * pl, w);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      bt_arrive(bars + 8 * A_FULL);
+    }
     float lse_r = 0.f, delta_r = 0.f;
     if (!DKV) {
       lse_r = __ldg(lse + (size_t)h * S + r0 + r);
       delta_r = __ldg(delta + (size_t)h * S + r0 + r);
     }
-    for (int j = 0; j < ntiles; ++j) {
-      const uint32_t ph = (uint32_t)j & 1u;
-      float lv[32], dl[32];
-      if (DKV) {                                  // per-column statistics of the streamed queries (warp-uniform addresses)
-        const float4* lp = reinterpret_cast<const float4*>(lse + (size_t)h * S + j * BT_BN + 32 * half);
-        const float4* dp = reinterpret_cast<const float4*>(delta + (size_t)h * S + j * BT_BN + 32 * half);
+    float lv[32], dl[32];
+    auto load_stats = [&](int j) {                // per-column statistics of the streamed queries (warp-uniform addresses)
+      const float4* lp = reinterpret_cast<const float4*>(lse + (size_t)h * S + j * BT_BN + 32 * half);
+      const float4* dp = reinterpret_cast<const float4*>(delta + (size_t)h * S + j * BT_BN + 32 * half);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 a = __ldg(lp + i), b = __ldg(dp + i);
-          lv[4 * i] = a.x; lv[4 * i + 1] = a.y; lv[4 * i + 2] = a.z; lv[4 * i + 3] = a.w;
-          dl[4 * i] = b.x; dl[4 * i + 1] = b.y; dl[4 * i + 2] = b.z; dl[4 * i + 3] = b.w;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = __ldg(lp + i), b = __ldg(dp + i);
+        lv[4 * i] = a.x; lv[4 * i + 1] = a.y; lv[4 * i + 2] = a.z; lv[4 * i + 3] = a.w;
+        dl[4 * i] = b.x; dl[4 * i + 1] = b.y; dl[4 * i + 2] = b.z; dl[4 * i + 3] = b.w;
       }
-      mbar_wait(bars + 8 * S_FULL, ph);
+    };
+    if (DKV) load_stats(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int sbuf = j & 1;
+      const uint32_t ts = trow + 128u * (uint32_t)sbuf;
+      mbar_wait(bars + 8 * (S_FULL + sbuf), ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
       float s[32], g[32];
-      tmem_ld32(trow + 32 * half, s);
-      tmem_ld32(trow + 64 + 32 * half, g);
-      tc_fence_before();
-      bt_arrive(bars + 8 * S_EMPTY);              // the score columns may be overwritten by tile j + 1
+      tmem_ld32x2(ts + 32 * half, ts + 64 + 32 * half, s, g);
+      // the bf16 results overwrite score columns the partner warp of this lane quarter reads: both must have loaded
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float p = bt_ex2(s[i] - (DKV ? lv[i] : lse_r));
         s[i] = p;
         g[i] = p * (g[i] - (DKV ? dl[i] : delta_r));
       }
-      mbar_wait(bars + 8 * E_EMPTY, ph ^ 1u);     // the accumulation MMAs of tile j - 1 have read the staging tiles
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t off = prow + ((((uint32_t)(4 * half + c)) ^ sw) << 4);
-        uint4 hi, lo;
-        if (DKV) {
-          bt_split8(s + 8 * c, hi, lo);
-          *reinterpret_cast<uint4*>(gPh + off) = hi;
-          *reinterpret_cast<uint4*>(gPl + off) = lo;
-        }
-        bt_split8(g + 8 * c, hi, lo);
-        *reinterpret_cast<uint4*>(gDh + off) = hi;
-        *reinterpret_cast<uint4*>(gDl + off) = lo;
+      if (DKV && j + 1 < ntiles) load_stats(j + 1);   // lands behind the conversions and the next tile's wait
+      uint32_t hi[16], lo[16];
+      if (DKV) {
+        bt_split32(s, hi, lo);
+        tmem_st16(ts + 16 * half, hi);            // P hi: columns [0,32), two queries per column
+        tmem_st16(ts + 32 + 16 * half, lo);       // P lo: columns [32,64)
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      bt_split32(g, hi, lo);
+      tmem_st16(ts + 64 + 16 * half, hi);         // dS hi: columns [64,96)
+      tmem_st16(ts + 96 + 16 * half, lo);         // dS lo: columns [96,128)
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      bt_arrive(bars + 8 * E_FULL);
+      bt_arrive(bars + 8 * (E_FULL + sbuf));
     }
     // ---- epilogue: the accumulators leave TMEM; this thread owns row r, columns [half*DV/2, (half+1)*DV/2)
     mbar_wait(bars + 8 * DONE, 0);
@@ -324,7 +421,7 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const float* __restric
       for (int c8 = 0; c8 < HC / 8; ++c8) {
         float a[8];
         const int c0 = half * HC + 8 * c8;
-        tmem_ld8(trow + (which == 0 ? 128 : 192) + c0, a);
+        tmem_ld8(trow + (which == 0 ? TM_ACC1 : TM_ACC2) + c0, a);
 #pragma unroll
         for (int i = 0; i < 8; i += 2)
           if (c0 + i < d) *reinterpret_cast<float2*>(orow + c0 + i) = make_float2(a[i] * sc, a[i + 1] * sc);
@@ -341,14 +438,14 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const float* __restric
 
 template <int DV>
 __global__ void __launch_bounds__(BT_THREADS, 1)
-sa_tc_bwd_kernel(const __grid_constant__ BtMaps kv, const __grid_constant__ BtMaps qm, const float* __restrict__ lse,
-                 const float* __restrict__ delta, float* __restrict__ dq, int64_t lddq, float* __restrict__ dk, int64_t lddk,
-                 float* __restrict__ dv, int64_t lddv, int S, int d, int ksteps, float scale) {
+sa_tc_bwd_kernel(const __grid_constant__ BtMaps kv, const __grid_constant__ BtMaps qm, const __nv_bfloat16* __restrict__ RP,
+                 size_t rp, const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq, int64_t lddq,
+                 float* __restrict__ dk, int64_t lddk, float* __restrict__ dv, int64_t lddv, int S, int d, int ksteps, float scale) {
   extern __shared__ uint8_t bt_smem_raw[];
-  if (blockIdx.z == 0)        // dK = ln 2 * dS^T Q'  (Q' carries scale * log2 e),  dV = P^T dO
-    bt_body<DV, true>(kv, lse, delta, dv, lddv, dk, lddk, S, d, ksteps, 0.6931471805599453f, bt_smem_raw);
-  else                        // dQ = scale * dS K
-    bt_body<DV, false>(qm, lse, delta, nullptr, 0, dq, lddq, S, d, ksteps, scale, bt_smem_raw);
+  if (blockIdx.z == 0)        // resident K, V;  dK = ln 2 * dS^T Q'  (Q' carries scale * log2 e),  dV = P^T dO
+    bt_body<DV, true>(kv, RP + 2 * rp, RP + 4 * rp, rp, lse, delta, dv, lddv, dk, lddk, S, d, ksteps, 0.6931471805599453f, bt_smem_raw);
+  else                        // resident Q', dO;  dQ = scale * dS K
+    bt_body<DV, false>(qm, RP, RP + 6 * rp, rp, lse, delta, nullptr, 0, dq, lddq, S, d, ksteps, scale, bt_smem_raw);
 }
 
 int bt_dv(int d) { return d <= 16 ? 16 : d <= 32 ? 32 : d <= 48 ? 48 : 64; }
@@ -364,10 +461,8 @@ int bt_launch(const __nv_bfloat16* RP, const __nv_bfloat16* TP, const float* lse
   int rc;
   const int rows = heads * S, trows = heads * DV;
 #define BT_MAP(dst, ptr, R, KP, BOX) if ((rc = tc_make_map(&(dst), (ptr), (R), (KP), (BOX)))) return rc
-  BT_MAP(kv.a1h, Kh, rows, 64, BT_BM); BT_MAP(kv.a1l, Kl, rows, 64, BT_BM); BT_MAP(kv.a2h, Vh, rows, 64, BT_BM); BT_MAP(kv.a2l, Vl, rows, 64, BT_BM);
   BT_MAP(kv.b1h, Qh, rows, 64, BT_BN); BT_MAP(kv.b1l, Ql, rows, 64, BT_BN); BT_MAP(kv.b2h, Dh, rows, 64, BT_BN); BT_MAP(kv.b2l, Dl, rows, 64, BT_BN);
   BT_MAP(kv.t1h, DTh, trows, S, DV); BT_MAP(kv.t1l, DTl, trows, S, DV); BT_MAP(kv.t2h, QTh, trows, S, DV); BT_MAP(kv.t2l, QTl, trows, S, DV);
-  BT_MAP(qm.a1h, Qh, rows, 64, BT_BM); BT_MAP(qm.a1l, Ql, rows, 64, BT_BM); BT_MAP(qm.a2h, Dh, rows, 64, BT_BM); BT_MAP(qm.a2l, Dl, rows, 64, BT_BM);
   BT_MAP(qm.b1h, Kh, rows, 64, BT_BN); BT_MAP(qm.b1l, Kl, rows, 64, BT_BN); BT_MAP(qm.b2h, Vh, rows, 64, BT_BN); BT_MAP(qm.b2l, Vl, rows, 64, BT_BN);
   BT_MAP(qm.t2h, KTh, trows, S, DV); BT_MAP(qm.t2l, KTl, trows, S, DV);
 #undef BT_MAP
@@ -375,12 +470,12 @@ int bt_launch(const __nv_bfloat16* RP, const __nv_bfloat16* TP, const float* lse
   qm.t1l = qm.t2l;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sa_tc_bwd_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(sa_tc_bwd_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem(DV));
     if (e != cudaSuccess) { set_error("self_attn_tc_bwd: smem attr: %s", cudaGetErrorString(e)); return SKP_ERR_LAUNCH; }
     configured = true;
   }
   dim3 grid(S / BT_BM, heads, 2);
-  sa_tc_bwd_kernel<DV><<<grid, BT_THREADS, BT_SMEM, st>>>(kv, qm, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, d, (d + 15) / 16, scale);
+  sa_tc_bwd_kernel<DV><<<grid, BT_THREADS, bt_smem(DV), st>>>(kv, qm, RP, rp, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, d, (d + 15) / 16, scale);
   SKP_CHECK_LAUNCH("sa_tc_bwd_kernel");
   return SKP_OK;
 }
