@@ -122,7 +122,7 @@ sa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(bars + 8 * Q_FULL, 2 * FT_Q_BYTES);
       tma_load_2d(sQh, &tm_q_hi, bars + 8 * Q_FULL, 0, h * S + q0);
       tma_load_2d(sQl, &tm_q_lo, bars + 8 * Q_FULL, 0, h * S + q0);
@@ -139,7 +139,7 @@ sa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // instruction descriptors: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (scores) / DV (output)
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FT_BN >> 3) << 17) | ((uint32_t)(FT_BM >> 4) << 24);
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(FT_BM >> 4) << 24);

@@ -43,19 +43,6 @@ struct BtMaps {
 __device__ __forceinline__ void bt_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// one elected lane of a converged warp: unlike `lane == 0` the compiler knows exactly one thread runs the region, so the
-// uniform-register operands of tcgen05.mma need no per-lane serialisation loop (ELECT / BRA.U.ANY around every UTCHMMA)
-__device__ __forceinline__ bool bt_elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ float bt_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -247,7 +234,7 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int j = 0; j < ntiles; ++j) {
         const int b = j & 1;
         const uint32_t full = bars + 8 * (B_FULL + b), dst = sB + (uint32_t)b * 4u * BT_B_BYTES;
@@ -260,7 +247,7 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
       }
     }
   } else if (warp == 2) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int j = 0; j < ntiles; ++j) {
         const int b = j & 1;
         const uint32_t full = bars + 8 * (T_FULL + b), dst = sT + (uint32_t)b * 4u * BT_T_BYTES;
@@ -275,7 +262,7 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
       }
     }
   } else if (warp == 1) {
-    if (bt_elect_one()) {
+    if (elect_one_sync()) {
       // instruction descriptors: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (scores) / DV (accumulators)
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT_BN >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);

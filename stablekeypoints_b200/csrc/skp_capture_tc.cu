@@ -341,7 +341,7 @@ __global__ void __launch_bounds__((9 + PW) * 32, 1) capture_tc_kernel(const CapT
 
   if (warp == 8 + PW - 1) {
     // =========================================================== DMA warp: source rows in, staged rows out
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const int max_rowfl = (p.slot_floats - 128) >> 2;      // floats of one source row inside a slot
       int lg = 0, lit = 0;                                   // next group to fetch and its first item
       int sit = 0;                                           // next item to store (STORE)
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__((9 + PW) * 32, 1) capture_tc_kernel(const CapT
     }
   } else if (warp == MMA_WARP) {
     // =========================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int it = 0; it < n_items; ++it) {
         int l, h, Y, iy;

@@ -96,7 +96,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   pdl_wait();   // barriers / TMEM are set up: from here on global memory written by the predecessor is touched
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -120,7 +120,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {

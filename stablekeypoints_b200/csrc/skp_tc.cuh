@@ -8,6 +8,22 @@ namespace skp {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp.  Unlike `lane == 0` the compiler knows exactly one thread runs the region, so the
+// uniform-register operands of tcgen05.mma / cp.async.bulk.tensor need no per-lane serialisation loop (the ELECT ... BRA.U.ANY
+// sequence ptxas otherwise wraps around every UTCHMMA / UTMALDG cost ~100 issue cycles per MMA: measured on the attention
+// backward, 33 -> 60 % tensor pipe).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }

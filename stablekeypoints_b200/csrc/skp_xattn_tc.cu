@@ -154,7 +154,7 @@ xa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(bars + 8 * Q_FULL, Cfg::Q_BYTES);
       for (int c = 0; c < KCH; ++c) {
         tma_load_2d(sQ + c * 2 * Cfg::Q_PLANE, &tm_q_hi, bars + 8 * Q_FULL, c * 64, h * Sq + q0);
@@ -175,7 +175,7 @@ xa_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(XA_BN >> 3) << 17) | ((uint32_t)(XA_BM >> 4) << 24);
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(XA_BM >> 4) << 24);
       const uint64_t dVh = make_smem_desc(sV), dVl = make_smem_desc(sV + Cfg::V_PLANE);
