@@ -164,8 +164,8 @@ int skp_self_attn_split(const float* q, int64_t ldq, const float* k, int64_t ldk
 /* Long-sequence self-attention BACKWARD on tcgen05 (skp_attn_tc_bwd.cu; the autograd pass through ptp_utils.py:493-506):
  * one launch whose CTAs own either 128 keys (dK, dV accumulated in TMEM over all query tiles) or 128 queries (dQ); scores
  * and dP recomputed per tile as tcgen05.mma, P / dS handed back to the tensor core through 128B-swizzled shared memory;
- * split-bf16 products, no atomics.  Same eligibility as skp_self_attn_tc_fwd (S % 128 == 0, even d <= 64), whose o and
- * base-2 lse it takes together with the fp32 q / k / v it re-splits; workspace = skp_self_attn_tc_bwd_workspace bytes,
+ * split-bf16 products, no atomics.  Needs S % 128 == 0 and even d <= 96; takes o and the base-2 lse of either forward
+ * (skp_self_attn_tc_fwd or skp_self_attn_fwd) together with the fp32 q / k / v it re-splits; workspace = skp_self_attn_tc_bwd_workspace bytes,
  * 128-byte aligned (0 = shape not eligible). */
 int64_t skp_self_attn_tc_bwd_workspace(int S, int heads, int d);
 int skp_self_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse, const float* q,

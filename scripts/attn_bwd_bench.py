@@ -15,7 +15,7 @@ from stablekeypoints_b200 import ops  # noqa: E402
 def main():
     reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 20
     dev = torch.device("cuda")
-    for (s, heads, d) in [(4096, 8, 40), (1024, 8, 64), (1024, 4, 32)]:
+    for (s, heads, d) in [(4096, 8, 40), (1024, 8, 80), (1024, 8, 64), (1024, 4, 32)]:
         c = heads * d
         for mode in ("tcgen05", "mma"):
             ops.SELF_ATTN_TC_BWD = mode == "tcgen05"

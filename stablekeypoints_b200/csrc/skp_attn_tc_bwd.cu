@@ -17,7 +17,8 @@
 // streamed transposed tiles, 3..10 = element-wise (two warps per TMEM lane quarter, 32 score columns each).
 // Operands come pre-split from sa_tc_bwd_split_kernel: Q' (scaled by scale*log2 e), K, V, dO as [heads*S][64] planes and
 // Q'^T, K^T, dO^T as [heads*DV][S] planes (the B operands of the accumulation products), delta = rowsum(dO * O).
-// Eligibility (host): S % 128 == 0, d even and <= 64 -- the shapes the tcgen05 forward takes.
+// Eligibility (host): S % 128 == 0, d even and <= 96.  Head dims above 64 use two 64-column chunks of the row planes and ONE
+// score buffer (tensor memory holds 128 + 4 * DV columns: scores, two accumulators, the four planes of the resident block).
 #include "skp_tc.cuh"
 #include <math_constants.h>
 
@@ -31,9 +32,11 @@ constexpr int BT_EW_WARPS = 8;
 constexpr int BT_THREADS = 96 + 32 * BT_EW_WARPS;   // 352
 constexpr int BT_B_BYTES = BT_BN * 128;
 constexpr int BT_TMEM_COLS = 512;                // the whole tensor memory of the SM: map in front of bt_body
-// double-buffered streamed row tiles [64][64] and transposed tiles [DV][64], four bf16 planes each (the resident block and
-// the P / dS staging live in tensor memory)
-constexpr int bt_smem(int DV) { return 8 * BT_B_BYTES + 8 * DV * 128 + 256 + 1024; }
+constexpr int bt_kch(int DV) { return DV > 64 ? 2 : 1; }     // 64-column chunks of a row plane
+constexpr int bt_nsb(int DV) { return DV > 64 ? 1 : 2; }     // score buffers in tensor memory
+// double-buffered streamed row tiles [chunks][64][64] and transposed tiles [DV][64], four bf16 planes each (the resident
+// block and the P / dS staging live in tensor memory)
+constexpr int bt_smem(int DV) { return 8 * bt_kch(DV) * BT_B_BYTES + 8 * DV * 128 + 256 + 1024; }
 
 struct BtMaps {
   CUtensorMap b1h, b1l, b2h, b2l;                // streamed tiles (64 rows):  Q', dO (z = 0) / K, V (z = 1)
@@ -108,6 +111,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) 
       "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
@@ -127,51 +135,67 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 // q,k,v [S, heads*d] and d_o, o [S, heads*d] fp32 (leading dims) ->
-//   row planes   RP[t][2][heads*S][64]  t = Q' (scaled), K, V, dO          (hi, lo; zero padded to 64 columns)
+//   row planes   RP[t][2][heads*S][KP]  t = Q' (scaled), K, V, dO          (hi, lo; zero padded to KP = 64 / 128 columns)
 //   transposed   TP[t][2][heads*DV][S]  t = Q'^T, K^T, dO^T
 //   delta[heads][S] = sum_c dO * O
 __global__ void sa_tc_bwd_split_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                                        const float* __restrict__ v, int64_t ldv, const float* __restrict__ d_o, int64_t lddo,
                                        const float* __restrict__ o, int64_t ldo, __nv_bfloat16* __restrict__ RP,
                                        __nv_bfloat16* __restrict__ TP, float* __restrict__ delta, int S, int heads, int d, int DV,
-                                       float qscale) {
-  const long nrow = (long)heads * S * 32;           // bf16 pairs of one row plane
-  const long ntr = (long)heads * DV * (S / 2);      // bf16 pairs of one transposed plane
+                                       int KP, float qscale) {
+  const int hp = KP >> 1;                           // bf16 pairs per plane row (KP = 64 or 128 columns)
+  const long nrow = (long)heads * S * hp;           // bf16 pairs of one row plane
+  const long ntr = (long)heads * DV * (S / 16);     // 16-row segments of one transposed plane
   const long nd = (long)heads * S;
   const long total = 4 * nrow + 3 * ntr + nd;
-  const size_t rp = (size_t)heads * S * 64, tp = (size_t)heads * DV * S;
+  const size_t rp = (size_t)heads * S * KP, tp = (size_t)heads * DV * S;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     float x, y;
     __nv_bfloat16 *hi, *lo;
     if (i < 4 * nrow) {
       const int t = (int)(i / nrow);
       const long r = i - (long)t * nrow;
-      const int c = (int)(r & 31) << 1;
-      const long hr = r >> 5;                        // h * S + row
+      const int c = (int)(r % hp) << 1;
+      const long hr = r / hp;                        // h * S + row
       const int h = (int)(hr / S), row = (int)(hr - (long)h * S);
       const float* src = (t == 0 ? q + (size_t)row * ldq : t == 1 ? k + (size_t)row * ldk : t == 2 ? v + (size_t)row * ldv
                                                                                                   : d_o + (size_t)row * lddo) + h * d;
       x = c < d ? __ldg(src + c) : 0.f;
       y = c + 1 < d ? __ldg(src + c + 1) : 0.f;
       if (t == 0) { x *= qscale; y *= qscale; }
-      hi = RP + (size_t)t * 2 * rp + (size_t)hr * 64 + c;
+      hi = RP + (size_t)t * 2 * rp + (size_t)hr * KP + c;
       lo = hi + rp;
     } else if (i < 4 * nrow + 3 * ntr) {
-      // channel fastest: the row reads are coalesced, the transposed 4-byte writes scatter (absorbed by L2)
+      // one thread = 16 consecutive rows of one channel: channel fastest across the warp, so each of the 16 row reads is a
+      // coalesced segment and every store is one full 32-byte sector of the transposed plane
       const long r0 = i - 4 * nrow;
       const int t = (int)(r0 / ntr);
       const long r = r0 - (long)t * ntr;
-      const int half = S >> 1;
+      const int seg = S >> 4;
       const int c = (int)(r % DV);
-      const long hs = r / DV;                        // h * half + row pair
-      const int h = (int)(hs / half), s2 = (int)(hs - (long)h * half) << 1;
-      const float* src = t == 0 ? q : t == 1 ? k : d_o;
+      const long hs = r / DV;                        // h * seg + 16-row segment
+      const int h = (int)(hs / seg), s0 = (int)(hs - (long)h * seg) << 4;
+      const float* src = (t == 0 ? q : t == 1 ? k : d_o) + h * d + c;
       const int64_t ld = t == 0 ? ldq : t == 1 ? ldk : lddo;
-      x = c < d ? __ldg(src + (size_t)s2 * ld + h * d + c) : 0.f;
-      y = c < d ? __ldg(src + (size_t)(s2 + 1) * ld + h * d + c) : 0.f;
-      if (t == 0) { x *= qscale; y *= qscale; }
-      hi = TP + (size_t)t * 2 * tp + ((size_t)h * DV + c) * S + s2;
-      lo = hi + tp;
+      const float sc = t == 0 ? qscale : 1.f;
+      uint32_t hw[8], lw[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x0 = c < d ? __ldg(src + (size_t)(s0 + 2 * e) * ld) * sc : 0.f;
+        const float x1 = c < d ? __ldg(src + (size_t)(s0 + 2 * e + 1) * ld) * sc : 0.f;
+        __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+        float2 f = __bfloat1622float2(hh);
+        __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+        hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+        lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+      }
+      uint4* ph = reinterpret_cast<uint4*>(TP + (size_t)t * 2 * tp + ((size_t)h * DV + c) * S + s0);
+      uint4* pl = reinterpret_cast<uint4*>(TP + (size_t)t * 2 * tp + tp + ((size_t)h * DV + c) * S + s0);
+      ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+      pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+      continue;
     } else {
       const long r = i - 4 * nrow - 3 * ntr;         // row * heads + h
       const int row = (int)(r / heads), h = (int)(r - (long)row * heads);
@@ -207,10 +231,14 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
   constexpr int BT_T_BYTES = DV * 128;
+  constexpr int KCH = bt_kch(DV), NSB = bt_nsb(DV), KP = 64 * KCH;
+  constexpr int BP_BYTES = KCH * BT_B_BYTES;       // one plane of a streamed row tile: [KCH chunks][64 rows][64 columns]
+  constexpr int ACOLS = DV / 2;                    // TMEM columns of one plane of the resident block (DV bf16 per row)
   const uint32_t sB = base;                        // [2 buffers][B1h, B1l, B2h, B2l]
-  const uint32_t sT = sB + 8 * BT_B_BYTES;         // [2 buffers][T1h, T1l, T2h, T2l]
+  const uint32_t sT = sB + 8 * BP_BYTES;           // [2 buffers][T1h, T1l, T2h, T2l]
   const uint32_t bars = sT + 8 * BT_T_BYTES;
-  // B_*, T_*, S_FULL, E_FULL exist per buffer (index + (j & 1), phase (j >> 1) & 1)
+  // B_*, T_* exist per shared-memory buffer (index + (j & 1), phase (j >> 1) & 1), S_FULL / E_FULL per score buffer
+  // (index + j % NSB, phase (j / NSB) & 1)
   enum { A_FULL = 0, B_FULL, B_FULL1, B_EMPTY, B_EMPTY1, T_FULL, T_FULL1, T_EMPTY, T_EMPTY1, S_FULL, S_FULL1, E_FULL, E_FULL1, DONE, NBARS };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * NBARS);
 
@@ -218,7 +246,8 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
   const int h = blockIdx.y, r0 = blockIdx.x * BT_BM;
   const int ntiles = S / BT_BN;
   constexpr uint32_t EW = 32u * BT_EW_WARPS;
-  constexpr uint32_t TM_ACC1 = 256, TM_ACC2 = 320, TM_A = 384;
+  constexpr uint32_t TM_ACC1 = 128 * NSB, TM_ACC2 = TM_ACC1 + DV, TM_A = TM_ACC2 + DV;
+  static_assert(TM_A + 4 * ACOLS <= 512, "tensor memory: scores + two accumulators + the resident block");
 
   if (warp == 0 && lane == 0) {
     for (int b = 0; b < NBARS; ++b) mbar_init(bars + 8 * b, (b == A_FULL || b == E_FULL || b == E_FULL1) ? EW : 1u);
@@ -237,13 +266,16 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
     if (elect_one_sync()) {
       for (int j = 0; j < ntiles; ++j) {
         const int b = j & 1;
-        const uint32_t full = bars + 8 * (B_FULL + b), dst = sB + (uint32_t)b * 4u * BT_B_BYTES;
+        const uint32_t full = bars + 8 * (B_FULL + b), dst = sB + (uint32_t)b * 4u * BP_BYTES;
         mbar_wait(bars + 8 * (B_EMPTY + b), (((uint32_t)j >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(full, 4 * BT_B_BYTES);
-        tma_load_2d(dst, &mp.b1h, full, 0, h * S + j * BT_BN);
-        tma_load_2d(dst + BT_B_BYTES, &mp.b1l, full, 0, h * S + j * BT_BN);
-        tma_load_2d(dst + 2 * BT_B_BYTES, &mp.b2h, full, 0, h * S + j * BT_BN);
-        tma_load_2d(dst + 3 * BT_B_BYTES, &mp.b2l, full, 0, h * S + j * BT_BN);
+        mbar_expect_tx(full, 4 * BP_BYTES);
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          tma_load_2d(dst + c * BT_B_BYTES, &mp.b1h, full, c * 64, h * S + j * BT_BN);
+          tma_load_2d(dst + BP_BYTES + c * BT_B_BYTES, &mp.b1l, full, c * 64, h * S + j * BT_BN);
+          tma_load_2d(dst + 2 * BP_BYTES + c * BT_B_BYTES, &mp.b2h, full, c * 64, h * S + j * BT_BN);
+          tma_load_2d(dst + 3 * BP_BYTES + c * BT_B_BYTES, &mp.b2l, full, c * 64, h * S + j * BT_BN);
+        }
       }
     }
   } else if (warp == 2) {
@@ -266,44 +298,43 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
       // instruction descriptors: D = f32, A = B = bf16, both K-major, M = 128, N = 64 (scores) / DV (accumulators)
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT_BN >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
-      const uint32_t tA1h = tmem + TM_A, tA1l = tA1h + 32, tA2h = tA1h + 64, tA2l = tA1h + 96;
+      const uint32_t tA1h = tmem + TM_A, tA1l = tA1h + ACOLS, tA2h = tA1h + 2 * ACOLS, tA2l = tA1h + 3 * ACOLS;
       auto issue_scores = [&](int j) {
-        const int b = j & 1;
-        const uint32_t ts = tmem + (uint32_t)b * 128u;
-        const uint32_t sb = sB + (uint32_t)b * 4u * BT_B_BYTES;
-        const uint64_t dB1h = make_smem_desc(sb), dB1l = make_smem_desc(sb + BT_B_BYTES);
-        const uint64_t dB2h = make_smem_desc(sb + 2 * BT_B_BYTES), dB2l = make_smem_desc(sb + 3 * BT_B_BYTES);
+        const int b = j & 1, sbuf = j % NSB;
+        const uint32_t ts = tmem + (uint32_t)sbuf * 128u;
+        const uint32_t sb = sB + (uint32_t)b * 4u * BP_BYTES;
         mbar_wait(bars + 8 * (B_FULL + b), ((uint32_t)j >> 1) & 1u);
         tc_fence_after();
-        // (the buffer's previous tenant, tile j - 2, was consumed by accumulation MMAs issued before these: in-order pipe)
+        // (the score buffer's previous tenant, tile j - NSB, was consumed by accumulation MMAs issued before these: in-order pipe)
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          const uint32_t koff = (uint32_t)(k >> 2) * BT_B_BYTES + (uint32_t)(k & 3) * 32u;   // chunk, then 16 bf16 = 32 B inside the swizzle row
           const uint32_t ka = 8u * (uint32_t)k;             // 16 bf16 of K = 8 TMEM columns
-          umma_bf16_ts(ts, tA1l + ka, dB1h + adv, idesc_s, k != 0);
-          umma_bf16_ts(ts, tA1h + ka, dB1l + adv, idesc_s, 1u);
-          umma_bf16_ts(ts, tA1h + ka, dB1h + adv, idesc_s, 1u);
+          const uint64_t dB1h = make_smem_desc(sb + koff), dB1l = make_smem_desc(sb + BP_BYTES + koff);
+          umma_bf16_ts(ts, tA1l + ka, dB1h, idesc_s, k != 0);
+          umma_bf16_ts(ts, tA1h + ka, dB1l, idesc_s, 1u);
+          umma_bf16_ts(ts, tA1h + ka, dB1h, idesc_s, 1u);
         }
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          const uint32_t koff = (uint32_t)(k >> 2) * BT_B_BYTES + (uint32_t)(k & 3) * 32u;
           const uint32_t ka = 8u * (uint32_t)k;
-          umma_bf16_ts(ts + 64, tA2l + ka, dB2h + adv, idesc_s, k != 0);
-          umma_bf16_ts(ts + 64, tA2h + ka, dB2l + adv, idesc_s, 1u);
-          umma_bf16_ts(ts + 64, tA2h + ka, dB2h + adv, idesc_s, 1u);
+          const uint64_t dB2h = make_smem_desc(sb + 2 * BP_BYTES + koff), dB2l = make_smem_desc(sb + 3 * BP_BYTES + koff);
+          umma_bf16_ts(ts + 64, tA2l + ka, dB2h, idesc_s, k != 0);
+          umma_bf16_ts(ts + 64, tA2h + ka, dB2l, idesc_s, 1u);
+          umma_bf16_ts(ts + 64, tA2h + ka, dB2h, idesc_s, 1u);
         }
-        umma_commit(bars + 8 * (B_EMPTY + b));   // this buffer of streamed row tiles is free once these MMAs retire
-        umma_commit(bars + 8 * (S_FULL + b));    // ... and both score tiles are complete
+        umma_commit(bars + 8 * (B_EMPTY + b));      // this buffer of streamed row tiles is free once these MMAs retire
+        umma_commit(bars + 8 * (S_FULL + sbuf));    // ... and both score tiles are complete
       };
       mbar_wait(bars + 8 * A_FULL, 0);            // the resident block is in tensor memory
       tc_fence_after();
-      issue_scores(0);
-      if (ntiles > 1) issue_scores(1);
+      for (int j = 0; j < NSB && j < ntiles; ++j) issue_scores(j);
       for (int j = 0; j < ntiles; ++j) {
-        const int b = j & 1;
-        const uint32_t par = ((uint32_t)j >> 1) & 1u, ts = tmem + (uint32_t)b * 128u;
+        const int b = j & 1, sbuf = j % NSB;
+        const uint32_t par = ((uint32_t)j >> 1) & 1u, ts = tmem + (uint32_t)sbuf * 128u;
         const uint32_t st = sT + (uint32_t)b * 4u * BT_T_BYTES;
         const uint64_t dT1h = make_smem_desc(st), dT1l = make_smem_desc(st + BT_T_BYTES);
         const uint64_t dT2h = make_smem_desc(st + 2 * BT_T_BYTES), dT2l = make_smem_desc(st + 3 * BT_T_BYTES);
-        mbar_wait(bars + 8 * (E_FULL + b), par);    // P^T / dS of tile j sit in the score buffer
+        mbar_wait(bars + 8 * (E_FULL + sbuf), (uint32_t)(j / NSB) & 1u);    // P^T / dS of tile j sit in the score buffer
         mbar_wait(bars + 8 * (T_FULL + b), par);
         tc_fence_after();
 #pragma unroll
@@ -321,7 +352,7 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
           umma_bf16_ts(tmem + TM_ACC2, ts + 64 + ka, dT2h + adv, idesc_o, 1u);
         }
         umma_commit(bars + 8 * (T_EMPTY + b));
-        if (j + 2 < ntiles) issue_scores(j + 2);   // runs while the element-wise warps work on tile j + 1
+        if (j + NSB < ntiles) issue_scores(j + NSB);   // NSB = 2: runs while the element-wise warps work on tile j + 1
       }
       umma_commit(bars + 8 * DONE);
     }
@@ -333,17 +364,16 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     // ---- the resident block goes to tensor memory: this thread's row of A1 (half 0) or A2 (half 1), hi and lo planes
     {
-      const __nv_bfloat16* src = (half == 0 ? a1_planes : a2_planes) + ((size_t)h * S + r0 + r) * 64;
+      const __nv_bfloat16* src = (half == 0 ? a1_planes : a2_planes) + ((size_t)h * S + r0 + r) * KP;
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
         const uint4* p4 = reinterpret_cast<const uint4*>(src + (size_t)pl * plane_stride);
-        uint32_t w[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 v = __ldg(p4 + i);
-          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        for (int i = 0; i < ACOLS / 8; ++i) {     // 8 TMEM columns = 16 bf16 = two 16-byte loads
+          const uint4 v0 = __ldg(p4 + 2 * i), v1 = __ldg(p4 + 2 * i + 1);
+          const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          tmem_st8(trow + TM_A + (2 * half + pl) * ACOLS + 8 * i, w);
         }
-        tmem_st32(trow + TM_A + 64 * half + 32 * pl, w);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -367,9 +397,9 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
     };
     if (DKV) load_stats(0);
     for (int j = 0; j < ntiles; ++j) {
-      const int sbuf = j & 1;
+      const int sbuf = j % NSB;
       const uint32_t ts = trow + 128u * (uint32_t)sbuf;
-      mbar_wait(bars + 8 * (S_FULL + sbuf), ((uint32_t)j >> 1) & 1u);
+      mbar_wait(bars + 8 * (S_FULL + sbuf), (uint32_t)(j / NSB) & 1u);
       tc_fence_after();
       float s[32], g[32];
       tmem_ld32x2(ts + 32 * half, ts + 64 + 32 * half, s, g);
@@ -435,12 +465,13 @@ sa_tc_bwd_kernel(const __grid_constant__ BtMaps kv, const __grid_constant__ BtMa
     bt_body<DV, false>(qm, RP, RP + 6 * rp, rp, lse, delta, nullptr, 0, dq, lddq, S, d, ksteps, scale, bt_smem_raw);
 }
 
-int bt_dv(int d) { return d <= 16 ? 16 : d <= 32 ? 32 : d <= 48 ? 48 : 64; }
+int bt_dv(int d) { return (d + 15) / 16 * 16; }   // 16 .. 96
 
 template <int DV>
 int bt_launch(const __nv_bfloat16* RP, const __nv_bfloat16* TP, const float* lse, const float* delta, float* dq, int64_t lddq,
               float* dk, int64_t lddk, float* dv, int64_t lddv, int S, int heads, int d, float scale, cudaStream_t st) {
-  const size_t rp = (size_t)heads * S * 64, tp = (size_t)heads * DV * S;
+  constexpr int KP = 64 * bt_kch(DV);
+  const size_t rp = (size_t)heads * S * KP, tp = (size_t)heads * DV * S;
   const __nv_bfloat16 *Qh = RP, *Ql = RP + rp, *Kh = RP + 2 * rp, *Kl = RP + 3 * rp, *Vh = RP + 4 * rp, *Vl = RP + 5 * rp;
   const __nv_bfloat16 *Dh = RP + 6 * rp, *Dl = RP + 7 * rp;
   const __nv_bfloat16 *QTh = TP, *QTl = TP + tp, *KTh = TP + 2 * tp, *KTl = TP + 3 * tp, *DTh = TP + 4 * tp, *DTl = TP + 5 * tp;
@@ -448,9 +479,9 @@ int bt_launch(const __nv_bfloat16* RP, const __nv_bfloat16* TP, const float* lse
   int rc;
   const int rows = heads * S, trows = heads * DV;
 #define BT_MAP(dst, ptr, R, KP, BOX) if ((rc = tc_make_map(&(dst), (ptr), (R), (KP), (BOX)))) return rc
-  BT_MAP(kv.b1h, Qh, rows, 64, BT_BN); BT_MAP(kv.b1l, Ql, rows, 64, BT_BN); BT_MAP(kv.b2h, Dh, rows, 64, BT_BN); BT_MAP(kv.b2l, Dl, rows, 64, BT_BN);
+  BT_MAP(kv.b1h, Qh, rows, KP, BT_BN); BT_MAP(kv.b1l, Ql, rows, KP, BT_BN); BT_MAP(kv.b2h, Dh, rows, KP, BT_BN); BT_MAP(kv.b2l, Dl, rows, KP, BT_BN);
   BT_MAP(kv.t1h, DTh, trows, S, DV); BT_MAP(kv.t1l, DTl, trows, S, DV); BT_MAP(kv.t2h, QTh, trows, S, DV); BT_MAP(kv.t2l, QTl, trows, S, DV);
-  BT_MAP(qm.b1h, Kh, rows, 64, BT_BN); BT_MAP(qm.b1l, Kl, rows, 64, BT_BN); BT_MAP(qm.b2h, Vh, rows, 64, BT_BN); BT_MAP(qm.b2l, Vl, rows, 64, BT_BN);
+  BT_MAP(qm.b1h, Kh, rows, KP, BT_BN); BT_MAP(qm.b1l, Kl, rows, KP, BT_BN); BT_MAP(qm.b2h, Vh, rows, KP, BT_BN); BT_MAP(qm.b2l, Vl, rows, KP, BT_BN);
   BT_MAP(qm.t2h, KTh, trows, S, DV); BT_MAP(qm.t2l, KTl, trows, S, DV);
 #undef BT_MAP
   qm.t1h = qm.t2h;
@@ -475,8 +506,9 @@ using namespace skp;
 
 // workspace bytes: 4 row-plane pairs [heads*S][64] + 3 transposed pairs [heads*DV][S] (bf16) + delta [heads][S] (fp32)
 extern "C" int64_t skp_self_attn_tc_bwd_workspace(int S, int heads, int d) {
-  if (S <= 0 || heads <= 0 || d <= 0 || d > 64 || (d & 1) || S % BT_BM != 0) return 0;
-  return ((int64_t)8 * heads * S * 64 + (int64_t)6 * heads * bt_dv(d) * S) * 2 + (int64_t)heads * S * 4;
+  if (S <= 0 || heads <= 0 || d <= 0 || d > 96 || (d & 1) || S % BT_BM != 0) return 0;
+  const int DV = bt_dv(d);
+  return ((int64_t)8 * heads * S * 64 * bt_kch(DV) + (int64_t)6 * heads * DV * S) * 2 + (int64_t)heads * S * 4;
 }
 
 extern "C" int skp_self_attn_tc_bwd(const float* d_o, int64_t lddo, const float* o, int64_t ldo, const float* lse, const float* q,
@@ -484,25 +516,28 @@ extern "C" int skp_self_attn_tc_bwd(const float* d_o, int64_t lddo, const float*
                                     float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, int S, int heads,
                                     int d, float scale, void* stream) {
   SKP_REQUIRE(d_o && o && lse && q && k && v && workspace && dq && dk && dv, "skp_self_attn_tc_bwd: null pointer");
-  SKP_REQUIRE(skp_self_attn_tc_bwd_workspace(S, heads, d) > 0, "skp_self_attn_tc_bwd: needs S %% 128 == 0 and even d <= 64 (S=%d d=%d)", S, d);
+  SKP_REQUIRE(skp_self_attn_tc_bwd_workspace(S, heads, d) > 0, "skp_self_attn_tc_bwd: needs S %% 128 == 0 and even d <= 96 (S=%d d=%d)", S, d);
   SKP_REQUIRE((lddq | lddk | lddv) % 2 == 0 && ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 7) == 0 &&
                   (reinterpret_cast<uintptr_t>(workspace) & 127) == 0 && (reinterpret_cast<uintptr_t>(lse) & 15) == 0,
               "skp_self_attn_tc_bwd: gradients must be 8-byte aligned with even ld, lse 16-byte and the workspace 128-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int DV = bt_dv(d);
   __nv_bfloat16* RP = (__nv_bfloat16*)workspace;
-  __nv_bfloat16* TP = RP + (size_t)8 * heads * S * 64;
+  const int KP = 64 * bt_kch(DV);
+  __nv_bfloat16* TP = RP + (size_t)8 * heads * S * KP;
   float* delta = reinterpret_cast<float*>(TP + (size_t)6 * heads * DV * S);
-  const long total = (long)4 * heads * S * 32 + (long)3 * heads * DV * (S / 2) + (long)heads * S;
+  const long total = (long)4 * heads * S * (KP / 2) + (long)3 * heads * DV * (S / 16) + (long)heads * S;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   sa_tc_bwd_split_kernel<<<(int)blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, d_o, lddo, o, ldo, RP, TP, delta, S, heads, d, DV,
-                                                      scale * 1.4426950408889634f);
+                                                      KP, scale * 1.4426950408889634f);
   SKP_CHECK_LAUNCH("sa_tc_bwd_split_kernel");
   switch (DV) {
     case 16: return bt_launch<16>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
     case 32: return bt_launch<32>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
     case 48: return bt_launch<48>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
-    default: return bt_launch<64>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
+    case 64: return bt_launch<64>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
+    case 80: return bt_launch<80>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
+    default: return bt_launch<96>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
   }
 }

@@ -616,9 +616,9 @@ SELF_ATTN_TC_BWD = os.environ.get("SKP_SELF_ATTN_TC_BWD", "1") != "0"
 
 class _SelfAttnCore(torch.autograd.Function):
     """softmax(q k^T scale) v per head from the packed projection qkv[S, 3C] (columns q | k | v, head-major inside
-    each): flash-style split-bf16 tensor-core kernels.  Forward: tcgen05 kernel (skp_attn_tc.cu) for long sequences,
-    mma.sync kernel (skp_selfattn.cu) otherwise; backward: mma.sync kernels on split operand planes (kept from the
-    forward, or re-made from qkv when the forward ran on tcgen05)."""
+    each): flash-style split-bf16 tensor-core kernels.  Forward: tcgen05 kernel (skp_attn_tc.cu) for long sequences with
+    d <= 64, mma.sync kernel (skp_selfattn.cu) otherwise; backward: tcgen05 kernel (skp_attn_tc_bwd.cu) for long sequences
+    with d <= 96, mma.sync kernels on split operand planes otherwise."""
 
     @staticmethod
     def forward(ctx, qkv, heads: int, scale: float):
@@ -635,6 +635,9 @@ class _SelfAttnCore(torch.autograd.Function):
         e = qkv.element_size()
         qp, kp, vp = qkv.data_ptr(), qkv.data_ptr() + c * e, qkv.data_ptr() + 2 * c * e
         ws_bytes = int(lib().skp_self_attn_tc_workspace(s, heads, d)) if (SELF_ATTN_TC and s >= SELF_ATTN_TC_MIN_S) else 0
+        # backward on tcgen05 (skp_attn_tc_bwd.cu: S % 128 == 0, d <= 96) whichever forward ran: both write o and a base-2 lse
+        ctx.tc_bwd = bool(SELF_ATTN_TC and SELF_ATTN_TC_BWD and s >= SELF_ATTN_TC_MIN_S
+                          and int(lib().skp_self_attn_tc_bwd_workspace(s, heads, d)) > 0)
         if ws_bytes > 0:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device)
             check(lib().skp_self_attn_tc_fwd(qp, c3, kp, c3, vp, c3, ptr(o), c, ptr(lse), ptr(ws), s, heads, d, scale, stream()),
@@ -645,7 +648,7 @@ class _SelfAttnCore(torch.autograd.Function):
             planes = torch.empty(6 * heads * s * dp, dtype=torch.bfloat16, device=qkv.device)
             check(lib().skp_self_attn_fwd(qp, c3, kp, c3, vp, c3, ptr(o), c, ptr(lse), ptr(planes), s, heads, d, scale, stream()),
                   "skp_self_attn_fwd")
-            ctx.save_for_backward(o, lse, planes)
+            ctx.save_for_backward(o, lse, qkv if ctx.tc_bwd else planes)
             ctx.tc = False
         ctx.meta = (s, c, heads, d, dp, scale)
         return o
@@ -655,7 +658,7 @@ class _SelfAttnCore(torch.autograd.Function):
         o, lse, third = ctx.saved_tensors
         s, c, heads, d, dp, scale = ctx.meta
         d_o = _f32c(d_o)
-        if ctx.tc and SELF_ATTN_TC_BWD:   # tcgen05 backward (skp_attn_tc_bwd.cu): re-splits q / k / v / dO into its own operand planes
+        if ctx.tc_bwd:   # tcgen05 backward: re-splits q / k / v / dO into its own operand planes
             qkv, e, c3 = third, third.element_size(), 3 * c
             ws = torch.empty(int(lib().skp_self_attn_tc_bwd_workspace(s, heads, d)), dtype=torch.uint8, device=o.device)
             dqkv = torch.empty(s, 3 * c, dtype=torch.float32, device=o.device)

@@ -217,7 +217,7 @@ def test_cross_attn_fwd_bwd(ops, monkeypatch, s, n, heads, d, impl, tol):
 # ----------------------------------------------------------------------------- self-attention (attn1)
 @pytest.mark.parametrize("s,heads,d", [(4096, 8, 40), (1024, 8, 80), (256, 8, 160), (64, 8, 160), (16, 4, 8), (100, 2, 16),
                                        (4, 4, 32), (1100, 3, 24), (77, 2, 48), (128, 2, 16), (256, 3, 64), (1024, 4, 32),
-                                       (384, 2, 48)])
+                                       (384, 2, 48), (256, 2, 96), (128, 4, 80), (640, 2, 72)])
 @pytest.mark.parametrize("tc", ["tcgen05", "tcgen05_fwd", "mma"])
 def test_self_attn_fwd_bwd(ops, s, heads, d, tc, monkeypatch):
     # tcgen05 forward + backward (eligible shapes only) / tcgen05 forward + mma.sync backward / mma.sync both

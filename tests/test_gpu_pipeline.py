@@ -272,7 +272,20 @@ def test_cfg5_sdxl_shaped_stage1_vs_oracle():
     theta = hp.affine_theta(-6.0, 0.92, -0.08, 0.05)
     ldm_o, ctl_o, _ = hp.load_oracle_ldm(pipe, 256)
     ctx_o = context.clone().requires_grad_(True)
-    ref = hp.stage1_iteration(ldm_o, ctl_o, image, ctx_o, theta, noise_a, noise_b, top_k=16, num_candidates=32, sigma=2.0)
+    # The sharpening loss centres its target on the ARG-MAX pixel of each selected map (optimize.py:157-180), and at R = 256
+    # (bicubic x8 from 32x32) the two largest pixels of a map can agree to 3e-5: below the 1e-3 parity budget, so the arg-max
+    # -- and with it 1 % of d(context) -- would be decided by rounding.  The forced token set is therefore the 16 of the
+    # oracle's 32 Gaussian-KL candidates whose arg-max is best separated (asserted >= 2e-4 relative).
+    maps_o = hp.run_and_find_attn(ldm_o, image, ctx_o, ctl_o, layers=(0, 1, 2, 3), noise=noise_a)[0]
+    maps_t_o = hp.run_and_find_attn(ldm_o, hp.affine_warp(image, theta), ctx_o, ctl_o, layers=(0, 1, 2, 3), noise=noise_b)[0]
+    cand = hp.find_top_k_gaussian(maps_o.detach(), 32, sigma=2.0)
+    top2 = maps_o.detach()[cand].reshape(32, -1).topk(2, dim=1).values
+    gap = (top2[:, 0] - top2[:, 1]) / top2[:, 0]
+    keep = gap.argsort(descending=True)[:16].sort().values
+    assert float(gap[keep].min()) >= 2e-4, gap[keep]
+    idx_o, sharp_o, equiv_o = hp.stage1_losses(maps_o, maps_t_o, theta, top_k=16, num_candidates=32, sigma=2.0, forced_indices=cand[keep])
+    (equiv_o * 1000.0 + sharp_o * 100.0).backward()
+    ref = {"maps": maps_o.detach(), "maps_t": maps_t_o.detach(), "indices": idx_o, "sharp": sharp_o.detach(), "equiv": equiv_o.detach()}
     ldm, controllers, _ = _product_ldm(pipe, 256)
     assert sum(1 for l in ldm.unet.cross_layers if l.in_up and l.channels == 1280) == 3 and ldm.unet.cfg.heads == 20
     ctx = context.clone().cuda().requires_grad_(True)
