@@ -1,1 +1,3 @@
-for i in 1 2 3 4; do timeout 600 python -m pytest tests/test_gpu_pipeline.py -x -q -m gpu -k "cfg5" -s 2>&1 | grep -E "cfg5 SDXL|passed|failed" | cut -c1-220; done
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "self_attn_fwd_bwd and tcgen05" 2>&1 | tail -2
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sa_tc_bwd -c 4 --csv python scripts/attn_bwd_bench.py --reps 1 2>/dev/null | grep -E "sa_tc_bwd" | awk -F'","' '{print substr($5,1,60), $NF}' | head -8
+timeout 300 python scripts/attn_bwd_bench.py 2>&1 | grep tcgen05

@@ -138,78 +138,86 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 //   row planes   RP[t][2][heads*S][KP]  t = Q' (scaled), K, V, dO          (hi, lo; zero padded to KP = 64 / 128 columns)
 //   transposed   TP[t][2][heads*DV][S]  t = Q'^T, K^T, dO^T
 //   delta[heads][S] = sum_c dO * O
+// blockIdx.y selects the section (0..3 row planes, 4..6 transposed planes, 7 delta); all index arithmetic is 32-bit (the first
+// version decomposed one flat 64-bit index with four 64-bit divisions per element and spent its time in them).
 __global__ void sa_tc_bwd_split_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                                        const float* __restrict__ v, int64_t ldv, const float* __restrict__ d_o, int64_t lddo,
                                        const float* __restrict__ o, int64_t ldo, __nv_bfloat16* __restrict__ RP,
                                        __nv_bfloat16* __restrict__ TP, float* __restrict__ delta, int S, int heads, int d, int DV,
-                                       int KP, float qscale) {
-  const int hp = KP >> 1;                           // bf16 pairs per plane row (KP = 64 or 128 columns)
-  const long nrow = (long)heads * S * hp;           // bf16 pairs of one row plane
-  const long ntr = (long)heads * DV * (S / 16);     // 16-row segments of one transposed plane
-  const long nd = (long)heads * S;
-  const long total = 4 * nrow + 3 * ntr + nd;
+                                       int kp_shift, float qscale) {
+  const int KP = 1 << kp_shift;
   const size_t rp = (size_t)heads * S * KP, tp = (size_t)heads * DV * S;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    float x, y;
-    __nv_bfloat16 *hi, *lo;
-    if (i < 4 * nrow) {
-      const int t = (int)(i / nrow);
-      const long r = i - (long)t * nrow;
-      const int c = (int)(r % hp) << 1;
-      const long hr = r / hp;                        // h * S + row
-      const int h = (int)(hr / S), row = (int)(hr - (long)h * S);
-      const float* src = (t == 0 ? q + (size_t)row * ldq : t == 1 ? k + (size_t)row * ldk : t == 2 ? v + (size_t)row * ldv
-                                                                                                  : d_o + (size_t)row * lddo) + h * d;
-      x = c < d ? __ldg(src + c) : 0.f;
-      y = c + 1 < d ? __ldg(src + c + 1) : 0.f;
-      if (t == 0) { x *= qscale; y *= qscale; }
-      hi = RP + (size_t)t * 2 * rp + (size_t)hr * KP + c;
-      lo = hi + rp;
-    } else if (i < 4 * nrow + 3 * ntr) {
-      // one thread = 16 consecutive rows of one channel: channel fastest across the warp, so each of the 16 row reads is a
-      // coalesced segment and every store is one full 32-byte sector of the transposed plane
-      const long r0 = i - 4 * nrow;
-      const int t = (int)(r0 / ntr);
-      const long r = r0 - (long)t * ntr;
-      const int seg = S >> 4;
-      const int c = (int)(r % DV);
-      const long hs = r / DV;                        // h * seg + 16-row segment
-      const int h = (int)(hs / seg), s0 = (int)(hs - (long)h * seg) << 4;
-      const float* src = (t == 0 ? q : t == 1 ? k : d_o) + h * d + c;
-      const int64_t ld = t == 0 ? ldq : t == 1 ? ldk : lddo;
-      const float sc = t == 0 ? qscale : 1.f;
-      uint32_t hw[8], lw[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float x0 = c < d ? __ldg(src + (size_t)(s0 + 2 * e) * ld) * sc : 0.f;
-        const float x1 = c < d ? __ldg(src + (size_t)(s0 + 2 * e + 1) * ld) * sc : 0.f;
-        __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-        float2 f = __bfloat1622float2(hh);
-        __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
-        hw[e] = *reinterpret_cast<uint32_t*>(&hh);
-        lw[e] = *reinterpret_cast<uint32_t*>(&ll);
-      }
-      uint4* ph = reinterpret_cast<uint4*>(TP + (size_t)t * 2 * tp + ((size_t)h * DV + c) * S + s0);
-      uint4* pl = reinterpret_cast<uint4*>(TP + (size_t)t * 2 * tp + tp + ((size_t)h * DV + c) * S + s0);
-      ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-      pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-      continue;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sec = blockIdx.y;
+  if (sec < 4) {
+    // one thread = eight adjacent columns of one row of one plane pair: 2 x 16-byte loads, 2 x 16-byte stores
+    const int cp_shift = kp_shift - 3;             // 8-column groups per row
+    if (idx >= (unsigned)heads * S << cp_shift) return;
+    const int t = sec;
+    const int c = (int)(idx & ((1u << cp_shift) - 1)) << 3;
+    const unsigned hr = idx >> cp_shift;           // h * S + row
+    const int h = (int)(hr / (unsigned)S), row = (int)(hr - (unsigned)h * S);
+    const float* src = (t == 0 ? q + (size_t)row * ldq : t == 1 ? k + (size_t)row * ldk : t == 2 ? v + (size_t)row * ldv
+                                                                                                : d_o + (size_t)row * lddo) + h * d + c;
+    float x[8];
+    if (c + 8 <= d && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b4 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b4.x; x[5] = b4.y; x[6] = b4.z; x[7] = b4.w;
     } else {
-      const long r = i - 4 * nrow - 3 * ntr;         // row * heads + h
-      const int row = (int)(r / heads), h = (int)(r - (long)row * heads);
-      const float* a = d_o + (size_t)row * lddo + h * d;
-      const float* b = o + (size_t)row * ldo + h * d;
-      float acc = 0.f;
-      for (int c = 0; c < d; ++c) acc = fmaf(__ldg(a + c), __ldg(b + c), acc);
-      delta[(size_t)h * S + row] = acc;
-      continue;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = c + i < d ? __ldg(src + i) : 0.f;
     }
-    __nv_bfloat162 hh = __floats2bfloat162_rn(x, y);
-    float2 f = __bfloat1622float2(hh);
-    *reinterpret_cast<__nv_bfloat162*>(hi) = hh;
-    *reinterpret_cast<__nv_bfloat162*>(lo) = __floats2bfloat162_rn(x - f.x, y - f.y);
+    const float sc = t == 0 ? qscale : 1.f;
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = x[2 * e] * sc, x1 = x[2 * e + 1] * sc;
+      __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      float2 f = __bfloat1622float2(hh);
+      __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+      hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+      lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    __nv_bfloat16* hi = RP + (size_t)t * 2 * rp + ((size_t)hr << kp_shift) + c;
+    *reinterpret_cast<uint4*>(hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(hi + rp) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  } else if (sec < 7) {
+    // one thread = 16 consecutive rows of one channel: channel fastest across the warp, so each of the 16 row reads is a
+    // coalesced segment and every store is one full 32-byte sector of the transposed plane
+    const int seg = S >> 4;
+    if (idx >= (unsigned)heads * DV * seg) return;
+    const int t = sec - 4;
+    const int c = (int)(idx % (unsigned)DV);
+    const unsigned hs = idx / (unsigned)DV;        // h * seg + 16-row segment
+    const int h = (int)(hs / (unsigned)seg), s0 = (int)(hs - (unsigned)h * seg) << 4;
+    const float* src = (t == 0 ? q : t == 1 ? k : d_o) + h * d + c;
+    const int64_t ld = t == 0 ? ldq : t == 1 ? ldk : lddo;
+    const float sc = t == 0 ? qscale : 1.f;
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x0 = c < d ? __ldg(src + (size_t)(s0 + 2 * e) * ld) * sc : 0.f;
+      const float x1 = c < d ? __ldg(src + (size_t)(s0 + 2 * e + 1) * ld) * sc : 0.f;
+      __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      float2 f = __bfloat1622float2(hh);
+      __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+      hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+      lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    uint4* ph = reinterpret_cast<uint4*>(TP + (size_t)t * 2 * tp + ((size_t)h * DV + c) * S + s0);
+    uint4* pl = reinterpret_cast<uint4*>(TP + (size_t)t * 2 * tp + tp + ((size_t)h * DV + c) * S + s0);
+    ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  } else {
+    if (idx >= (unsigned)heads * S) return;
+    const int row = (int)(idx / (unsigned)heads), h = (int)(idx - (unsigned)row * heads);
+    const float* a = d_o + (size_t)row * lddo + h * d;
+    const float* b = o + (size_t)row * ldo + h * d;
+    float acc = 0.f;
+    for (int c = 0; c < d; ++c) acc = fmaf(__ldg(a + c), __ldg(b + c), acc);
+    delta[(size_t)h * S + row] = acc;
   }
 }
 
@@ -526,11 +534,12 @@ extern "C" int skp_self_attn_tc_bwd(const float* d_o, int64_t lddo, const float*
   const int KP = 64 * bt_kch(DV);
   __nv_bfloat16* TP = RP + (size_t)8 * heads * S * KP;
   float* delta = reinterpret_cast<float*>(TP + (size_t)6 * heads * DV * S);
-  const long total = (long)4 * heads * S * (KP / 2) + (long)3 * heads * DV * (S / 16) + (long)heads * S;
-  long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  sa_tc_bwd_split_kernel<<<(int)blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, d_o, lddo, o, ldo, RP, TP, delta, S, heads, d, DV,
-                                                      KP, scale * 1.4426950408889634f);
+  const long n_row = (long)heads * S * (KP / 8), n_tr = (long)heads * DV * (S / 16), n_delta = (long)heads * S;
+  const long widest = n_row > n_tr ? (n_row > n_delta ? n_row : n_delta) : (n_tr > n_delta ? n_tr : n_delta);   // threads of the largest section
+  SKP_REQUIRE((long)heads * S * KP < (1L << 31), "skp_self_attn_tc_bwd: problem too large for 32-bit indexing");
+  dim3 sgrid((unsigned)((widest + 255) / 256), 8);
+  sa_tc_bwd_split_kernel<<<sgrid, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, d_o, lddo, o, ldo, RP, TP, delta, S, heads, d, DV,
+                                                KP == 128 ? 7 : 6, scale * 1.4426950408889634f);
   SKP_CHECK_LAUNCH("sa_tc_bwd_split_kernel");
   switch (DV) {
     case 16: return bt_launch<16>(RP, TP, lse, delta, dq, lddq, dk, lddk, dv, lddv, S, heads, d, scale, st);
