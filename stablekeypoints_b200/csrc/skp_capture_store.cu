@@ -44,7 +44,9 @@ __device__ __forceinline__ void group_bar(int id, int count) { asm volatile("bar
 
 constexpr int FS_THREADS = 512;
 constexpr int FS_ROWS = 2;           // consecutive output rows per unit (one vertical pass when they share their source rows)
-static_assert(FS_ROWS == 2, "the vertical pass selects between two rows");
+constexpr int FS_ROWS4 = 4;          // compile-time shapes with R / s a multiple of 8: four rows share their source rows, and the
+                                     // source-row buffer is ALIASED with the staging tile (dead after the vertical pass), which
+                                     // halves the per-row share of the CTA prologue (tables, source-row fetch, barriers)
 constexpr float FS_PAD = -1.0e4f;    // token padding of the vertical tile: exp2(pad * log2(e) - U) == 0 exactly
 
 struct FsPlan {
@@ -55,9 +57,11 @@ struct FsPlan {
 // Compile-time shape of the hot configurations (0 everywhere = the run-time arguments are used).  With the shape known the
 // index arithmetic of the x-block loop and of the vertical pass folds into immediates (ncu on cfg5: 140 of the 260 warp
 // instructions per x-block iteration and most of the 690-instruction prologue were address / parameter arithmetic).
-template <int S_, int N_, int R_, int NV_, int P_, int TS_, int ROWS_>
+// PX = output pixels per thread: 2 = a thread owns two adjacent pixels that share their four source columns (R / s a multiple
+// of 4), so every 128-bit shared load of the vertical tile feeds two pixels (the shared-memory pipe was the top stall).
+template <int S_, int N_, int R_, int NV_, int P_, int TS_, int ROWS_, int PX_ = 1>
 struct FsShape {
-  static constexpr int S = S_, N = N_, R = R_, NV = NV_, P = P_, TS = TS_, ROWS = ROWS_;
+  static constexpr int S = S_, N = N_, R = R_, NV = NV_, P = P_, TS = TS_, ROWS = ROWS_, PX = PX_;
   static constexpr bool FIXED = S_ != 0;
   static constexpr int pad_shift() {
     int sh = 0;
@@ -71,7 +75,7 @@ using FsDynamic = FsShape<0, 0, 0, 0, 0, 0, 0>;
 // contribute exact zeros), VEC4 = the token axis is a multiple of 4 (128-bit staging stores), RAW = the source rows are
 // staged in shared memory by the copy engine (else read through L1 with 128-bit loads), SH = compile-time shape or FsDynamic.
 template <int PER, bool VEC4, bool RAW, class SH>
-__global__ void __launch_bounds__(FS_THREADS, 2)
+__global__ void __launch_bounds__(FS_THREADS / SH::PX, 2)
 capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ probs, int s_, int N_, int R_, int NV_, int P_, int TS_,
                          int rows_per_cta_, int stage_floats_, int pad_shift_) {
   const int s = SH::FIXED ? SH::S : s_, N = SH::FIXED ? SH::N : N_, R = SH::FIXED ? SH::R : R_, NV = SH::FIXED ? SH::NV : NV_;
@@ -82,15 +86,18 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
   const int vs_floats = (s + 4) * NV;
   const int row_floats = s * N;                                      // one low-res source row [s][N], contiguous
   float* stage = reinterpret_cast<float*>(fs_smem);                  // [P][N]: an x-block of the output row, global layout
-  float* raw = stage + stage_floats;                                 // RAW: [4][s*N] source rows (iy-1 .. iy+2, clamped)
-  float* Vs = raw + (RAW ? 4 * row_floats : 0);                      // [rows_per_cta][s+4][NV] vertically interpolated logits (+ halos)
+  constexpr int MAXR = (SH::FIXED && SH::ROWS > FS_ROWS) ? SH::ROWS : FS_ROWS;
+  constexpr bool ALIAS = SH::FIXED && SH::ROWS == FS_ROWS4;          // source rows live in the staging tile's memory
+  float* raw = ALIAS ? stage : stage + stage_floats;                 // RAW: [4][s*N] source rows (iy-1 .. iy+2, clamped)
+  float* Vs = ALIAS ? stage + (stage_floats > 4 * row_floats ? stage_floats : 4 * row_floats)
+                    : raw + (RAW ? 4 * row_floats : 0);              // [rows_per_cta][s+4][NV] vertically interpolated logits (+ halos)
   float4* wtab = reinterpret_cast<float4*>(Vs + (size_t)rows_per_cta * vs_floats);   // [R] horizontal taps * log2(e)
   float* utab = reinterpret_cast<float*>(wtab + R);                  // [R] sum |taps| * log2(e)
   int* ctab = reinterpret_cast<int*>(utab + R);                      // [R] first (halo'd) source column
-  float* red = reinterpret_cast<float*>(ctab + R);                   // [FS_ROWS][32]
-  float* psum = red + FS_ROWS * 32;                                  // [TS][P]
+  float* red = reinterpret_cast<float*>(ctab + R);                   // [MAXR][32]
+  float* psum = red + MAXR * 32;                                     // [TS][P]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(psum + TS * P);       // RAW: arrival of the source rows
-  const int tid = threadIdx.x, NT = SH::FIXED ? SH::P * SH::TS : (int)blockDim.x, lane = tid & 31;
+  const int tid = threadIdx.x, NT = SH::FIXED ? SH::P * SH::TS / SH::PX : (int)blockDim.x, lane = tid & 31;
   const float scale = (float)s / (float)R;
   const int X_lane = tid % P, part = tid / P;
   const int pg = X_lane >> 5;                                        // pixel group (32 lanes x TS slices) and its named barrier
@@ -159,10 +166,10 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
   }
   // ---- 1. vertical pass of all rows of the CTA: 128-bit reads of the four source rows, scattered into the padded tiles
   {
-    float wy[FS_ROWS][4];
-    float amax[FS_ROWS];
+    float wy[MAXR][4];
+    float amax[MAXR];
 #pragma unroll
-    for (int rr = 0; rr < FS_ROWS; ++rr) {
+    for (int rr = 0; rr < MAXR; ++rr) {
       const float ry = scale * (Y0 + rr + 0.5f) - 0.5f;
       cubic_coeffs(ry - (float)iy, wy[rr]);                           // rows of a CTA share floor(ry) (host-checked)
       amax[rr] = 0.f;
@@ -198,7 +205,7 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
       const int kw = N - n;                                           // elements k >= kw belong to the next column (one wrap at most)
       const bool edge = xs == 0 || xs >= s - 2;
 #pragma unroll
-      for (int rr = 0; rr < FS_ROWS; ++rr) {
+      for (int rr = 0; rr < MAXR; ++rr) {
         if (rr < nrows) {
           const float* w = wy[rr];
           const u64 w0 = pk2(w[0], w[0]), w1 = pk2(w[1], w[1]), w2 = pk2(w[2], w[2]), w3 = pk2(w[3], w[3]);
@@ -228,13 +235,142 @@ capture_store_reg_kernel(const float* __restrict__ logits, float* __restrict__ p
       }
     }
 #pragma unroll
-    for (int rr = 0; rr < FS_ROWS; ++rr) {
+    for (int rr = 0; rr < MAXR; ++rr) {
       const float m = warp_max(amax[rr]);
       if (lane == 0) red[rr * 32 + (tid >> 5)] = m;
     }
   }
   __syncthreads();                                                    // vertical tiles are published
 
+  if constexpr (SH::PX == 2) {
+    // ---- two pixels per thread (compile-time shapes with N % 4 != 0 only): slot 0 / slot 1 = pixels 2*pl + pa / 2*pl + 1 - pa.
+    // Lanes 16..31 take the odd pixel first (pa = 1): the staging rows of a warp's slot-0 pixels then start in 16 even + 16 odd
+    // banks (row pitch N = 77 words, 2 * 77 = 26 mod 32), so the scalar staging stores stay conflict-free.
+    static_assert(!VEC4, "the two-pixel path stores scalars");
+    constexpr int PL = SH::P / 2;                                     // pixel pairs per x-block
+    const int pl = tid % PL, part2 = tid / PL;
+    const int pg2 = pl >> 5;                                          // group = 32 pair lanes x TS slices = 64 pixels
+    const int pa = (lane >> 4) & 1;
+    const int g02 = part2 * PER;
+    const bool issuer2 = part2 == 0 && lane == 0;
+    bool pending = false;
+    for (int rr = 0; rr < nrows; ++rr) {
+      const int Y = Y0 + rr;
+      const float M = warp_max(lane < nwarps ? red[rr * 32 + lane] : 0.f);
+      const float4* V4 = reinterpret_cast<const float4*>(Vs + rr * vs_floats);
+      for (int xb0 = 0; xb0 < R; xb0 += P) {
+        if (xb0 + 64 * pg2 >= R) break;
+        const int lp0 = 2 * pl + pa, lp1 = 2 * pl + 1 - pa;          // pixels of slot 0 / 1 inside the x-block
+        const bool live = xb0 + 2 * pl < R;                          // R is even: both pixels or none
+        u64 e0[2 * PER], e1[2 * PER];
+        float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+        int c0 = 1;
+        if (live) {
+          wa = wtab[xb0 + lp0];
+          wb = wtab[xb0 + lp1];
+          c0 = ctab[xb0 + 2 * pl];                                    // shared by the pair (host-checked: R / s % 4 == 0)
+          const float Ua = utab[xb0 + lp0] * M, Ub = utab[xb0 + lp1] * M;
+          const u64 a0 = pk2(wa.x, wa.x), a1 = pk2(wa.y, wa.y), a2 = pk2(wa.z, wa.z), a3 = pk2(wa.w, wa.w), na = pk2(-Ua, -Ua);
+          const u64 b0 = pk2(wb.x, wb.x), b1 = pk2(wb.y, wb.y), b2 = pk2(wb.z, wb.z), b3 = pk2(wb.w, wb.w), nb = pk2(-Ub, -Ub);
+          const ulonglong2* v0 = reinterpret_cast<const ulonglong2*>(V4 + (size_t)c0 * NV4 + g02);
+          const ulonglong2* v1 = v0 + NV4;
+          const ulonglong2* v2 = v1 + NV4;
+          const ulonglong2* v3 = v2 + NV4;
+          u64 sa2 = pk2(0.f, 0.f), sb2 = sa2;
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const ulonglong2 a = v0[i], b = v1[i], c = v2[i], d = v3[i];
+            float x0, x1, x2, x3;
+            upk2(fma2(a3, d.x, fma2(a2, c.x, fma2(a1, b.x, fma2(a0, a.x, na)))), x0, x1);
+            upk2(fma2(a3, d.y, fma2(a2, c.y, fma2(a1, b.y, fma2(a0, a.y, na)))), x2, x3);
+            e0[2 * i] = pk2(ex2f(x0), ex2f(x1));
+            e0[2 * i + 1] = pk2(ex2f(x2), ex2f(x3));
+            sa2 = add2(sa2, add2(e0[2 * i], e0[2 * i + 1]));
+            upk2(fma2(b3, d.x, fma2(b2, c.x, fma2(b1, b.x, fma2(b0, a.x, nb)))), x0, x1);
+            upk2(fma2(b3, d.y, fma2(b2, c.y, fma2(b1, b.y, fma2(b0, a.y, nb)))), x2, x3);
+            e1[2 * i] = pk2(ex2f(x0), ex2f(x1));
+            e1[2 * i + 1] = pk2(ex2f(x2), ex2f(x3));
+            sb2 = add2(sb2, add2(e1[2 * i], e1[2 * i + 1]));
+          }
+          float s0, s1;
+          upk2(sa2, s0, s1);
+          psum[part2 * P + lp0] = s0 + s1;
+          upk2(sb2, s0, s1);
+          psum[part2 * P + lp1] = s0 + s1;
+        }
+        if (issuer2 && pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the group's segment is free
+        group_bar(1 + pg2, gcount);
+        if (live) {
+          auto finish = [&](const u64* e, int lp, const float4& wx) {   // normalise one pixel out of the registers into its staging row
+            float total = 0.f;
+#pragma unroll
+            for (int q = 0; q < SH::TS; ++q) total += psum[q * P + lp];
+            float* orow = stage + (size_t)lp * N;
+            if (!(total > 1e-30f) || !(total < 1e30f)) {
+              if (part2 == 0) {                                       // exact-max redo of the whole pixel (pathological logits)
+                const float* vs0 = Vs + rr * vs_floats + (size_t)c0 * NV;
+                float m = -CUDART_INF_F;
+                for (int n = 0; n < N; ++n) {
+                  float x = fmaf(wx.w, vs0[3 * NV + n], fmaf(wx.z, vs0[2 * NV + n], fmaf(wx.y, vs0[NV + n], wx.x * vs0[n])));
+                  orow[n] = x;
+                  m = fmaxf(m, x);
+                }
+                float tt = 0.f;
+                for (int n = 0; n < N; ++n) {
+                  float ee = exp2f(orow[n] - m);
+                  orow[n] = ee;
+                  tt += ee;
+                }
+                const float inv = 1.f / tt;
+                for (int n = 0; n < N; ++n) orow[n] *= inv;
+              }
+              return;
+            }
+            const float inv = 1.f / total;
+            const u64 inv2 = pk2(inv, inv);
+            float* o = orow + 4 * g02;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+              float q0, q1, q2, q3;
+              upk2(mul2(e[2 * i], inv2), q0, q1);
+              upk2(mul2(e[2 * i + 1], inv2), q2, q3);
+              const int g = g02 + i;
+              if (g < Gfull) {
+                o[4 * i] = q0;
+                o[4 * i + 1] = q1;
+                o[4 * i + 2] = q2;
+                o[4 * i + 3] = q3;
+              } else if (g == Gfull) {                                // the partial group: only its tail_valid tokens exist
+                if (tail_valid > 0) o[4 * i] = q0;
+                if (tail_valid > 1) o[4 * i + 1] = q1;
+                if (tail_valid > 2) o[4 * i + 2] = q2;
+              }
+            }
+          };
+          finish(e0, lp0, wa);
+          finish(e1, lp1, wb);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        group_bar(1 + pg2, gcount);
+        if (issuer2) {
+          const int x0 = xb0 + 64 * pg2;
+          const int npx = min(64, R - x0);
+          const uint32_t bytes = (uint32_t)((size_t)npx * N * sizeof(float));
+          char* dst = reinterpret_cast<char*>(probs + (((size_t)h * R + Y) * R + x0) * N);
+          const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage + (size_t)(64 * pg2) * N);
+          for (uint32_t off = 0; off < bytes; off += 16384u) {
+            const uint32_t nb = bytes - off < 16384u ? bytes - off : 16384u;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src + off), "r"(nb)
+                         : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          pending = true;
+        }
+      }
+    }
+    if (issuer2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    return;
+  }
   for (int rr = 0; rr < nrows; ++rr) {
     const int Y = Y0 + rr;
     const float M = warp_max(lane < nwarps ? red[rr * 32 + lane] : 0.f);   // max |V| of the row: x_n <= (sum_i |wx_i|) * M
@@ -408,6 +544,22 @@ bool fs_plan(int s, int N, int R, FsPlan* pl) {
   return big && pl->bytes <= 200 * 1024;
 }
 
+// Four rows per CTA (see FS_ROWS4): valid when every aligned group of four output rows shares its source rows and the aliased
+// layout fits half an SM.  Derived from the two-row plan so that the planner stays the single source of truth.
+bool fs_plan4(int s, int N, int R, const FsPlan& pl, FsPlan* p4) {
+  static const bool off = getenv("SKP_ATTN_STORE_ROWS") && getenv("SKP_ATTN_STORE_ROWS")[0] == '2';   // A/B: two rows per CTA
+  if (off || !pl.raw || pl.rows != FS_ROWS || R % FS_ROWS4 != 0) return false;
+  const float scale = (float)s / (float)R;
+  for (int Y = 0; Y < R; Y += FS_ROWS4)
+    for (int k = 1; k < FS_ROWS4; ++k)
+      if (floorf(scale * (Y + k + 0.5f) - 0.5f) != floorf(scale * (Y + 0.5f) - 0.5f)) return false;
+  *p4 = pl;
+  p4->rows = FS_ROWS4;
+  const size_t shared = pl.stage_floats > 4 * (size_t)s * N ? pl.stage_floats : 4 * (size_t)s * N;
+  p4->bytes = (shared + (size_t)FS_ROWS4 * (s + 4) * pl.NV + 4 * (size_t)R + 2 * (size_t)R + FS_ROWS4 * 32 + (size_t)pl.TS * pl.P + 4) * sizeof(float);
+  return p4->bytes <= 112 * 1024;
+}
+
 template <int PER, bool VEC4, bool RAW, class SH>
 int fs_launch(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st) {
   static size_t configured = 0;
@@ -424,7 +576,7 @@ int fs_launch(const float* logits, float* probs, int heads, int s, int N, int R,
   int pad_shift = 0;
   while ((1 << pad_shift) < pl.NV - N) ++pad_shift;
   dim3 grid((R + pl.rows - 1) / pl.rows, heads);
-  kern<<<grid, pl.threads, pl.bytes, st>>>(logits, probs, s, N, R, pl.NV, pl.P, pl.TS, pl.rows, (int)pl.stage_floats, pad_shift);
+  kern<<<grid, pl.threads / SH::PX, pl.bytes, st>>>(logits, probs, s, N, R, pl.NV, pl.P, pl.TS, pl.rows, (int)pl.stage_floats, pad_shift);
   SKP_CHECK_LAUNCH("capture_store_reg");
   return SKP_OK;
 }
@@ -456,6 +608,22 @@ bool fs_try_fixed(const float* logits, float* probs, int heads, int s, int N, in
 }
 
 bool fs_fixed_dispatch(const float* logits, float* probs, int heads, int s, int N, int R, const FsPlan& pl, cudaStream_t st, int* rc) {
+  static const bool px2 = !(getenv("SKP_ATTN_STORE_PX") && getenv("SKP_ATTN_STORE_PX")[0] == '1');   // "1": one pixel per thread (A/B)
+  FsPlan p4;
+  if (fs_plan4(s, N, R, pl, &p4)) {   // four rows per CTA, source rows aliased with the staging tile
+    if (px2) {
+      if (fs_try_fixed<5, false, true, FsShape<32, 77, 256, 84, 128, 4, 4, 2>>(logits, probs, heads, s, N, R, p4, st, rc)) return true;
+      if (fs_try_fixed<5, false, true, FsShape<16, 77, 128, 84, 128, 4, 4, 2>>(logits, probs, heads, s, N, R, p4, st, rc)) return true;
+    }
+    if (fs_try_fixed<5, false, true, FsShape<32, 77, 256, 84, 128, 4, 4>>(logits, probs, heads, s, N, R, p4, st, rc)) return true;
+    if (fs_try_fixed<5, false, true, FsShape<16, 77, 128, 84, 128, 4, 4>>(logits, probs, heads, s, N, R, p4, st, rc)) return true;
+    if (fs_try_fixed<7, true, true, FsShape<16, 100, 128, 116, 128, 4, 4>>(logits, probs, heads, s, N, R, p4, st, rc)) return true;
+  }
+  if (px2) {   // two pixels per thread: R / s is a multiple of 4 in all three
+    if (fs_try_fixed<5, false, true, FsShape<32, 77, 256, 84, 128, 4, 2, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+    if (fs_try_fixed<5, false, true, FsShape<16, 77, 128, 84, 128, 4, 2, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+    if (fs_try_fixed<5, false, true, FsShape<32, 77, 128, 84, 128, 4, 2, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
+  }
   //                                          S   N    R    NV   P   TS  ROWS
   if (fs_try_fixed<5, false, true, FsShape<32, 77, 256, 84, 128, 4, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
   if (fs_try_fixed<5, false, true, FsShape<16, 77, 128, 84, 128, 4, 2>>(logits, probs, heads, s, N, R, pl, st, rc)) return true;
