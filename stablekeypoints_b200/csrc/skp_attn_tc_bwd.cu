@@ -138,7 +138,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 //   row planes   RP[t][2][heads*S][KP]  t = Q' (scaled), K, V, dO          (hi, lo; zero padded to KP = 64 / 128 columns)
 //   transposed   TP[t][2][heads*DV][S]  t = Q'^T, K^T, dO^T
 //   delta[heads][S] = sum_c dO * O
-// blockIdx.y selects the section (0..3 row planes, 4..6 transposed planes, 7 delta); all index arithmetic is 32-bit (the first
+// blockIdx.y selects the section (0..3 row planes -- the dO section also makes delta --, 4..6 transposed planes); all index arithmetic is 32-bit (the first
 // version decomposed one flat 64-bit index with four 64-bit divisions per element and spent its time in them).
 __global__ void sa_tc_bwd_split_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                                        const float* __restrict__ v, int64_t ldv, const float* __restrict__ d_o, int64_t lddo,
@@ -166,6 +166,21 @@ __global__ void sa_tc_bwd_split_kernel(const float* __restrict__ q, int64_t ldq,
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = c + i < d ? __ldg(src + i) : 0.f;
+    }
+    if (t == 3) {
+      // delta = rowsum(dO * O): partial dot of this thread's eight columns, reduced over the 8 / 16 adjacent lanes of the row
+      // (whole warps take this branch: heads * S * KP / 8 is a multiple of 32)
+      const float* op = o + (size_t)row * ldo + h * d + c;
+      float acc = 0.f;
+      if (c + 8 <= d && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(op)), b4 = __ldg(reinterpret_cast<const float4*>(op) + 1);
+        acc = x[0] * a.x + x[1] * a.y + x[2] * a.z + x[3] * a.w + x[4] * b4.x + x[5] * b4.y + x[6] * b4.z + x[7] * b4.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(x[i], c + i < d ? __ldg(op + i) : 0.f, acc);
+      }
+      for (int off = 1; off < (1 << cp_shift); off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (c == 0) delta[(size_t)h * S + row] = acc;
     }
     const float sc = t == 0 ? qscale : 1.f;
     uint32_t hw[4], lw[4];
@@ -210,14 +225,6 @@ __global__ void sa_tc_bwd_split_kernel(const float* __restrict__ q, int64_t ldq,
     ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
     pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-  } else {
-    if (idx >= (unsigned)heads * S) return;
-    const int row = (int)(idx / (unsigned)heads), h = (int)(idx - (unsigned)row * heads);
-    const float* a = d_o + (size_t)row * lddo + h * d;
-    const float* b = o + (size_t)row * ldo + h * d;
-    float acc = 0.f;
-    for (int c = 0; c < d; ++c) acc = fmaf(__ldg(a + c), __ldg(b + c), acc);
-    delta[(size_t)h * S + row] = acc;
   }
 }
 
@@ -534,10 +541,10 @@ extern "C" int skp_self_attn_tc_bwd(const float* d_o, int64_t lddo, const float*
   const int KP = 64 * bt_kch(DV);
   __nv_bfloat16* TP = RP + (size_t)8 * heads * S * KP;
   float* delta = reinterpret_cast<float*>(TP + (size_t)6 * heads * DV * S);
-  const long n_row = (long)heads * S * (KP / 8), n_tr = (long)heads * DV * (S / 16), n_delta = (long)heads * S;
-  const long widest = n_row > n_tr ? (n_row > n_delta ? n_row : n_delta) : (n_tr > n_delta ? n_tr : n_delta);   // threads of the largest section
+  const long n_row = (long)heads * S * (KP / 8), n_tr = (long)heads * DV * (S / 16);
+  const long widest = n_row > n_tr ? n_row : n_tr;   // threads of the largest section
   SKP_REQUIRE((long)heads * S * KP < (1L << 31), "skp_self_attn_tc_bwd: problem too large for 32-bit indexing");
-  dim3 sgrid((unsigned)((widest + 255) / 256), 8);
+  dim3 sgrid((unsigned)((widest + 255) / 256), 7);
   sa_tc_bwd_split_kernel<<<sgrid, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, d_o, lddo, o, ldo, RP, TP, delta, S, heads, d, DV,
                                                 KP == 128 ? 7 : 6, scale * 1.4426950408889634f);
   SKP_CHECK_LAUNCH("sa_tc_bwd_split_kernel");
