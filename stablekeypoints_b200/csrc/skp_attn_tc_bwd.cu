@@ -28,8 +28,15 @@ namespace {
 
 constexpr int BT_BM = 128;                       // resident rows per CTA
 constexpr int BT_BN = 64;                        // streamed rows per step
-constexpr int BT_EW_WARPS = 8;
-constexpr int BT_THREADS = 96 + 32 * BT_EW_WARPS;   // 352
+#ifndef SKP_BT_EW_WARPS
+#define SKP_BT_EW_WARPS 8
+#endif
+constexpr int BT_EW_WARPS = SKP_BT_EW_WARPS;     // element-wise warps: 8 (32 score columns each) or 16 (16 columns each;
+                                                 // measured slower on B200: 283 vs 267 us at S = 4096)
+static_assert(BT_EW_WARPS == 8 || BT_EW_WARPS == 16, "two or four element-wise warps per TMEM lane quarter");
+constexpr int BT_NPART = BT_EW_WARPS / 4;        // warps per lane quarter
+constexpr int BT_CW = 64 / BT_NPART;             // score columns per element-wise warp
+constexpr int BT_THREADS = 96 + 32 * BT_EW_WARPS;
 constexpr int BT_B_BYTES = BT_BN * 128;
 constexpr int BT_TMEM_COLS = 512;                // the whole tensor memory of the SM: map in front of bt_body
 constexpr int bt_kch(int DV) { return DV > 64 ? 2 : 1; }     // 64-column chunks of a row plane
@@ -88,10 +95,37 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, float a[32
     b[i] = __uint_as_float(q[i]);
   }
 }
-// 32 consecutive fp32 -> 16 bf16 pairs of the hi plane and 16 of the lo plane (element 2c in the low half of word c)
-__device__ __forceinline__ void bt_split32(const float* x, uint32_t hi[16], uint32_t lo[16]) {
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float a[16], float b[16]) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]),
+        "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
+  for (int i = 0; i < 16; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(q[i]);
+  }
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 2*W consecutive fp32 -> W bf16 pairs of the hi plane and W of the lo plane (element 2c in the low half of word c)
+template <int W>
+__device__ __forceinline__ void bt_split(const float* x, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
     __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
     float2 f = __bfloat1622float2(hh);
     __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * e] - f.x, x[2 * e + 1] - f.y);
@@ -99,6 +133,8 @@ __device__ __forceinline__ void bt_split32(const float* x, uint32_t hi[16], uint
     lo[e] = *reinterpret_cast<uint32_t*>(&ll);
   }
 }
+template <int W>
+__device__ __forceinline__ void tmem_st_w(uint32_t taddr, const uint32_t* r);
 // tcgen05.st: this thread's TMEM lane, 32 / 16 consecutive columns (completion: tcgen05.wait::st by the caller)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
   asm volatile(
@@ -123,6 +159,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) 
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+template <>
+__device__ __forceinline__ void tmem_st_w<16>(uint32_t taddr, const uint32_t* r) { tmem_st16(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_st_w<8>(uint32_t taddr, const uint32_t* r) { tmem_st8(taddr, r); }
 // tcgen05.mma with the A operand in tensor memory (lane = row, 16 bf16 of K = 8 columns), B through a shared-memory descriptor
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -374,20 +414,22 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
     __syncwarp();
   } else {
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 3) >> 2;             // which 32 of the 64 score columns
+    constexpr int CW = BT_CW, NPART = BT_NPART;
+    const int part = (warp - 3) >> 2;             // which CW of the 64 score columns
     const int r = quarter * 32 + lane;            // resident row inside the block
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-    // ---- the resident block goes to tensor memory: this thread's row of A1 (half 0) or A2 (half 1), hi and lo planes
+    // ---- the resident block goes to tensor memory: this thread's row of planes part, part + NPART, .. (A1 hi, A1 lo, A2 hi, A2 lo)
     {
-      const __nv_bfloat16* src = (half == 0 ? a1_planes : a2_planes) + ((size_t)h * S + r0 + r) * KP;
 #pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
-        const uint4* p4 = reinterpret_cast<const uint4*>(src + (size_t)pl * plane_stride);
+      for (int pl = 0; pl < 4; ++pl) {
+        if (pl % NPART != part) continue;
+        const __nv_bfloat16* src = (pl < 2 ? a1_planes : a2_planes) + (size_t)(pl & 1) * plane_stride + ((size_t)h * S + r0 + r) * KP;
+        const uint4* p4 = reinterpret_cast<const uint4*>(src);
 #pragma unroll
         for (int i = 0; i < ACOLS / 8; ++i) {     // 8 TMEM columns = 16 bf16 = two 16-byte loads
           const uint4 v0 = __ldg(p4 + 2 * i), v1 = __ldg(p4 + 2 * i + 1);
           const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          tmem_st8(trow + TM_A + (2 * half + pl) * ACOLS + 8 * i, w);
+          tmem_st8(trow + TM_A + pl * ACOLS + 8 * i, w);
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -399,12 +441,12 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
       lse_r = __ldg(lse + (size_t)h * S + r0 + r);
       delta_r = __ldg(delta + (size_t)h * S + r0 + r);
     }
-    float lv[32], dl[32];
+    float lv[CW], dl[CW];
     auto load_stats = [&](int j) {                // per-column statistics of the streamed queries (warp-uniform addresses)
-      const float4* lp = reinterpret_cast<const float4*>(lse + (size_t)h * S + j * BT_BN + 32 * half);
-      const float4* dp = reinterpret_cast<const float4*>(delta + (size_t)h * S + j * BT_BN + 32 * half);
+      const float4* lp = reinterpret_cast<const float4*>(lse + (size_t)h * S + j * BT_BN + CW * part);
+      const float4* dp = reinterpret_cast<const float4*>(delta + (size_t)h * S + j * BT_BN + CW * part);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < CW / 4; ++i) {
         const float4 a = __ldg(lp + i), b = __ldg(dp + i);
         lv[4 * i] = a.x; lv[4 * i + 1] = a.y; lv[4 * i + 2] = a.z; lv[4 * i + 3] = a.w;
         dl[4 * i] = b.x; dl[4 * i + 1] = b.y; dl[4 * i + 2] = b.z; dl[4 * i + 3] = b.w;
@@ -416,46 +458,47 @@ __device__ __forceinline__ void bt_body(const BtMaps& mp, const __nv_bfloat16* _
       const uint32_t ts = trow + 128u * (uint32_t)sbuf;
       mbar_wait(bars + 8 * (S_FULL + sbuf), (uint32_t)(j / NSB) & 1u);
       tc_fence_after();
-      float s[32], g[32];
-      tmem_ld32x2(ts + 32 * half, ts + 64 + 32 * half, s, g);
-      // the bf16 results overwrite score columns the partner warp of this lane quarter reads: both must have loaded
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      float s[CW], g[CW];
+      if constexpr (CW == 32) tmem_ld32x2(ts + CW * part, ts + 64 + CW * part, s, g);
+      else tmem_ld16x2(ts + CW * part, ts + 64 + CW * part, s, g);
+      // the bf16 results overwrite score columns the other warps of this lane quarter read: all must have loaded
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NPART) : "memory");
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < CW; ++i) {
         const float p = bt_ex2(s[i] - (DKV ? lv[i] : lse_r));
         s[i] = p;
         g[i] = p * (g[i] - (DKV ? dl[i] : delta_r));
       }
       if (DKV && j + 1 < ntiles) load_stats(j + 1);   // lands behind the conversions and the next tile's wait
-      uint32_t hi[16], lo[16];
+      uint32_t hi[CW / 2], lo[CW / 2];
       if (DKV) {
-        bt_split32(s, hi, lo);
-        tmem_st16(ts + 16 * half, hi);            // P hi: columns [0,32), two queries per column
-        tmem_st16(ts + 32 + 16 * half, lo);       // P lo: columns [32,64)
+        bt_split<CW / 2>(s, hi, lo);
+        tmem_st_w<CW / 2>(ts + (CW / 2) * part, hi);            // P hi: columns [0,32), two queries per column
+        tmem_st_w<CW / 2>(ts + 32 + (CW / 2) * part, lo);       // P lo: columns [32,64)
       }
-      bt_split32(g, hi, lo);
-      tmem_st16(ts + 64 + 16 * half, hi);         // dS hi: columns [64,96)
-      tmem_st16(ts + 96 + 16 * half, lo);         // dS lo: columns [96,128)
+      bt_split<CW / 2>(g, hi, lo);
+      tmem_st_w<CW / 2>(ts + 64 + (CW / 2) * part, hi);         // dS hi: columns [64,96)
+      tmem_st_w<CW / 2>(ts + 96 + (CW / 2) * part, lo);         // dS lo: columns [96,128)
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       bt_arrive(bars + 8 * (E_FULL + sbuf));
     }
-    // ---- epilogue: the accumulators leave TMEM; this thread owns row r, columns [half*DV/2, (half+1)*DV/2)
+    // ---- epilogue: the accumulators leave TMEM; this thread owns row r, columns [part*DV/NPART, (part+1)*DV/NPART)
     mbar_wait(bars + 8 * DONE, 0);
     tc_fence_after();
     const int row = r0 + r;
-    constexpr int HC = DV / 2;
+    constexpr int HC = DV / NPART;
 #pragma unroll
     for (int which = DKV ? 0 : 1; which < 2; ++which) {
       float* orow = (which == 0 ? out1 + (size_t)row * ld1 : out2 + (size_t)row * ld2) + h * d;
       const float sc = which == 0 ? 1.f : scale2;
 #pragma unroll
-      for (int c8 = 0; c8 < HC / 8; ++c8) {
-        float a[8];
-        const int c0 = half * HC + 8 * c8;
-        tmem_ld8(trow + (which == 0 ? TM_ACC1 : TM_ACC2) + c0, a);
+      for (int c4 = 0; c4 < HC / 4; ++c4) {
+        float a[4];
+        const int c0 = part * HC + 4 * c4;
+        tmem_ld4(trow + (which == 0 ? TM_ACC1 : TM_ACC2) + c0, a);
 #pragma unroll
-        for (int i = 0; i < 8; i += 2)
+        for (int i = 0; i < 4; i += 2)
           if (c0 + i < d) *reinterpret_cast<float2*>(orow + c0 + i) = make_float2(a[i] * sc, a[i + 1] * sc);
       }
     }
