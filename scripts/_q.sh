@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "self_attn_fwd_bwd and tcgen05" 2>&1 | tail -2
-ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:sa_tc_bwd_kernel -c 4 --csv python scripts/attn_bwd_bench.py --reps 1 2>/dev/null | grep -E "sa_tc_bwd" | awk -F'","' '{print substr($5,1,50), $(NF-2), $NF}' | head -8
+for i in 1 2 3 4 5 6; do python scripts/_fwd_dbg.py 2>&1 | grep -vE "'[0-9.]+e-05', '[0-9.]+e-05', '[0-9.]+e-05'\] bad rows 0" | cut -c1-120; done; echo soak-done
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "self_attn" 2>&1 | tail -1
+python scripts/attn_bwd_bench.py 2>&1 | grep forward
+SKP_ATTN_FWD_PIPE=0 python scripts/attn_bwd_bench.py 2>&1 | grep forward | head -1

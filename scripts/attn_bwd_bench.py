@@ -17,6 +17,18 @@ def main():
     dev = torch.device("cuda")
     for (s, heads, d) in [(4096, 8, 40), (1024, 8, 80), (1024, 8, 64), (1024, 4, 32)]:
         c = heads * d
+        if d <= 64:      # forward on tcgen05 (skp_attn_tc.cu): CUDA events around the op (operand split + kernel)
+            x = torch.randn(s, 3 * c, device=dev) * 1.5
+            ts = []
+            for i in range(reps + 3):
+                st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                st.record()
+                ops.self_attn_core(x, heads, d ** -0.5)
+                en.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(st.elapsed_time(en))
+            print(json.dumps({"S": s, "heads": heads, "d": d, "forward": "tcgen05", "us": round(sorted(ts)[len(ts) // 2] * 1e3, 1)}), flush=True)
         for mode in ("tcgen05", "mma"):
             ops.SELF_ATTN_TC_BWD = mode == "tcgen05"
             x = (torch.randn(s, 3 * c, device=dev) * 1.5).requires_grad_(True)

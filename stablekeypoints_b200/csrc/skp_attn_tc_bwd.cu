@@ -135,18 +135,7 @@ __device__ __forceinline__ void bt_split(const float* x, uint32_t* hi, uint32_t*
 }
 template <int W>
 __device__ __forceinline__ void tmem_st_w(uint32_t taddr, const uint32_t* r);
-// tcgen05.st: this thread's TMEM lane, 32 / 16 consecutive columns (completion: tcgen05.wait::st by the caller)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-      "r"(r[31])
-      : "memory");
-}
+// tcgen05.st: this thread's TMEM lane, 8 / 16 consecutive columns (32: skp_tc.cuh; completion: tcgen05.wait::st by the caller)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -163,17 +152,6 @@ template <>
 __device__ __forceinline__ void tmem_st_w<16>(uint32_t taddr, const uint32_t* r) { tmem_st16(taddr, r); }
 template <>
 __device__ __forceinline__ void tmem_st_w<8>(uint32_t taddr, const uint32_t* r) { tmem_st8(taddr, r); }
-// tcgen05.mma with the A operand in tensor memory (lane = row, 16 bf16 of K = 8 columns), B through a shared-memory descriptor
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-
 // q,k,v [S, heads*d] and d_o, o [S, heads*d] fp32 (leading dims) ->
 //   row planes   RP[t][2][heads*S][KP]  t = Q' (scaled), K, V, dO          (hi, lo; zero padded to KP = 64 / 128 columns)
 //   transposed   TP[t][2][heads*DV][S]  t = Q'^T, K^T, dO^T
