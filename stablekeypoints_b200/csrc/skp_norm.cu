@@ -588,10 +588,11 @@ __global__ void __launch_bounds__(GN_THREADS) gn_group_bwd_kernel(const float* _
 // of the cluster (1, 2, 4 or 8 CTAs: 32 .. 256 CTAs in flight); beyond that the two-kernel path streams better
 constexpr int GN_SLAB_PER_CTA = 20480;
 static int g_gn_cluster_max = getenv("SKP_GN_CLUSTER") ? atoi(getenv("SKP_GN_CLUSTER")) : 8;
+static int g_gn_cta_elems = getenv("SKP_GN_CTA_ELEMS") ? atoi(getenv("SKP_GN_CTA_ELEMS")) : 4096;   // elements per CTA before the cluster grows
 static inline int gn_cluster_size(int rows, int cg) {
   const size_t slab = (size_t)rows * cg;
   int cl = 1;
-  while (cl < g_gn_cluster_max && slab > (size_t)4096 * cl) cl *= 2;     // ~4K elements per CTA: the sweep is latency-bound
+  while (cl < g_gn_cluster_max && slab > (size_t)g_gn_cta_elems * cl) cl *= 2;     // the sweep is latency-bound
   while (cl > 1 && rows / cl < 1) cl /= 2;
   return cl;
 }
