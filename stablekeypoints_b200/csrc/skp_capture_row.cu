@@ -279,25 +279,28 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_store_row_kernel(c
 __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kernel(const float* __restrict__ logits,
                                                                                const float* __restrict__ d_maps,
                                                                                float* __restrict__ dvrow, int s, int N, int R,
-                                                                               int NV, int P, int TS, int XB, float w) {
+                                                                               int NV, int P, int TS, int XB, int XBW, float w) {
   extern __shared__ __align__(16) unsigned char row_smem[];
-  float* stage = reinterpret_cast<float*>(row_smem);                 // [XB][N]  e_n, then dS_n
-  float* Vs = stage + (((size_t)XB * N + 3) & ~(size_t)3);           // [s+4][NV] vertically interpolated logits
+  const int NS = (N + 3) & ~3;                                       // staging row pitch: whole float4 token groups; the padding
+                                                                     // tokens carry exp = 0 (vertical tile padded with a large
+                                                                     // negative number), so every N runs the 128-bit path
+  float* stage = reinterpret_cast<float*>(row_smem);                 // [XB][NS]  e_n, then dS_n
+  float* Vs = stage + (size_t)XB * NS;                               // [s+4][NV] vertically interpolated logits
   float* dVs = Vs + (size_t)(s + 4) * NV;                            // [s+4][NV] gradient wrt Vs (accumulated over the x-blocks)
   float* red = dVs + (size_t)(s + 4) * NV;                           // [32]
   float* psum = red + 32;                                            // [2][TS][P]  partial (sum e, sum e*g)
   float* wtab = psum + 2 * TS * P;                                   // [XB][4] raw horizontal weights
   int* c0tab = reinterpret_cast<int*>(wtab + 4 * XB);                // [XB]    first halo'd column of the pixel's taps
   int* xrange = c0tab + XB;                                          // [s+4][2] pixel range (local) touching a column
+  float* wcol = reinterpret_cast<float*>(xrange + 2 * (s + 4));      // [s+4][XBW] transposed-stencil weights per (column, pixel of its range)
   const int Y = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, NT = blockDim.x;
   const float scale = (float)s / (float)R;
   const float LOG2E = 1.4426950408889634f;
-  const int N4 = N >> 2;
+  const int N4 = NS >> 2;
   const int X_lane = tid % P, part = tid / P;
   const int g0 = (part * N4) / TS, g1 = ((part + 1) * N4) / TS;
-  const int n_lo = 4 * g0, n_hi = (part == TS - 1) ? N : 4 * g1;
-  (void)g1;
+  const int n_lo = 4 * g0, n_hi = 4 * g1;                            // whole groups; tokens >= N are padding
 
   // vertical weights / rows of this output row
   float wy[4];
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         int n = n0 + k;
-        float a = 0.f;
+        float a = -1.0e4f;                                           // padding token: exp2(w . pad - U) == 0 exactly
         if (n < N) {
           int o = xs * N + n;
           a = wy[0] * __ldg(rows[0] + o);
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
       float wx[4] = {0.f, 0.f, 0.f, 0.f};
       int c0 = 1;
       float U = 0.f, s1 = 0.f, s2 = 0.f;
-      float* orow = stage + (size_t)(live ? xi : 0) * N;
+      float* orow = stage + (size_t)(live ? xi : 0) * NS;
       const float* grow = d_maps + (size_t)Y * R + (live ? X : 0);     // + n*R*R per token
       if (live) {
         c0 = c0tab[xi];
@@ -396,13 +399,26 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
           U += fabsf(wx[i]);
         }
         U *= M;
-        for (int n = n_lo; n < n_hi; ++n) {
-          float x = fmaf(wx[3], Vs[(c0 + 3) * NV + n], fmaf(wx[2], Vs[(c0 + 2) * NV + n],
-                    fmaf(wx[1], Vs[(c0 + 1) * NV + n], fmaf(wx[0], Vs[c0 * NV + n], -U))));
-          float e = ex2_approx(x);
-          orow[n] = e;
-          s1 += e;
-          s2 = fmaf(e, __ldg(grow + (size_t)n * R * R), s2);
+        {                                                            // four tokens per step: 128-bit tile loads and staging stores
+          const float4* v0 = reinterpret_cast<const float4*>(Vs + c0 * NV);
+          const float4* v1 = reinterpret_cast<const float4*>(Vs + (c0 + 1) * NV);
+          const float4* v2 = reinterpret_cast<const float4*>(Vs + (c0 + 2) * NV);
+          const float4* v3 = reinterpret_cast<const float4*>(Vs + (c0 + 3) * NV);
+          const size_t RR = (size_t)R * R;
+          for (int n = n_lo; n < n_hi; n += 4) {
+            const float4 a = v0[n >> 2], b = v1[n >> 2], c = v2[n >> 2], dd = v3[n >> 2];
+            const float* gp = grow + (size_t)n * RR;
+            const float g0v = __ldg(gp), g1v = n + 1 < N ? __ldg(gp + RR) : 0.f, g2v = n + 2 < N ? __ldg(gp + 2 * RR) : 0.f,
+                        g3v = n + 3 < N ? __ldg(gp + 3 * RR) : 0.f;
+            float4 e;
+            e.x = ex2_approx(fmaf(wx[3], dd.x, fmaf(wx[2], c.x, fmaf(wx[1], b.x, fmaf(wx[0], a.x, -U)))));
+            e.y = ex2_approx(fmaf(wx[3], dd.y, fmaf(wx[2], c.y, fmaf(wx[1], b.y, fmaf(wx[0], a.y, -U)))));
+            e.z = ex2_approx(fmaf(wx[3], dd.z, fmaf(wx[2], c.z, fmaf(wx[1], b.z, fmaf(wx[0], a.z, -U)))));
+            e.w = ex2_approx(fmaf(wx[3], dd.w, fmaf(wx[2], c.w, fmaf(wx[1], b.w, fmaf(wx[0], a.w, -U)))));
+            *reinterpret_cast<float4*>(orow + n) = e;
+            s1 += (e.x + e.y) + (e.z + e.w);
+            s2 = fmaf(e.x, g0v, fmaf(e.y, g1v, fmaf(e.z, g2v, fmaf(e.w, g3v, s2))));
+          }
         }
         psum[part * P + X_lane] = s1;
         psum[(TS + part) * P + X_lane] = s2;
@@ -433,22 +449,60 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
             }
             const float inv = 1.f / a1, dot = a2 * inv;
             for (int n = 0; n < N; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+            for (int n = N; n < NS; ++n) orow[n] = 0.f;
           }
         } else {
           const float inv = 1.f / t1, dot = t2 * inv;
-          for (int n = n_lo; n < n_hi; ++n) orow[n] = orow[n] * inv * (__ldg(grow + (size_t)n * R * R) - dot) * w;
+          const float iw = inv * w;
+          const size_t RR = (size_t)R * R;
+          for (int n = n_lo; n < n_hi; n += 4) {
+            const float* gp = grow + (size_t)n * RR;
+            float4 e = *reinterpret_cast<const float4*>(orow + n);
+            e.x *= (__ldg(gp) - dot) * iw;
+            e.y *= ((n + 1 < N ? __ldg(gp + RR) : 0.f) - dot) * iw;   // (padding tokens: e == 0)
+            e.z *= ((n + 2 < N ? __ldg(gp + 2 * RR) : 0.f) - dot) * iw;
+            e.w *= ((n + 3 < N ? __ldg(gp + 3 * RR) : 0.f) - dot) * iw;
+            *reinterpret_cast<float4*>(orow + n) = e;
+          }
         }
       }
       __syncthreads();
     }
     // ---- 3. transposed horizontal stencil as a gather, accumulated over the x-blocks:
-    //         dVs[c][n] += sum_X wx[X][c - c0[X]] * dS[X][n]   (thread <-> (c, n) is the same in every x-block: no race)
-    for (int i = tid; i < (s + 4) * N; i += NT) {
-      const int c = i / N, n = i - c * N;
-      const int lo = xrange[2 * c], hi = xrange[2 * c + 1];
-      float a = 0.f;
-      for (int xi = lo; xi <= hi; ++xi) a = fmaf(wtab[4 * xi + (c - c0tab[xi])], stage[(size_t)xi * N + n], a);
-      dVs[c * NV + n] += a;
+    //         dVs[c][n] += sum_X wx[X][c - c0[X]] * dS[X][n]
+    // The weights of a column do not depend on the token: they are tabulated once per x-block (wcol), then a warp takes one
+    // (column, 128-token chunk) item at a time -- four tokens per lane, 128-bit staging loads -- so the inner loop is one
+    // broadcast weight load, one staging load and four FMAs.  (The first version looked the weight up per (column, token,
+    // pixel) through two dependent table loads and divided a flat index by N per item: half of the kernel's instructions.)
+    for (int i = tid; i < (s + 4) * XBW; i += NT) {
+      const int c = i / XBW, k = i - c * XBW;
+      const int xi = xrange[2 * c] + k;
+      wcol[i] = xi <= xrange[2 * c + 1] ? wtab[4 * xi + (c - c0tab[xi])] : 0.f;
+    }
+    __syncthreads();
+    {
+      const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+      const int nchunks = (NS + 127) / 128;                          // 128 tokens per item
+      for (int item = warp; item < (s + 4) * nchunks; item += nwarps) {
+        const int c = item / nchunks, ch = item - c * nchunks;
+        const int lo = xrange[2 * c], cnt = xrange[2 * c + 1] - lo + 1;
+        if (cnt <= 0) continue;
+        const float* wc = wcol + c * XBW;
+        const int n = ch * 128 + 4 * lane;
+        if (n < NS) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* sp = stage + (size_t)lo * NS + n;
+          for (int k = 0; k < cnt; ++k) {
+            const float wk = wc[k];
+            const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)k * NS);
+            a.x = fmaf(wk, v.x, a.x); a.y = fmaf(wk, v.y, a.y); a.z = fmaf(wk, v.z, a.z); a.w = fmaf(wk, v.w, a.w);
+          }
+          float4* d4 = reinterpret_cast<float4*>(dVs + c * NV + n);
+          float4 o = *d4;
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          *d4 = o;
+        }
+      }
     }
     __syncthreads();
   }
@@ -513,6 +567,12 @@ __global__ void __launch_bounds__(256) capture_mean_vgather_kernel(const float* 
   }
 }
 
+// pixels of one x-block that can touch a given low-res column: 4 taps x ceil(R / s) pixels per source cell (+ slack), at most XB
+static int mean_row_bwd_xbw(int s, int R, int XB) {
+  const int wmax = 4 * ((R + s - 1) / s) + 8;
+  return wmax < XB ? wmax : XB;
+}
+
 // shared-memory plan of the backward row kernel: pixels per x-block (0 = does not fit) and bytes
 static int mean_row_bwd_plan(int s, int N, int R, int* NV_out, int* P_out, int* TS_out, size_t* bytes_out) {
   int Np4 = (N + 3) & ~3;
@@ -526,8 +586,8 @@ static int mean_row_bwd_plan(int s, int N, int R, int* NV_out, int* P_out, int* 
     int P = ((XB + 31) / 32) * 32;
     if (P > 256) P = 256;
     const int TS = row_token_slices(N, P);
-    size_t floats = (((size_t)XB * N + 3) & ~(size_t)3) + 2 * (size_t)(s + 4) * NV + 32 + 2 * (size_t)TS * P + 5 * (size_t)XB +
-                    2 * (size_t)(s + 4);
+    size_t floats = (size_t)XB * ((N + 3) & ~3) + 2 * (size_t)(s + 4) * NV + 32 + 2 * (size_t)TS * P + 5 * (size_t)XB +
+                    2 * (size_t)(s + 4) + (size_t)(s + 4) * mean_row_bwd_xbw(s, R, XB);
     if (floats * sizeof(float) <= 200 * 1024) {
       *NV_out = NV; *P_out = P; *TS_out = TS; *bytes_out = floats * sizeof(float);
       return XB;
@@ -566,7 +626,7 @@ int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logi
     configured = bytes;
   }
   dim3 grid(R, heads);
-  capture_mean_row_bwd_kernel<<<grid, P * TS, bytes, st>>>(logits, d_maps, workspace, s, N, R, NV, P, TS, XB, w);
+  capture_mean_row_bwd_kernel<<<grid, P * TS, bytes, st>>>(logits, d_maps, workspace, s, N, R, NV, P, TS, XB, mean_row_bwd_xbw(s, R, XB), w);
   SKP_CHECK_LAUNCH("capture_mean_row_bwd");
   capture_mean_vgather_kernel<<<dim3(s, heads), 256, 0, st>>>(workspace, d_logits, s, N, R);
   SKP_CHECK_LAUNCH("capture_mean_vgather");
