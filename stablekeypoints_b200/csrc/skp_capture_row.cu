@@ -560,10 +560,28 @@ __global__ void __launch_bounds__(256) capture_mean_vgather_kernel(const float* 
   const float* src = dvrow + (size_t)h * R * row_stride;
   float* dst = d_logits + ((size_t)h * s + ys) * row_stride;
   const int total = s * N;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    float acc = 0.f;
-    for (int k = 0; k < nrows; ++k) acc = fmaf(wtab[k], __ldg(src + (size_t)ytab[k] * row_stride + i), acc);
-    dst[i] += acc;
+  // blockIdx.z splits the (xs, token) range so that long token axes fill the GPU (N = 500: 128 -> 512 CTAs)
+  const int chunk = (((total + (int)gridDim.z - 1) / (int)gridDim.z) + 3) & ~3;
+  const int i0 = (int)blockIdx.z * chunk, i1 = min(total, i0 + chunk);
+  if ((row_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(dvrow) | reinterpret_cast<uintptr_t>(d_logits)) & 15) == 0) {
+    for (int i = i0 + 4 * (int)threadIdx.x; i < i1; i += 4 * 256) {      // total % 4 == 0: whole float4 groups
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < nrows; ++k) {
+        const float wk = wtab[k];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)ytab[k] * row_stride + i));
+        acc.x = fmaf(wk, v.x, acc.x); acc.y = fmaf(wk, v.y, acc.y); acc.z = fmaf(wk, v.z, acc.z); acc.w = fmaf(wk, v.w, acc.w);
+      }
+      float4* d4 = reinterpret_cast<float4*>(dst + i);
+      float4 o = *d4;
+      o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+      *d4 = o;
+    }
+  } else {
+    for (int i = i0 + (int)threadIdx.x; i < i1; i += 256) {
+      float acc = 0.f;
+      for (int k = 0; k < nrows; ++k) acc = fmaf(wtab[k], __ldg(src + (size_t)ytab[k] * row_stride + i), acc);
+      dst[i] += acc;
+    }
   }
 }
 
@@ -628,7 +646,8 @@ int capture_mean_row_bwd(const float* logits, const float* d_maps, float* d_logi
   dim3 grid(R, heads);
   capture_mean_row_bwd_kernel<<<grid, P * TS, bytes, st>>>(logits, d_maps, workspace, s, N, R, NV, P, TS, XB, mean_row_bwd_xbw(s, R, XB), w);
   SKP_CHECK_LAUNCH("capture_mean_row_bwd");
-  capture_mean_vgather_kernel<<<dim3(s, heads), 256, 0, st>>>(workspace, d_logits, s, N, R);
+  const int vz = (s * N + 2047) / 2048;                                  // ~2K elements per CTA
+  capture_mean_vgather_kernel<<<dim3(s, heads, vz < 1 ? 1 : vz), 256, 0, st>>>(workspace, d_logits, s, N, R);
   SKP_CHECK_LAUNCH("capture_mean_vgather");
   *handled = true;
   return SKP_OK;
