@@ -371,15 +371,20 @@ __global__ void __launch_bounds__(ROW_MAX_THREADS, 2) capture_mean_row_bwd_kerne
       c0tab[i] = (int)fx + 1;
     }
     __syncthreads();
-    // pixel range of every halo'd column (c0tab is non-decreasing in X): pixels with c0 <= c <= c0 + 3
+    // pixel range of every halo'd column: pixels with c0 <= c <= c0 + 3.  One shared-memory atomic min / max per (pixel, tap)
+    // (the first version let s + 4 threads scan all nx pixels serially: ~2 us of one warp per x-block with everybody waiting)
     for (int c = tid; c < s + 4; c += NT) {
-      int lo = nx, hi = -1;
-      for (int i = 0; i < nx; ++i) {
-        const int d = c - c0tab[i];
-        if (d >= 0 && d <= 3) { lo = min(lo, i); hi = i; }
+      xrange[2 * c] = nx;
+      xrange[2 * c + 1] = -1;
+    }
+    __syncthreads();
+    for (int i = tid; i < nx; i += NT) {
+      const int c0 = c0tab[i];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        atomicMin(&xrange[2 * (c0 + d)], i);
+        atomicMax(&xrange[2 * (c0 + d) + 1], i);
       }
-      xrange[2 * c] = lo;
-      xrange[2 * c + 1] = hi;
     }
     // ---- 2. horizontal pass: e_n staged, partial (sum e, sum e*g) per token slice; g read coalesced over X from d_maps
     for (int X0 = 0; X0 < nx; X0 += P) {
