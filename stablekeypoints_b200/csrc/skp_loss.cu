@@ -110,6 +110,15 @@ __global__ void __launch_bounds__(256) equiv_fwd_kernel(const float* __restrict_
   if (threadIdx.x == 0) atomicAdd(loss, acc / ((float)K * (float)P));
 }
 
+// Backward of the equivariance loss.  d_maps gets one contribution per pixel.  d_maps_t is the transposed bilinear
+// sampling: instead of scattering four float atomics per source pixel (whose arrival order -- hence the rounding of the
+// sum -- changes from run to run), every destination pixel q GATHERS, in a fixed order, from the source pixels whose
+// bilinear footprint covers it.  The sampling position is affine in the pixel coordinates, (ix, iy) = A (x, y) + b, and
+// a footprint covers q iff (ix, iy) lies in q + [-1, 1)^2, so the candidates sit in the bounding box of A^-1 applied to
+// that square around A^-1 (q - b); membership is then decided by the very affine_tap() the forward uses, which makes
+// every term bit-identical to the scattered one.  A near-singular theta (box wider than GATHER_MAX) keeps the scatter.
+constexpr float EQUIV_GATHER_MAX = 6.f;
+
 __global__ void equiv_bwd_kernel(const float* __restrict__ maps, const float* __restrict__ maps_t, int H, int W,
                                  const int64_t* __restrict__ sel, int K, const float* __restrict__ theta_inv,
                                  const float* __restrict__ d_loss, float weight, float* __restrict__ d_maps,
@@ -119,21 +128,51 @@ __global__ void equiv_bwd_kernel(const float* __restrict__ maps, const float* __
   __syncthreads();
   const int P = H * W;
   const float c = 2.f * weight * (d_loss ? *d_loss : 1.f) / ((float)K * (float)P);
+  // pixel-space form of affine_tap: ix = a00 x + a01 y + bx, iy = a10 x + a11 y + by
+  const float a00 = th[0], a01 = th[1] * (float)W / (float)H, a10 = th[3] * (float)H / (float)W, a11 = th[4];
+  const float bx = ((th[0] * (1.f / (float)W - 1.f) + th[1] * (1.f / (float)H - 1.f) + th[2] + 1.f) * (float)W - 1.f) * 0.5f;
+  const float by = ((th[3] * (1.f / (float)W - 1.f) + th[4] * (1.f / (float)H - 1.f) + th[5] + 1.f) * (float)H - 1.f) * 0.5f;
+  const float det = a00 * a11 - a01 * a10;
+  const float rdet = det != 0.f ? 1.f / det : 0.f;
+  const float i00 = a11 * rdet, i01 = -a01 * rdet, i10 = -a10 * rdet, i11 = a00 * rdet;
+  const float rx = fabsf(i00) + fabsf(i01) + 0.02f, ry = fabsf(i10) + fabsf(i11) + 0.02f;   // half extents of A^-1 [-1,1)^2
+  const bool gather = det != 0.f && rx <= EQUIV_GATHER_MAX && ry <= EQUIV_GATHER_MAX;            // uniform over the grid
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * P; i += gridDim.x * blockDim.x) {
     int k = i / P, pix = i - k * P;
     int y = pix / W, x = pix - y * W;
-    BilinearTap t = affine_tap(th, y, x, H, W);
     size_t base = (size_t)sel[k] * P;
-    float g = c * (maps[base + pix] - sample_tap(maps_t + base, t, H, W));
-    if (d_maps) atomicAdd(d_maps + base + pix, g);
-    if (d_maps_t) {
-      float* dt = d_maps_t + base;
-      bool xa = t.x0 >= 0 && t.x0 < W, xb = t.x0 + 1 >= 0 && t.x0 + 1 < W;
-      bool ya = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-      if (ya && xa) atomicAdd(dt + t.y0 * W + t.x0, -g * t.w00);
-      if (ya && xb) atomicAdd(dt + t.y0 * W + t.x0 + 1, -g * t.w01);
-      if (yb && xa) atomicAdd(dt + (t.y0 + 1) * W + t.x0, -g * t.w10);
-      if (yb && xb) atomicAdd(dt + (t.y0 + 1) * W + t.x0 + 1, -g * t.w11);
+    const float* mt = maps_t + base;
+    if (d_maps || !gather) {
+      BilinearTap t = affine_tap(th, y, x, H, W);
+      float g = c * (maps[base + pix] - sample_tap(mt, t, H, W));
+      if (d_maps) atomicAdd(d_maps + base + pix, g);
+      if (d_maps_t && !gather) {
+        float* dt = d_maps_t + base;
+        bool xa = t.x0 >= 0 && t.x0 < W, xb = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+        bool ya = t.y0 >= 0 && t.y0 < H, yb = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+        if (ya && xa) atomicAdd(dt + t.y0 * W + t.x0, -g * t.w00);
+        if (ya && xb) atomicAdd(dt + t.y0 * W + t.x0 + 1, -g * t.w01);
+        if (yb && xa) atomicAdd(dt + (t.y0 + 1) * W + t.x0, -g * t.w10);
+        if (yb && xb) atomicAdd(dt + (t.y0 + 1) * W + t.x0 + 1, -g * t.w11);
+      }
+    }
+    if (d_maps_t && gather) {
+      // (x, y) now plays the destination pixel q of d_maps_t
+      const float qx = (float)x - bx, qy = (float)y - by;
+      const float cx = i00 * qx + i01 * qy, cy = i10 * qx + i11 * qy;
+      const int px0 = max(0, (int)ceilf(cx - rx)), px1 = min(W - 1, (int)floorf(cx + rx));
+      const int py0 = max(0, (int)ceilf(cy - ry)), py1 = min(H - 1, (int)floorf(cy + ry));
+      float acc = 0.f;
+      for (int py = py0; py <= py1; ++py)
+        for (int px = px0; px <= px1; ++px) {
+          BilinearTap t = affine_tap(th, py, px, H, W);
+          const int ddx = x - t.x0, ddy = y - t.y0;
+          if ((unsigned)ddx > 1u || (unsigned)ddy > 1u) continue;
+          const float wq = ddy ? (ddx ? t.w11 : t.w10) : (ddx ? t.w01 : t.w00);
+          const float g = c * (maps[base + py * W + px] - sample_tap(mt, t, H, W));
+          acc += -g * wq;
+        }
+      atomicAdd(d_maps_t + base + pix, acc);   // one contribution per address (atomic only against duplicate tokens in sel)
     }
   }
 }

@@ -541,6 +541,39 @@ def test_losses_golden(ops):
     assert rel_err(maps_t.grad.cpu(), post["dmaps_t"]) < 1e-5
 
 
+@pytest.mark.parametrize("theta,gathered", [
+    ([[0.85, 0.20, 0.10], [-0.20, 0.85, -0.15]], True),      # rotation + scale + translation (the augmentation's range)
+    ([[1.20, -0.31, -0.30], [0.31, 1.20, 0.25]], True),      # an inverse transform: magnification, part of the map leaves the frame
+    ([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]], True),              # identity: every footprint is a single pixel
+    ([[0.05, 0.0, 0.0], [0.0, 0.05, 0.0]], False),           # near-singular: pre-image box too wide, the scatter path serves it
+])
+def test_equivariance_backward_gather_vs_autograd(ops, theta, gathered):
+    """d(maps_t) of the equivariance loss (optimize.py:157-163 through invertable_transform.py:74-92) is a deterministic
+    GATHER over the bilinear footprints: equal to torch's grid_sample autograd (fp64) and bit-identical from run to run."""
+    g = torch.Generator().manual_seed(5)
+    n, r, k = 24, 128, 10
+    maps, maps_t = torch.rand(n, r, r, generator=g), torch.rand(n, r, r, generator=g)
+    sel = torch.randperm(n, generator=g)[:k]
+    th = torch.tensor(theta, dtype=torch.float32)
+    mr, mtr = maps.double().requires_grad_(True), maps_t.double().requires_grad_(True)
+    grid = F.affine_grid(th.double()[None], (1, k, r, r), align_corners=False)
+    un = F.grid_sample(mtr[sel][None], grid, mode="bilinear", padding_mode="zeros", align_corners=False)[0]
+    want = F.mse_loss(mr[sel], un)
+    want.backward()
+    runs = []
+    for _ in range(4):
+        mc, mtc = cu(maps).requires_grad_(True), cu(maps_t).requires_grad_(True)
+        loss = ops.equivariance_loss_op(mc, mtc, cu(sel), cu(th))
+        loss.backward()
+        runs.append((loss.detach().cpu(), mc.grad.cpu(), mtc.grad.cpu()))
+    # uncorrelated pixels: the fp32 sampling coordinate (ulp 8e-6 at 128) times a unit pixel-to-pixel step bounds the error
+    assert rel_err(runs[0][0], want.detach()) < 5e-6
+    assert rel_err(runs[0][1], mr.grad) < 1e-4
+    assert rel_err(runs[0][2], mtr.grad) < 1e-4
+    if gathered:
+        assert all(torch.equal(runs[0][2], r_[2]) and torch.equal(runs[0][1], r_[1]) for r_ in runs[1:])
+
+
 def test_reference_style_loss_api(ops):
     """optimize.sharpening_loss / equivariance_loss called the way optimize.py:397-401 calls them."""
     from stablekeypoints_b200 import optimize
