@@ -35,7 +35,8 @@ def main():
     heads = int(os.environ.get("SAN_HEADS", "2"))
     res = int(os.environ.get("SAN_RES", "64"))
     worst = 0.0
-    for row in (3, 2, 1, 0):   # 3: tcgen05 kernels forced where eligible; 2: register store kernel + row backward; 1: SIMT row kernels; 0: tile kernels
+    rows = tuple(int(r) for r in os.environ.get("SAN_ROWS", "3,2,1,0").split(","))
+    for row in rows:   # 3: tcgen05 kernels forced where eligible; 2: register store kernel + row backward; 1: SIMT row kernels; 0: tile kernels
         lib().skp_capture_tc(2 if row == 3 else 0)
         lib().skp_capture_select(min(row, 2), 1 if row else 0)
         ops.CAPTURE_MEAN_FWD = "store" if row else "fused"

@@ -525,6 +525,18 @@ def test_selection_vs_oracle_full_size(ops, t, h, seed):
                               hp.furthest_point_sampling(maps_t, k, cand_ref).numpy())
 
 
+def test_fps_edge_cases_vs_oracle(ops):
+    """ptp_utils.py:115-159 at its edges: fewer candidates than top_k (a shorter list comes back, as the reference's loop
+    gives), coincident peaks (zero distances, strict-'>' tie-breaks), the pair only; the oracle is pinned to the reference
+    on the same cases by tests/test_oracle_vs_reference.py::test_fps_edge_cases_vs_reference."""
+    from stablekeypoints_b200 import ptp_utils
+    from tests.test_oracle_vs_reference import _fps_edge_cases
+    for maps, top_k, cand in _fps_edge_cases():
+        want = hp.furthest_point_sampling(maps, top_k, cand)
+        got = ptp_utils.furthest_point_sampling(cu(maps), top_k, cu(cand))
+        assert np.array_equal(got.cpu().numpy(), want.numpy()), (top_k, cand.tolist(), got.tolist(), want.tolist())
+
+
 # ----------------------------------------------------------------------------- losses
 def test_losses_golden(ops):
     post = load_golden("post_unet.npz")

@@ -69,3 +69,26 @@ def test_hook_on_standin_tree(ref):
         assert rel_err(b, a) < 2e-6
     for a, b in zip(sa, sb):
         assert a.shape == b.shape == (4, 64, 6) and rel_err(b, a) < 2e-6
+
+
+def _fps_edge_cases():
+    """(maps, top_k, candidates): fewer candidates than top_k (the reference returns a SHORTER list, ptp_utils.py:139-159),
+    candidates whose peaks coincide (zero distances, ties resolved by the strict '>' scans), top_k == 2 (the pair only)."""
+    g = torch.Generator().manual_seed(7)
+    T, H = 12, 16
+    maps = torch.rand(T, H, H, generator=g) * 0.5
+    peaks = [(3, 4), (3, 4), (10, 12), (0, 0), (15, 15), (3, 4), (8, 8), (8, 9), (0, 15), (15, 0), (7, 7), (10, 12)]
+    for t, (y, x) in enumerate(peaks):
+        maps[t, y, x] = 1.0 + 0.01 * t
+    yield maps, 10, torch.tensor([5, 0, 2, 7])                   # 4 candidates for top_k = 10
+    yield maps, 6, torch.tensor([0, 1, 5, 2, 11, 6, 7])          # three coincident peaks + one coincident pair
+    yield maps, 2, torch.tensor([3, 4, 8, 9])                    # only the furthest pair (two diagonals tie)
+    yield maps, 5, torch.tensor([0, 1, 5])                       # every distance is zero: the pair is the first (i < j)
+    yield maps, 12, torch.arange(12)                             # candidates == top_k == all tokens
+
+
+def test_fps_edge_cases_vs_reference(ref):
+    for maps, top_k, cand in _fps_edge_cases():
+        want = ref.ptp_utils.furthest_point_sampling(maps, top_k, cand)
+        got = hp.furthest_point_sampling(maps, top_k, cand)
+        assert np.array_equal(got.numpy(), want.numpy()), (top_k, cand.tolist(), got.tolist(), want.tolist())
