@@ -22,16 +22,40 @@ def set_precision(mode: str) -> None:
     torch.backends.cudnn.benchmark = os.environ.get("SKP_CUDNN_BENCHMARK", "1") == "1"
 
 
+# AutoencoderKL mid-block attention: diffusers 0.8.0 (the reference's pin, requirements.yaml:174) names the projections
+# query / key / value / proj_attn (nn.Linear [C, C]); checkpoints re-saved by diffusers >= 0.18 call them
+# to_q / to_k / to_v / to_out.0, and CompVis-converted ones keep them as 1x1 convolutions [C, C, 1, 1].
+_VAE_ATTN_RENAMES = ((".to_q.", ".query."), (".to_k.", ".key."), (".to_v.", ".value."), (".to_out.0.", ".proj_attn."))
+
+
+def _normalize_vae_keys(sd):
+    """Bring a VAE state dict to the diffusers-0.8.0 key names / shapes the engine's parameter table uses."""
+    out = {}
+    for k, v in sd.items():
+        if ".attentions." in k:
+            for new, old in _VAE_ATTN_RENAMES:
+                k = k.replace(new, old)
+            if k.endswith(".weight") and v.dim() == 4 and v.shape[-2:] == (1, 1) and any(n in k for n in (".query.", ".key.", ".value.", ".proj_attn.")):
+                v = v.reshape(v.shape[0], v.shape[1])
+        out[k] = v
+    return out
+
+
 def _load_safetensors_dir(path: str, sub: str):
     from safetensors.torch import load_file
+    sd = None
     for name in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.fp16.safetensors"):
         f = os.path.join(path, sub, name)
         if os.path.exists(f):
-            return load_file(f)
-    f = os.path.join(path, sub, "diffusion_pytorch_model.bin")
-    if os.path.exists(f):
-        return torch.load(f, map_location="cpu")
-    raise FileNotFoundError(f"no diffusers weights under {os.path.join(path, sub)}")
+            sd = load_file(f)
+            break
+    if sd is None:
+        f = os.path.join(path, sub, "diffusion_pytorch_model.bin")
+        if os.path.exists(f):
+            sd = torch.load(f, map_location="cpu")
+    if sd is None:
+        raise FileNotFoundError(f"no diffusers weights under {os.path.join(path, sub)}")
+    return _normalize_vae_keys(sd) if sub == "vae" else sd
 
 
 def load_ldm(device, type="CompVis/stable-diffusion-v1-4", feature_upsample_res=256, my_token=None, *,

@@ -133,6 +133,22 @@ def test_diffusers_format_weight_directory_loader(tmp_path):
             assert torch.equal(sd[k], ref[k])
     with pytest.raises(FileNotFoundError):
         optimize_token._load_safetensors_dir(str(tmp_path), "text_encoder")
+    # a VAE re-saved by a newer diffusers (to_q / to_k / to_v / to_out.0) or converted from CompVis (1x1-conv projections,
+    # fp16 file) lands on the same diffusers-0.8.0 names and shapes
+    ren = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+    new_sd = {}
+    for k, v in pipe.vae.state_dict().items():
+        for old_name, new_name in ren.items():
+            if old_name in k:
+                k = k.replace(old_name, new_name)
+                v = v.reshape(*v.shape, 1, 1) if v.dim() == 2 else v
+        new_sd[k] = v.contiguous()
+    (tmp_path / "new" / "vae").mkdir(parents=True)
+    save_file(new_sd, str(tmp_path / "new" / "vae" / "diffusion_pytorch_model.fp16.safetensors"))
+    vae_new = optimize_token._load_safetensors_dir(str(tmp_path / "new"), "vae")
+    for k, shp in vae_encoder_param_shapes(vcfg).items():
+        assert k in vae_new and tuple(vae_new[k].shape) == tuple(shp), k
+        assert torch.equal(vae_new[k], pipe.vae.state_dict()[k])
 
 
 def test_reference_surface_signatures():
