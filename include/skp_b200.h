@@ -57,6 +57,11 @@ int skp_split_bf16(const float* x, int64_t ld, int rows, int cols, int cols_pad,
 int skp_gemm_nt_tc_plan(int M, int N, int Kpad);
 /* Tuning hook: force the N tile (64/96/128/160/256; 0 = planner) of skp_gemm_nt_tc / skp_conv3x3_tc (scripts/gemm_sweep.py). */
 void skp_gemm_tc_force_bn(int bn);
+/* Persistent form of the two kernels above (one CTA per SM walking several output tiles, two accumulators in tensor memory so
+ * that the epilogue of a tile overlaps the main loop of the next): 0 (default) never, 1 un-split problems with more tiles
+ * than SMs, 2 every un-split problem with several tiles per CTA (tests).  Env: SKP_GEMM_PERSIST.  Opt-in: faster per launch
+ * and bit-identical in isolation, not yet stable inside the multi-stream step (profiles/r02_gemm_persist.md). */
+void skp_gemm_tc_persist(int mode);
 int skp_gemm_nt_tc(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int Kpad,
                    float* C, int64_t ldc, int M, int N, float alpha, const float* bias,
                    const float* residual, int64_t ldr, int splits, float* splitk_ws, void* stream);

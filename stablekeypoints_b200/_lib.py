@@ -31,6 +31,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_split_bf16": [_P, _L, _I, _I, _I, _P, _P, _P],
     "skp_gemm_nt_tc_plan": [_I, _I, _I],
     "skp_gemm_tc_force_bn": [_I],
+    "skp_gemm_tc_persist": [_I],
     "skp_gemm_nt_tc": [_P, _P, _P, _P, _I, _P, _L, _I, _I, _F, _P, _P, _L, _I, _P, _P],
     "skp_im2col3x3_split": [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "skp_conv3x3_tc": [_P, _P, _I, _I, _I, _P, _P, _P, _L, _I, _F, _P, _P, _L, _I, _P, _P],
@@ -91,7 +92,7 @@ _SIGNATURES: Dict[str, list] = {
     "skp_adam_step": [_P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _P],
     "skp_adam_step_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }
-_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None, "skp_capture_select": None, "skp_capture_tc": None, "skp_capture_tc_trace": None,
+_RESTYPE = {"skp_last_error": C.c_char_p, "skp_launch_count": C.c_int64, "skp_gemm_tc_force_bn": None, "skp_gemm_tc_persist": None, "skp_capture_select": None, "skp_capture_tc": None, "skp_capture_tc_trace": None,
             "skp_self_attn_tc_workspace": C.c_int64, "skp_self_attn_tc_bwd_workspace": C.c_int64,
             "skp_capture_tc_workspace": C.c_int64, "skp_xattn_tc_workspace": C.c_int64,
             "skp_capture_mean_bwd_workspace": C.c_int64}

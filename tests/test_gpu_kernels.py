@@ -124,6 +124,45 @@ def test_groupnorm_fused_ops_vs_torch(ops, h, w, c, cout, groups, silu):
     assert rel_err(x1.grad.cpu(), cl(g1)) < 10 * tol
 
 
+@pytest.mark.parametrize("mode", [2, 1])
+def test_gemm_conv_persistent_kernel(ops, mode):
+    """gemm_nt_tc_persist_kernel (one CTA walks several output tiles, two accumulators in tensor memory): bit-identical to the
+    one-tile-per-CTA kernel -- same MMAs in the same order per tile, same epilogue arithmetic -- and within the GEMM
+    tolerance of fp64.  mode 2 forces it on every un-split problem with ~3 tiles per CTA (ragged M / N tails, non-vector N,
+    bias / residual, implicit convolution with image borders); mode 1 is the rule `SKP_GEMM_PERSIST=1` applies (more tiles
+    than SMs).  The kernel is opt-in (default 0): see profiles/r02_gemm_persist.md."""
+    from stablekeypoints_b200._lib import lib
+    g = torch.Generator().manual_seed(11 + mode)
+    gemms = [(1300, 200, 128), (513, 70, 200), (4096, 640, 320), (300, 1280, 64)] if mode == 2 else [(20000, 256, 192), (4096, 2560, 320)]
+    convs = [(64, 64, 64, 320), (24, 40, 128, 96), (32, 32, 192, 64)] if mode == 2 else [(128, 128, 64, 320)]
+    try:
+        for m, n, k in gemms:
+            a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** 0.5
+            bias, res = torch.randn(n, generator=g), torch.randn(m, n, generator=g)
+            fw = ops.FrozenWeight(cu(b))
+            outs = []
+            for md in (0, mode):
+                lib().skp_gemm_tc_persist(md)
+                outs.append((ops.frozen_linear(cu(a), fw, cu(bias), residual=cu(res)), ops.frozen_linear(cu(a), fw)))
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (m, n, k)
+            assert rel_err(outs[1][0].cpu(), a.double() @ b.double().t() + bias.double() + res.double()) < 3e-5
+        for h, w, cin, cout in convs:
+            x = torch.randn(1, cin, h, w, generator=g)
+            wt = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+            bias = torch.randn(cout, generator=g)
+            want = F.conv2d(x.double(), wt.double(), bias.double(), padding=1)[0].permute(1, 2, 0).reshape(h * w, cout)
+            xc = cu(x[0].permute(1, 2, 0).reshape(h * w, cin).contiguous())
+            fcw = ops.FrozenConv3x3(cu(wt))
+            outs = []
+            for md in (0, mode):
+                lib().skp_gemm_tc_persist(md)
+                outs.append(ops.frozen_conv3x3(xc, h, w, fcw, cu(bias))[0])
+            assert torch.equal(outs[0], outs[1]), (h, w, cin, cout)
+            assert rel_err(outs[1].cpu(), want) < 3e-5 * max(1.0, (9 * cin / 1024) ** 0.5)
+    finally:
+        lib().skp_gemm_tc_persist(0)
+
+
 # ----------------------------------------------------------------------------- LayerNorm / GEGLU fused projections
 @pytest.mark.parametrize("rows,c,n_out", [(4096, 320, 960), (256, 1280, 1280), (64, 1280, 10240), (16, 32, 48), (100, 64, 40)])
 def test_ln_linear_fwd_bwd(ops, rows, c, n_out):
